@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- marker-reads/sec per LLK evaluation on BASELINE.json configs[1]
+(synthetic pileup, 1000g.phase3.100k.b37 panel, 100k markers x 30x, NumPC=2, alpha=0.02).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one evaluation of the contamination log-likelihood (one call of the reference's
+ComputeMixLLKs) over the whole sample.  With N GPUs the markers are sharded across ranks
+(32-marker slices, round-robin) and a step is: every rank evaluates its shard, then ONE NCCL
+allreduce of the scalar partial -- strong scaling of a fixed sample.
+
+Keys of the JSON line (rank 0):
+  value     marker-reads/s with everything resident in HBM, device-timed (CUDA events on the launching
+            stream) over K back-to-back steps that rotate through enough resident copies of the sample
+            to exceed L2, so every step streams from HBM;
+  e2e       the same metric through the public call with HOST parameter buffers: each step copies the
+            step's inputs (2k+1 doubles) to the device and reads the scalar result back;
+  roofline  algorithmic bytes (2*R + 4*(k+2)*M') / measured kernel time vs measured HBM peak;
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref, else the C port) on this host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "marker-reads/sec per LLK eval"
+UNIT = "marker-reads/s"
+PANEL = "1000g.phase3.100k.b37"
+N_PC, DEPTH, ALPHA, SEED = 2, 30.0, 0.02, 1
+WORKLOAD = "synthetic pileup, %s panel, 100k markers x 30x, NumPC=2, alpha=0.02, sanity filter on (seed 1)" % PANEL
+L2_BYTES = 126 * 1024 * 1024
+
+
+def make_workload():
+    from verifybamid_b200 import panels, synth
+    panel = panels.load_bundled(PANEL)
+    return synth.make_sample(panel, n_pc=N_PC, depth=DEPTH, alpha=ALPHA, seed=SEED, sanity_check=True)
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU implementation on this host's cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(sample, evals: int, warmup: int, threads: int):
+    """Time `evals` evaluations of the whole workload on the CPU.  Returns (seconds, kind, reads_used)."""
+    from oracle import vb2_oracle as vo  # checker / baseline only -- never on the product path
+    p = sample.problem
+    if vo.ref_available():
+        from verifybamid_b200 import panels
+        with tempfile.TemporaryDirectory() as td:
+            prefix = panels.write_text_panel(sample.panel, os.path.join(td, "panel"))
+            pile = sample.write_pileup(os.path.join(td, "sample.pileup"))
+            recs = vo.run_ref(["--SVDPrefix", prefix, "--PileupFile", pile, "--NumPC", str(N_PC), "--NumThread",
+                               str(threads), "--NoOptimize", "--BenchEvals", str(evals), "--BenchWarmup", str(warmup),
+                               "--Output", os.path.join(td, "o")])
+        b = [r for r in recs if r["phase"] == "bench"][0]
+        return float(b["seconds"]), "reference", int(b["reads_used"])
+    ora = vo.Problem(p.ud, p.means, p.base_info_index, p.alt_base, p.info_offset, p.bases, p.quals, None,
+                     p.sanity_disabled, p.avg_depth, p.sd_depth, threads)
+    for _ in range(warmup):
+        ora.compute_mix_llks([0.01] * N_PC, [0.01] * N_PC, 0.03)
+    t0 = time.perf_counter()
+    for i in range(evals):
+        ora.compute_mix_llks([0.01 + 1e-6 * i] + [0.01] * (N_PC - 1), [0.01] * N_PC, 0.03)
+    return time.perf_counter() - t0, "port", ora.used_counts()[1]
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = make_workload()
+    threads = os.cpu_count() or 1
+    secs, kind, reads = cpu_reference_run(sample, args.steps, args.warmup, threads)
+    ms = secs / args.steps * 1e3
+    value = reads / (secs / args.steps)
+    cpu = {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+           "sample": "%d full evaluations of the workload (all %d reads each), %d threads" % (args.steps, reads, threads)}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "reads_per_step": reads},
+                      "cpu_baseline": cpu,
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import verifybamid_b200 as vb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the LLK engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+
+    sample = make_workload()
+    p = sample.problem
+    k = p.n_pc
+    # enough resident copies of this rank's shard to exceed L2 -> every step streams from HBM
+    probe = vb.LLKEngine(p, device=local, shard_rank=rank, shard_count=world, stream=stream.cuda_stream)
+    info = probe.info()
+    copies = max(2, int(np.ceil(2.0 * L2_BYTES / max(1, info["device_bytes"]))))
+    copies = min(copies, 256)
+    engines = [probe] + [vb.LLKEngine(p, device=local, shard_rank=rank, shard_count=world, stream=stream.cuda_stream)
+                         for _ in range(copies - 1)]
+    reads_total = p.used_counts()[1]           # whole sample, all shards
+    markers_total = p.used_counts()[0]
+    d_out = torch.zeros(1, dtype=torch.float64, device=dev)
+    pc_a = np.full((1, k), 0.01); pc_b = np.full((1, k), 0.01); al = np.array([0.03])
+
+    def step(i: int):
+        pc_a[0, 0] = 0.01 + 1e-7 * (i % 1000)
+        engines[i % copies].eval_batch_device(pc_a, pc_b, al, d_out.data_ptr())
+        if world > 1:
+            dist.all_reduce(d_out)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: device-timed, K back-to-back steps -------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i)
+        ev1.record(stream)
+        barrier()
+        dev_ms = ev0.elapsed_time(ev1)
+        # keep the sampler alive long enough to see the load for very short runs
+        if dev_ms < 300:
+            t_end = time.perf_counter() + 0.4
+            j = 0
+            while time.perf_counter() < t_end:
+                step(j); j += 1
+            barrier()
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = reads_total / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant (only) kernel at N=1: kernel-only timing, no collective -----
+    def kernel_only(i: int):
+        engines[i % copies].eval_batch_device(pc_a, pc_b, al, d_out.data_ptr())
+    for i in range(args.warmup):
+        kernel_only(i)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for i in range(args.steps):
+        kernel_only(i)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    kern_ms = ev0.elapsed_time(ev1) / args.steps
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes = info["algorithmic_bytes"]       # this rank's shard
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "llk_kernel", "kernel_us": kern_ms * 1e3,
+                "algorithmic_bytes_per_launch": alg_bytes, "device_bytes_per_launch": info["device_bytes"],
+                "note": "co-bound by FP64 issue rate: 12 fp64 ops per streamed read (DESIGN.md)"}
+
+    # ---- e2e: public call with host buffers, H2D of the parameters + D2H of the scalar each step
+    e2e_eng = engines[0]
+    host_pc_a = np.full(k, 0.01); host_pc_b = np.full(k, 0.01)
+    if world > 1:
+        host_out = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def e2e_step(i: int) -> float:
+        host_pc_a[0] = 0.01 + 1e-7 * (i % 1000)
+        eng = engines[i % copies]
+        if world == 1:
+            return eng.compute_mix_llks(host_pc_a, host_pc_b, 0.03)      # sync call: params in, scalar out
+        eng.eval_batch_device(host_pc_a[None, :], host_pc_b[None, :], al, d_out.data_ptr())
+        dist.all_reduce(d_out)
+        host_out.copy_(d_out, non_blocking=False)
+        return float(host_out[0])
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    last = 0.0
+    for i in range(args.steps):
+        last = e2e_step(args.warmup + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e = {"value": reads_total / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": (2 * k + 1) * 8,
+           "d2h_bytes_per_step": 8, "us_per_step": e2e_s / args.steps * 1e6, "last_llk": last}
+
+    # ---- cpu baseline beside it (rank 0, N=1 only) --------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_eval = 100
+        secs, kind, reads = cpu_reference_run(sample, n_eval, 3, threads)
+        cpu = {"value": reads / (secs / n_eval), "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": "%d full evaluations of the same workload (%d reads each), %d OpenMP threads; %.2f ms/eval"
+                         % (n_eval, reads, threads, secs / n_eval * 1e3)}
+
+    for e in engines:
+        e.close()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "reads_per_step": reads_total, "markers_used": markers_total,
+                           "n_pc": k, "parallelism": "marker shards x%d + 1 scalar allreduce/step" % world if world > 1
+                           else "single GPU", "l2": "steps rotate through %d resident copies of the sample "
+                           "(%.0f MB > 126 MB L2): every step streams from HBM" % (copies, copies * info["device_bytes"] / 1e6),
+                           "panel_dtype": "fp32 UD/mu in HBM, fp64 arithmetic"},
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps is None:            # defaults that finish within minutes on either arm
+        args.steps = 2000 if args.impl == "ours" else 200
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,189 @@
+/* vb2_llk.h -- C ABI of the B200 contamination-likelihood engine (libvb2llk.so).
+ *
+ * This is the drop-in boundary for ONE path of Griffan/VerifyBamID (VerifyBamID2):
+ *
+ *     double FullLLKFunc::ComputeMixLLKs(const std::vector<double>& tPC1,
+ *                                        const std::vector<double>& tPC2, const double alpha)
+ *                                                   (reference ContaminationEstimator.h:194-314)
+ *
+ * the genotype-mixture log-likelihood that FullLLKFunc::Evaluate (h:339-442), Initialize
+ * (h:316-332) and CalculateLLK0 (h:334-337) call, hundreds of times per sample, from
+ * AmoebaMinimizer::Minimize (MathGenMin.cpp:326-423).  The reference has no FFI; the line this
+ * ABI cuts at is that one pure function plus the data it reads.  INTEGRATION.md shows the
+ * five-line change a maintainer would make in ContaminationEstimator.h to bind it.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no C++/CUDA/torch types cross the boundary;
+ *   - every entry point returns VB2_OK (0) or a VB2_ERR_* code; the message is available from
+ *     vb2_last_error().  No exceptions cross the boundary (the reference's error() throws,
+ *     statgen/Error.cpp:26-40: the host wrapper converts);
+ *   - a context is NOT re-entrant: evaluations on one context are issued from one host thread
+ *     at a time, like the serial Nelder-Mead loop of the reference;
+ *   - there is no CPU fallback: without a usable CUDA device every call fails with
+ *     VB2_ERR_NO_DEVICE / VB2_ERR_CUDA.
+ */
+#ifndef VB2_LLK_H_
+#define VB2_LLK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB2_ABI_VERSION 1
+#define VB2_MAX_PC 16        /* largest n_pc a context accepts                               */
+#define VB2_MAX_BATCH 4096   /* largest n in one vb2_llk_eval_batch / vb2_llk_eval_many call */
+
+enum vb2_status {
+  VB2_OK = 0,
+  VB2_ERR_INVALID = 1,   /* bad argument / inconsistent descriptor                */
+  VB2_ERR_NO_DEVICE = 2, /* no CUDA device, or desc.device out of range           */
+  VB2_ERR_CUDA = 3,      /* a CUDA runtime call or kernel failed                  */
+  VB2_ERR_NOMEM = 4,     /* host or device allocation failed                      */
+  VB2_ERR_TIMEOUT = 5    /* the device did not answer (VB2_LLK_SPIN_TIMEOUT_MS)   */
+};
+
+enum vb2_panel_dtype {
+  VB2_PANEL_FP32 = 0, /* UD and mu stored fp32 in HBM (north-star layout; LLK agrees with the
+                         fp64 reference to ~1e-10 relative)                                  */
+  VB2_PANEL_FP64 = 1  /* UD and mu stored fp64: AF = UD.PC + mu reproduces the reference's
+                         double arithmetic operation for operation                           */
+};
+
+enum vb2_flags {
+  VB2_FLAG_NO_SPIN = 1u << 0 /* wait with cudaStreamSynchronize instead of polling the
+                                host-mapped result mailbox                                   */
+};
+
+typedef struct vb2_llk_ctx vb2_llk_ctx;
+
+/* Everything ComputeMixLLKs reads, as flat arrays.  The nested vectors of the reference
+ * become one CSR pair; all pointers are HOST pointers, copied at create (the caller may free
+ * them afterwards).
+ *
+ *   reference object                                        field
+ *   ------------------------------------------------------  ---------------------------------
+ *   ContaminationEstimator::NumMarker          (h:446)      n_marker
+ *   ContaminationEstimator::numPC              (h:49)       n_pc
+ *   ContaminationEstimator::UD[i][k]           (h:452)      ud[i*ud_stride + k]
+ *   ContaminationEstimator::means[i]           (h:454)      means[i]
+ *   resolvedMarkers[i].baseInfoIndex           (h:471)      base_info_index[i]   (-1 = absent)
+ *   resolvedMarkers[i].altBase                 (h:472)      alt_base[i]
+ *   resolvedMarkers[i].knownAFValue, isAFknown (h:473,:44)  known_af[i] or NULL
+ *   viewer.baseInfo[b] / viewer.qualInfo[b]    (SimplePileupViewer.h:94-95)
+ *                                                           bases/quals[info_offset[b] ..
+ *                                                                       info_offset[b+1])
+ *   isSanityCheckDisabled                      (h:47)       sanity_disabled
+ *   viewer.avgDepth, viewer.sdDepth            (SimplePileupViewer.h:100-101)
+ *                                                           avg_depth, sd_depth
+ *   FullLLKFunc::min_af, max_af                (h:94-95)    min_af, max_af (0,0 = defaults)
+ */
+typedef struct vb2_llk_desc {
+  uint32_t struct_size; /* = sizeof(vb2_llk_desc); ABI guard */
+  uint32_t n_marker;
+  uint32_t n_pc;
+  uint32_t ud_stride; /* doubles between consecutive rows of ud (>= n_pc) */
+  const double *ud;
+  const double *means;
+  const int32_t *base_info_index;
+  const char *alt_base;
+  const double *known_af;
+  const int64_t *info_offset;
+  const char *bases;
+  const char *quals;
+  int32_t sanity_disabled;
+  int32_t device;      /* CUDA device ordinal */
+  double avg_depth;
+  double sd_depth;
+  double min_af;
+  double max_af;
+  int32_t panel_dtype; /* enum vb2_panel_dtype */
+  uint32_t flags;      /* enum vb2_flags */
+  /* Marker shard owned by this context (multi-GPU): the used markers are cut into 32-marker
+   * slices and slice s belongs to shard s % shard_count.  0/0 and 0/1 mean "everything".
+   * vb2_llk_eval then returns this shard's partial sum; the caller adds the partials
+   * (one allreduce of a double per evaluation).                                             */
+  uint32_t shard_rank;
+  uint32_t shard_count;
+  void *stream; /* cudaStream_t to launch on; NULL = a stream owned by the context */
+} vb2_llk_desc;
+
+typedef struct vb2_llk_info {
+  uint32_t struct_size;
+  uint32_t n_pc;
+  uint64_t markers_used;     /* markers surviving the skip rules h:238-249 (this shard)     */
+  uint64_t reads_used;       /* sum of their depths: R_used, the unit of the metric          */
+  uint64_t reads_streamed;   /* ref+alt reads actually visited per evaluation                */
+  uint64_t reads_folded;     /* class-2 ("other") reads folded into one constant at create   */
+  uint64_t algorithmic_bytes;/* 2*R_used + 4*(n_pc+2)*markers_used              */
+  uint64_t device_bytes;     /* bytes one evaluation really reads from HBM                   */
+  uint32_t n_slices;         /* 32-marker warp slices                                        */
+  uint32_t grid_x;           /* CTAs per evaluation                                          */
+  uint32_t block_threads;
+  uint32_t smem_bytes;       /* dynamic shared memory per CTA                                */
+  int32_t device;
+  int32_t sm_count;
+  double log_other_const;    /* sum over folded reads of log(2e/3)                           */
+} vb2_llk_info;
+
+int vb2_abi_version(void);
+int vb2_device_count(void); /* number of CUDA devices, 0 if none / no driver */
+
+/* Flatten (classify, filter, sort, pack), upload to HBM, allocate the result mailbox.        */
+int vb2_llk_create(const vb2_llk_desc *desc, vb2_llk_ctx **out);
+void vb2_llk_destroy(vb2_llk_ctx *ctx);
+int vb2_llk_get_info(const vb2_llk_ctx *ctx, vb2_llk_info *info);
+
+/* One evaluation: *llk_out = ComputeMixLLKs(pc_contam, pc_intended, alpha)  (+LLK; the caller
+ * negates, h:344).  Host pointers; returns after the result is in *llk_out.                  */
+int vb2_llk_eval(vb2_llk_ctx *ctx, const double *pc_contam, const double *pc_intended, double alpha,
+                 double *llk_out);
+
+/* n evaluations of the same sample in ONE pass (e.g. all Nelder-Mead candidates of a step):
+ * pc_contam / pc_intended are [n][n_pc] row-major, alphas and llk_out are [n].               */
+int vb2_llk_eval_batch(vb2_llk_ctx *ctx, int n, const double *pc_contam, const double *pc_intended,
+                       const double *alphas, double *llk_out);
+
+/* Same as vb2_llk_eval_batch but asynchronous and with the results left in DEVICE memory
+ * (d_llk_out[n], on the context's stream) -- the form a caller uses when the partial sums of
+ * several marker shards go straight into an NCCL allreduce.                                  */
+int vb2_llk_eval_batch_device(vb2_llk_ctx *ctx, int n, const double *pc_contam, const double *pc_intended,
+                              const double *alphas, double *d_llk_out);
+
+/* One evaluation of each of n DIFFERENT samples (contexts on the same device) in one launch:
+ * job j uses ctxs[j] with parameters pc_contam[j][n_pc], pc_intended[j][n_pc], alphas[j].
+ * All contexts must share n_pc.  Results and synchronisation follow ctxs[0]'s stream.        */
+int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
+                      const double *alphas, double *llk_out);
+
+/* Block until everything queued on the context's stream has finished. */
+int vb2_llk_sync(vb2_llk_ctx *ctx);
+
+/* Message of the last failing call on this thread (ctx may be NULL); never NULL. */
+const char *vb2_last_error(const vb2_llk_ctx *ctx);
+
+/* ---- diagnostics (host only, no CUDA call): the flattened image vb2_llk_create uploads ------
+ * Lets CPU-only tests check the flatten (skip rules, classification, folding, slice layout,
+ * sharding) without a GPU.  All pointers are owned by the view until vb2_llk_pack_free.     */
+typedef struct vb2_packed_view {
+  uint32_t struct_size;
+  uint32_t n_pc, n_used, n_slices, m_pad, max_slice_words;
+  uint64_t reads_used, reads_streamed, reads_folded, n_words;
+  double log_other_const;
+  const uint32_t *words;        /* [n_words]: slice s, word t, lane l at slice_desc[2s] + t*32 + l */
+  const uint32_t *slice_desc;   /* [n_slices][2]: word offset, ref_words | alt_words << 16        */
+  const double *ud;             /* [n_pc][m_pad]                                                  */
+  const double *mu;             /* [m_pad]                                                        */
+  const double *diag;           /* [3][m_pad]                                                     */
+  const double *known_af;       /* [m_pad] or NULL                                                */
+  const uint32_t *marker_index; /* [m_pad] panel row, 0xFFFFFFFF = padding                        */
+  void *owner;
+} vb2_packed_view;
+int vb2_llk_pack_host(const vb2_llk_desc *desc, vb2_packed_view *view);
+void vb2_llk_pack_free(vb2_packed_view *view);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VB2_LLK_H_ */

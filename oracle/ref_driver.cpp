@@ -13,6 +13,7 @@
 //   --EvalPoints <file>   one "pc_contam[k] pc_intended[k] alpha" per line; prints the
 //                         value of FullLLKFunc::ComputeMixLLKs at each (%.17g)
 //   --BenchEvals <n>      time n back-to-back ComputeMixLLKs calls at the start point
+//   --BenchWarmup <w>     untimed calls before them (default 1)
 //   --NoOptimize          skip OptimizeLLK (with --EvalPoints / --BenchEvals)
 // and one machine-readable "VB2REF {json}" line on stdout per action.
 #include <chrono>
@@ -43,7 +44,7 @@ struct Args {
   std::string out = "result", fixPC = "Empty", knownAF = "Empty", evalPoints = "Empty";
   double fixAlpha = -1., epsilon = 1e-8;
   bool within = false, disableSanity = false, verbose = false, noOptimize = false;
-  int nPC = 2, nthread = 4, seed = 12345, benchEvals = 0;
+  int nPC = 2, nthread = 4, seed = 12345, benchEvals = 0, benchWarmup = 1;
 };
 
 bool parse(int argc, char **argv, Args &a) {
@@ -72,6 +73,7 @@ bool parse(int argc, char **argv, Args &a) {
     else if (f == "--Verbose") a.verbose = true;
     else if (f == "--EvalPoints") a.evalPoints = val("--EvalPoints");
     else if (f == "--BenchEvals") a.benchEvals = atoi(val("--BenchEvals"));
+    else if (f == "--BenchWarmup") a.benchWarmup = atoi(val("--BenchWarmup"));
     else if (f == "--NoOptimize") a.noOptimize = true;
     else { fprintf(stderr, "unknown option %s\n", f.c_str()); return false; }
   }
@@ -170,7 +172,8 @@ int main(int argc, char **argv) {
       }
       if (a.benchEvals > 0) {
         std::vector<double> p1(a.nPC, 0.01), p2(a.nPC, 0.01);
-        double sink = Estimator.fn.ComputeMixLLKs(p1, p2, 0.03);  // warm-up
+        double sink = 0;
+        for (int i = 0; i < a.benchWarmup; ++i) sink += Estimator.fn.ComputeMixLLKs(p1, p2, 0.03);  // warm-up
         double b0 = now_s();
         for (int i = 0; i < a.benchEvals; ++i) {
           p1[0] = 0.01 + 1e-6 * i;

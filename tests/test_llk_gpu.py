@@ -1,0 +1,193 @@
+"""Parity of the sm_100a path with the CPU oracle, through the C ABI (ctypes -> libvb2llk.so).
+
+Tolerances (fp64 arithmetic on both sides, different operation order):
+  REL_FP64  panel stored fp64 in HBM: only rounding-order differences          -> 1e-11 relative
+  REL_FP32  panel stored fp32 (north-star layout): UD/mu rounded to fp32 once  -> 1e-9  relative
+(BASELINE north_star: final alpha and PCs within 1e-4; SURVEY section 7: LLK <= 1e-8 relative.)
+"""
+import os
+
+import numpy as np
+import pytest
+
+import verifybamid_b200 as vb
+from verifybamid_b200 import panels, synth
+from helpers import (KAT_LONGREAD, KAT_POINTS, KAT_RESULT, LONGREAD_PILEUP, RESULT_PILEUP, golden_problem, to_oracle,
+                     to_product)
+
+pytestmark = pytest.mark.gpu
+
+REL_FP64 = 1e-11
+REL_FP32 = 1e-9
+
+POINTS = [([0.01, 0.01], [0.01, 0.01], 0.03), ([0.02, -0.01], [-0.01, 0.027], 0.05), ([0.0, 0.0], [0.0, 0.0], 0.5),
+          ([-0.0101, 0.0269], [-0.0101, 0.0269], 0.0), ([0.05, -0.02], [0.01, 0.01], 0.999)]
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+@pytest.mark.parametrize("pileup,kat", [(RESULT_PILEUP, KAT_RESULT), (LONGREAD_PILEUP, KAT_LONGREAD)])
+@pytest.mark.parametrize("dtype", [vb.VB2_PANEL_FP64, vb.VB2_PANEL_FP32])
+def test_reference_known_answers(pileup, kat, dtype):
+    tol = REL_FP64 if dtype == vb.VB2_PANEL_FP64 else REL_FP32
+    with vb.LLKEngine(to_product(golden_problem(pileup)), panel_dtype=dtype) as eng:
+        for (pc1, pc2, a), want in zip(KAT_POINTS, kat):
+            assert rel(eng.compute_mix_llks(pc1, pc2, a), want) <= tol
+
+
+@pytest.fixture(scope="module")
+def sample10k():
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    return synth.make_sample(panel, n_pc=2, depth=30.0, alpha=0.02, seed=4)
+
+
+@pytest.mark.parametrize("dtype,tol", [(vb.VB2_PANEL_FP64, REL_FP64), (vb.VB2_PANEL_FP32, REL_FP32)])
+def test_synthetic_10k_matches_oracle(sample10k, dtype, tol):
+    p = sample10k.problem
+    ora = to_oracle(p)
+    with vb.LLKEngine(p, panel_dtype=dtype) as eng:
+        info = eng.info()
+        assert (info["markers_used"], info["reads_used"]) == ora.used_counts()
+        assert info["reads_streamed"] + info["reads_folded"] == info["reads_used"]
+        for pc1, pc2, a in POINTS:
+            assert rel(eng.compute_mix_llks(pc1, pc2, a), ora.compute_mix_llks(pc1, pc2, a)) <= tol
+
+
+def test_four_pcs(sample10k):
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    s = synth.make_sample(panel, n_pc=4, depth=20.0, alpha=0.03, seed=9, n_markers=5000)
+    ora = to_oracle(s.problem)
+    with vb.LLKEngine(s.problem, panel_dtype=vb.VB2_PANEL_FP64) as eng:
+        for pc in ([0.01] * 4, list(s.pc_intended), [0.03, -0.02, 0.01, 0.005]):
+            assert rel(eng.compute_mix_llks(pc, list(s.pc_intended), 0.03),
+                       ora.compute_mix_llks(pc, list(s.pc_intended), 0.03)) <= REL_FP64
+
+
+def test_bit_reproducible_and_batch_equals_single(sample10k):
+    with vb.LLKEngine(sample10k.problem) as eng:
+        single = [eng.compute_mix_llks(*pt) for pt in POINTS]
+        again = [eng.compute_mix_llks(*pt) for pt in POINTS]
+        assert single == again                                   # identical bits for identical inputs
+        pc1 = np.array([pt[0] for pt in POINTS]); pc2 = np.array([pt[1] for pt in POINTS])
+        al = np.array([pt[2] for pt in POINTS])
+        assert eng.eval_batch(pc1, pc2, al).tolist() == single   # candidates in one pass: same bits
+        # more candidates than fit in the kernel arguments -> parameters staged through HBM
+        rep = 5
+        big = eng.eval_batch(np.tile(pc1, (rep, 1)), np.tile(pc2, (rep, 1)), np.tile(al, rep))
+        assert big.tolist() == single * rep
+
+
+def test_stream_sync_wait_mode(sample10k):
+    with vb.LLKEngine(sample10k.problem, spin=False) as a, vb.LLKEngine(sample10k.problem, spin=True) as b:
+        for pt in POINTS[:3]:
+            assert a.compute_mix_llks(*pt) == b.compute_mix_llks(*pt)
+
+
+@pytest.mark.parametrize("n_shards", [2, 8])
+def test_marker_shards_sum_to_whole(sample10k, n_shards):
+    p = sample10k.problem
+    with vb.LLKEngine(p) as whole:
+        parts = [vb.LLKEngine(p, shard_rank=r, shard_count=n_shards) for r in range(n_shards)]
+        try:
+            assert sum(e.info()["reads_used"] for e in parts) == whole.info()["reads_used"]
+            for pt in POINTS[:3]:
+                total = sum(e.compute_mix_llks(*pt) for e in parts)
+                assert rel(total, whole.compute_mix_llks(*pt)) <= 1e-12
+        finally:
+            for e in parts:
+                e.close()
+
+
+def test_eval_many_samples_one_launch():
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    samples = [synth.make_sample(panel, n_pc=2, depth=d, alpha=0.02, seed=100 + i, n_markers=3000 + 500 * i)
+               for i, d in enumerate((8.0, 30.0, 55.0))]
+    engines = [vb.LLKEngine(s.problem) for s in samples]
+    try:
+        order = [0, 1, 2, 1]                                    # a context may appear more than once
+        pc1 = np.array([[0.01, 0.01], [0.02, -0.01], [0.0, 0.0], [0.03, 0.01]])
+        pc2 = np.array([[0.01, 0.01], [-0.01, 0.027], [0.0, 0.0], [0.01, 0.01]])
+        al = np.array([0.03, 0.05, 0.5, 0.2])
+        got = vb.eval_many([engines[i] for i in order], pc1, pc2, al)
+        want = [engines[i].compute_mix_llks(pc1[j], pc2[j], al[j]) for j, i in enumerate(order)]
+        assert got.tolist() == want
+    finally:
+        for e in engines:
+            e.close()
+
+
+def test_deep_coverage_multi_stage(monkeypatch):
+    """200x depth with a tiny shared-memory stage: every slice needs several double-buffered TMA stages."""
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    s = synth.make_sample(panel, n_pc=2, depth=200.0, alpha=0.02, seed=5, n_markers=2000)
+    ora = to_oracle(s.problem)
+    want = [ora.compute_mix_llks(*pt) for pt in POINTS[:3]]
+    for stage in ("3", "7", "64"):
+        monkeypatch.setenv("VB2_LLK_STAGE_WORDS", stage)
+        with vb.LLKEngine(s.problem, panel_dtype=vb.VB2_PANEL_FP64) as eng:
+            got = [eng.compute_mix_llks(*pt) for pt in POINTS[:3]]
+        assert all(rel(g, w) <= REL_FP64 for g, w in zip(got, want)), (stage, got, want)
+
+
+def test_known_af_mode(sample10k):
+    p = sample10k.problem
+    rng = np.random.default_rng(3)
+    kaf = rng.uniform(0.0, 1.0, p.n_marker)
+    kaf[:50] = 0.0                                               # exercises the 5e-5 clamp
+    q = vb.PileupProblem(p.ud, p.means, p.base_info_index, p.alt_base, p.info_offset, p.bases, p.quals, kaf,
+                         p.sanity_disabled, p.avg_depth, p.sd_depth)
+    ora = to_oracle(q)
+    with vb.LLKEngine(q) as eng:
+        for a in (0.03, 0.3):
+            assert rel(eng.compute_mix_llks([0, 0], [0, 0], a), ora.compute_mix_llks([0, 0], [0, 0], a)) <= REL_FP64
+
+
+def test_edge_inputs():
+    g = to_product(golden_problem(RESULT_PILEUP))
+    # no usable marker -> the reference's empty sum, 0.0
+    none = vb.PileupProblem(g.ud, g.means, np.full(g.n_marker, -1, np.int32), g.alt_base, np.zeros(1, np.int64),
+                            np.zeros(0, np.uint8), np.zeros(0, np.uint8))
+    with vb.LLKEngine(none) as eng:
+        assert eng.compute_mix_llks([0, 0], [0, 0], 0.5) == 0.0
+        assert eng.eval_batch(np.zeros((3, 2)), np.zeros((3, 2)), np.full(3, 0.1)).tolist() == [0.0] * 3
+    # qualities outside Phred+33 are clamped to [0, 93] (h:296-298); 'N' and unknown bases are class "other"
+    ud = np.array([[0.5, -0.2], [0.1, 0.3]]); mu = np.array([0.8, 1.1])
+    bases = np.frombuffer(b".,Aa" + b"NnGg*.", dtype=np.uint8)
+    quals = np.array([0, 20, 33, 255, 40, 126, 33 + 93, 33 + 94, 60, 34], dtype=np.uint8)
+    p = vb.PileupProblem(ud, mu, np.array([0, 1], np.int32), np.frombuffer(b"AG", dtype=np.uint8),
+                         np.array([0, 4, 10], np.int64), bases, quals)
+    ora = to_oracle(p)
+    with vb.LLKEngine(p, panel_dtype=vb.VB2_PANEL_FP64) as eng:
+        for a in (0.0, 0.2, 1.0):
+            assert rel(eng.compute_mix_llks([0.1, 0.1], [-0.1, 0.2], a),
+                       ora.compute_mix_llks([0.1, 0.1], [-0.1, 0.2], a)) <= REL_FP64
+    # argument checking: wrong vector length is refused on the host side
+    with vb.LLKEngine(g) as eng:
+        with pytest.raises(ValueError):
+            eng.compute_mix_llks([0.0], [0.0, 0.0], 0.1)
+
+
+def test_full_size_invariants():
+    """BASELINE config 2 (100k x 30x): size-independent properties at full size + oracle agreement."""
+    panel = panels.load_bundled("1000g.phase3.100k.b37")
+    s = synth.make_sample(panel, n_pc=2, depth=30.0, alpha=0.02, seed=1)
+    p = s.problem
+    ora = to_oracle(p, num_thread=os.cpu_count() or 1)
+    with vb.LLKEngine(p) as eng:
+        info = eng.info()
+        assert info["reads_used"] == p.used_counts()[1] and info["markers_used"] == p.used_counts()[0]
+        truth = (list(s.pc_contam), list(s.pc_intended), 0.02)
+        l_true = eng.compute_mix_llks(*truth)
+        assert rel(l_true, ora.compute_mix_llks(*truth)) <= REL_FP32
+        # the likelihood prefers the generating parameters to the optimiser's start and to the null model
+        assert l_true > eng.compute_mix_llks([0.01, 0.01], [0.01, 0.01], 0.03)
+        assert l_true > eng.compute_mix_llks(truth[0], truth[1], 0.0)
+        # additivity over marker shards (a checksum of checksums)
+        parts = [vb.LLKEngine(p, shard_rank=r, shard_count=4) for r in range(4)]
+        try:
+            assert rel(sum(e.compute_mix_llks(*truth) for e in parts), l_true) <= 1e-12
+        finally:
+            for e in parts:
+                e.close()

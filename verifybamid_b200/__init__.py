@@ -1,0 +1,12 @@
+"""verifybamid_b200 -- B200-native contamination-likelihood engine for the VerifyBamID2 hot path.
+
+Only what that one path needs lives here:
+  csrc/        hand-written sm_100a kernel + C ABI (libvb2llk.so) + the C++ host side / CLI
+  engine.py    ctypes binding of the C ABI (what tests and bench.py call)
+  problem.py   the flat image of the reference's estimator data the ABI takes
+  panels.py    bundled SVD panels, text <-> packed
+  synth.py     synthetic contaminated pileups (BASELINE.json configs)
+"""
+from .problem import PileupProblem  # noqa: F401
+from .engine import (LLKEngine, VB2Error, eval_many, load_library, build_library, device_count,  # noqa: F401
+                     pack_host, VB2_PANEL_FP32, VB2_PANEL_FP64, ABI_SYMBOLS)

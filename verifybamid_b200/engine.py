@@ -1,0 +1,281 @@
+"""ctypes binding of libvb2llk.so (include/vb2_llk.h) -- the call a Python user makes.
+
+`LLKEngine.compute_mix_llks(pc_contam, pc_intended, alpha)` has the signature and the value
+contract of the reference's FullLLKFunc::ComputeMixLLKs (ContaminationEstimator.h:194-195):
+it returns +LLK and the caller negates.
+
+There is no CPU fallback: if the CUDA library is missing or no device is usable this module
+raises -- it never routes through oracle/.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .problem import PileupProblem
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libvb2llk.so")
+
+VB2_OK = 0
+VB2_PANEL_FP32 = 0
+VB2_PANEL_FP64 = 1
+VB2_FLAG_NO_SPIN = 1
+VB2_MAX_PC = 16
+VB2_MAX_BATCH = 4096
+
+_STATUS = {1: "VB2_ERR_INVALID", 2: "VB2_ERR_NO_DEVICE", 3: "VB2_ERR_CUDA", 4: "VB2_ERR_NOMEM", 5: "VB2_ERR_TIMEOUT"}
+
+# every symbol include/vb2_llk.h declares (tests check the library exports exactly these)
+ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_create", "vb2_llk_destroy", "vb2_llk_get_info",
+               "vb2_llk_eval", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many",
+               "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free")
+
+
+class VB2Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("%s: %s" % (_STATUS.get(code, "VB2_ERR_%d" % code), msg))
+        self.code = code
+
+
+class _Desc(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("n_marker", ctypes.c_uint32), ("n_pc", ctypes.c_uint32),
+                ("ud_stride", ctypes.c_uint32), ("ud", ctypes.c_void_p), ("means", ctypes.c_void_p),
+                ("base_info_index", ctypes.c_void_p), ("alt_base", ctypes.c_void_p), ("known_af", ctypes.c_void_p),
+                ("info_offset", ctypes.c_void_p), ("bases", ctypes.c_void_p), ("quals", ctypes.c_void_p),
+                ("sanity_disabled", ctypes.c_int32), ("device", ctypes.c_int32),
+                ("avg_depth", ctypes.c_double), ("sd_depth", ctypes.c_double),
+                ("min_af", ctypes.c_double), ("max_af", ctypes.c_double),
+                ("panel_dtype", ctypes.c_int32), ("flags", ctypes.c_uint32),
+                ("shard_rank", ctypes.c_uint32), ("shard_count", ctypes.c_uint32), ("stream", ctypes.c_void_p)]
+
+
+class _Info(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("n_pc", ctypes.c_uint32),
+                ("markers_used", ctypes.c_uint64), ("reads_used", ctypes.c_uint64),
+                ("reads_streamed", ctypes.c_uint64), ("reads_folded", ctypes.c_uint64),
+                ("algorithmic_bytes", ctypes.c_uint64), ("device_bytes", ctypes.c_uint64),
+                ("n_slices", ctypes.c_uint32), ("grid_x", ctypes.c_uint32), ("block_threads", ctypes.c_uint32),
+                ("smem_bytes", ctypes.c_uint32), ("device", ctypes.c_int32), ("sm_count", ctypes.c_int32),
+                ("log_other_const", ctypes.c_double)]
+
+
+class _PackedView(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("n_pc", ctypes.c_uint32), ("n_used", ctypes.c_uint32),
+                ("n_slices", ctypes.c_uint32), ("m_pad", ctypes.c_uint32), ("max_slice_words", ctypes.c_uint32),
+                ("reads_used", ctypes.c_uint64), ("reads_streamed", ctypes.c_uint64),
+                ("reads_folded", ctypes.c_uint64), ("n_words", ctypes.c_uint64),
+                ("log_other_const", ctypes.c_double),
+                ("words", ctypes.POINTER(ctypes.c_uint32)), ("slice_desc", ctypes.POINTER(ctypes.c_uint32)),
+                ("ud", ctypes.POINTER(ctypes.c_double)), ("mu", ctypes.POINTER(ctypes.c_double)),
+                ("diag", ctypes.POINTER(ctypes.c_double)), ("known_af", ctypes.POINTER(ctypes.c_double)),
+                ("marker_index", ctypes.POINTER(ctypes.c_uint32)), ("owner", ctypes.c_void_p)]
+
+
+_lib = None
+
+
+def build_library(quiet: bool = True) -> None:
+    """Compile libvb2llk.so (and the CLI) in-tree with nvcc for sm_100a."""
+    subprocess.run(["make", "-C", os.path.join(PKG_DIR, "csrc"), "all"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the CUDA engine.  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the likelihood path has no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.vb2_abi_version.restype = ctypes.c_int
+    lib.vb2_device_count.restype = ctypes.c_int
+    lib.vb2_last_error.restype = ctypes.c_char_p
+    lib.vb2_last_error.argtypes = [ctypes.c_void_p]
+    lib.vb2_llk_create.restype = ctypes.c_int
+    lib.vb2_llk_create.argtypes = [ctypes.POINTER(_Desc), ctypes.POINTER(ctypes.c_void_p)]
+    lib.vb2_llk_destroy.restype = None
+    lib.vb2_llk_destroy.argtypes = [ctypes.c_void_p]
+    lib.vb2_llk_get_info.restype = ctypes.c_int
+    lib.vb2_llk_get_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Info)]
+    lib.vb2_llk_eval.restype = ctypes.c_int
+    lib.vb2_llk_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+                                 ctypes.POINTER(ctypes.c_double)]
+    for name in ("vb2_llk_eval_batch", "vb2_llk_eval_batch_device"):
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.vb2_llk_eval_many.restype = ctypes.c_int
+    lib.vb2_llk_eval_many.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p]
+    lib.vb2_llk_sync.restype = ctypes.c_int
+    lib.vb2_llk_sync.argtypes = [ctypes.c_void_p]
+    lib.vb2_llk_pack_host.restype = ctypes.c_int
+    lib.vb2_llk_pack_host.argtypes = [ctypes.POINTER(_Desc), ctypes.POINTER(_PackedView)]
+    lib.vb2_llk_pack_free.restype = None
+    lib.vb2_llk_pack_free.argtypes = [ctypes.POINTER(_PackedView)]
+    if lib.vb2_abi_version() != 1:
+        raise RuntimeError("libvb2llk.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def device_count() -> int:
+    return int(load_library().vb2_device_count())
+
+
+def _f64(a, shape=None) -> np.ndarray:
+    out = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and out.shape != shape:
+        out = out.reshape(shape)
+    return out
+
+
+def make_desc(problem: PileupProblem, device: int = 0, panel_dtype: int = VB2_PANEL_FP32, shard_rank: int = 0,
+              shard_count: int = 1, stream: Optional[int] = None, spin: bool = True, min_af: float = 0.0,
+              max_af: float = 0.0) -> _Desc:
+    """vb2_llk_desc over the numpy arrays of `problem` (which must stay alive during the call)."""
+    d = _Desc()
+    d.struct_size = ctypes.sizeof(_Desc)
+    d.n_marker = problem.n_marker
+    d.n_pc = problem.n_pc
+    d.ud_stride = problem.n_pc
+    d.ud = problem.ud.ctypes.data
+    d.means = problem.means.ctypes.data
+    d.base_info_index = problem.base_info_index.ctypes.data
+    d.alt_base = problem.alt_base.ctypes.data
+    d.known_af = problem.known_af.ctypes.data if problem.known_af is not None else None
+    d.info_offset = problem.info_offset.ctypes.data
+    d.bases = problem.bases.ctypes.data if problem.bases.size else None
+    d.quals = problem.quals.ctypes.data if problem.quals.size else None
+    d.sanity_disabled = int(problem.sanity_disabled)
+    d.device = int(device)
+    d.avg_depth = float(problem.avg_depth)
+    d.sd_depth = float(problem.sd_depth)
+    d.min_af, d.max_af = float(min_af), float(max_af)
+    d.panel_dtype = int(panel_dtype)
+    d.flags = 0 if spin else VB2_FLAG_NO_SPIN
+    d.shard_rank, d.shard_count = int(shard_rank), int(shard_count)
+    d.stream = stream
+    return d
+
+
+def pack_host(problem: PileupProblem, shard_rank: int = 0, shard_count: int = 1) -> dict:
+    """Host-only: the flattened image vb2_llk_create would upload, as numpy copies (no CUDA call)."""
+    lib = load_library()
+    d = make_desc(problem, shard_rank=shard_rank, shard_count=shard_count)
+    v = _PackedView()
+    v.struct_size = ctypes.sizeof(_PackedView)
+    rc = lib.vb2_llk_pack_host(ctypes.byref(d), ctypes.byref(v))
+    if rc != VB2_OK:
+        raise VB2Error(rc, "vb2_llk_pack_host failed")
+    try:
+        def arr(ptr, n, dt):
+            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+        out = {name: getattr(v, name) for name in ("n_pc", "n_used", "n_slices", "m_pad", "max_slice_words",
+                                                    "reads_used", "reads_streamed", "reads_folded", "log_other_const")}
+        out["words"] = arr(v.words, v.n_words, np.uint32)
+        out["slice_desc"] = arr(v.slice_desc, 2 * v.n_slices, np.uint32).reshape(-1, 2)
+        out["ud"] = arr(v.ud, v.n_pc * v.m_pad, np.float64).reshape(v.n_pc, v.m_pad)
+        out["mu"] = arr(v.mu, v.m_pad, np.float64)
+        out["diag"] = arr(v.diag, 3 * v.m_pad, np.float64).reshape(3, v.m_pad)
+        out["known_af"] = arr(v.known_af, v.m_pad, np.float64) if v.known_af else None
+        out["marker_index"] = arr(v.marker_index, v.m_pad, np.uint32)
+        return out
+    finally:
+        lib.vb2_llk_pack_free(ctypes.byref(v))
+
+
+class LLKEngine:
+    """One sample resident in the HBM of one GPU (or one marker shard of it)."""
+
+    def __init__(self, problem: PileupProblem, device: int = 0, panel_dtype: int = VB2_PANEL_FP32,
+                 shard_rank: int = 0, shard_count: int = 1, stream: Optional[int] = None, spin: bool = True,
+                 min_af: float = 0.0, max_af: float = 0.0):
+        self._lib = load_library()
+        self._ctx = ctypes.c_void_p()
+        self.problem = problem
+        d = make_desc(problem, device, panel_dtype, shard_rank, shard_count, stream, spin, min_af, max_af)
+        rc = self._lib.vb2_llk_create(ctypes.byref(d), ctypes.byref(self._ctx))
+        if rc != VB2_OK:
+            raise VB2Error(rc, self._lib.vb2_last_error(None).decode())
+        self.n_pc = problem.n_pc
+
+    # -- lifetime --------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.vb2_llk_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != VB2_OK:
+            raise VB2Error(rc, self._lib.vb2_last_error(self._ctx).decode())
+
+    # -- the reference interface -------------------------------------------------------------
+    def compute_mix_llks(self, pc_contam: Sequence[float], pc_intended: Sequence[float], alpha: float) -> float:
+        """ComputeMixLLKs(tPC1, tPC2, alpha): tPC1 = contaminating, tPC2 = intended sample PCs."""
+        a, b = _f64(pc_contam), _f64(pc_intended)
+        if a.size != self.n_pc or b.size != self.n_pc:
+            raise ValueError("PC vectors must have n_pc=%d entries" % self.n_pc)
+        out = ctypes.c_double()
+        self._check(self._lib.vb2_llk_eval(self._ctx, a.ctypes.data, b.ctypes.data, float(alpha), ctypes.byref(out)))
+        return float(out.value)
+
+    def eval_batch(self, pc_contam, pc_intended, alphas) -> np.ndarray:
+        al = _f64(alphas).ravel()
+        n = al.size
+        a, b = _f64(pc_contam, (n, self.n_pc)), _f64(pc_intended, (n, self.n_pc))
+        out = np.empty(n, dtype=np.float64)
+        self._check(self._lib.vb2_llk_eval_batch(self._ctx, n, a.ctypes.data, b.ctypes.data, al.ctypes.data,
+                                                 out.ctypes.data))
+        return out
+
+    def eval_batch_device(self, pc_contam, pc_intended, alphas, d_out_ptr: int) -> None:
+        """Asynchronous; results stay in device memory at `d_out_ptr` (n doubles)."""
+        al = _f64(alphas).ravel()
+        n = al.size
+        a, b = _f64(pc_contam, (n, self.n_pc)), _f64(pc_intended, (n, self.n_pc))
+        self._check(self._lib.vb2_llk_eval_batch_device(self._ctx, n, a.ctypes.data, b.ctypes.data, al.ctypes.data,
+                                                        ctypes.c_void_p(d_out_ptr)))
+
+    def sync(self) -> None:
+        self._check(self._lib.vb2_llk_sync(self._ctx))
+
+    def info(self) -> dict:
+        i = _Info()
+        i.struct_size = ctypes.sizeof(_Info)
+        self._check(self._lib.vb2_llk_get_info(self._ctx, ctypes.byref(i)))
+        return {name: getattr(i, name) for name, _ in _Info._fields_ if name != "struct_size"}
+
+
+def eval_many(engines: List[LLKEngine], pc_contam, pc_intended, alphas) -> np.ndarray:
+    """One evaluation of each of n different samples (same device, same n_pc) in one launch."""
+    n = len(engines)
+    k = engines[0].n_pc
+    al = _f64(alphas).ravel()
+    a, b = _f64(pc_contam, (n, k)), _f64(pc_intended, (n, k))
+    arr = (ctypes.c_void_p * n)(*[e._ctx for e in engines])
+    out = np.empty(n, dtype=np.float64)
+    lib = load_library()
+    rc = lib.vb2_llk_eval_many(arr, n, a.ctypes.data, b.ctypes.data, al.ctypes.data, out.ctypes.data)
+    if rc != VB2_OK:
+        raise VB2Error(rc, lib.vb2_last_error(engines[0]._ctx).decode())
+    return out
