@@ -170,7 +170,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
+    # a non-default stream shared by torch (events, NCCL) and every engine context
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
 
     sample = make_workload()
     p = sample.problem
@@ -199,25 +201,39 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    start_pc = np.full(k, 0.01)
+
+    def keep_busy(seconds: float):
+        t_end = time.perf_counter() + seconds
+        while time.perf_counter() < t_end:
+            if world == 1:
+                vb.time_device(engines, 0, 200, start_pc, start_pc, 0.03)
+            else:
+                for j in range(50):
+                    step(j)
+                torch.cuda.synchronize()
+
     # ---- value: device-timed, K back-to-back steps -------------------------------------------
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # N=1: the steps are issued from C (vb2_llk_time_device) so the launch rate is not limited by the
+    # Python interpreter; N>1: each step is kernel + NCCL allreduce of the scalar, issued from Python.
     with ClockSampler(local) as clocks:
-        ev0.record(stream)
-        for i in range(args.steps):
-            step(args.warmup + i)
-        ev1.record(stream)
+        keep_busy(0.3)                      # let nvidia-smi attach before the timed region
         barrier()
-        dev_ms = ev0.elapsed_time(ev1)
-        # keep the sampler alive long enough to see the load for very short runs
-        if dev_ms < 300:
-            t_end = time.perf_counter() + 0.4
-            j = 0
-            while time.perf_counter() < t_end:
-                step(j); j += 1
+        if world == 1:
+            dev_ms = vb.time_device(engines, args.warmup, args.steps, start_pc, start_pc, 0.03)
+        else:
+            for i in range(args.warmup):
+                step(i)
             barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for i in range(args.steps):
+                step(args.warmup + i)
+            ev1.record(stream)
+            barrier()
+            dev_ms = ev0.elapsed_time(ev1)
+        keep_busy(0.5)                      # clocks under the same load, for the sampler
+        barrier()
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -225,18 +241,8 @@ def run_ours(args):
     ms_per_step = dev_ms / args.steps
     value = reads_total / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant (only) kernel at N=1: kernel-only timing, no collective -----
-    def kernel_only(i: int):
-        engines[i % copies].eval_batch_device(pc_a, pc_b, al, d_out.data_ptr())
-    for i in range(args.warmup):
-        kernel_only(i)
-    torch.cuda.synchronize()
-    ev0.record(stream)
-    for i in range(args.steps):
-        kernel_only(i)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    kern_ms = ev0.elapsed_time(ev1) / args.steps
+    # ---- roofline of the dominant (only) kernel: kernel-only timing of this rank's shard --------
+    kern_ms = vb.time_device(engines, args.warmup, args.steps, start_pc, start_pc, 0.03) / args.steps
     peak, peak_src = measured_peak_gbs()
     alg_bytes = info["algorithmic_bytes"]       # this rank's shard
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
@@ -245,36 +251,43 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg_bytes, "device_bytes_per_launch": info["device_bytes"],
                 "note": "co-bound by FP64 issue rate: 12 fp64 ops per streamed read (DESIGN.md)"}
 
-    # ---- e2e: public call with host buffers, H2D of the parameters + D2H of the scalar each step
-    e2e_eng = engines[0]
-    host_pc_a = np.full(k, 0.01); host_pc_b = np.full(k, 0.01)
-    if world > 1:
+    # ---- e2e: the public C-ABI call with HOST buffers; every step moves the step's inputs (2k+1 doubles)
+    # to the device and the scalar result back to the host ------------------------------------------------
+    if world == 1:
+        e2e_s, last = vb.time_host(engines, args.warmup, args.steps, start_pc, start_pc, 0.03)
+        # the same call through the Python binding (interpreter + ctypes overhead included)
+        t0 = time.perf_counter()
+        for i in range(200):
+            engines[i % copies].compute_mix_llks(start_pc, start_pc, 0.03)
+        py_us = (time.perf_counter() - t0) / 200 * 1e6
+    else:
         host_out = torch.zeros(1, dtype=torch.float64).pin_memory()
+        host_pc = np.full((1, k), 0.01)
 
-    def e2e_step(i: int) -> float:
-        host_pc_a[0] = 0.01 + 1e-7 * (i % 1000)
-        eng = engines[i % copies]
-        if world == 1:
-            return eng.compute_mix_llks(host_pc_a, host_pc_b, 0.03)      # sync call: params in, scalar out
-        eng.eval_batch_device(host_pc_a[None, :], host_pc_b[None, :], al, d_out.data_ptr())
-        dist.all_reduce(d_out)
-        host_out.copy_(d_out, non_blocking=False)
-        return float(host_out[0])
-    for i in range(args.warmup):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    last = 0.0
-    for i in range(args.steps):
-        last = e2e_step(args.warmup + i)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+        def e2e_step(i: int) -> float:
+            host_pc[0, 0] = 0.01 + 1e-7 * (i % 1000)
+            engines[i % copies].eval_batch_device(host_pc, pc_b, al, d_out.data_ptr())
+            dist.all_reduce(d_out)
+            host_out.copy_(d_out, non_blocking=False)
+            return float(host_out[0])
+        for i in range(args.warmup):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        last = 0.0
+        for i in range(args.steps):
+            last = e2e_step(args.warmup + i)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        py_us = None
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e = {"value": reads_total / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": (2 * k + 1) * 8,
-           "d2h_bytes_per_step": 8, "us_per_step": e2e_s / args.steps * 1e6, "last_llk": last}
+           "d2h_bytes_per_step": 8, "us_per_step": e2e_s / args.steps * 1e6, "last_llk": last,
+           "caller": "C loop over vb2_llk_eval (host buffers)" if world == 1 else "python: kernel + NCCL allreduce + D2H",
+           "python_binding_us_per_step": py_us}
 
     # ---- cpu baseline beside it (rank 0, N=1 only) --------------------------------------------
     cpu = None

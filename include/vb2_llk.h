@@ -163,24 +163,43 @@ int vb2_llk_sync(vb2_llk_ctx *ctx);
 /* Message of the last failing call on this thread (ctx may be NULL); never NULL. */
 const char *vb2_last_error(const vb2_llk_ctx *ctx);
 
+/* ---- measurement helpers (used by bench.py; they launch exactly what vb2_llk_eval launches) ---
+ * vb2_llk_time_device: `warmup` untimed then `steps` timed single-candidate evaluations issued
+ * back to back from C, step i on ctxs[i % n_ctx] (all on ctxs[0]'s stream/device), bracketed by
+ * CUDA events on that stream; results stay in device memory.  *elapsed_ms = the timed span.
+ * vb2_llk_time_host: `steps` synchronous vb2_llk_eval calls (host parameter buffers in, host
+ * scalar out, every step) timed with the host's steady clock; *elapsed_s = wall time.          */
+int vb2_llk_time_device(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup, int steps, const double *pc_contam,
+                        const double *pc_intended, double alpha, float *elapsed_ms);
+int vb2_llk_time_host(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup, int steps, const double *pc_contam,
+                      const double *pc_intended, double alpha, double *elapsed_s, double *last_llk);
+
 /* ---- diagnostics (host only, no CUDA call): the flattened image vb2_llk_create uploads ------
  * Lets CPU-only tests check the flatten (skip rules, classification, folding, slice layout,
  * sharding) without a GPU.  All pointers are owned by the view until vb2_llk_pack_free.     */
 typedef struct vb2_packed_view {
   uint32_t struct_size;
-  uint32_t n_pc, n_used, n_slices, m_pad, max_slice_words;
-  uint64_t reads_used, reads_streamed, reads_folded, n_words;
+  uint32_t n_pc, n_used, n_slices;
+  uint32_t grid_x;       /* CTAs per launch: min(max_ctas, ceil(n_slices / 4))               */
+  uint32_t n_bins;       /* 4 * grid_x: one bin per SM sub-partition                         */
+  uint32_t conc_rounds;  /* rounds a CTA runs concurrently (it has 4 * conc_rounds warps)    */
+  uint32_t n_rounds;     /* ceil(n_slices / n_bins)                                          */
+  uint32_t max_stride;   /* largest blob stride in bytes                                     */
+  uint32_t known_af;     /* 1: blobs carry known AF instead of UD/mu                         */
+  uint32_t panel_elem;   /* 4 (fp32) or 8 (fp64): UD/mu element size inside the blobs        */
+  uint32_t off_ud, off_mu, off_kaf, off_diag, off_words; /* byte offsets inside a blob       */
+  uint64_t reads_used, reads_streamed, reads_folded, blob_bytes;
   double log_other_const;
-  const uint32_t *words;        /* [n_words]: slice s, word t, lane l at slice_desc[2s] + t*32 + l */
-  const uint32_t *slice_desc;   /* [n_slices][2]: word offset, ref_words | alt_words << 16        */
-  const double *ud;             /* [n_pc][m_pad]                                                  */
-  const double *mu;             /* [m_pad]                                                        */
-  const double *diag;           /* [3][m_pad]                                                     */
-  const double *known_af;       /* [m_pad] or NULL                                                */
-  const uint32_t *marker_index; /* [m_pad] panel row, 0xFFFFFFFF = padding                        */
+  const uint8_t *blob;          /* [blob_bytes]; bin b's blob of round r at
+                                   base_r + (b - first_bin_r) * stride_r;
+                                   16-byte header = u32 ref_words, alt_words, n_valid, 0     */
+  const uint32_t *rounds;       /* [n_rounds][6]: base lo, base hi, stride, first_bin, count, rows */
+  const uint32_t *marker_index; /* [n_slices*32] panel row per (slice, lane), 0xFFFFFFFF pad;
+                                   slice j (heaviest first) lives in round j / n_bins        */
   void *owner;
 } vb2_packed_view;
-int vb2_llk_pack_host(const vb2_llk_desc *desc, vb2_packed_view *view);
+/* max_ctas = SMs of the target device (0 = 148, a B200) */
+int vb2_llk_pack_host(const vb2_llk_desc *desc, uint32_t max_ctas, vb2_packed_view *view);
 void vb2_llk_pack_free(vb2_packed_view *view);
 
 #ifdef __cplusplus

@@ -52,26 +52,52 @@ def job_coefficients(alpha: float):
     return pairs, np.array(c0), np.array(c1)
 
 
+def bin_of(n_slices: int, n_bins: int, j: int) -> int:
+    """The dealing rule of llk_pack.cpp (bin_of)."""
+    r, i = divmod(j, n_bins)
+    rem = n_slices % n_bins
+    n_short = n_bins - rem
+    if (r + 1) * n_bins > n_slices:
+        return n_short + i
+    if i < n_short:
+        return n_short - 1 - i if (r & 1) else i
+    k = i - n_short
+    return n_short + (rem - 1 - k if (r & 1) else k)
+
+
+def iter_blobs(pk: dict):
+    """Yield (slice_index, bin, blob_bytes); slice j (heaviest first) lives in round j // n_bins."""
+    nb = pk["n_bins"]
+    for j in range(pk["n_slices"]):
+        R = pk["rounds"][j // nb]
+        b = bin_of(pk["n_slices"], nb, j)
+        assert R["first_bin"] <= b < R["first_bin"] + R["count"]
+        off = R["base"] + (b - R["first_bin"]) * R["stride"]
+        yield j, b, pk["blob"][off:off + R["stride"]]
+
+
 def emulate_packed_llk(pk: dict, pc1, pc2, alpha: float, min_af=5e-5, max_af=0.99995) -> float:
     """numpy restatement of llk_kernel over the packed image (CPU check of the flatten + the maths)."""
     phred = np.power(10.0, np.arange(94) / -10.0)
     pairs, c0, c1 = job_coefficients(alpha)
-    m_pad, total = pk["m_pad"], 0.0
-    if pk["known_af"] is not None:
-        af1 = af2 = pk["known_af"]
-    else:
-        af1 = (np.asarray(pc1) @ pk["ud"] + pk["mu"]) / 2.0
-        af2 = (np.asarray(pc2) @ pk["ud"] + pk["mu"]) / 2.0
+    pdt = np.float64 if pk["panel_elem"] == 8 else np.float32
+    k, total = pk["n_pc"], 0.0
 
     def gf(af):
         af = np.clip(af, min_af, max_af)
         return np.stack([(1 - af) * (1 - af), 2 * af * (1 - af), af * af])
-    g1v, g2v = gf(af1), gf(af2)
-    for s in range(pk["n_slices"]):
-        base, wrwa = int(pk["slice_desc"][s, 0]), int(pk["slice_desc"][s, 1])
-        wr, wa = wrwa & 0xFFFF, wrwa >> 16
-        blk = pk["words"][base:base + (wr + wa) * 32].reshape(wr + wa, 32)
-        byts = blk.view(np.uint8).reshape(wr + wa, 32, 4)          # little-endian bytes of each word
+    for _, _, blob in iter_blobs(pk):
+        wr, wa, n_valid, _ = blob[:16].view(np.uint32)
+        if pk["known_af"]:
+            af1 = af2 = blob[pk["off_kaf"]:pk["off_kaf"] + 256].view(np.float64)
+        else:
+            ud = blob[pk["off_ud"]:pk["off_ud"] + k * 32 * pk["panel_elem"]].view(pdt).reshape(k, 32).astype(np.float64)
+            mu = blob[pk["off_mu"]:pk["off_mu"] + 32 * pk["panel_elem"]].view(pdt).astype(np.float64)
+            af1 = (np.asarray(pc1, dtype=np.float64) @ ud + mu) / 2.0
+            af2 = (np.asarray(pc2, dtype=np.float64) @ ud + mu) / 2.0
+        g1v, g2v = gf(af1), gf(af2)
+        diag = blob[pk["off_diag"]:pk["off_diag"] + 768].view(np.float64).reshape(3, 32)
+        byts = blob[pk["off_words"]:pk["off_words"] + (wr + wa) * 128].reshape(wr + wa, 32, 4)
         acc = np.ones((6, 32))
         for sect, lo, hi in (("ref", 0, wr), ("alt", wr, wr + wa)):
             q = byts[lo:hi].transpose(1, 0, 2).reshape(32, -1)      # [lane, reads]
@@ -79,12 +105,10 @@ def emulate_packed_llk(pk: dict, pc1, pc2, alpha: float, min_af=5e-5, max_af=0.9
             e = phred[np.where(pad, 0, q)]
             for p in range(6):
                 f = np.where(pad, 1.0, c1[p] * e + c0[p])
-                tgt = p if sect == "ref" else 5 - p
-                acc[tgt] *= f.prod(axis=1)
-        pm = np.arange(s * 32, s * 32 + 32)
-        L = sum(pk["diag"][g, pm] * g1v[g, pm] * g2v[g, pm] for g in range(3))
+                acc[p if sect == "ref" else 5 - p] *= f.prod(axis=1)
+        L = sum(diag[g] * g1v[g] * g2v[g] for g in range(3))
         for p, (a, b) in enumerate(pairs):
-            L = L + acc[p] * g1v[a, pm] * g2v[b, pm]
-        valid = (pm < pk["n_used"]) & (L > 0)
+            L = L + acc[p] * g1v[a] * g2v[b]
+        valid = (np.arange(32) < n_valid) & (L > 0)
         total += float(np.log(L[valid]).sum())
     return total + pk["log_other_const"]

@@ -5,7 +5,7 @@ import pytest
 
 import verifybamid_b200 as vb
 from verifybamid_b200 import panels, synth
-from helpers import (KAT_POINTS, KAT_RESULT, KAT_LONGREAD, LONGREAD_PILEUP, RESULT_PILEUP, emulate_packed_llk,
+from helpers import (KAT_POINTS, KAT_RESULT, KAT_LONGREAD, LONGREAD_PILEUP, RESULT_PILEUP, emulate_packed_llk, iter_blobs,
                      golden_problem, to_oracle, to_product)
 
 
@@ -22,14 +22,38 @@ def test_pack_counts_and_layout():
     pk = vb.pack_host(p)
     assert pk["n_used"] == 13 and pk["reads_used"] == 432
     assert pk["reads_streamed"] + pk["reads_folded"] == pk["reads_used"]
-    assert pk["n_slices"] == 1 and pk["m_pad"] == 32
+    assert pk["n_slices"] == 1 and pk["grid_x"] == 1 and pk["n_bins"] == 4 and pk["n_rounds"] == 1
     # padding lanes are marked and carry no reads
     assert (pk["marker_index"][13:] == 0xFFFFFFFF).all()
-    wr, wa = pk["slice_desc"][0, 1] & 0xFFFF, pk["slice_desc"][0, 1] >> 16
-    assert pk["words"].size == (wr + wa) * 32
-    byts = pk["words"].view(np.uint8)
+    (_, _, blob), = list(iter_blobs(pk))
+    wr, wa, n_valid, _ = blob[:16].view(np.uint32)
+    assert n_valid == 13 and blob.size == pk["off_words"] + (wr + wa) * 128 == pk["rounds"][0]["stride"]
+    byts = blob[pk["off_words"]:]
     assert ((byts <= 93) | (byts == 0xFF)).all()
     assert int((byts != 0xFF).sum()) == pk["reads_streamed"]
+
+
+def test_rounds_are_balanced_and_aligned():
+    """Snake dealing: every SM sub-partition bin gets (nearly) the same number of word rows; every blob is
+    16-byte aligned (TMA bulk copy) and its size a multiple of 16."""
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    p = synth.make_sample(panel, n_pc=2, depth=30.0, alpha=0.02, seed=3).problem
+    pk = vb.pack_host(p, max_ctas=8)                       # 32 bins, 313 slices -> 10 rounds
+    assert pk["n_bins"] == 32 and pk["n_rounds"] == -(-pk["n_slices"] // 32) and pk["conc_rounds"] == 6
+    work = np.zeros(pk["n_bins"])
+    seen = set()
+    for j, b, blob in iter_blobs(pk):
+        wr, wa = blob[:8].view(np.uint32)
+        work[b] += wr + wa
+        assert (j // pk["n_bins"], b) not in seen           # one blob per (round, bin)
+        seen.add((j // pk["n_bins"], b))
+    assert work.max() <= 1.08 * work.mean()
+    for R in pk["rounds"]:
+        assert R["base"] % 16 == 0 and R["stride"] % 16 == 0
+        assert R["stride"] == pk["off_words"] + 128 * R["rows"]
+        assert R["first_bin"] + R["count"] == pk["n_bins"] or R["first_bin"] == 0
+    strides = [R["stride"] for R in pk["rounds"]]
+    assert strides == sorted(strides, reverse=True)         # heaviest slices first
 
 
 @pytest.fixture(scope="module")
@@ -48,6 +72,11 @@ def test_packed_synthetic_matches_oracle(small_sample):
         want = ora.compute_mix_llks(pc1, pc2, a)
         got = emulate_packed_llk(pk, pc1, pc2, a)
         assert abs(got - want) <= 1e-11 * abs(want)
+    # the same sample dealt to a small launch (many rounds per bin) gives the same likelihood
+    pk8 = vb.pack_host(p, max_ctas=3)
+    assert pk8["n_rounds"] > 2
+    assert abs(emulate_packed_llk(pk8, [0.02, -0.01], [-0.01, 0.027], 0.05)
+               - emulate_packed_llk(pk, [0.02, -0.01], [-0.01, 0.027], 0.05)) <= 1e-9
 
 
 def test_sanity_filter_matches_reference_rule(small_sample):
@@ -78,5 +107,5 @@ def test_empty_and_absent_markers():
     none = vb.PileupProblem(p.ud, p.means, np.full(p.n_marker, -1, np.int32), p.alt_base, np.zeros(1, np.int64),
                             np.zeros(0, np.uint8), np.zeros(0, np.uint8))
     pk = vb.pack_host(none)
-    assert pk["n_used"] == 0 and pk["n_slices"] == 0 and pk["words"].size == 0
+    assert pk["n_used"] == 0 and pk["n_slices"] == 0 and pk["blob"].size == 0 and pk["n_rounds"] == 0
     assert emulate_packed_llk(pk, [0, 0], [0, 0], 0.5) == 0.0   # reference: empty sum (h:231)

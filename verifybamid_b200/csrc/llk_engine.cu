@@ -30,11 +30,12 @@
 
 namespace {
 
-constexpr int kWarpsPerCta = 4;
-constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kMaxArgJobs = 8;     // evaluations whose parameters travel in the kernel arguments
-constexpr int kStageWordsCap = 64; // words per lane per shared-memory stage (256 reads)
-constexpr int kNumPairs = 6;       // off-diagonal genotype pairs
+constexpr int kMaxWarps = 4 * vb2::kMaxConcRounds;  // 24 warps: 6 per SM sub-partition
+constexpr int kMaxThreads = kMaxWarps * 32;
+constexpr int kMaxArgJobs = 4;    // evaluations whose parameters travel in the kernel arguments
+constexpr int kMaxArgRounds = 16; // round-table entries that travel in the kernel arguments
+constexpr int kNumPairs = 6;      // off-diagonal genotype pairs
+constexpr uint32_t kChunkTargetBytes = 4096;  // shared-memory stage per warp
 
 // Pair p = (g1 contaminant, g2 intended): 0:(0,1) 1:(0,2) 2:(1,0) 3:(1,2) 4:(2,0) 5:(2,1).
 // The alt-allele emission is the ref-allele one with g -> 2-g (COND_LK, h:164-177), and
@@ -49,20 +50,20 @@ struct JobParams {  // one evaluation (352 bytes)
   double pc1[VB2_MAX_PC], pc2[VB2_MAX_PC];  // contaminant / intended PCs
 };
 
-struct SampleDev {  // one sample resident in HBM
-  const uint32_t *words;
-  const uint2 *slice_desc;
-  const void *ud;          // [n_pc][m_pad] float or double
-  const void *mu;          // [m_pad]
-  const double *diag;      // [3][m_pad]
-  const double *known_af;  // [m_pad] or nullptr
-  const double *phred;     // [128]; entries >= 94 unused
-  double *partials;        // [slots][grid_x]
-  unsigned int *tickets;   // [slots]
+struct SampleDev {  // one sample resident in HBM (see llk_pack.h for the blob/round layout)
+  const uint8_t *blob;
+  const vb2::Round *rounds;  // [n_rounds] in HBM
+  double *partials;          // [slots][grid_x]
+  unsigned int *tickets;     // [slots]
   double log_other_const, min_af, max_af;
-  uint32_t n_used, n_slices, m_pad, n_pc;
-  uint32_t grid_x, panel_fp64, stage_words, n_buf;
+  uint32_t n_rounds, n_bins, grid_x, conc_rounds;
+  uint32_t n_pc, panel_fp64, known_af, n_buf;
+  uint32_t off_ud, off_mu, off_kaf, off_diag, off_words;
+  uint32_t chunk_rows;  // word rows per shared-memory stage
+  uint32_t buf_bytes;   // off_words + chunk_rows * 128
+  uint32_t pad_;
 };
+static_assert(sizeof(SampleDev) % 8 == 0 && sizeof(SampleDev) <= 8 * 32, "SampleDev copy loop");
 
 struct Mailbox {  // host-mapped, written by the last CTA of a launch
   volatile unsigned long long seq;
@@ -81,8 +82,11 @@ struct LaunchArgs {
   unsigned long long seq;
   uint32_t n_jobs;
   uint32_t pad_;
+  vb2::Round rounds[kMaxArgRounds];  // copy of sample.rounds[0..n_rounds) when it fits
   JobParams jobs[kMaxArgJobs];
+  double phred[vb2::kNumQual];       // 10^(-q/10), ContaminationEstimator.h:65-74
 };
+static_assert(sizeof(LaunchArgs) <= 4000, "kernel arguments must stay below 4 KiB");
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
@@ -117,21 +121,45 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                : "memory");
 }
 
+// acc[i] *= f[i] for the six genotype pairs unless the quality byte is the 0xFF filler:
+// one ISETP + six predicated DMULs, no branch.
+__device__ __forceinline__ void mul6_if_read(double &a0, double &a1, double &a2, double &a3, double &a4, double &a5,
+                                             double f0, double f1, double f2, double f3, double f4, double f5,
+                                             uint32_t q) {
+  asm("{\n"
+      ".reg .pred P;\n"
+      "setp.ne.u32 P, %12, 255;\n"
+      "@P mul.f64 %0, %0, %6;\n"
+      "@P mul.f64 %1, %1, %7;\n"
+      "@P mul.f64 %2, %2, %8;\n"
+      "@P mul.f64 %3, %3, %9;\n"
+      "@P mul.f64 %4, %4, %10;\n"
+      "@P mul.f64 %5, %5, %11;\n"
+      "}\n"
+      : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "+d"(a4), "+d"(a5)
+      : "d"(f0), "d"(f1), "d"(f2), "d"(f3), "d"(f4), "d"(f5), "r"(q));
+}
+
 // Four reads (one word) of one lane.  ALT = the word holds alt-allele reads.
 template <bool ALT>
 __device__ __forceinline__ void eat_word(uint32_t w, const double *s_e, const double (&c0)[kNumPairs],
                                          const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
+  uint32_t q[4];
+  double e[4];
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
-    const uint32_t q = (w >> (8 * b)) & 0xFFu;
-    if (q != 0xFFu) {
-      const double e = s_e[q];
+    q[b] = (w >> (8 * b)) & 0xFFu;
+    e[b] = s_e[q[b]];  // s_e[255] = 1.0: the filler byte reads a finite value and is masked below
+  }
 #pragma unroll
-      for (int p = 0; p < kNumPairs; ++p) {
-        const double f = fma(c1[p], e, c0[p]);
-        acc[ALT ? (kNumPairs - 1 - p) : p] *= f;
-      }
-    }
+  for (int b = 0; b < 4; ++b) {
+    double f[kNumPairs];
+#pragma unroll
+    for (int p = 0; p < kNumPairs; ++p) f[p] = fma(c1[p], e[b], c0[p]);
+    if (ALT)
+      mul6_if_read(acc[5], acc[4], acc[3], acc[2], acc[1], acc[0], f[0], f[1], f[2], f[3], f[4], f[5], q[b]);
+    else
+      mul6_if_read(acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], f[0], f[1], f[2], f[3], f[4], f[5], q[b]);
   }
 }
 
@@ -145,146 +173,196 @@ __device__ __forceinline__ void initial_gf(double af, double min_af, double max_
 }
 
 template <typename PanelT>
-__device__ __forceinline__ void marker_af(const SampleDev &S, const JobParams &J, uint32_t pm, double &af1,
-                                          double &af2) {
+__device__ __forceinline__ void marker_af(const uint8_t *blob, const SampleDev &S, const JobParams &J, int lane,
+                                          double &af1, double &af2) {
   // h:251-267: AF = (sum_k UD[i][k]*PC[k] + means[i]) / 2, accumulated in k order in fp64.
-  const PanelT *ud = static_cast<const PanelT *>(S.ud);
-  const PanelT *mu = static_cast<const PanelT *>(S.mu);
+  const PanelT *ud = reinterpret_cast<const PanelT *>(blob + S.off_ud);
+  const PanelT *mu = reinterpret_cast<const PanelT *>(blob + S.off_mu);
   double a1 = 0., a2 = 0.;
   for (uint32_t k = 0; k < S.n_pc; ++k) {
-    const double u = (double)__ldg(ud + (size_t)k * S.m_pad + pm);
+    const double u = (double)ud[k * 32 + lane];
     a1 = __dadd_rn(a1, __dmul_rn(u, J.pc1[k]));
     a2 = __dadd_rn(a2, __dmul_rn(u, J.pc2[k]));
   }
-  const double m = (double)__ldg(mu + pm);
+  const double m = (double)mu[lane];
   af1 = (a1 + m) * 0.5;
   af2 = (a2 + m) * 0.5;
 }
 
-__global__ void __launch_bounds__(kThreads)
+// One persistent CTA per SM.  Warp w issues on SM sub-partition w % 4 and owns bin
+// blockIdx.x*4 + w%4; it serves rounds w/4, w/4 + conc_rounds, ... of that bin.
+__global__ void __launch_bounds__(kMaxThreads, 1)
 llk_kernel(const __grid_constant__ LaunchArgs A) {
-  extern __shared__ __align__(128) uint32_t s_words[];  // [warp][buf][stage_words][32]
-  __shared__ double s_e[128];
+  extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][n_buf][buf_bytes]
+  __shared__ double s_e[256];
   __shared__ JobParams s_job;
-  __shared__ double s_red[kWarpsPerCta];
-  __shared__ __align__(8) uint64_t s_bar[kWarpsPerCta][2];
   __shared__ SampleDev s_sample;
+  __shared__ vb2::Round s_rounds[kMaxArgRounds];
+  __shared__ double s_red[kMaxWarps];
+  __shared__ __align__(8) uint64_t s_bar[kMaxWarps][2];
   __shared__ int s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_warps = blockDim.x >> 5;
   const uint32_t job = blockIdx.y;
 
-  // ---- per-CTA set-up: which sample, which parameters ----------------------------------------
-  if (A.samples) {
-    if (threadIdx.x < sizeof(SampleDev) / 8)
-      reinterpret_cast<uint64_t *>(&s_sample)[threadIdx.x] =
-          reinterpret_cast<const uint64_t *>(A.samples + job)[threadIdx.x];
-  } else {
-    if (threadIdx.x < sizeof(SampleDev) / 8)
-      reinterpret_cast<uint64_t *>(&s_sample)[threadIdx.x] =
-          reinterpret_cast<const uint64_t *>(&A.sample)[threadIdx.x];
-  }
-  if (threadIdx.x < sizeof(JobParams) / 8) {
+  // ---- per-CTA set-up: which sample, which parameters, Phred table ----------------------------
+  if (threadIdx.x < sizeof(SampleDev) / 8) {
+    const uint64_t *src = A.samples ? reinterpret_cast<const uint64_t *>(A.samples + job)
+                                    : reinterpret_cast<const uint64_t *>(&A.sample);
+    reinterpret_cast<uint64_t *>(&s_sample)[threadIdx.x] = src[threadIdx.x];
+  } else if (threadIdx.x >= 64 && threadIdx.x < 64 + sizeof(JobParams) / 8) {
+    const int i = threadIdx.x - 64;
     const double *src = A.jobs_dev ? reinterpret_cast<const double *>(A.jobs_dev + job)
                                    : reinterpret_cast<const double *>(&A.jobs[job < kMaxArgJobs ? job : 0]);
-    reinterpret_cast<double *>(&s_job)[threadIdx.x] = src[threadIdx.x];
+    reinterpret_cast<double *>(&s_job)[i] = src[i];
   }
-  __syncthreads();
-  const SampleDev &S = s_sample;
-  if (blockIdx.x >= S.grid_x) return;  // eval_many: this sample needs fewer CTAs than the grid has
-  s_e[threadIdx.x] = __ldg(S.phred + threadIdx.x);  // kThreads == 128 entries
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_e[i] = i < vb2::kNumQual ? A.phred[i] : 1.0;
   if (lane == 0) {
     mbar_init(&s_bar[warp][0], 1);
     mbar_init(&s_bar[warp][1], 1);
     mbar_fence_init();
   }
   __syncthreads();
+  const SampleDev &S = s_sample;
+  if (blockIdx.x >= S.grid_x) return;  // eval_many: this sample needs fewer CTAs than the grid has
+  const bool rounds_in_smem = S.n_rounds <= kMaxArgRounds;
+  if (rounds_in_smem && threadIdx.x < S.n_rounds * (sizeof(vb2::Round) / 8)) {
+    const uint64_t *src = A.samples ? reinterpret_cast<const uint64_t *>(S.rounds)
+                                    : reinterpret_cast<const uint64_t *>(A.rounds);
+    reinterpret_cast<uint64_t *>(s_rounds)[threadIdx.x] = src[threadIdx.x];
+  }
+  __syncthreads();
 
   const uint32_t slot = A.slots ? A.slots[job] : job;
-  const uint32_t slice = blockIdx.x * kWarpsPerCta + warp;
-  double v = 0.0;
-  if (slice < S.n_slices) {
-    const uint2 sd = S.slice_desc[slice];
-    const uint32_t wr = sd.y & 0xFFFFu, wa = sd.y >> 16, W = wr + wa;
-    const uint32_t stage_words = S.stage_words;
-    uint32_t *buf0 = s_words + (size_t)warp * S.n_buf * stage_words * 32;
-    const uint32_t *gsrc = S.words + sd.x;
+  const uint32_t bin = blockIdx.x * vb2::kBinsPerCta + (warp & 3);
+  const uint32_t kc = S.conc_rounds;
+  const uint32_t n_rounds = S.n_rounds;
+  const uint32_t chunk_rows = S.chunk_rows;
+  uint8_t *mybuf = s_buf + (size_t)warp * S.n_buf * S.buf_bytes;
 
-    // ---- (ii-a) kick off the first read tile: one TMA bulk copy per warp -----------------------
-    uint32_t n0 = W < stage_words ? W : stage_words;
-    if (lane == 0 && n0) {
-      mbar_arrive_expect_tx(&s_bar[warp][0], n0 * 128u);
-      bulk_g2s(buf0, gsrc, n0 * 128u, &s_bar[warp][0]);
+  auto get_round = [&](uint32_t r) -> vb2::Round { return rounds_in_smem ? s_rounds[r] : S.rounds[r]; };
+  // first round >= r (stepping by kc) in which this bin owns a blob, or n_rounds
+  auto next_round = [&](uint32_t r) -> uint32_t {
+    while (r < n_rounds) {
+      const vb2::Round R = get_round(r);
+      if (bin - R.first_bin < R.count) break;  // unsigned: also false when bin < first_bin
+      r += kc;
     }
-
-    // ---- (i) allele frequencies and genotype priors -------------------------------------------
-    const uint32_t pm = slice * 32 + lane;
-    const bool valid = pm < S.n_used;
-    double af1, af2;
-    if (S.known_af) {
-      af1 = af2 = __ldg(S.known_af + pm);  // h:251-252
-    } else if (S.panel_fp64) {
-      marker_af<double>(S, s_job, pm, af1, af2);
+    return r;
+  };
+  auto n_chunks = [&](const vb2::Round &R) -> uint32_t {
+    return R.rows <= chunk_rows ? 1u : (R.rows + chunk_rows - 1) / chunk_rows;
+  };
+  // TMA: chunk c of this bin's blob of round r -> buffer b.  Chunk 0 = header + panel + diag + the
+  // first chunk_rows word rows; chunk c >= 1 = the next chunk_rows word rows.
+  auto issue = [&](uint32_t r, uint32_t c, uint32_t b) {
+    const vb2::Round R = get_round(r);
+    const uint8_t *src = S.blob + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
+    uint32_t off, bytes;
+    if (c == 0) {
+      off = 0;
+      bytes = S.off_words + (R.rows < chunk_rows ? R.rows : chunk_rows) * 128u;
     } else {
-      marker_af<float>(S, s_job, pm, af1, af2);
+      off = S.off_words + c * chunk_rows * 128u;
+      const uint32_t left = R.rows - c * chunk_rows;
+      bytes = (left < chunk_rows ? left : chunk_rows) * 128u;
     }
-    double gf[3], gf2[3];
-    initial_gf(af1, S.min_af, S.max_af, gf);   // contaminating sample
-    initial_gf(af2, S.min_af, S.max_af, gf2);  // intended sample
-    const double d0 = __ldg(S.diag + pm), d1 = __ldg(S.diag + S.m_pad + pm),
-                 d2 = __ldg(S.diag + 2 * (size_t)S.m_pad + pm);
+    mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
+    bulk_g2s(mybuf + (size_t)b * S.buf_bytes, src + off, bytes, &s_bar[warp][b]);
+  };
 
-    double c0[kNumPairs], c1[kNumPairs], acc[kNumPairs];
+  double vsum = 0.0;
+  if ((uint32_t)(warp >> 2) < kc) {
+    double c0[kNumPairs], c1[kNumPairs];
 #pragma unroll
     for (int p = 0; p < kNumPairs; ++p) {
       c0[p] = s_job.c0[p];
       c1[p] = s_job.c1[p];
-      acc[p] = 1.0;
     }
-
-    // ---- (ii-b) stream the read tile(s) ---------------------------------------------------------
-    uint32_t parity = 0u;  // bit b = phase of buffer b's mbarrier
-    uint32_t b = 0;
-    for (uint32_t t0 = 0; t0 < W; t0 += stage_words) {
-      const uint32_t n = (W - t0) < stage_words ? (W - t0) : stage_words;
-      const uint32_t t1 = t0 + stage_words;  // start of the next stage (only reached when n_buf == 2)
-      if (t1 < W) {
-        // prefetch the next stage into the other buffer; every lane finished reading it in the
-        // previous iteration
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t nn = (W - t1) < stage_words ? (W - t1) : stage_words;
-          mbar_arrive_expect_tx(&s_bar[warp][b ^ 1], nn * 128u);
-          bulk_g2s(buf0 + (size_t)(b ^ 1) * stage_words * 32, gsrc + (size_t)t1 * 32, nn * 128u,
-                   &s_bar[warp][b ^ 1]);
-        }
+    // consume cursor (r, c) and issue cursor (ir, ic); both advance through the same sequence
+    uint32_t r = next_round((uint32_t)(warp >> 2)), c = 0;
+    uint32_t ir = r, ic = 0, ib = 0, cb = 0, parity = 0;
+    auto advance_issue = [&]() {
+      if (ir >= n_rounds) return;
+      const vb2::Round R = get_round(ir);
+      if (ic + 1 < n_chunks(R)) { ++ic; } else { ir = next_round(ir + kc); ic = 0; }
+    };
+    if (ir < n_rounds) {
+      if (lane == 0) issue(ir, ic, ib);
+      advance_issue();
+      ib ^= (S.n_buf - 1);
+    }
+    double acc[kNumPairs], af1 = 0., af2 = 0., ldiag = 0.;
+    uint32_t wr = 0, wa = 0, n_valid = 0;
+    while (r < n_rounds) {
+      if (ir < n_rounds && S.n_buf == 2) {
+        __syncwarp();  // every lane finished reading the buffer about to be overwritten
+        if (lane == 0) issue(ir, ic, ib);
+        advance_issue();
+        ib ^= 1u;
       }
-      mbar_wait(&s_bar[warp][b], (parity >> b) & 1u);
-      parity ^= 1u << b;
-      const uint32_t *buf = buf0 + (size_t)b * stage_words * 32 + lane;
-      const uint32_t n_ref = wr > t0 ? ((wr - t0) < n ? (wr - t0) : n) : 0u;
-      uint32_t t = 0;
-      for (; t < n_ref; ++t) eat_word<false>(buf[t * 32], s_e, c0, c1, acc);
-      for (; t < n; ++t) eat_word<true>(buf[t * 32], s_e, c0, c1, acc);
-      b ^= 1u;
-    }
-
-    // ---- (iii) marginal over the nine genotype pairs, log ---------------------------------------
-    // h:307-311: markerLK = sum_{g1,g2} exp(acc) * GF[g1] * GF2[g2]; here exp(acc) is the running
-    // product itself, and the diagonal products are the create-time constants d0..d2.
-    double L = d0 * (gf[0] * gf2[0]) + d1 * (gf[1] * gf2[1]) + d2 * (gf[2] * gf2[2]);
+      mbar_wait(&s_bar[warp][cb], (parity >> cb) & 1u);
+      parity ^= 1u << cb;
+      const uint8_t *buf = mybuf + (size_t)cb * S.buf_bytes;
+      const vb2::Round R = get_round(r);
+      if (c == 0) {
+        // ---- (i) header, allele frequencies, genotype priors, diagonal pairs ----------------------
+        const uint4 hdr = *reinterpret_cast<const uint4 *>(buf);
+        wr = hdr.x; wa = hdr.y; n_valid = hdr.z;
+        if (S.known_af) {
+          af1 = af2 = reinterpret_cast<const double *>(buf + S.off_kaf)[lane];  // h:251-252
+        } else if (S.panel_fp64) {
+          marker_af<double>(buf, S, s_job, lane, af1, af2);
+        } else {
+          marker_af<float>(buf, S, s_job, lane, af1, af2);
+        }
+        double gf[3], gf2[3];
+        initial_gf(af1, S.min_af, S.max_af, gf);   // contaminating sample
+        initial_gf(af2, S.min_af, S.max_af, gf2);  // intended sample
+        const double *dg = reinterpret_cast<const double *>(buf + S.off_diag);
+        ldiag = dg[lane] * (gf[0] * gf2[0]) + dg[32 + lane] * (gf[1] * gf2[1]) + dg[64 + lane] * (gf[2] * gf2[2]);
 #pragma unroll
-    for (int p = 0; p < kNumPairs; ++p) L += acc[p] * (gf[pair_g1(p)] * gf2[pair_g2(p)]);
-    if (valid && L > 0) v = log(L);
+        for (int p = 0; p < kNumPairs; ++p) acc[p] = 1.0;
+      }
+      // ---- (ii) stream this chunk's word rows: ref rows first, then alt rows --------------------
+      const uint32_t t_lo = c * chunk_rows;
+      uint32_t t_hi = t_lo + chunk_rows;
+      if (t_hi > wr + wa) t_hi = wr + wa;
+      const uint32_t *rows = reinterpret_cast<const uint32_t *>(buf + (c == 0 ? S.off_words : 0u)) + lane;
+      const uint32_t t_ref_hi = wr < t_hi ? wr : t_hi;
+      uint32_t t = t_lo;
+      for (; t < t_ref_hi; ++t) eat_word<false>(rows[(t - t_lo) * 32], s_e, c0, c1, acc);
+      for (; t < t_hi; ++t) eat_word<true>(rows[(t - t_lo) * 32], s_e, c0, c1, acc);
+
+      if (c + 1 == n_chunks(R)) {
+        // ---- (iii) marginal over the nine genotype pairs, log -------------------------------------
+        // h:307-311: markerLK = sum_{g1,g2} exp(acc) * GF[g1] * GF2[g2]; here exp(acc) is the running
+        // product itself, and the diagonal pairs were folded into ldiag above.
+        double gf[3], gf2[3];
+        initial_gf(af1, S.min_af, S.max_af, gf);
+        initial_gf(af2, S.min_af, S.max_af, gf2);
+        double L = ldiag;
+#pragma unroll
+        for (int p = 0; p < kNumPairs; ++p) L += acc[p] * (gf[pair_g1(p)] * gf2[pair_g2(p)]);
+        if ((uint32_t)lane < n_valid && L > 0) vsum += log(L);
+        r = next_round(r + kc);
+        c = 0;
+      } else {
+        ++c;
+      }
+      if (S.n_buf == 2) cb ^= 1u;
+    }
   }
 
   // ---- fixed-order reduction: warp shuffle tree -> CTA -> last CTA sums the grid ---------------
 #pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-  if (lane == 0) s_red[warp] = v;
+  for (int o = 16; o; o >>= 1) vsum += __shfl_xor_sync(0xFFFFFFFFu, vsum, o);
+  if (lane == 0) s_red[warp] = vsum;
   __syncthreads();
   if (threadIdx.x == 0) {
-    const double cta = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+    double cta = 0.0;
+    for (int w = 0; w < n_warps; ++w) cta += s_red[w];
     S.partials[(size_t)slot * S.grid_x + blockIdx.x] = cta;
     __threadfence();
     const unsigned int t = atomicAdd(S.tickets + slot, 1u);
@@ -341,6 +419,9 @@ struct vb2_llk_ctx {
   uint64_t device_bytes = 0;
   uint32_t slots = 0;
   uint32_t smem_bytes = 0;
+  uint32_t block_threads = 0;
+  std::vector<vb2::Round> rounds;  // host copy (kernel arguments)
+  double phred[vb2::kNumQual];
   Mailbox *h_mbox = nullptr, *d_mbox = nullptr;
   unsigned int *d_jobs_done = nullptr;
   JobParams *h_jobs = nullptr;  // pinned staging [VB2_MAX_BATCH]
@@ -463,6 +544,9 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
   A.sample = ctx->S;
   A.n_jobs = (uint32_t)n;
   A.d_out = d_out;
+  memcpy(A.phred, ctx->phred, sizeof(A.phred));
+  if (ctx->rounds.size() <= (size_t)kMaxArgRounds)
+    memcpy(A.rounds, ctx->rounds.data(), ctx->rounds.size() * sizeof(vb2::Round));
   const uint32_t k = ctx->S.n_pc;
   if (n <= kMaxArgJobs) {
     for (int j = 0; j < n; ++j) fill_job(&A.jobs[j], k, pc1 + (size_t)j * k, pc2 + (size_t)j * k, alphas[j]);
@@ -481,7 +565,7 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
     if (seq_out) *seq_out = A.seq;
   }
   if (ctx->S.grid_x == 0) return VB2_OK;  // no usable marker: handled by the callers
-  dim3 grid(ctx->S.grid_x, (unsigned)n, 1), block(kThreads, 1, 1);
+  dim3 grid(ctx->S.grid_x, (unsigned)n, 1), block(ctx->block_threads, 1, 1);
   llk_kernel<<<grid, block, ctx->smem_bytes, ctx->stream>>>(A);
   VB2_CUDA(ctx, cudaGetLastError());
   return VB2_OK;
@@ -552,60 +636,53 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   if (const char *t = getenv("VB2_LLK_SPIN_TIMEOUT_MS")) ctx->spin_timeout_ms = atof(t);
 
   // ---- flatten on the host ----------------------------------------------------------------------
-  double phred[128];
-  vb2::build_phred_table(phred);
-  for (int q = vb2::kNumQual; q < 128; ++q) phred[q] = 1.0;
+  vb2::build_phred_table(ctx->phred);
+  if (desc->panel_dtype != VB2_PANEL_FP64 && desc->panel_dtype != VB2_PANEL_FP32)
+    return set_err(ctx, VB2_ERR_INVALID, "unknown panel_dtype");
+  vb2::PackConfig cfg;
+  cfg.max_ctas = (uint32_t)ctx->sm_count;  // one persistent CTA per SM
+  cfg.panel_fp64 = desc->panel_dtype == VB2_PANEL_FP64;
+  if (const char *t = getenv("VB2_LLK_MAX_CTAS")) cfg.max_ctas = (uint32_t)std::max(1, atoi(t));
   vb2::PackedSample &P = ctx->meta;
   std::string perr;
-  int rc = vb2::pack_sample(*desc, phred, &P, &perr);
+  int rc = vb2::pack_sample(*desc, cfg, ctx->phred, &P, &perr);
   if (rc) return set_err(ctx, rc, perr);
+  ctx->rounds = P.rounds;
 
   // ---- upload ---------------------------------------------------------------------------------
   SampleDev &S = ctx->S;
-  const uint32_t *d_words = nullptr, *d_desc = nullptr;
-  const double *d_diag = nullptr, *d_kaf = nullptr, *d_phred = nullptr;
-  if ((rc = upload(ctx, P.words, &d_words))) return rc;
-  if ((rc = upload(ctx, P.slice_desc, &d_desc))) return rc;
-  if ((rc = upload(ctx, P.diag, &d_diag))) return rc;
-  if ((rc = upload(ctx, P.known_af, &d_kaf))) return rc;
-  std::vector<double> phred_v(phred, phred + 128);
-  if ((rc = upload(ctx, phred_v, &d_phred, false))) return rc;
-  std::vector<float> ud32, mu32;
-  const bool fp64 = desc->panel_dtype == VB2_PANEL_FP64;
-  if (desc->panel_dtype != VB2_PANEL_FP64 && desc->panel_dtype != VB2_PANEL_FP32)
-    return set_err(ctx, VB2_ERR_INVALID, "unknown panel_dtype");
-  if (P.known_af.empty()) {
-    if (fp64) {
-      const double *d_ud = nullptr, *d_mu = nullptr;
-      if ((rc = upload(ctx, P.ud, &d_ud))) return rc;
-      if ((rc = upload(ctx, P.mu, &d_mu))) return rc;
-      S.ud = d_ud; S.mu = d_mu;
-    } else {
-      ud32.assign(P.ud.begin(), P.ud.end());
-      mu32.assign(P.mu.begin(), P.mu.end());
-      const float *d_ud = nullptr, *d_mu = nullptr;
-      if ((rc = upload(ctx, ud32, &d_ud))) return rc;
-      if ((rc = upload(ctx, mu32, &d_mu))) return rc;
-      S.ud = d_ud; S.mu = d_mu;
-    }
-  }
-  S.words = d_words;
-  S.slice_desc = reinterpret_cast<const uint2 *>(d_desc);
-  S.diag = d_diag;
-  S.known_af = d_kaf;
-  S.phred = d_phred;
+  const uint8_t *d_blob = nullptr;
+  const vb2::Round *d_rounds = nullptr;
+  if ((rc = upload(ctx, P.blob, &d_blob))) return rc;
+  if ((rc = upload(ctx, P.rounds, &d_rounds, false))) return rc;
+  S.blob = d_blob;
+  S.rounds = d_rounds;
   S.log_other_const = P.log_other_const;
   S.min_af = desc->min_af != 0.0 ? desc->min_af : 0.00005;  // h:94
   S.max_af = desc->max_af != 0.0 ? desc->max_af : 0.99995;  // h:95
-  S.n_used = P.n_used; S.n_slices = P.n_slices; S.m_pad = P.m_pad; S.n_pc = P.n_pc;
-  S.grid_x = (P.n_slices + kWarpsPerCta - 1) / kWarpsPerCta;
-  S.panel_fp64 = fp64 ? 1u : 0u;
-  uint32_t cap = kStageWordsCap;
-  if (const char *t = getenv("VB2_LLK_STAGE_WORDS")) cap = (uint32_t)std::max(1, atoi(t));
-  S.stage_words = std::max(1u, std::min(P.max_slice_words, cap));
-  S.n_buf = P.max_slice_words > S.stage_words ? 2u : 1u;
-  ctx->smem_bytes = kWarpsPerCta * S.n_buf * S.stage_words * 128u;
-  VB2_CUDA(ctx, cudaFuncSetAttribute(llk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  S.n_rounds = (uint32_t)P.rounds.size();
+  S.n_bins = P.n_bins;
+  S.grid_x = P.n_slices ? P.grid_x : 0u;
+  S.conc_rounds = P.conc_rounds;
+  S.n_pc = P.n_pc;
+  S.panel_fp64 = cfg.panel_fp64 ? 1u : 0u;
+  S.known_af = P.known_af ? 1u : 0u;
+  S.off_ud = P.layout.off_ud; S.off_mu = P.layout.off_mu; S.off_kaf = P.layout.off_kaf;
+  S.off_diag = P.layout.off_diag; S.off_words = P.layout.off_words;
+  // shared-memory stage: as many word rows as fit next to the fixed part in ~4 KiB (at least 4),
+  // never more than the deepest blob needs; VB2_LLK_STAGE_WORDS overrides (tests)
+  uint32_t max_rows = 0;
+  for (const vb2::Round &R : P.rounds) max_rows = std::max(max_rows, R.rows);
+  uint32_t cap_rows = kChunkTargetBytes > S.off_words + 4u * 128u ? (kChunkTargetBytes - S.off_words) / 128u : 4u;
+  if (const char *t = getenv("VB2_LLK_STAGE_WORDS")) cap_rows = (uint32_t)std::max(1, atoi(t));
+  S.chunk_rows = std::max(1u, std::min(std::max(max_rows, 1u), cap_rows));
+  S.buf_bytes = S.off_words + S.chunk_rows * 128u;
+  const bool one_item_per_warp = S.n_rounds <= S.conc_rounds && max_rows <= S.chunk_rows;
+  S.n_buf = one_item_per_warp ? 1u : 2u;
+  ctx->block_threads = 128u * std::max(1u, S.conc_rounds);
+  ctx->smem_bytes = (ctx->block_threads / 32u) * S.n_buf * S.buf_bytes;
+  if (ctx->smem_bytes > 200u * 1024u) return set_err(ctx, VB2_ERR_INVALID, "shared-memory stage too large (n_pc too big?)");
+  VB2_CUDA(ctx, cudaFuncSetAttribute(llk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 
   // ---- result plumbing ---------------------------------------------------------------------------
   VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_mbox, sizeof(Mailbox), cudaHostAllocMapped));
@@ -620,7 +697,7 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   if ((rc = ensure_slots(ctx, kMaxArgJobs))) return rc;
   VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   // keep only the sizes
-  P.words = {}; P.slice_desc = {}; P.ud = {}; P.mu = {}; P.diag = {}; P.known_af = {}; P.marker_index = {};
+  P.blob = {}; P.marker_index = {};
   return VB2_OK;
 }
 
@@ -660,7 +737,7 @@ int vb2_llk_get_info(const vb2_llk_ctx *ctx, vb2_llk_info *info) {
   info->device_bytes = ctx->device_bytes;
   info->n_slices = P.n_slices;
   info->grid_x = ctx->S.grid_x;
-  info->block_threads = kThreads;
+  info->block_threads = ctx->block_threads;
   info->smem_bytes = ctx->smem_bytes;
   info->device = ctx->device;
   info->sm_count = ctx->sm_count;
@@ -714,7 +791,7 @@ int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
   }
   VB2_CUDA(lead, cudaStreamSynchronize(lead->stream));  // staging buffers are free again
   const uint32_t k = lead->S.n_pc;
-  uint32_t grid_x = 0, smem = 0;
+  uint32_t grid_x = 0, smem = 0, threads = 0;
   // slot of job j inside its sample = number of earlier jobs on the same context
   for (int j = 0; j < n; ++j) {
     vb2_llk_ctx *c = ctxs[j];
@@ -734,6 +811,7 @@ int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
     // every sample indexes its shared-memory stage with the launch-wide geometry
     grid_x = std::max(grid_x, c->S.grid_x);
     smem = std::max(smem, c->smem_bytes);
+    threads = std::max(threads, c->block_threads);
     any |= c->S.grid_x > 0;
     fill_job(&lead->h_jobs[j], k, pc_contam + (size_t)j * k, pc_intended + (size_t)j * k, alphas[j]);
   }
@@ -756,12 +834,63 @@ int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
   A.mbox = lead->d_mbox;
   A.jobs_done = lead->d_jobs_done;
   A.seq = ++lead->seq;
-  dim3 grid(grid_x, (unsigned)n, 1), block(kThreads, 1, 1);
+  memcpy(A.phred, lead->phred, sizeof(A.phred));
+  dim3 grid(grid_x, (unsigned)n, 1), block(threads, 1, 1);
   llk_kernel<<<grid, block, smem, lead->stream>>>(A);
   VB2_CUDA(lead, cudaGetLastError());
   int rc = wait_mailbox(lead, A.seq);
   if (rc) return rc;
   for (int j = 0; j < n; ++j) llk_out[j] = lead->h_mbox->val[j];
+  return VB2_OK;
+}
+
+
+int vb2_llk_time_device(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup, int steps, const double *pc_contam,
+                        const double *pc_intended, double alpha, float *elapsed_ms) {
+  if (!ctxs || n_ctx <= 0 || !ctxs[0] || steps <= 0 || !elapsed_ms) return set_err(nullptr, VB2_ERR_INVALID, "bad argument");
+  vb2_llk_ctx *lead = ctxs[0];
+  VB2_CUDA(lead, cudaSetDevice(lead->device));
+  for (int i = 0; i < n_ctx; ++i)
+    if (!ctxs[i] || ctxs[i]->stream != lead->stream)
+      return set_err(lead, VB2_ERR_INVALID, "vb2_llk_time_device: contexts must share one stream");
+  cudaEvent_t e0, e1;
+  VB2_CUDA(lead, cudaEventCreate(&e0));
+  VB2_CUDA(lead, cudaEventCreate(&e1));
+  std::vector<double> pc1(pc_contam, pc_contam + lead->S.n_pc);
+  int rc = VB2_OK;
+  for (int i = -warmup; i < steps && rc == VB2_OK; ++i) {
+    if (i == 0) cudaEventRecord(e0, lead->stream);
+    pc1[0] = pc_contam[0] + 1e-7 * ((i + warmup) % 1000);  // a different point every step
+    vb2_llk_ctx *c = ctxs[(i + warmup) % n_ctx];
+    rc = launch_batch(c, 1, pc1.data(), pc_intended, &alpha, c->d_out, false, nullptr);
+  }
+  cudaEventRecord(e1, lead->stream);
+  cudaError_t e = cudaEventSynchronize(e1);
+  if (rc == VB2_OK && e != cudaSuccess) rc = set_err(lead, VB2_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == VB2_OK) cudaEventElapsedTime(elapsed_ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
+int vb2_llk_time_host(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup, int steps, const double *pc_contam,
+                      const double *pc_intended, double alpha, double *elapsed_s, double *last_llk) {
+  if (!ctxs || n_ctx <= 0 || !ctxs[0] || steps <= 0 || !elapsed_s) return set_err(nullptr, VB2_ERR_INVALID, "bad argument");
+  vb2_llk_ctx *lead = ctxs[0];
+  std::vector<double> pc1(pc_contam, pc_contam + lead->S.n_pc);
+  double llk = 0.0;
+  std::chrono::steady_clock::time_point t0;
+  for (int i = -warmup; i < steps; ++i) {
+    if (i == 0) {
+      VB2_CUDA(lead, cudaStreamSynchronize(lead->stream));
+      t0 = std::chrono::steady_clock::now();
+    }
+    pc1[0] = pc_contam[0] + 1e-7 * ((i + warmup) % 1000);
+    int rc = vb2_llk_eval(ctxs[(i + warmup) % n_ctx], pc1.data(), pc_intended, alpha, &llk);
+    if (rc) return rc;
+  }
+  *elapsed_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (last_llk) *last_llk = llk;
   return VB2_OK;
 }
 

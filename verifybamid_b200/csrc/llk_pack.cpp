@@ -39,7 +39,22 @@ struct MarkerTmp {
 
 }  // namespace
 
-int pack_sample(const vb2_llk_desc &d, const double *phred, PackedSample *out, std::string *err) {
+// Dealing rule.  Slices are sorted heaviest first; slice j goes to round j / n_bins.  If the last
+// round is partial (rem = n_slices % n_bins blobs) its blobs go to the LONG bins, the last rem bins.
+// To compensate, every full round gives its n_bins - rem heaviest slices to the short bins and its
+// rem lightest slices to the long bins; inside each group the direction alternates from round to
+// round (snake) so the group's bins stay level.
+uint32_t bin_of(uint32_t n_slices, uint32_t n_bins, uint32_t j) {
+  const uint32_t r = j / n_bins, i = j % n_bins;
+  const uint32_t rem = n_slices % n_bins, n_short = n_bins - rem;
+  if ((uint64_t)(r + 1) * n_bins > n_slices) return n_short + i;  // the partial last round
+  if (i < n_short) return (r & 1u) ? n_short - 1u - i : i;
+  const uint32_t k = i - n_short;
+  return n_short + ((r & 1u) ? rem - 1u - k : k);
+}
+
+int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phred, PackedSample *out,
+                std::string *err) {
   auto fail = [&](const char *m) { if (err) *err = m; return (int)VB2_ERR_INVALID; };
   if (d.n_pc == 0 || d.n_pc > VB2_MAX_PC) return fail("n_pc must be in [1, VB2_MAX_PC]");
   if (d.ud_stride < d.n_pc) return fail("ud_stride < n_pc");
@@ -51,6 +66,7 @@ int pack_sample(const vb2_llk_desc &d, const double *phred, PackedSample *out, s
   PackedSample &P = *out;
   P = PackedSample();
   P.n_pc = d.n_pc;
+  P.known_af = d.known_af != nullptr;
 
   // Per-(class, q, g) single-read emission A_bc[g] = E[g]*e + N[g]*(1-e)
   // (COND_LK, ContaminationEstimator.h:164-177; same expression as h:223-224 with g1 == g2).
@@ -91,6 +107,9 @@ int pack_sample(const vb2_llk_desc &d, const double *phred, PackedSample *out, s
   }
 
   // ---- 2. order markers so that the 32 lanes of a warp run the same trip counts --------------
+  // A warp executes max(ref words) + max(alt words) over its lanes, so markers are grouped by alt
+  // words and, inside a group, ordered by ref words -- alternating direction from group to group so
+  // that the slice straddling a group boundary mixes similar ref depths.
   auto words_of = [](uint32_t n) { return (n + kReadsPerWord - 1) / kReadsPerWord; };
   std::vector<uint32_t> order(used.size());
   std::iota(order.begin(), order.end(), 0u);
@@ -98,83 +117,131 @@ int pack_sample(const vb2_llk_desc &d, const double *phred, PackedSample *out, s
     const uint32_t wa_a = words_of(used[a].n_alt), wa_b = words_of(used[b].n_alt);
     if (wa_a != wa_b) return wa_a > wa_b;
     const uint32_t wr_a = words_of(used[a].n_ref), wr_b = words_of(used[b].n_ref);
-    if (wr_a != wr_b) return wr_a > wr_b;
+    if (wr_a != wr_b) return (wa_a & 1u) ? wr_a < wr_b : wr_a > wr_b;
     return used[a].panel_row < used[b].panel_row;
   });
 
-  // ---- 3. cut into 32-marker slices; slice s belongs to shard s % shard_count -----------------
+  // ---- 3. cut into 32-marker slices, heaviest first; slice s belongs to shard s % shard_count ----
   const size_t total_slices = (order.size() + kSliceMarkers - 1) / kSliceMarkers;
-  std::vector<size_t> my_slices;
-  for (size_t s = d.shard_rank; s < total_slices; s += shard_count) my_slices.push_back(s);
-  P.n_slices = (uint32_t)my_slices.size();
-  P.m_pad = P.n_slices * kSliceMarkers;
-  P.slice_desc.assign((size_t)P.n_slices * 2, 0u);
-  P.ud.assign((size_t)P.n_pc * P.m_pad, 0.0);
-  P.mu.assign(P.m_pad, 1.0);
-  P.diag.assign((size_t)3 * P.m_pad, 0.0);
-  if (d.known_af) P.known_af.assign(P.m_pad, 0.5);
-  P.marker_index.assign(P.m_pad, 0xFFFFFFFFu);
-
-  uint64_t total_words = 0;
-  for (uint32_t ls = 0; ls < P.n_slices; ++ls) {
-    const size_t s = my_slices[ls];
+  struct SliceGeom { uint32_t wr, wa; size_t first; };
+  std::vector<SliceGeom> all_geom(total_slices);
+  for (size_t s = 0; s < total_slices; ++s) {
     uint32_t wr = 0, wa = 0;
-    for (size_t l = 0; l < kSliceMarkers; ++l) {
+    for (size_t l = 0; l < (size_t)kSliceMarkers; ++l) {
       const size_t o = s * kSliceMarkers + l;
       if (o >= order.size()) break;
       wr = std::max(wr, words_of(used[order[o]].n_ref));
       wa = std::max(wa, words_of(used[order[o]].n_alt));
     }
-    if (wr > 0xFFFFu || wa > 0xFFFFu) return fail("marker deeper than 262140 reads of one class");
-    if (total_words * kSliceMarkers > 0xFFFFFFFFull - (uint64_t)(wr + wa) * kSliceMarkers)
-      return fail("sample too large for 32-bit word offsets (>16 GiB of reads)");
-    P.slice_desc[2 * ls] = (uint32_t)(total_words * kSliceMarkers);
-    P.slice_desc[2 * ls + 1] = wr | (wa << 16);
-    P.max_slice_words = std::max(P.max_slice_words, wr + wa);
-    total_words += wr + wa;
+    all_geom[s] = {wr, wa, s * kSliceMarkers};
   }
-  P.words.assign((size_t)total_words * kSliceMarkers, 0xFFFFFFFFu);
-  uint8_t *bytes = reinterpret_cast<uint8_t *>(P.words.data());
+  std::stable_sort(all_geom.begin(), all_geom.end(),
+                   [](const SliceGeom &a, const SliceGeom &b) { return a.wr + a.wa > b.wr + b.wa; });
+  std::vector<SliceGeom> geom;
+  for (size_t s = d.shard_rank; s < total_slices; s += shard_count) geom.push_back(all_geom[s]);
+  P.n_slices = (uint32_t)geom.size();
+  P.marker_index.assign((size_t)P.n_slices * kSliceMarkers, 0xFFFFFFFFu);
 
-  // ---- 4. fill ----------------------------------------------------------------------------------
+  // ---- 4. blob layout ------------------------------------------------------------------------------
+  BlobLayout &L = P.layout;
+  L.panel_elem = cfg.panel_fp64 ? 8u : 4u;
+  uint32_t off = kBlobHeaderBytes;
+  if (P.known_af) {
+    L.off_kaf = off; off += kSliceMarkers * 8u;
+  } else {
+    L.off_ud = off;  off += P.n_pc * kSliceMarkers * L.panel_elem;
+    L.off_mu = off;  off += kSliceMarkers * L.panel_elem;
+    off = (off + 7u) & ~7u;
+  }
+  L.off_diag = off;  off += 3u * kSliceMarkers * 8u;
+  L.off_words = off;
+
+  // ---- 5. deal the slices to SM sub-partition bins in rounds (snake order) -----------------------
+  P.grid_x = std::max(1u, std::min(cfg.max_ctas ? cfg.max_ctas : 1u, (P.n_slices + kBinsPerCta - 1) / kBinsPerCta));
+  P.n_bins = P.grid_x * kBinsPerCta;
+  uint64_t total_bytes = 0;
+  for (uint32_t j0 = 0, r = 0; j0 < P.n_slices; j0 += P.n_bins, ++r) {
+    const uint32_t cnt = std::min(P.n_bins, P.n_slices - j0);
+    uint32_t wmax = 0;
+    for (uint32_t j = j0; j < j0 + cnt; ++j) wmax = std::max(wmax, geom[j].wr + geom[j].wa);
+    const uint64_t stride64 = (uint64_t)L.off_words + (uint64_t)wmax * 128u;  // off_words % 16 == 0
+    if (stride64 > 0x7FFFFFF0ull) return fail("marker too deep: one blob would exceed 2 GiB");
+    // a partial last round goes to the LONG bins, the last `cnt` ones (see bin_of below)
+    Round R{total_bytes, (uint32_t)stride64, P.n_bins - cnt, cnt, wmax};
+    P.rounds.push_back(R);
+    P.max_stride = std::max(P.max_stride, R.stride);
+    total_bytes += (uint64_t)R.stride * cnt;
+    total_bytes = (total_bytes + 127u) & ~127ull;
+  }
+  P.conc_rounds = std::max(1u, std::min((uint32_t)P.rounds.size(), kMaxConcRounds));
+  P.blob.assign((size_t)total_bytes, 0xFF);  // 0xFF = pad byte everywhere a read is not written
+
+  // ---- 6. fill ------------------------------------------------------------------------------------
   long double other_sum = 0.0L;
-  for (uint32_t ls = 0; ls < P.n_slices; ++ls) {
-    const size_t s = my_slices[ls];
-    const uint32_t base = P.slice_desc[2 * ls];
-    const uint32_t wr = P.slice_desc[2 * ls + 1] & 0xFFFFu;
+  for (uint32_t j = 0; j < P.n_slices; ++j) {
+    const Round &R = P.rounds[j / P.n_bins];
+    const uint32_t bin = bin_of(P.n_slices, P.n_bins, j);
+    uint8_t *blob = P.blob.data() + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
+    const uint32_t wr = geom[j].wr, wa = geom[j].wa;
+    uint32_t n_valid = 0;
+    // neutral values for padding lanes
     for (uint32_t l = 0; l < (uint32_t)kSliceMarkers; ++l) {
-      const size_t o = s * kSliceMarkers + l;
+      if (P.known_af) {
+        reinterpret_cast<double *>(blob + L.off_kaf)[l] = 0.5;
+      } else {
+        for (uint32_t k = 0; k <= P.n_pc; ++k) {  // k == n_pc: mu
+          uint8_t *p = blob + (k < P.n_pc ? L.off_ud + k * kSliceMarkers * L.panel_elem : L.off_mu) + l * L.panel_elem;
+          const double v = k < P.n_pc ? 0.0 : 1.0;
+          if (cfg.panel_fp64) *reinterpret_cast<double *>(p) = v;
+          else *reinterpret_cast<float *>(p) = (float)v;
+        }
+      }
+      for (int g = 0; g < 3; ++g) reinterpret_cast<double *>(blob + L.off_diag)[g * kSliceMarkers + l] = 0.0;
+    }
+    for (uint32_t l = 0; l < (uint32_t)kSliceMarkers; ++l) {
+      const size_t o = geom[j].first + l;
       if (o >= order.size()) break;
+      ++n_valid;
       const MarkerTmp &m = used[order[o]];
-      const uint32_t pm = ls * kSliceMarkers + l;  // packed marker id
-      P.marker_index[pm] = m.panel_row;
-      for (uint32_t k = 0; k < P.n_pc; ++k)
-        P.ud[(size_t)k * P.m_pad + pm] = d.ud[(size_t)m.panel_row * d.ud_stride + k];
-      P.mu[pm] = d.means[m.panel_row];
-      if (d.known_af) P.known_af[pm] = d.known_af[m.panel_row];
+      P.marker_index[(size_t)j * kSliceMarkers + l] = m.panel_row;
+      if (P.known_af) {
+        reinterpret_cast<double *>(blob + L.off_kaf)[l] = d.known_af[m.panel_row];
+      } else {
+        for (uint32_t k = 0; k < P.n_pc; ++k) {
+          uint8_t *p = blob + L.off_ud + (k * kSliceMarkers + l) * L.panel_elem;
+          const double v = d.ud[(size_t)m.panel_row * d.ud_stride + k];
+          if (cfg.panel_fp64) *reinterpret_cast<double *>(p) = v;
+          else *reinterpret_cast<float *>(p) = (float)v;
+        }
+        uint8_t *p = blob + L.off_mu + l * L.panel_elem;
+        if (cfg.panel_fp64) *reinterpret_cast<double *>(p) = d.means[m.panel_row];
+        else *reinterpret_cast<float *>(p) = (float)d.means[m.panel_row];
+      }
       double dg[3] = {1.0, 1.0, 1.0};
       uint32_t ir = 0, ia = 0;
       const char alt = d.alt_base[m.panel_row];
-      for (int64_t j = m.beg; j < m.end; ++j) {
-        const int bc = classify_base(d.bases[j], alt);
-        const int q = clamp_qual(d.quals[j]);
+      uint8_t *wbytes = blob + L.off_words;
+      for (int64_t jj = m.beg; jj < m.end; ++jj) {
+        const int bc = classify_base(d.bases[jj], alt);
+        const int q = clamp_qual(d.quals[jj]);
         if (bc == 2) {
           other_sum += (long double)log_other[q];
           ++P.reads_folded;
           continue;
         }
-        // byte address: word t of this lane lives at words[base + t*32 + l]
         uint32_t r, t0;
         if (bc == 0) { r = ir++; t0 = 0; for (int g = 0; g < 3; ++g) dg[g] *= a_ref[q][g]; }
         else         { r = ia++; t0 = wr; for (int g = 0; g < 3; ++g) dg[g] *= a_alt[q][g]; }
-        const size_t word = (size_t)base + (size_t)(t0 + r / kReadsPerWord) * kSliceMarkers + l;
-        bytes[word * 4 + (r % kReadsPerWord)] = (uint8_t)q;  // little-endian: byte b = bits 8b..8b+7
+        // row t = t0 + r/4 of lane l; little-endian: byte b of the word = bits 8b..8b+7
+        wbytes[((size_t)(t0 + r / kReadsPerWord) * kSliceMarkers + l) * 4 + (r % kReadsPerWord)] = (uint8_t)q;
         ++P.reads_streamed;
       }
-      for (int g = 0; g < 3; ++g) P.diag[(size_t)g * P.m_pad + pm] = dg[g];
+      for (int g = 0; g < 3; ++g) reinterpret_cast<double *>(blob + L.off_diag)[g * kSliceMarkers + l] = dg[g];
       P.reads_used += (uint64_t)(m.end - m.beg);
       ++P.n_used;
     }
+    uint32_t hdr[4] = {wr, wa, n_valid, 0u};
+    std::memcpy(blob, hdr, sizeof(hdr));
   }
   P.log_other_const = (double)other_sum;
   return VB2_OK;
@@ -185,26 +252,34 @@ int pack_sample(const vb2_llk_desc &d, const double *phred, PackedSample *out, s
 // ---------------------------------------------------------------------------------------------
 // host-only diagnostics of the C ABI (include/vb2_llk.h): expose the packed image to tests
 // ---------------------------------------------------------------------------------------------
-extern "C" int vb2_llk_pack_host(const vb2_llk_desc *desc, vb2_packed_view *view) {
+extern "C" int vb2_llk_pack_host(const vb2_llk_desc *desc, uint32_t max_ctas, vb2_packed_view *view) {
   if (!desc || !view || desc->struct_size != sizeof(vb2_llk_desc) || view->struct_size != sizeof(vb2_packed_view))
     return VB2_ERR_INVALID;
   double phred[vb2::kNumQual];
   vb2::build_phred_table(phred);
   auto *P = new vb2::PackedSample();
   std::string err;
-  int rc = vb2::pack_sample(*desc, phred, P, &err);
+  vb2::PackConfig cfg;
+  cfg.max_ctas = max_ctas ? max_ctas : 148u;
+  cfg.panel_fp64 = desc->panel_dtype == VB2_PANEL_FP64;
+  int rc = vb2::pack_sample(*desc, cfg, phred, P, &err);
   if (rc != VB2_OK) {
     delete P;
     return rc;
   }
-  view->n_pc = P->n_pc; view->n_used = P->n_used; view->n_slices = P->n_slices; view->m_pad = P->m_pad;
-  view->max_slice_words = P->max_slice_words;
+  static_assert(sizeof(vb2::Round) == 24, "vb2_packed_view.rounds layout");
+  view->n_pc = P->n_pc; view->n_used = P->n_used; view->n_slices = P->n_slices;
+  view->grid_x = P->grid_x; view->n_bins = P->n_bins; view->conc_rounds = P->conc_rounds;
+  view->n_rounds = (uint32_t)P->rounds.size();
+  view->max_stride = P->max_stride; view->known_af = P->known_af ? 1u : 0u;
+  view->panel_elem = P->layout.panel_elem;
+  view->off_ud = P->layout.off_ud; view->off_mu = P->layout.off_mu; view->off_kaf = P->layout.off_kaf;
+  view->off_diag = P->layout.off_diag; view->off_words = P->layout.off_words;
   view->reads_used = P->reads_used; view->reads_streamed = P->reads_streamed; view->reads_folded = P->reads_folded;
-  view->n_words = P->words.size();
+  view->blob_bytes = P->blob.size();
   view->log_other_const = P->log_other_const;
-  view->words = P->words.data(); view->slice_desc = P->slice_desc.data();
-  view->ud = P->ud.data(); view->mu = P->mu.data(); view->diag = P->diag.data();
-  view->known_af = P->known_af.empty() ? nullptr : P->known_af.data();
+  view->blob = P->blob.data();
+  view->rounds = reinterpret_cast<const uint32_t *>(P->rounds.data());
   view->marker_index = P->marker_index.data();
   view->owner = P;
   return VB2_OK;

@@ -1,5 +1,5 @@
 // llk_pack.h -- host-side flatten of the reference's per-marker base/qual vectors into the
-// SoA image the sm_100a likelihood kernel streams from HBM.
+// image the sm_100a likelihood kernel streams from HBM.
 //
 // What is folded in here, once per sample, because it does not change between evaluations
 // (reference file:line in parentheses):
@@ -10,7 +10,15 @@
 //     stream and become one scalar, log_other_const
 //   * the three diagonal genotype pairs g1 == g2: alpha*A[g] + (1-alpha)*A[g] = A[g] does not
 //     depend on alpha or the PCs -> three per-marker constants diag[g]
-// See DESIGN.md "Data layout in HBM".
+//
+// Layout ("blobs in rounds", DESIGN.md "Data layout in HBM"):
+//   markers are sorted by (total words, alt words) so the 32 lanes of a warp run equal trip
+//   counts, cut into 32-marker SLICES, and the slices are dealt to BINS -- one bin per SM
+//   sub-partition of the launch (4 per CTA, one CTA per SM) -- in ROUNDS, heaviest first, in
+//   snake order, so every sub-partition's FP64 pipe gets the same amount of work.  Everything a
+//   warp needs for one slice -- header, UD columns, mu, diag, the packed quality bytes -- is ONE
+//   contiguous BLOB, and all blobs of a round have the same stride, so a warp finds its blob
+//   with arithmetic only (no descriptor load) and fetches it with one TMA bulk copy.
 #ifndef VB2_LLK_PACK_H_
 #define VB2_LLK_PACK_H_
 
@@ -26,30 +34,60 @@ constexpr int kSliceMarkers = 32;       // one warp = one slice = 32 markers, on
 constexpr int kReadsPerWord = 4;        // four quality bytes per 32-bit word
 constexpr uint8_t kPadByte = 0xFF;      // "no read" filler inside a lane's last word
 constexpr int kNumQual = 94;            // Phred 0..93 (h:60-74)
+constexpr uint32_t kBlobHeaderBytes = 16;
+
+constexpr uint32_t kBinsPerCta = 4;     // SM sub-partitions: warp w of a CTA issues on SMSP w % 4
+constexpr uint32_t kMaxConcRounds = 6;  // rounds a CTA runs concurrently (4*6 = 24 warps)
+
+struct PackConfig {
+  uint32_t max_ctas = 148;   // CTAs of one launch = SMs of the device (one persistent CTA per SM)
+  bool panel_fp64 = false;   // UD / mu element type inside the blobs
+};
+
+// Byte offsets inside a blob (identical for every blob of a sample).
+struct BlobLayout {
+  uint32_t panel_elem = 4;  // sizeof(float) or sizeof(double)
+  uint32_t off_ud = 0;      // [n_pc][32] panel_elem   (absent when known_af)
+  uint32_t off_mu = 0;      // [32] panel_elem         (absent when known_af)
+  uint32_t off_kaf = 0;     // [32] double             (only when known_af)
+  uint32_t off_diag = 0;    // [3][32] double
+  uint32_t off_words = 0;   // [wr + wa][32] uint32: row t, lane l at off_words + (t*32 + l)*4
+};
+
+struct Round {
+  uint64_t base;       // byte offset of the round's first blob
+  uint32_t stride;     // bytes per blob in this round (multiple of 16)
+  uint32_t first_bin;  // bins [first_bin, first_bin + count) own a blob in this round;
+  uint32_t count;      //   bin b's blob is at base + (b - first_bin) * stride
+  uint32_t rows;       // word rows per blob = (stride - off_words) / 128
+};
 
 struct PackedSample {
   uint32_t n_pc = 0;
   uint32_t n_used = 0;          // markers of this shard that survive the skip rules
   uint32_t n_slices = 0;        // ceil(n_used / 32) for this shard
-  uint32_t m_pad = 0;           // n_slices * 32
-  uint32_t max_slice_words = 0; // max over slices of (ref words + alt words) per lane
+  uint32_t grid_x = 0;          // CTAs of a launch: min(max_ctas, ceil(n_slices / 4))
+  uint32_t n_bins = 0;          // 4 * grid_x
+  uint32_t conc_rounds = 0;     // min(rounds, kMaxConcRounds): a CTA has 4 * conc_rounds warps
+  uint32_t max_stride = 0;      // largest blob stride (bytes)
+  bool known_af = false;
   uint64_t reads_used = 0, reads_streamed = 0, reads_folded = 0;
   double log_other_const = 0.0;
-
-  // words[slice_desc[2s] + t*32 + lane]: t-th word of lane `lane` of slice s; the first
-  // wr = slice_desc[2s+1] & 0xFFFF words hold ref-class reads, the next
-  // wa = slice_desc[2s+1] >> 16 hold alt-class reads; each byte is a clamped quality or 0xFF.
-  std::vector<uint32_t> words;
-  std::vector<uint32_t> slice_desc;   // [n_slices][2]
-  std::vector<double> ud;             // [n_pc][m_pad]  (column-major: coalesced per PC)
-  std::vector<double> mu;             // [m_pad]
-  std::vector<double> diag;           // [3][m_pad]
-  std::vector<double> known_af;       // [m_pad] or empty
-  std::vector<uint32_t> marker_index; // [m_pad] panel row of each packed marker (0xFFFFFFFF pad)
+  BlobLayout layout;
+  std::vector<Round> rounds;
+  // Blob header (16 bytes): u32 wr (ref words per lane), u32 wa (alt words per lane),
+  // u32 n_valid (lanes 0..n_valid-1 hold markers), u32 reserved.
+  std::vector<uint8_t> blob;          // the whole image
+  std::vector<uint32_t> marker_index; // [n_slices*32] panel row per (slice, lane); slice j (heaviest
+                                      // first) is the blob of round j / n_bins, bin bin_of(j)
 };
 
+// Bin of slice j (slices heaviest first); see llk_pack.cpp for the dealing rule.
+uint32_t bin_of(uint32_t n_slices, uint32_t n_bins, uint32_t j);
+
 // Returns VB2_OK or VB2_ERR_INVALID (message in *err).  phred[q] = 10^(-q/10), q = 0..93.
-int pack_sample(const vb2_llk_desc &d, const double *phred, PackedSample *out, std::string *err);
+int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phred, PackedSample *out,
+                std::string *err);
 
 // phred table exactly as the reference builds it (ContaminationEstimator.h:65-74).
 void build_phred_table(double *phred94);

@@ -33,7 +33,8 @@ _STATUS = {1: "VB2_ERR_INVALID", 2: "VB2_ERR_NO_DEVICE", 3: "VB2_ERR_CUDA", 4: "
 # every symbol include/vb2_llk.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_create", "vb2_llk_destroy", "vb2_llk_get_info",
                "vb2_llk_eval", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many",
-               "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free")
+               "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free",
+               "vb2_llk_time_device", "vb2_llk_time_host")
 
 
 class VB2Error(RuntimeError):
@@ -66,13 +67,15 @@ class _Info(ctypes.Structure):
 
 class _PackedView(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_uint32), ("n_pc", ctypes.c_uint32), ("n_used", ctypes.c_uint32),
-                ("n_slices", ctypes.c_uint32), ("m_pad", ctypes.c_uint32), ("max_slice_words", ctypes.c_uint32),
+                ("n_slices", ctypes.c_uint32), ("grid_x", ctypes.c_uint32), ("n_bins", ctypes.c_uint32),
+                ("conc_rounds", ctypes.c_uint32), ("n_rounds", ctypes.c_uint32), ("max_stride", ctypes.c_uint32),
+                ("known_af", ctypes.c_uint32), ("panel_elem", ctypes.c_uint32),
+                ("off_ud", ctypes.c_uint32), ("off_mu", ctypes.c_uint32), ("off_kaf", ctypes.c_uint32),
+                ("off_diag", ctypes.c_uint32), ("off_words", ctypes.c_uint32),
                 ("reads_used", ctypes.c_uint64), ("reads_streamed", ctypes.c_uint64),
-                ("reads_folded", ctypes.c_uint64), ("n_words", ctypes.c_uint64),
+                ("reads_folded", ctypes.c_uint64), ("blob_bytes", ctypes.c_uint64),
                 ("log_other_const", ctypes.c_double),
-                ("words", ctypes.POINTER(ctypes.c_uint32)), ("slice_desc", ctypes.POINTER(ctypes.c_uint32)),
-                ("ud", ctypes.POINTER(ctypes.c_double)), ("mu", ctypes.POINTER(ctypes.c_double)),
-                ("diag", ctypes.POINTER(ctypes.c_double)), ("known_af", ctypes.POINTER(ctypes.c_double)),
+                ("blob", ctypes.POINTER(ctypes.c_uint8)), ("rounds", ctypes.POINTER(ctypes.c_uint32)),
                 ("marker_index", ctypes.POINTER(ctypes.c_uint32)), ("owner", ctypes.c_void_p)]
 
 
@@ -116,8 +119,16 @@ def load_library() -> ctypes.CDLL:
                                       ctypes.c_void_p, ctypes.c_void_p]
     lib.vb2_llk_sync.restype = ctypes.c_int
     lib.vb2_llk_sync.argtypes = [ctypes.c_void_p]
+    lib.vb2_llk_time_device.restype = ctypes.c_int
+    lib.vb2_llk_time_device.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+                                        ctypes.POINTER(ctypes.c_float)]
+    lib.vb2_llk_time_host.restype = ctypes.c_int
+    lib.vb2_llk_time_host.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.vb2_llk_pack_host.restype = ctypes.c_int
-    lib.vb2_llk_pack_host.argtypes = [ctypes.POINTER(_Desc), ctypes.POINTER(_PackedView)]
+    lib.vb2_llk_pack_host.argtypes = [ctypes.POINTER(_Desc), ctypes.c_uint32, ctypes.POINTER(_PackedView)]
     lib.vb2_llk_pack_free.restype = None
     lib.vb2_llk_pack_free.argtypes = [ctypes.POINTER(_PackedView)]
     if lib.vb2_abi_version() != 1:
@@ -166,27 +177,29 @@ def make_desc(problem: PileupProblem, device: int = 0, panel_dtype: int = VB2_PA
     return d
 
 
-def pack_host(problem: PileupProblem, shard_rank: int = 0, shard_count: int = 1) -> dict:
-    """Host-only: the flattened image vb2_llk_create would upload, as numpy copies (no CUDA call)."""
+def pack_host(problem: PileupProblem, shard_rank: int = 0, shard_count: int = 1, max_ctas: int = 148,
+              panel_dtype: int = VB2_PANEL_FP64) -> dict:
+    """Host-only: the flattened image vb2_llk_create would upload, as numpy copies (no CUDA call).
+
+    Returns the scalars of vb2_packed_view plus `blob` (uint8), `rounds` (list of dicts with base, stride,
+    first_bin, count, rows) and `marker_index`."""
     lib = load_library()
-    d = make_desc(problem, shard_rank=shard_rank, shard_count=shard_count)
+    d = make_desc(problem, shard_rank=shard_rank, shard_count=shard_count, panel_dtype=panel_dtype)
     v = _PackedView()
     v.struct_size = ctypes.sizeof(_PackedView)
-    rc = lib.vb2_llk_pack_host(ctypes.byref(d), ctypes.byref(v))
+    rc = lib.vb2_llk_pack_host(ctypes.byref(d), int(max_ctas), ctypes.byref(v))
     if rc != VB2_OK:
         raise VB2Error(rc, "vb2_llk_pack_host failed")
     try:
         def arr(ptr, n, dt):
             return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
-        out = {name: getattr(v, name) for name in ("n_pc", "n_used", "n_slices", "m_pad", "max_slice_words",
-                                                    "reads_used", "reads_streamed", "reads_folded", "log_other_const")}
-        out["words"] = arr(v.words, v.n_words, np.uint32)
-        out["slice_desc"] = arr(v.slice_desc, 2 * v.n_slices, np.uint32).reshape(-1, 2)
-        out["ud"] = arr(v.ud, v.n_pc * v.m_pad, np.float64).reshape(v.n_pc, v.m_pad)
-        out["mu"] = arr(v.mu, v.m_pad, np.float64)
-        out["diag"] = arr(v.diag, 3 * v.m_pad, np.float64).reshape(3, v.m_pad)
-        out["known_af"] = arr(v.known_af, v.m_pad, np.float64) if v.known_af else None
-        out["marker_index"] = arr(v.marker_index, v.m_pad, np.uint32)
+        out = {name: getattr(v, name) for name, _ in _PackedView._fields_
+               if name not in ("struct_size", "blob", "rounds", "marker_index", "owner")}
+        out["blob"] = arr(v.blob, v.blob_bytes, np.uint8)
+        rr = arr(v.rounds, 6 * v.n_rounds, np.uint32).reshape(-1, 6)
+        out["rounds"] = [{"base": int(r[0]) | (int(r[1]) << 32), "stride": int(r[2]), "first_bin": int(r[3]),
+                          "count": int(r[4]), "rows": int(r[5])} for r in rr]
+        out["marker_index"] = arr(v.marker_index, 32 * v.n_slices, np.uint32)
         return out
     finally:
         lib.vb2_llk_pack_free(ctypes.byref(v))
@@ -279,3 +292,31 @@ def eval_many(engines: List[LLKEngine], pc_contam, pc_intended, alphas) -> np.nd
     if rc != VB2_OK:
         raise VB2Error(rc, lib.vb2_last_error(engines[0]._ctx).decode())
     return out
+
+
+def time_device(engines: List[LLKEngine], warmup: int, steps: int, pc_contam, pc_intended, alpha: float) -> float:
+    """Milliseconds (CUDA events on the engines' stream) for `steps` back-to-back evaluations issued from C,
+    step i on engines[i % n]."""
+    lib = load_library()
+    n = len(engines)
+    arr = (ctypes.c_void_p * n)(*[e._ctx for e in engines])
+    a, b = _f64(pc_contam), _f64(pc_intended)
+    ms = ctypes.c_float()
+    rc = lib.vb2_llk_time_device(arr, n, warmup, steps, a.ctypes.data, b.ctypes.data, float(alpha), ctypes.byref(ms))
+    if rc != VB2_OK:
+        raise VB2Error(rc, lib.vb2_last_error(engines[0]._ctx).decode())
+    return float(ms.value)
+
+
+def time_host(engines: List[LLKEngine], warmup: int, steps: int, pc_contam, pc_intended, alpha: float):
+    """(seconds, last LLK) for `steps` synchronous vb2_llk_eval calls with host buffers, issued from C."""
+    lib = load_library()
+    n = len(engines)
+    arr = (ctypes.c_void_p * n)(*[e._ctx for e in engines])
+    a, b = _f64(pc_contam), _f64(pc_intended)
+    s, last = ctypes.c_double(), ctypes.c_double()
+    rc = lib.vb2_llk_time_host(arr, n, warmup, steps, a.ctypes.data, b.ctypes.data, float(alpha), ctypes.byref(s),
+                               ctypes.byref(last))
+    if rc != VB2_OK:
+        raise VB2Error(rc, lib.vb2_last_error(engines[0]._ctx).decode())
+    return float(s.value), float(last.value)
