@@ -207,20 +207,31 @@ def run_ours(args):
         t_end = time.perf_counter() + seconds
         while time.perf_counter() < t_end:
             if world == 1:
-                vb.time_device(engines, 0, 200, start_pc, start_pc, 0.03)
+                vb.time_device_many(engines, 0, 20, start_pc, start_pc, 0.03)
             else:
                 for j in range(50):
                     step(j)
                 torch.cuda.synchronize()
 
-    # ---- value: device-timed, K back-to-back steps -------------------------------------------
-    # N=1: the steps are issued from C (vb2_llk_time_device) so the launch rate is not limited by the
-    # Python interpreter; N>1: each step is kernel + NCCL allreduce of the scalar, issued from Python.
+    # ---- value: device-timed, EXACTLY K steps ---------------------------------------------------
+    # N=1: steps are issued from C, `copies` steps per launch (vb2_llk_eval_many's kernel: step i
+    # evaluates resident copy i % copies, so every step streams its sample from HBM and the launch
+    # cost is shared by the steps of a launch).  N>1: each step is kernel + NCCL allreduce of the
+    # scalar, one launch per step, issued from Python.
+    def timed_steps(n_steps: int, warm: int) -> float:
+        full, rem = divmod(n_steps, copies)
+        ms = 0.0
+        if full:
+            ms += vb.time_device_many(engines, max(1, warm // copies), full, start_pc, start_pc, 0.03)
+        if rem:
+            ms += vb.time_device_many(engines[:rem], 1, 1, start_pc, start_pc, 0.03)
+        return ms
     with ClockSampler(local) as clocks:
         keep_busy(0.3)                      # let nvidia-smi attach before the timed region
         barrier()
         if world == 1:
-            dev_ms = vb.time_device(engines, args.warmup, args.steps, start_pc, start_pc, 0.03)
+            dev_ms = timed_steps(args.steps, args.warmup)
+            launches = args.steps // copies + (1 if args.steps % copies else 0)
         else:
             for i in range(args.warmup):
                 step(i)
@@ -232,6 +243,7 @@ def run_ours(args):
             ev1.record(stream)
             barrier()
             dev_ms = ev0.elapsed_time(ev1)
+            launches = args.steps
         keep_busy(0.5)                      # clocks under the same load, for the sampler
         barrier()
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -241,15 +253,22 @@ def run_ours(args):
     ms_per_step = dev_ms / args.steps
     value = reads_total / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant (only) kernel: kernel-only timing of this rank's shard --------
-    kern_ms = vb.time_device(engines, args.warmup, args.steps, start_pc, start_pc, 0.03) / args.steps
+    # ---- roofline of the dominant (only) kernel -------------------------------------------------
+    # N=1: the kernel of the timed region above (algorithmic bytes of one launch / its duration).
+    # Also reported: the same kernel launched once per step (latency geometry), which on this part
+    # cannot go below the ~4 us cost of any launch that contains a block-wide barrier.
+    one_ms = vb.time_device(engines, args.warmup, min(args.steps, 2000), start_pc, start_pc, 0.03) / min(args.steps, 2000)
     peak, peak_src = measured_peak_gbs()
-    alg_bytes = info["algorithmic_bytes"]       # this rank's shard
-    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    alg_bytes = info["algorithmic_bytes"]       # this rank's shard, one evaluation
+    kern_us = (dev_ms / args.steps if world == 1 else one_ms) * 1e3       # per evaluation
+    achieved = alg_bytes / (kern_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "llk_kernel", "kernel_us": kern_ms * 1e3,
-                "algorithmic_bytes_per_launch": alg_bytes, "device_bytes_per_launch": info["device_bytes"],
-                "note": "co-bound by FP64 issue rate: 12 fp64 ops per streamed read (DESIGN.md)"}
+                "traffic": None, "peak_source": peak_src, "kernel": "llk_kernel",
+                "evaluations_per_launch": copies if world == 1 else 1,
+                "us_per_evaluation": kern_us, "us_per_evaluation_one_launch_each": one_ms * 1e3,
+                "algorithmic_bytes_per_evaluation": alg_bytes, "device_bytes_per_evaluation": info["device_bytes"],
+                "note": "co-bound by FP64 issue rate: 12 fp64 ops per streamed read -> >= 2.5 us per evaluation "
+                        "at 64 DFMA/clk/SM (DESIGN.md)"}
 
     # ---- e2e: the public C-ABI call with HOST buffers; every step moves the step's inputs (2k+1 doubles)
     # to the device and the scalar result back to the host ------------------------------------------------
@@ -309,8 +328,9 @@ def run_ours(args):
                            "n_pc": k, "parallelism": "marker shards x%d + 1 scalar allreduce/step" % world if world > 1
                            else "single GPU", "l2": "steps rotate through %d resident copies of the sample "
                            "(%.0f MB > 126 MB L2): every step streams from HBM" % (copies, copies * info["device_bytes"] / 1e6),
+                           "steps_per_launch": copies if world == 1 else 1,
                            "panel_dtype": "fp32 UD/mu in HBM, fp64 arithmetic"},
-                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline,
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

@@ -171,6 +171,10 @@ const char *vb2_last_error(const vb2_llk_ctx *ctx);
  * scalar out, every step) timed with the host's steady clock; *elapsed_s = wall time.          */
 int vb2_llk_time_device(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup, int steps, const double *pc_contam,
                         const double *pc_intended, double alpha, float *elapsed_ms);
+/* vb2_llk_time_device_many: `launches` timed launches, each evaluating ALL n_ctx samples once (the
+ * vb2_llk_eval_many kernel, results left in device memory): n_ctx steps per launch.             */
+int vb2_llk_time_device_many(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup_launches, int launches,
+                             const double *pc_contam, const double *pc_intended, double alpha, float *elapsed_ms);
 int vb2_llk_time_host(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup, int steps, const double *pc_contam,
                       const double *pc_intended, double alpha, double *elapsed_s, double *last_llk);
 
@@ -192,7 +196,8 @@ typedef struct vb2_packed_view {
   double log_other_const;
   const uint8_t *blob;          /* [blob_bytes]; bin b's blob of round r at
                                    base_r + (b - first_bin_r) * stride_r;
-                                   16-byte header = u32 ref_words, alt_words, n_valid, 0     */
+                                   16-byte header = u32 ref_rows, alt_rows, n_valid,
+                                   full_ref_rows | full_alt_rows << 16                       */
   const uint32_t *rounds;       /* [n_rounds][6]: base lo, base hi, stride, first_bin, count, rows */
   const uint32_t *marker_index; /* [n_slices*32] panel row per (slice, lane), 0xFFFFFFFF pad;
                                    slice j (heaviest first) lives in round j / n_bins        */

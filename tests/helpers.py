@@ -87,7 +87,7 @@ def emulate_packed_llk(pk: dict, pc1, pc2, alpha: float, min_af=5e-5, max_af=0.9
         af = np.clip(af, min_af, max_af)
         return np.stack([(1 - af) * (1 - af), 2 * af * (1 - af), af * af])
     for _, _, blob in iter_blobs(pk):
-        wr, wa, n_valid, _ = blob[:16].view(np.uint32)
+        wr, wa, n_valid, full = blob[:16].view(np.uint32)
         if pk["known_af"]:
             af1 = af2 = blob[pk["off_kaf"]:pk["off_kaf"] + 256].view(np.float64)
         else:
@@ -98,6 +98,10 @@ def emulate_packed_llk(pk: dict, pc1, pc2, alpha: float, min_af=5e-5, max_af=0.9
         g1v, g2v = gf(af1), gf(af2)
         diag = blob[pk["off_diag"]:pk["off_diag"] + 768].view(np.float64).reshape(3, 32)
         byts = blob[pk["off_words"]:pk["off_words"] + (wr + wa) * 128].reshape(wr + wa, 32, 4)
+        # header promise: the leading full_ref / full_alt rows carry no filler byte in any valid lane
+        fr, fa = int(full) & 0xFFFF, int(full) >> 16
+        assert fr <= wr and fa <= wa
+        assert not (byts[:fr, :n_valid] == 0xFF).any() and not (byts[wr:wr + fa, :n_valid] == 0xFF).any()
         acc = np.ones((6, 32))
         for sect, lo, hi in (("ref", 0, wr), ("alt", wr, wr + wa)):
             q = byts[lo:hi].transpose(1, 0, 2).reshape(32, -1)      # [lane, reads]

@@ -195,3 +195,19 @@ def test_full_size_invariants():
         finally:
             for e in parts:
                 e.close()
+
+
+def test_timing_helpers_run_the_real_kernel(sample10k):
+    """bench.py's C-side loops launch exactly what the evaluation calls launch."""
+    engines = [vb.LLKEngine(sample10k.problem) for _ in range(3)]
+    try:
+        one = engines[:1]                    # (contexts of one timed loop must share a stream)
+        assert vb.time_device(one, 2, 6, [0.01, 0.01], [0.01, 0.01], 0.03) > 0
+        assert vb.time_device_many(engines, 1, 4, [0.01, 0.01], [0.01, 0.01], 0.03) > 0
+        secs, last = vb.time_host(engines, 2, 6, [0.01, 0.01], [0.01, 0.01], 0.03)
+        assert secs > 0
+        # the last timed call evaluated pc1[0] = 0.01 + 1e-7 * 7 on engines[7 % 3]
+        assert last == engines[1].compute_mix_llks([0.01 + 1e-7 * 7, 0.01], [0.01, 0.01], 0.03)
+    finally:
+        for e in engines:
+            e.close()

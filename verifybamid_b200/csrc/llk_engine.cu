@@ -1,21 +1,23 @@
 // llk_engine.cu -- the sm_100a contamination-likelihood kernel and the C ABI around it
 // (include/vb2_llk.h).  Replaces, for one sample resident in HBM,
 //     FullLLKFunc::ComputeMixLLKs            reference ContaminationEstimator.h:194-314
-// One evaluation = one launch of llk_kernel:
-//   (i)   AF = (UD.PC + mu)/2 per marker (h:251-267), coalesced column-major panel reads,
-//         Hardy-Weinberg genotype priors (h:186-192);
+// One evaluation = one launch of llk_kernel, one persistent CTA per SM:
+//   (i)   AF = (UD.PC + mu)/2 per marker (h:251-267) and Hardy-Weinberg priors (h:186-192);
 //   (ii)  per read, the six alpha-dependent genotype-pair emissions of the 3x3 mixture
 //         (h:213-229, in the closed form of SURVEY.md Appendix A: each is LINEAR in the Phred
 //         error e, F_p(e) = c0_p + c1_p*e, so one DFMA forms it and one DMUL accumulates it);
-//         the read tile of each warp is staged into shared memory by one TMA bulk copy
-//         (cp.async.bulk + mbarrier);
-//   (iii) log of the marginal per marker (h:307-311), fixed-order warp-shuffle / block / grid
-//         reduction in fp64 (h:232-236 is an OpenMP reduction) -> one double.
+//         everything a warp needs for 32 markers is one contiguous blob fetched by ONE TMA
+//         bulk copy (cp.async.bulk + mbarrier) whose address is pure arithmetic;
+//   (iii) log of the marginal per marker (h:307-311), fixed-order warp-shuffle / CTA reduction
+//         in fp64 (h:232-236 is an OpenMP reduction); the per-CTA partials are either written
+//         straight into a host-mapped mailbox and added by the host in CTA order, or added by
+//         the last CTA on the device (results that stay in HBM for an NCCL allreduce).
 // Everything that is evaluation-invariant was folded at create time by llk_pack.cpp.
 //
 // There is NO CPU fallback in this file: without a CUDA device every entry point fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -53,7 +55,7 @@ struct JobParams {  // one evaluation (352 bytes)
 struct SampleDev {  // one sample resident in HBM (see llk_pack.h for the blob/round layout)
   const uint8_t *blob;
   const vb2::Round *rounds;  // [n_rounds] in HBM
-  double *partials;          // [slots][grid_x]
+  double *partials;          // [slots][grid_x]   (device-side reduction only)
   unsigned int *tickets;     // [slots]
   double log_other_const, min_af, max_af;
   uint32_t n_rounds, n_bins, grid_x, conc_rounds;
@@ -65,28 +67,33 @@ struct SampleDev {  // one sample resident in HBM (see llk_pack.h for the blob/r
 };
 static_assert(sizeof(SampleDev) % 8 == 0 && sizeof(SampleDev) <= 8 * 32, "SampleDev copy loop");
 
-struct Mailbox {  // host-mapped, written by the last CTA of a launch
-  volatile unsigned long long seq;
-  unsigned long long pad_[7];
-  volatile double val[VB2_MAX_BATCH];
+// Host-mapped result slot.  Value and sequence number travel in ONE 16-byte store, so the host,
+// which polls `seq`, never sees a new sequence number next to an old value.
+struct __align__(16) Slot {
+  double val;
+  unsigned long long seq;
 };
 
 struct LaunchArgs {
-  SampleDev sample;           // used when samples == nullptr
-  const SampleDev *samples;   // eval_many: job j evaluates samples[j]
-  const uint32_t *slots;      // eval_many: partial/ticket slot of job j inside its sample
-  const JobParams *jobs_dev;  // parameters in HBM (n_jobs > kMaxArgJobs or eval_many)
-  double *d_out;              // [n_jobs] device results (may be nullptr)
-  Mailbox *mbox;              // device view of the host mailbox (may be nullptr)
-  unsigned int *jobs_done;    // second-level ticket
+  SampleDev sample;           // ARGS kernels: the sample itself
+  const SampleDev *samples;   // generic kernel: job j evaluates samples[j]
+  const uint32_t *slots;      // generic kernel: partial/ticket slot of job j inside its sample
+  const JobParams *jobs_dev;  // generic kernel: parameters in HBM
+  double *d_out;              // [n_jobs] device results (device-side reduction; may be nullptr)
+  Slot *mbox;                 // device view of the host mailbox (may be nullptr)
   unsigned long long seq;
   uint32_t n_jobs;
+  uint32_t kc;     // rounds a CTA runs concurrently in THIS launch (it has 4*kc warps)
+  uint32_t n_buf;  // shared-memory stages per warp in THIS launch (1 or 2)
   uint32_t pad_;
-  vb2::Round rounds[kMaxArgRounds];  // copy of sample.rounds[0..n_rounds) when it fits
-  JobParams jobs[kMaxArgJobs];
-  double phred[vb2::kNumQual];       // 10^(-q/10), ContaminationEstimator.h:65-74
+  vb2::Round rounds[kMaxArgRounds];  // ARGS kernels: sample.rounds[0..n_rounds)
+  JobParams jobs[kMaxArgJobs];       // ARGS kernels: parameters of job blockIdx.y
 };
 static_assert(sizeof(LaunchArgs) <= 4000, "kernel arguments must stay below 4 KiB");
+
+// 10^(-q/10) for q = 0..93 exactly as the host computes it (ContaminationEstimator.h:65-74);
+// entries 94..255 are 1.0 (the 0xFF filler byte indexes 255).  One copy per device, L2-resident.
+__device__ double g_phred[256];
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
@@ -121,46 +128,45 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                : "memory");
 }
 
-// acc[i] *= f[i] for the six genotype pairs unless the quality byte is the 0xFF filler:
-// one ISETP + six predicated DMULs, no branch.
-__device__ __forceinline__ void mul6_if_read(double &a0, double &a1, double &a2, double &a3, double &a4, double &a5,
-                                             double f0, double f1, double f2, double f3, double f4, double f5,
-                                             uint32_t q) {
-  asm("{\n"
-      ".reg .pred P;\n"
-      "setp.ne.u32 P, %12, 255;\n"
-      "@P mul.f64 %0, %0, %6;\n"
-      "@P mul.f64 %1, %1, %7;\n"
-      "@P mul.f64 %2, %2, %8;\n"
-      "@P mul.f64 %3, %3, %9;\n"
-      "@P mul.f64 %4, %4, %10;\n"
-      "@P mul.f64 %5, %5, %11;\n"
-      "}\n"
-      : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "+d"(a4), "+d"(a5)
-      : "d"(f0), "d"(f1), "d"(f2), "d"(f3), "d"(f4), "d"(f5), "r"(q));
+// Four reads (one word) of one lane, all four bytes real reads.  ALT = alt-allele reads.
+template <bool ALT>
+__device__ __forceinline__ void eat_word_full(uint32_t w, const double *s_e, const double (&c0)[kNumPairs],
+                                              const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
+  const double e0 = s_e[w & 0xFFu], e1 = s_e[(w >> 8) & 0xFFu], e2 = s_e[(w >> 16) & 0xFFu], e3 = s_e[w >> 24];
+#pragma unroll
+  for (int p = 0; p < kNumPairs; ++p) {
+    // (F(e0)*F(e1)) * (F(e2)*F(e3)): same multiply count as a chain, one link on the accumulator
+    const double f01 = fma(c1[p], e0, c0[p]) * fma(c1[p], e1, c0[p]);
+    const double f23 = fma(c1[p], e2, c0[p]) * fma(c1[p], e3, c0[p]);
+    acc[ALT ? (kNumPairs - 1 - p) : p] *= f01 * f23;
+  }
 }
 
-// Four reads (one word) of one lane.  ALT = the word holds alt-allele reads.
+// A word that may carry 0xFF filler bytes (the last word of a lane's ref or alt section).
 template <bool ALT>
-__device__ __forceinline__ void eat_word(uint32_t w, const double *s_e, const double (&c0)[kNumPairs],
-                                         const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
-  uint32_t q[4];
-  double e[4];
+__device__ __forceinline__ void eat_word_checked(uint32_t w, const double *s_e, const double (&c0)[kNumPairs],
+                                                 const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
-    q[b] = (w >> (8 * b)) & 0xFFu;
-    e[b] = s_e[q[b]];  // s_e[255] = 1.0: the filler byte reads a finite value and is masked below
-  }
+    const uint32_t q = (w >> (8 * b)) & 0xFFu;
+    if (q != 0xFFu) {
+      const double e = s_e[q];
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    double f[kNumPairs];
-#pragma unroll
-    for (int p = 0; p < kNumPairs; ++p) f[p] = fma(c1[p], e[b], c0[p]);
-    if (ALT)
-      mul6_if_read(acc[5], acc[4], acc[3], acc[2], acc[1], acc[0], f[0], f[1], f[2], f[3], f[4], f[5], q[b]);
-    else
-      mul6_if_read(acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], f[0], f[1], f[2], f[3], f[4], f[5], q[b]);
+      for (int p = 0; p < kNumPairs; ++p) acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(c1[p], e, c0[p]);
+    }
   }
+}
+
+// n_full rows in which every lane holds four real reads, then n_ragged rows that may hold fillers.
+template <bool ALT>
+__device__ __forceinline__ void eat_rows(const uint32_t *rows, uint32_t n_full, uint32_t n_ragged, const double *s_e,
+                                         const double (&c0)[kNumPairs], const double (&c1)[kNumPairs],
+                                         double (&acc)[kNumPairs]) {
+  uint32_t t = 0;
+#pragma unroll 1
+  for (; t < n_full; ++t) eat_word_full<ALT>(rows[t * 32], s_e, c0, c1, acc);
+#pragma unroll 1
+  for (; t < n_full + n_ragged; ++t) eat_word_checked<ALT>(rows[t * 32], s_e, c0, c1, acc);
 }
 
 // ContaminationEstimator.h:186-192 with the reference's comparison order (NaN passes through).
@@ -191,6 +197,11 @@ __device__ __forceinline__ void marker_af(const uint8_t *blob, const SampleDev &
 
 // One persistent CTA per SM.  Warp w issues on SM sub-partition w % 4 and owns bin
 // blockIdx.x*4 + w%4; it serves rounds w/4, w/4 + conc_rounds, ... of that bin.
+//   ARGS         sample, round table and job parameters are read from the kernel arguments
+//                (constant bank, uniform addresses); otherwise they are staged from HBM.
+//   HOST_REDUCE  every CTA publishes {partial, seq} into the host-mapped mailbox and the host adds
+//                them in CTA order; otherwise the last CTA to finish adds the partials on the device.
+template <bool ARGS, bool HOST_REDUCE>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 llk_kernel(const __grid_constant__ LaunchArgs A) {
   extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][n_buf][buf_bytes]
@@ -206,189 +217,207 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   const int n_warps = blockDim.x >> 5;
   const uint32_t job = blockIdx.y;
 
-  // ---- per-CTA set-up: which sample, which parameters, Phred table ----------------------------
-  if (threadIdx.x < sizeof(SampleDev) / 8) {
-    const uint64_t *src = A.samples ? reinterpret_cast<const uint64_t *>(A.samples + job)
-                                    : reinterpret_cast<const uint64_t *>(&A.sample);
-    reinterpret_cast<uint64_t *>(&s_sample)[threadIdx.x] = src[threadIdx.x];
-  } else if (threadIdx.x >= 64 && threadIdx.x < 64 + sizeof(JobParams) / 8) {
-    const int i = threadIdx.x - 64;
-    const double *src = A.jobs_dev ? reinterpret_cast<const double *>(A.jobs_dev + job)
-                                   : reinterpret_cast<const double *>(&A.jobs[job < kMaxArgJobs ? job : 0]);
-    reinterpret_cast<double *>(&s_job)[i] = src[i];
-  }
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_e[i] = i < vb2::kNumQual ? A.phred[i] : 1.0;
+  // ---- per-CTA set-up --------------------------------------------------------------------------
+  // ARGS kernels read everything from the constant bank, so a warp can arm its own mbarrier and fire
+  // its first TMA bulk copy before the CTA-wide barrier that publishes the Phred table: the HBM
+  // latency of the blob overlaps the set-up.
   if (lane == 0) {
     mbar_init(&s_bar[warp][0], 1);
     mbar_init(&s_bar[warp][1], 1);
     mbar_fence_init();
   }
-  __syncthreads();
-  const SampleDev &S = s_sample;
-  if (blockIdx.x >= S.grid_x) return;  // eval_many: this sample needs fewer CTAs than the grid has
-  const bool rounds_in_smem = S.n_rounds <= kMaxArgRounds;
-  if (rounds_in_smem && threadIdx.x < S.n_rounds * (sizeof(vb2::Round) / 8)) {
-    const uint64_t *src = A.samples ? reinterpret_cast<const uint64_t *>(S.rounds)
-                                    : reinterpret_cast<const uint64_t *>(A.rounds);
-    reinterpret_cast<uint64_t *>(s_rounds)[threadIdx.x] = src[threadIdx.x];
+  __syncwarp();
+  if constexpr (!ARGS) {
+    if (threadIdx.x < sizeof(SampleDev) / 8) {
+      reinterpret_cast<uint64_t *>(&s_sample)[threadIdx.x] =
+          reinterpret_cast<const uint64_t *>(A.samples ? A.samples + job : &A.sample)[threadIdx.x];
+    } else if (threadIdx.x >= 64 && threadIdx.x < 64 + sizeof(JobParams) / 8) {
+      reinterpret_cast<double *>(&s_job)[threadIdx.x - 64] =
+          reinterpret_cast<const double *>(A.jobs_dev + job)[threadIdx.x - 64];
+    }
+    __syncthreads();
+    if (s_sample.n_rounds <= kMaxArgRounds && threadIdx.x < s_sample.n_rounds * (sizeof(vb2::Round) / 8))
+      reinterpret_cast<uint64_t *>(s_rounds)[threadIdx.x] =
+          reinterpret_cast<const uint64_t *>(s_sample.rounds)[threadIdx.x];
+    __syncthreads();
   }
-  __syncthreads();
+  const SampleDev &S = ARGS ? A.sample : s_sample;
+  const JobParams &J = ARGS ? A.jobs[job] : s_job;
+  const bool active_cta = blockIdx.x < S.grid_x;  // eval_many: a sample may need fewer CTAs than the grid has
+  const bool rounds_cached = ARGS || S.n_rounds <= kMaxArgRounds;
 
-  const uint32_t slot = A.slots ? A.slots[job] : job;
   const uint32_t bin = blockIdx.x * vb2::kBinsPerCta + (warp & 3);
-  const uint32_t kc = S.conc_rounds;
-  const uint32_t n_rounds = S.n_rounds;
+  const uint32_t kc = A.kc;
+  const uint32_t n_rounds = active_cta ? S.n_rounds : 0u;
   const uint32_t chunk_rows = S.chunk_rows;
-  uint8_t *mybuf = s_buf + (size_t)warp * S.n_buf * S.buf_bytes;
+  const uint32_t n_buf = A.n_buf, buf_bytes = S.buf_bytes, off_words = S.off_words;
+  uint8_t *mybuf = s_buf + (size_t)warp * n_buf * buf_bytes;
 
-  auto get_round = [&](uint32_t r) -> vb2::Round { return rounds_in_smem ? s_rounds[r] : S.rounds[r]; };
-  // first round >= r (stepping by kc) in which this bin owns a blob, or n_rounds
-  auto next_round = [&](uint32_t r) -> uint32_t {
+  auto get_round = [&](uint32_t r) -> vb2::Round {
+    if constexpr (ARGS) return A.rounds[r];
+    else return rounds_cached ? s_rounds[r] : S.rounds[r];
+  };
+  // The warp walks a sequence of (round, chunk) items; `cur` is being consumed, `nxt` is the next one
+  // to fetch.  Both cursors keep their round descriptor in registers.  Warp kk = warp/4 serves the
+  // rounds kk, 2kc-1-kk, 2kc+kk, 4kc-1-kk, ... (a snake over groups of kc rounds): rounds are sorted
+  // heaviest first, so pairing the heaviest with the lightest gives every warp about the same work.
+  struct Cursor {
+    uint32_t r, c, n_ch, rows;
+    const uint8_t *src;
+  };
+  const uint32_t kk = (uint32_t)(warp >> 2);
+  auto snake_next = [&](uint32_t r) -> uint32_t {  // the round this warp serves after round r
+    const uint32_t g = r / kc, i = r - g * kc;     // group, position inside it
+    return (g + 1) * kc + (kc - 1 - i);
+  };
+  auto seek = [&](Cursor &k, uint32_t r) {  // first round at or after r (in this warp's order) with a blob for this bin
+    k.c = 0;
     while (r < n_rounds) {
       const vb2::Round R = get_round(r);
-      if (bin - R.first_bin < R.count) break;  // unsigned: also false when bin < first_bin
-      r += kc;
+      if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
+        k.rows = R.rows;
+        k.n_ch = R.rows <= chunk_rows ? 1u : (R.rows + chunk_rows - 1) / chunk_rows;
+        k.src = S.blob + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
+        break;
+      }
+      r = snake_next(r);
     }
-    return r;
+    k.r = r;
   };
-  auto n_chunks = [&](const vb2::Round &R) -> uint32_t {
-    return R.rows <= chunk_rows ? 1u : (R.rows + chunk_rows - 1) / chunk_rows;
+  auto step = [&](Cursor &k) {
+    if (k.c + 1 < k.n_ch) ++k.c;
+    else seek(k, snake_next(k.r));
   };
-  // TMA: chunk c of this bin's blob of round r -> buffer b.  Chunk 0 = header + panel + diag + the
-  // first chunk_rows word rows; chunk c >= 1 = the next chunk_rows word rows.
-  auto issue = [&](uint32_t r, uint32_t c, uint32_t b) {
-    const vb2::Round R = get_round(r);
-    const uint8_t *src = S.blob + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
-    uint32_t off, bytes;
-    if (c == 0) {
-      off = 0;
-      bytes = S.off_words + (R.rows < chunk_rows ? R.rows : chunk_rows) * 128u;
-    } else {
-      off = S.off_words + c * chunk_rows * 128u;
-      const uint32_t left = R.rows - c * chunk_rows;
-      bytes = (left < chunk_rows ? left : chunk_rows) * 128u;
+  // TMA: chunk 0 = header + panel + diag + the first chunk_rows word rows; chunk c >= 1 = the next rows
+  auto issue = [&](const Cursor &k, uint32_t b) {
+    uint32_t off = 0, n = k.rows < chunk_rows ? k.rows : chunk_rows, bytes = off_words + n * 128u;
+    if (k.c) {
+      off = off_words + k.c * chunk_rows * 128u;
+      n = k.rows - k.c * chunk_rows;
+      bytes = (n < chunk_rows ? n : chunk_rows) * 128u;
     }
     mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
-    bulk_g2s(mybuf + (size_t)b * S.buf_bytes, src + off, bytes, &s_bar[warp][b]);
+    bulk_g2s(mybuf + (size_t)b * buf_bytes, k.src + off, bytes, &s_bar[warp][b]);
   };
+  Cursor cur, nxt;
+  cur.r = n_rounds; cur.c = 0; cur.n_ch = 1; cur.rows = 0; cur.src = nullptr;
+  if (kk < kc) seek(cur, kk);
+  nxt = cur;
+  uint32_t ib = 0, cb = 0, parity = 0;
+  if (nxt.r < n_rounds) {
+    if (lane == 0) issue(nxt, ib);
+    step(nxt);
+    ib ^= (n_buf - 1);
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_e[i] = g_phred[i];
+  __syncthreads();
 
   double vsum = 0.0;
-  if ((uint32_t)(warp >> 2) < kc) {
+  if (cur.r < n_rounds) {
     double c0[kNumPairs], c1[kNumPairs];
 #pragma unroll
     for (int p = 0; p < kNumPairs; ++p) {
-      c0[p] = s_job.c0[p];
-      c1[p] = s_job.c1[p];
+      c0[p] = J.c0[p];
+      c1[p] = J.c1[p];
     }
-    // consume cursor (r, c) and issue cursor (ir, ic); both advance through the same sequence
-    uint32_t r = next_round((uint32_t)(warp >> 2)), c = 0;
-    uint32_t ir = r, ic = 0, ib = 0, cb = 0, parity = 0;
-    auto advance_issue = [&]() {
-      if (ir >= n_rounds) return;
-      const vb2::Round R = get_round(ir);
-      if (ic + 1 < n_chunks(R)) { ++ic; } else { ir = next_round(ir + kc); ic = 0; }
-    };
-    if (ir < n_rounds) {
-      if (lane == 0) issue(ir, ic, ib);
-      advance_issue();
-      ib ^= (S.n_buf - 1);
-    }
-    double acc[kNumPairs], af1 = 0., af2 = 0., ldiag = 0.;
-    uint32_t wr = 0, wa = 0, n_valid = 0;
-    while (r < n_rounds) {
-      if (ir < n_rounds && S.n_buf == 2) {
+    double acc[kNumPairs], ldiag = 0.;
+    uint32_t wr = 0, wa = 0, n_valid = 0, fr = 0, fa = 0;
+    while (cur.r < n_rounds) {
+      if (n_buf == 2 && nxt.r < n_rounds) {
         __syncwarp();  // every lane finished reading the buffer about to be overwritten
-        if (lane == 0) issue(ir, ic, ib);
-        advance_issue();
+        if (lane == 0) issue(nxt, ib);
+        step(nxt);
         ib ^= 1u;
       }
       mbar_wait(&s_bar[warp][cb], (parity >> cb) & 1u);
       parity ^= 1u << cb;
-      const uint8_t *buf = mybuf + (size_t)cb * S.buf_bytes;
-      const vb2::Round R = get_round(r);
-      if (c == 0) {
+      const uint8_t *buf = mybuf + (size_t)cb * buf_bytes;
+      if (cur.c == 0) {
         // ---- (i) header, allele frequencies, genotype priors, diagonal pairs ----------------------
         const uint4 hdr = *reinterpret_cast<const uint4 *>(buf);
-        wr = hdr.x; wa = hdr.y; n_valid = hdr.z;
+        wr = hdr.x; wa = hdr.y; n_valid = hdr.z; fr = hdr.w & 0xFFFFu; fa = hdr.w >> 16;
+        double af1, af2;
         if (S.known_af) {
           af1 = af2 = reinterpret_cast<const double *>(buf + S.off_kaf)[lane];  // h:251-252
         } else if (S.panel_fp64) {
-          marker_af<double>(buf, S, s_job, lane, af1, af2);
+          marker_af<double>(buf, S, J, lane, af1, af2);
         } else {
-          marker_af<float>(buf, S, s_job, lane, af1, af2);
+          marker_af<float>(buf, S, J, lane, af1, af2);
         }
         double gf[3], gf2[3];
         initial_gf(af1, S.min_af, S.max_af, gf);   // contaminating sample
         initial_gf(af2, S.min_af, S.max_af, gf2);  // intended sample
         const double *dg = reinterpret_cast<const double *>(buf + S.off_diag);
         ldiag = dg[lane] * (gf[0] * gf2[0]) + dg[32 + lane] * (gf[1] * gf2[1]) + dg[64 + lane] * (gf[2] * gf2[2]);
+        // h:307-311 weights GF[g1]*GF2[g2]: start each running product at its weight, so the marginal
+        // is just ldiag + sum(acc) at the end
 #pragma unroll
-        for (int p = 0; p < kNumPairs; ++p) acc[p] = 1.0;
+        for (int p = 0; p < kNumPairs; ++p) acc[p] = gf[pair_g1(p)] * gf2[pair_g2(p)];
       }
       // ---- (ii) stream this chunk's word rows: ref rows first, then alt rows --------------------
-      const uint32_t t_lo = c * chunk_rows;
-      uint32_t t_hi = t_lo + chunk_rows;
-      if (t_hi > wr + wa) t_hi = wr + wa;
-      const uint32_t *rows = reinterpret_cast<const uint32_t *>(buf + (c == 0 ? S.off_words : 0u)) + lane;
-      const uint32_t t_ref_hi = wr < t_hi ? wr : t_hi;
-      uint32_t t = t_lo;
-      for (; t < t_ref_hi; ++t) eat_word<false>(rows[(t - t_lo) * 32], s_e, c0, c1, acc);
-      for (; t < t_hi; ++t) eat_word<true>(rows[(t - t_lo) * 32], s_e, c0, c1, acc);
-
-      if (c + 1 == n_chunks(R)) {
-        // ---- (iii) marginal over the nine genotype pairs, log -------------------------------------
-        // h:307-311: markerLK = sum_{g1,g2} exp(acc) * GF[g1] * GF2[g2]; here exp(acc) is the running
-        // product itself, and the diagonal pairs were folded into ldiag above.
-        double gf[3], gf2[3];
-        initial_gf(af1, S.min_af, S.max_af, gf);
-        initial_gf(af2, S.min_af, S.max_af, gf2);
-        double L = ldiag;
-#pragma unroll
-        for (int p = 0; p < kNumPairs; ++p) L += acc[p] * (gf[pair_g1(p)] * gf2[pair_g2(p)]);
-        if ((uint32_t)lane < n_valid && L > 0) vsum += log(L);
-        r = next_round(r + kc);
-        c = 0;
-      } else {
-        ++c;
+      // rows [0,fr) and [wr, wr+fa) are filler-free in every lane; the rest may hold 0xFF fillers
+      {
+        const uint32_t t_lo = cur.c * chunk_rows;
+        uint32_t t_hi = t_lo + chunk_rows;
+        if (t_hi > wr + wa) t_hi = wr + wa;
+        const uint32_t *rows = reinterpret_cast<const uint32_t *>(buf + (cur.c == 0 ? off_words : 0u)) + lane;
+        auto clampu = [&](uint32_t x) { return x < t_lo ? t_lo : (x > t_hi ? t_hi : x); };
+        const uint32_t a0 = clampu(fr), a1 = clampu(wr), a2 = clampu(wr + fa);
+        if (t_hi > t_lo) {
+          eat_rows<false>(rows, a0 - t_lo, a1 - a0, s_e, c0, c1, acc);
+          eat_rows<true>(rows + (size_t)(a1 - t_lo) * 32, a2 - a1, t_hi - a2, s_e, c0, c1, acc);
+        }
       }
-      if (S.n_buf == 2) cb ^= 1u;
+      if (cur.c + 1 == cur.n_ch) {
+        // ---- (iii) marginal over the nine genotype pairs, log -------------------------------------
+        // h:307-311: markerLK = sum_{g1,g2} exp(acc)*GF[g1]*GF2[g2]; the running products carry their
+        // weights and the diagonal pairs were folded into ldiag.
+        const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));
+        if ((uint32_t)lane < n_valid && L > 0) vsum += log(L);
+      }
+      step(cur);
+      if (n_buf == 2) cb ^= 1u;
     }
   }
 
-  // ---- fixed-order reduction: warp shuffle tree -> CTA -> last CTA sums the grid ---------------
+  // ---- fixed-order reduction: warp shuffle tree -> CTA -> (host | last CTA) --------------------
 #pragma unroll
   for (int o = 16; o; o >>= 1) vsum += __shfl_xor_sync(0xFFFFFFFFu, vsum, o);
   if (lane == 0) s_red[warp] = vsum;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double cta = 0.0;
-    for (int w = 0; w < n_warps; ++w) cta += s_red[w];
-    S.partials[(size_t)slot * S.grid_x + blockIdx.x] = cta;
-    __threadfence();
-    const unsigned int t = atomicAdd(S.tickets + slot, 1u);
-    s_last = (t == S.grid_x - 1);
-  }
-  __syncthreads();
-  if (s_last && warp == 0) {
-    __threadfence();
-    const double *part = S.partials + (size_t)slot * S.grid_x;
-    double s = 0.0;
-    for (uint32_t i = lane; i < S.grid_x; i += 32) s += __ldcg(part + i);
+  if (!active_cta) return;
+  if constexpr (HOST_REDUCE) {
+    if (threadIdx.x == 0) {
+      double cta = 0.0;
+      for (int w = 0; w < n_warps; ++w) cta += s_red[w];
+      Slot *slot = A.mbox + (size_t)job * S.grid_x + blockIdx.x;
+      *reinterpret_cast<ulonglong2 *>(slot) = make_ulonglong2((unsigned long long)__double_as_longlong(cta), A.seq);
+    }
+  } else {
+    const uint32_t pslot = A.slots ? A.slots[job] : job;
+    if (threadIdx.x == 0) {
+      double cta = 0.0;
+      for (int w = 0; w < n_warps; ++w) cta += s_red[w];
+      S.partials[(size_t)pslot * S.grid_x + blockIdx.x] = cta;
+      __threadfence();
+      const unsigned int t = atomicAdd(S.tickets + pslot, 1u);
+      s_last = (t == S.grid_x - 1);
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+      __threadfence();
+      const double *part = S.partials + (size_t)pslot * S.grid_x;
+      double s = 0.0;
+      for (uint32_t i = lane; i < S.grid_x; i += 32) s += __ldcg(part + i);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-    if (lane == 0) {
-      S.tickets[slot] = 0u;  // ready for the next launch on this stream
-      const double out = s + S.log_other_const;
-      if (A.d_out) A.d_out[job] = out;
-      if (A.mbox) {
-        A.mbox->val[job] = out;
-        __threadfence_system();
-        const unsigned int done = atomicAdd(A.jobs_done, 1u);
-        if (done == A.n_jobs - 1) {
-          *A.jobs_done = 0u;
-          __threadfence_system();
-          A.mbox->seq = A.seq;
-        }
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+      if (lane == 0) {
+        S.tickets[pslot] = 0u;  // ready for the next launch on this stream
+        const double out = s + S.log_other_const;
+        if (A.d_out) A.d_out[job] = out;
+        if (A.mbox)
+          *reinterpret_cast<ulonglong2 *>(A.mbox + job) =
+              make_ulonglong2((unsigned long long)__double_as_longlong(out), A.seq);
       }
     }
   }
@@ -398,11 +427,6 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
 // host side
 // ---------------------------------------------------------------------------------------------
 thread_local std::string g_last_error;
-
-struct DevBuf {
-  void *p = nullptr;
-  size_t bytes = 0;
-};
 
 }  // namespace
 
@@ -421,15 +445,15 @@ struct vb2_llk_ctx {
   uint32_t smem_bytes = 0;
   uint32_t block_threads = 0;
   std::vector<vb2::Round> rounds;  // host copy (kernel arguments)
-  double phred[vb2::kNumQual];
-  Mailbox *h_mbox = nullptr, *d_mbox = nullptr;
-  unsigned int *d_jobs_done = nullptr;
+  Slot *h_mbox = nullptr, *d_mbox = nullptr;
+  uint32_t mbox_slots = 0;
   JobParams *h_jobs = nullptr;  // pinned staging [VB2_MAX_BATCH]
   JobParams *d_jobs = nullptr;
   double *d_out = nullptr;      // [VB2_MAX_BATCH]
   // eval_many staging (owned by the leading context)
   SampleDev *h_many = nullptr, *d_many = nullptr;
   uint32_t *h_slots = nullptr, *d_slots = nullptr;
+  uint32_t many_n = 0, many_grid_x = 0, many_kc = 1, many_buf_bytes = 0;  // last staged eval_many launch
   unsigned long long seq = 0;
   double spin_timeout_ms = 20000.0;
   std::string err;
@@ -485,6 +509,7 @@ void fill_job(JobParams *J, uint32_t n_pc, const double *pc1, const double *pc2,
   }
 }
 
+// Device-side reduction scratch: one row of grid_x partials + one ticket per concurrent job.
 int ensure_slots(vb2_llk_ctx *ctx, uint32_t need) {
   if (need <= ctx->slots) return VB2_OK;
   uint32_t n = ctx->slots ? ctx->slots : 8;
@@ -506,21 +531,26 @@ int ensure_slots(vb2_llk_ctx *ctx, uint32_t need) {
   return VB2_OK;
 }
 
-int wait_mailbox(vb2_llk_ctx *ctx, unsigned long long seq) {
+// Wait until mailbox slots [0, n_slots) all carry sequence number `seq`.
+int wait_mailbox(vb2_llk_ctx *ctx, uint32_t n_slots, unsigned long long seq) {
+  volatile Slot *mb = ctx->h_mbox;
   if (!ctx->spin) {
     VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_mbox->seq != seq) return set_err(ctx, VB2_ERR_CUDA, "kernel finished without publishing its result");
+    for (uint32_t i = 0; i < n_slots; ++i)
+      if (mb[i].seq != seq) return set_err(ctx, VB2_ERR_CUDA, "kernel finished without publishing its result");
     return VB2_OK;
   }
-  // Poll the host-mapped sequence word: cheaper than a stream synchronise for a ~5 us kernel.
+  // Poll the host-mapped sequence words: cheaper than a stream synchronise for a ~5 us kernel.
   unsigned long spins = 0;
   auto t0 = std::chrono::steady_clock::now();
-  while (ctx->h_mbox->seq != seq) {
-    if ((++spins & 0x3FFFu) == 0) {
+  uint32_t i = 0;
+  while (i < n_slots) {
+    if (mb[i].seq == seq) { ++i; continue; }
+    if ((++spins & 0xFFFFu) == 0) {
       cudaError_t q = cudaStreamQuery(ctx->stream);
       if (q != cudaSuccess && q != cudaErrorNotReady)
         return set_err(ctx, VB2_ERR_CUDA, std::string("llk_kernel: ") + cudaGetErrorString(q));
-      if (q == cudaSuccess && ctx->h_mbox->seq != seq)
+      if (q == cudaSuccess && mb[i].seq != seq)
         return set_err(ctx, VB2_ERR_CUDA, "kernel finished without publishing its result");
       double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       if (ms > ctx->spin_timeout_ms) return set_err(ctx, VB2_ERR_TIMEOUT, "timed out waiting for the device");
@@ -529,26 +559,59 @@ int wait_mailbox(vb2_llk_ctx *ctx, unsigned long long seq) {
   return VB2_OK;
 }
 
-// Launch n evaluations of ONE sample.  Results go to d_out (device) and, if to_mailbox, to the
-// host mailbox with sequence number *seq_out.
+enum class Reduce { kHost, kDevice };
+
+// Launch geometry.  One evaluation per launch: every warp serves one round (lowest latency).  Several
+// evaluations per launch: half as many warps per CTA, two CTAs co-resident per SM, so one CTA's data
+// wait and reduction tail hide behind the other's arithmetic (highest throughput).
+struct Geometry {
+  uint32_t kc, n_buf, threads, smem;
+};
+Geometry geometry(const vb2_llk_ctx *ctx, bool throughput) {
+  Geometry g;
+  const SampleDev &S = ctx->S;
+  g.kc = std::max(1u, S.conc_rounds);
+  g.n_buf = S.n_buf;
+  if (throughput && g.kc > 1) {
+    g.kc = (g.kc + 1) / 2;
+    if (const char *t = getenv("VB2_LLK_TPUT_KC")) g.kc = (uint32_t)std::min<int>(std::max(1, atoi(t)), (int)S.conc_rounds);
+    g.n_buf = g.kc < S.n_rounds || S.n_buf == 2 ? 2u : 1u;
+  }
+  g.threads = 128u * g.kc;
+  g.smem = 4u * g.kc * g.n_buf * S.buf_bytes;
+  return g;
+}
+
+// Launch n evaluations of ONE sample.
+//   Reduce::kHost    n <= kMaxArgJobs: per-CTA partials go to mailbox slots [j*grid_x + cta]
+//   Reduce::kDevice  the last CTA of job j writes d_out[j] (if given) and mailbox slot [j] (if to_mailbox)
 int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, const double *alphas,
-                 double *d_out, bool to_mailbox, unsigned long long *seq_out) {
+                 Reduce mode, double *d_out, bool to_mailbox, unsigned long long *seq_out) {
   if (!ctx) return set_err(nullptr, VB2_ERR_INVALID, "null context");
   if (n <= 0 || n > VB2_MAX_BATCH) return set_err(ctx, VB2_ERR_INVALID, "batch size out of range");
   if (!pc1 || !pc2 || !alphas) return set_err(ctx, VB2_ERR_INVALID, "null parameter array");
+  if (ctx->S.grid_x == 0) return VB2_OK;  // no usable marker: handled by the callers
   VB2_CUDA(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, (uint32_t)n);
-  if (rc) return rc;
-  LaunchArgs A;
-  memset(&A, 0, sizeof(A));
-  A.sample = ctx->S;
-  A.n_jobs = (uint32_t)n;
-  A.d_out = d_out;
-  memcpy(A.phred, ctx->phred, sizeof(A.phred));
-  if (ctx->rounds.size() <= (size_t)kMaxArgRounds)
-    memcpy(A.rounds, ctx->rounds.data(), ctx->rounds.size() * sizeof(vb2::Round));
   const uint32_t k = ctx->S.n_pc;
-  if (n <= kMaxArgJobs) {
+  const bool args = n <= kMaxArgJobs && ctx->rounds.size() <= (size_t)kMaxArgRounds;
+  if (mode == Reduce::kHost && !args) return set_err(ctx, VB2_ERR_INVALID, "internal: host reduction needs ARGS");
+  if (mode == Reduce::kDevice) {
+    int rc = ensure_slots(ctx, (uint32_t)n);
+    if (rc) return rc;
+  }
+  LaunchArgs A;
+  A.sample = ctx->S;
+  A.samples = nullptr; A.slots = nullptr; A.jobs_dev = nullptr;
+  A.d_out = d_out;
+  A.mbox = nullptr;
+  A.seq = 0;
+  A.n_jobs = (uint32_t)n;
+  A.pad_ = 0;
+  const Geometry g = geometry(ctx, n > 1);
+  A.kc = g.kc;
+  A.n_buf = g.n_buf;
+  if (args) {
+    memcpy(A.rounds, ctx->rounds.data(), ctx->rounds.size() * sizeof(vb2::Round));
     for (int j = 0; j < n; ++j) fill_job(&A.jobs[j], k, pc1 + (size_t)j * k, pc2 + (size_t)j * k, alphas[j]);
   } else {
     // the pinned staging buffer may still be read by the previous batch's copy
@@ -558,16 +621,29 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
                                   ctx->stream));
     A.jobs_dev = ctx->d_jobs;
   }
-  if (to_mailbox) {
+  if (to_mailbox || mode == Reduce::kHost) {
     A.mbox = ctx->d_mbox;
-    A.jobs_done = ctx->d_jobs_done;
     A.seq = ++ctx->seq;
     if (seq_out) *seq_out = A.seq;
   }
-  if (ctx->S.grid_x == 0) return VB2_OK;  // no usable marker: handled by the callers
-  dim3 grid(ctx->S.grid_x, (unsigned)n, 1), block(ctx->block_threads, 1, 1);
-  llk_kernel<<<grid, block, ctx->smem_bytes, ctx->stream>>>(A);
+  dim3 grid(ctx->S.grid_x, (unsigned)n, 1), block(g.threads, 1, 1);
+  if (mode == Reduce::kHost) llk_kernel<true, true><<<grid, block, g.smem, ctx->stream>>>(A);
+  else if (args) llk_kernel<true, false><<<grid, block, g.smem, ctx->stream>>>(A);
+  else llk_kernel<false, false><<<grid, block, g.smem, ctx->stream>>>(A);
   VB2_CUDA(ctx, cudaGetLastError());
+  return VB2_OK;
+}
+
+int init_device_tables(vb2_llk_ctx *ctx) {
+  double phred[256];
+  vb2::build_phred_table(phred);
+  for (int q = vb2::kNumQual; q < 256; ++q) phred[q] = 1.0;
+  VB2_CUDA(ctx, cudaMemcpyToSymbolAsync(g_phred, phred, sizeof(phred), 0, cudaMemcpyHostToDevice, ctx->stream));
+  VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int smem_max = 200 * 1024;
+  VB2_CUDA(ctx, cudaFuncSetAttribute(llk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  VB2_CUDA(ctx, cudaFuncSetAttribute(llk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  VB2_CUDA(ctx, cudaFuncSetAttribute(llk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   return VB2_OK;
 }
 
@@ -599,7 +675,6 @@ void vb2_llk_destroy(vb2_llk_ctx *ctx) {
   if (ctx->S.partials) cudaFree(ctx->S.partials);
   if (ctx->S.tickets) cudaFree(ctx->S.tickets);
   if (ctx->d_sample) cudaFree(ctx->d_sample);
-  if (ctx->d_jobs_done) cudaFree(ctx->d_jobs_done);
   if (ctx->d_jobs) cudaFree(ctx->d_jobs);
   if (ctx->d_out) cudaFree(ctx->d_out);
   if (ctx->d_many) cudaFree(ctx->d_many);
@@ -634,9 +709,12 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   }
   ctx->spin = !(desc->flags & VB2_FLAG_NO_SPIN);
   if (const char *t = getenv("VB2_LLK_SPIN_TIMEOUT_MS")) ctx->spin_timeout_ms = atof(t);
+  int rc = init_device_tables(ctx);
+  if (rc) return rc;
 
   // ---- flatten on the host ----------------------------------------------------------------------
-  vb2::build_phred_table(ctx->phred);
+  double phred[vb2::kNumQual];
+  vb2::build_phred_table(phred);
   if (desc->panel_dtype != VB2_PANEL_FP64 && desc->panel_dtype != VB2_PANEL_FP32)
     return set_err(ctx, VB2_ERR_INVALID, "unknown panel_dtype");
   vb2::PackConfig cfg;
@@ -645,7 +723,7 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   if (const char *t = getenv("VB2_LLK_MAX_CTAS")) cfg.max_ctas = (uint32_t)std::max(1, atoi(t));
   vb2::PackedSample &P = ctx->meta;
   std::string perr;
-  int rc = vb2::pack_sample(*desc, cfg, ctx->phred, &P, &perr);
+  rc = vb2::pack_sample(*desc, cfg, phred, &P, &perr);
   if (rc) return set_err(ctx, rc, perr);
   ctx->rounds = P.rounds;
 
@@ -682,22 +760,19 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   ctx->block_threads = 128u * std::max(1u, S.conc_rounds);
   ctx->smem_bytes = (ctx->block_threads / 32u) * S.n_buf * S.buf_bytes;
   if (ctx->smem_bytes > 200u * 1024u) return set_err(ctx, VB2_ERR_INVALID, "shared-memory stage too large (n_pc too big?)");
-  VB2_CUDA(ctx, cudaFuncSetAttribute(llk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 
   // ---- result plumbing ---------------------------------------------------------------------------
-  VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_mbox, sizeof(Mailbox), cudaHostAllocMapped));
-  memset(ctx->h_mbox, 0, sizeof(Mailbox));
+  ctx->mbox_slots = std::max<uint32_t>(VB2_MAX_BATCH, kMaxArgJobs * std::max(1u, S.grid_x));
+  VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_mbox, sizeof(Slot) * ctx->mbox_slots, cudaHostAllocMapped));
+  memset(ctx->h_mbox, 0, sizeof(Slot) * ctx->mbox_slots);
   VB2_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->d_mbox, ctx->h_mbox, 0));
-  VB2_CUDA(ctx, cudaMalloc(&ctx->d_jobs_done, sizeof(unsigned int)));
-  VB2_CUDA(ctx, cudaMemsetAsync(ctx->d_jobs_done, 0, sizeof(unsigned int), ctx->stream));
   VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_jobs, sizeof(JobParams) * VB2_MAX_BATCH, cudaHostAllocDefault));
   VB2_CUDA(ctx, cudaMalloc(&ctx->d_jobs, sizeof(JobParams) * VB2_MAX_BATCH));
   VB2_CUDA(ctx, cudaMalloc(&ctx->d_out, sizeof(double) * VB2_MAX_BATCH));
   VB2_CUDA(ctx, cudaMalloc(&ctx->d_sample, sizeof(SampleDev)));
-  if ((rc = ensure_slots(ctx, kMaxArgJobs))) return rc;
+  if ((rc = ensure_slots(ctx, 8))) return rc;
   VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  // keep only the sizes
-  P.blob = {}; P.marker_index = {};
+  P.blob = {}; P.marker_index = {};  // keep only the sizes
   return VB2_OK;
 }
 
@@ -749,15 +824,37 @@ int vb2_llk_eval_batch(vb2_llk_ctx *ctx, int n, const double *pc_contam, const d
                        const double *alphas, double *llk_out) {
   if (!ctx) return set_err(nullptr, VB2_ERR_INVALID, "null context");
   if (!llk_out) return set_err(ctx, VB2_ERR_INVALID, "null output pointer");
+  if (n <= 0 || n > VB2_MAX_BATCH) return set_err(ctx, VB2_ERR_INVALID, "batch size out of range");
+  const uint32_t gx = ctx->S.grid_x;
+  const bool host_reduce = n <= kMaxArgJobs && ctx->rounds.size() <= (size_t)kMaxArgRounds;
   unsigned long long seq = 0;
-  int rc = launch_batch(ctx, n, pc_contam, pc_intended, alphas, nullptr, true, &seq);
+  int rc = launch_batch(ctx, n, pc_contam, pc_intended, alphas, host_reduce ? Reduce::kHost : Reduce::kDevice,
+                        nullptr, true, &seq);
   if (rc) return rc;
-  if (ctx->S.grid_x == 0) {  // no usable marker: the reference's empty sum (h:231, :313)
+  if (gx == 0) {  // no usable marker: the reference's empty sum (h:231, :313)
     for (int j = 0; j < n; ++j) llk_out[j] = 0.0;
     return VB2_OK;
   }
-  if ((rc = wait_mailbox(ctx, seq))) return rc;
-  for (int j = 0; j < n; ++j) llk_out[j] = ctx->h_mbox->val[j];
+  if ((rc = wait_mailbox(ctx, host_reduce ? (uint32_t)n * gx : (uint32_t)n, seq))) return rc;
+  volatile Slot *mb = ctx->h_mbox;
+  if (host_reduce) {
+    // Same fixed order as the device-side reduction (lane-strided sums, then a butterfly), so both
+    // paths return identical bits for identical inputs.
+    for (int j = 0; j < n; ++j) {
+      double s[32], t[32];
+      for (uint32_t l = 0; l < 32; ++l) {
+        s[l] = 0.0;
+        for (uint32_t c = l; c < gx; c += 32) s[l] += mb[(size_t)j * gx + c].val;
+      }
+      for (uint32_t o = 16; o; o >>= 1) {
+        for (uint32_t l = 0; l < 32; ++l) t[l] = s[l] + s[l ^ o];
+        memcpy(s, t, sizeof(s));
+      }
+      llk_out[j] = s[0] + ctx->S.log_other_const;
+    }
+  } else {
+    for (int j = 0; j < n; ++j) llk_out[j] = mb[j].val;
+  }
   return VB2_OK;
 }
 
@@ -770,18 +867,20 @@ int vb2_llk_eval_batch_device(vb2_llk_ctx *ctx, int n, const double *pc_contam, 
                               const double *alphas, double *d_llk_out) {
   if (!ctx) return set_err(nullptr, VB2_ERR_INVALID, "null context");
   if (!d_llk_out) return set_err(ctx, VB2_ERR_INVALID, "null device output pointer");
-  int rc = launch_batch(ctx, n, pc_contam, pc_intended, alphas, d_llk_out, false, nullptr);
+  if (n <= 0 || n > VB2_MAX_BATCH) return set_err(ctx, VB2_ERR_INVALID, "batch size out of range");
+  int rc = launch_batch(ctx, n, pc_contam, pc_intended, alphas, Reduce::kDevice, d_llk_out, false, nullptr);
   if (rc) return rc;
   if (ctx->S.grid_x == 0) VB2_CUDA(ctx, cudaMemsetAsync(d_llk_out, 0, sizeof(double) * n, ctx->stream));
   return VB2_OK;
 }
 
-int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
-                      const double *alphas, double *llk_out) {
+// eval_many, step 1: stage the sample table, slots and parameters of an n-sample launch in HBM.
+static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
+                      const double *alphas, bool *nothing_to_do) {
   if (!ctxs || n <= 0 || !ctxs[0]) return set_err(nullptr, VB2_ERR_INVALID, "null/empty context list");
   vb2_llk_ctx *lead = ctxs[0];
   if (n > VB2_MAX_BATCH) return set_err(lead, VB2_ERR_INVALID, "batch size out of range");
-  if (!pc_contam || !pc_intended || !alphas || !llk_out) return set_err(lead, VB2_ERR_INVALID, "null argument");
+  if (!pc_contam || !pc_intended || !alphas) return set_err(lead, VB2_ERR_INVALID, "null argument");
   VB2_CUDA(lead, cudaSetDevice(lead->device));
   if (!lead->h_many) {
     VB2_CUDA(lead, cudaHostAlloc((void **)&lead->h_many, sizeof(SampleDev) * VB2_MAX_BATCH, cudaHostAllocDefault));
@@ -791,7 +890,6 @@ int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
   }
   VB2_CUDA(lead, cudaStreamSynchronize(lead->stream));  // staging buffers are free again
   const uint32_t k = lead->S.n_pc;
-  uint32_t grid_x = 0, smem = 0, threads = 0;
   // slot of job j inside its sample = number of earlier jobs on the same context
   for (int j = 0; j < n; ++j) {
     vb2_llk_ctx *c = ctxs[j];
@@ -805,45 +903,105 @@ int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
     lead->h_slots[j] = slot;
   }
   bool any = false;
+  uint32_t grid_x = 0, kc = 1, buf_bytes = 0;
   for (int j = 0; j < n; ++j) {
     vb2_llk_ctx *c = ctxs[j];
     lead->h_many[j] = c->S;
-    // every sample indexes its shared-memory stage with the launch-wide geometry
+    // the launch uses the largest geometry; every sample indexes shared memory with its own buf_bytes
+    const Geometry g = geometry(c, true);
     grid_x = std::max(grid_x, c->S.grid_x);
-    smem = std::max(smem, c->smem_bytes);
-    threads = std::max(threads, c->block_threads);
+    kc = std::max(kc, g.kc);
+    buf_bytes = std::max(buf_bytes, c->S.buf_bytes);
     any |= c->S.grid_x > 0;
     fill_job(&lead->h_jobs[j], k, pc_contam + (size_t)j * k, pc_intended + (size_t)j * k, alphas[j]);
   }
-  if (!any) {
-    for (int j = 0; j < n; ++j) llk_out[j] = 0.0;
-    return VB2_OK;
-  }
+  *nothing_to_do = !any;
+  lead->many_n = 0;
+  if (!any) return VB2_OK;
   for (int j = 0; j < n; ++j)
     if (ctxs[j]->S.grid_x == 0)
       return set_err(lead, VB2_ERR_INVALID, "vb2_llk_eval_many: a sample has no usable marker");
   VB2_CUDA(lead, cudaMemcpyAsync(lead->d_many, lead->h_many, sizeof(SampleDev) * n, cudaMemcpyHostToDevice, lead->stream));
   VB2_CUDA(lead, cudaMemcpyAsync(lead->d_slots, lead->h_slots, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, lead->stream));
   VB2_CUDA(lead, cudaMemcpyAsync(lead->d_jobs, lead->h_jobs, sizeof(JobParams) * n, cudaMemcpyHostToDevice, lead->stream));
+  lead->many_n = (uint32_t)n;
+  lead->many_grid_x = grid_x;
+  lead->many_kc = kc;
+  lead->many_buf_bytes = buf_bytes;
+  return VB2_OK;
+}
+
+// eval_many, step 2: one launch over whatever stage_many staged last (generic kernel, device reduction).
+static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq_out) {
+  if (!lead->many_n) return set_err(lead, VB2_ERR_INVALID, "internal: nothing staged");
   LaunchArgs A;
   memset(&A, 0, sizeof(A));
   A.samples = lead->d_many;
   A.slots = lead->d_slots;
   A.jobs_dev = lead->d_jobs;
-  A.n_jobs = (uint32_t)n;
-  A.mbox = lead->d_mbox;
-  A.jobs_done = lead->d_jobs_done;
-  A.seq = ++lead->seq;
-  memcpy(A.phred, lead->phred, sizeof(A.phred));
-  dim3 grid(grid_x, (unsigned)n, 1), block(threads, 1, 1);
-  llk_kernel<<<grid, block, smem, lead->stream>>>(A);
+  A.n_jobs = lead->many_n;
+  A.d_out = lead->d_out;
+  A.kc = lead->many_kc;
+  A.n_buf = 2;
+  if (to_mailbox) {
+    A.mbox = lead->d_mbox;
+    A.seq = ++lead->seq;
+    if (seq_out) *seq_out = A.seq;
+  }
+  dim3 grid(lead->many_grid_x, lead->many_n, 1), block(128u * lead->many_kc, 1, 1);
+  llk_kernel<false, false><<<grid, block, 4u * lead->many_kc * 2u * lead->many_buf_bytes, lead->stream>>>(A);
   VB2_CUDA(lead, cudaGetLastError());
-  int rc = wait_mailbox(lead, A.seq);
-  if (rc) return rc;
-  for (int j = 0; j < n; ++j) llk_out[j] = lead->h_mbox->val[j];
   return VB2_OK;
 }
 
+int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
+                      const double *alphas, double *llk_out) {
+  if (!llk_out) return set_err(ctxs && n > 0 ? ctxs[0] : nullptr, VB2_ERR_INVALID, "null output pointer");
+  unsigned long long seq = 0;
+  bool nothing = false;
+  int rc = stage_many(ctxs, n, pc_contam, pc_intended, alphas, &nothing);
+  if (rc) return rc;
+  if (nothing) {
+    for (int j = 0; j < n; ++j) llk_out[j] = 0.0;
+    return VB2_OK;
+  }
+  vb2_llk_ctx *lead = ctxs[0];
+  if ((rc = fire_many(lead, true, &seq))) return rc;
+  if ((rc = wait_mailbox(lead, (uint32_t)n, seq))) return rc;
+  for (int j = 0; j < n; ++j) llk_out[j] = lead->h_mbox[j].val;
+  return VB2_OK;
+}
+
+int vb2_llk_time_device_many(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup_launches, int launches,
+                             const double *pc_contam, const double *pc_intended, double alpha, float *elapsed_ms) {
+  if (!ctxs || n_ctx <= 0 || !ctxs[0] || launches <= 0 || !elapsed_ms) return set_err(nullptr, VB2_ERR_INVALID, "bad argument");
+  vb2_llk_ctx *lead = ctxs[0];
+  const uint32_t k = lead->S.n_pc;
+  std::vector<double> pc1((size_t)n_ctx * k), pc2((size_t)n_ctx * k), al(n_ctx, alpha);
+  for (int j = 0; j < n_ctx; ++j)
+    for (uint32_t d = 0; d < k; ++d) {
+      pc1[(size_t)j * k + d] = pc_contam[d] + (d == 0 ? 1e-7 * j : 0.0);  // a different point per sample
+      pc2[(size_t)j * k + d] = pc_intended[d];
+    }
+  bool nothing = false;
+  int rc = stage_many(ctxs, n_ctx, pc1.data(), pc2.data(), al.data(), &nothing);
+  if (rc) return rc;
+  if (nothing) return set_err(lead, VB2_ERR_INVALID, "no usable marker in any sample");
+  cudaEvent_t e0, e1;
+  VB2_CUDA(lead, cudaEventCreate(&e0));
+  VB2_CUDA(lead, cudaEventCreate(&e1));
+  for (int i = -warmup_launches; i < launches && rc == VB2_OK; ++i) {
+    if (i == 0) cudaEventRecord(e0, lead->stream);
+    rc = fire_many(lead, false, nullptr);
+  }
+  cudaEventRecord(e1, lead->stream);
+  cudaError_t e = cudaEventSynchronize(e1);
+  if (rc == VB2_OK && e != cudaSuccess) rc = set_err(lead, VB2_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == VB2_OK) cudaEventElapsedTime(elapsed_ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
 
 int vb2_llk_time_device(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup, int steps, const double *pc_contam,
                         const double *pc_intended, double alpha, float *elapsed_ms) {
@@ -862,7 +1020,7 @@ int vb2_llk_time_device(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup, int ste
     if (i == 0) cudaEventRecord(e0, lead->stream);
     pc1[0] = pc_contam[0] + 1e-7 * ((i + warmup) % 1000);  // a different point every step
     vb2_llk_ctx *c = ctxs[(i + warmup) % n_ctx];
-    rc = launch_batch(c, 1, pc1.data(), pc_intended, &alpha, c->d_out, false, nullptr);
+    rc = launch_batch(c, 1, pc1.data(), pc_intended, &alpha, Reduce::kDevice, c->d_out, false, nullptr);
   }
   cudaEventRecord(e1, lead->stream);
   cudaError_t e = cudaEventSynchronize(e1);

@@ -183,7 +183,7 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
     const uint32_t bin = bin_of(P.n_slices, P.n_bins, j);
     uint8_t *blob = P.blob.data() + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
     const uint32_t wr = geom[j].wr, wa = geom[j].wa;
-    uint32_t n_valid = 0;
+    uint32_t n_valid = 0, full_ref = wr, full_alt = wa;  // leading rows with four real reads in EVERY lane
     // neutral values for padding lanes
     for (uint32_t l = 0; l < (uint32_t)kSliceMarkers; ++l) {
       if (P.known_af) {
@@ -203,6 +203,8 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
       if (o >= order.size()) break;
       ++n_valid;
       const MarkerTmp &m = used[order[o]];
+      full_ref = std::min(full_ref, m.n_ref / kReadsPerWord);
+      full_alt = std::min(full_alt, m.n_alt / kReadsPerWord);
       P.marker_index[(size_t)j * kSliceMarkers + l] = m.panel_row;
       if (P.known_af) {
         reinterpret_cast<double *>(blob + L.off_kaf)[l] = d.known_af[m.panel_row];
@@ -240,7 +242,7 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
       P.reads_used += (uint64_t)(m.end - m.beg);
       ++P.n_used;
     }
-    uint32_t hdr[4] = {wr, wa, n_valid, 0u};
+    uint32_t hdr[4] = {wr, wa, n_valid, full_ref | (full_alt << 16)};
     std::memcpy(blob, hdr, sizeof(hdr));
   }
   P.log_other_const = (double)other_sum;

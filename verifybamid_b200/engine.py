@@ -34,7 +34,7 @@ _STATUS = {1: "VB2_ERR_INVALID", 2: "VB2_ERR_NO_DEVICE", 3: "VB2_ERR_CUDA", 4: "
 ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_create", "vb2_llk_destroy", "vb2_llk_get_info",
                "vb2_llk_eval", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many",
                "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free",
-               "vb2_llk_time_device", "vb2_llk_time_host")
+               "vb2_llk_time_device", "vb2_llk_time_device_many", "vb2_llk_time_host")
 
 
 class VB2Error(RuntimeError):
@@ -123,6 +123,8 @@ def load_library() -> ctypes.CDLL:
     lib.vb2_llk_time_device.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
                                         ctypes.POINTER(ctypes.c_float)]
+    lib.vb2_llk_time_device_many.restype = ctypes.c_int
+    lib.vb2_llk_time_device_many.argtypes = lib.vb2_llk_time_device.argtypes
     lib.vb2_llk_time_host.restype = ctypes.c_int
     lib.vb2_llk_time_host.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
@@ -303,6 +305,22 @@ def time_device(engines: List[LLKEngine], warmup: int, steps: int, pc_contam, pc
     a, b = _f64(pc_contam), _f64(pc_intended)
     ms = ctypes.c_float()
     rc = lib.vb2_llk_time_device(arr, n, warmup, steps, a.ctypes.data, b.ctypes.data, float(alpha), ctypes.byref(ms))
+    if rc != VB2_OK:
+        raise VB2Error(rc, lib.vb2_last_error(engines[0]._ctx).decode())
+    return float(ms.value)
+
+
+def time_device_many(engines: List[LLKEngine], warmup_launches: int, launches: int, pc_contam, pc_intended,
+                     alpha: float) -> float:
+    """Milliseconds for `launches` launches that each evaluate every engine's sample once (len(engines) steps
+    per launch, vb2_llk_eval_many's kernel), issued back to back from C."""
+    lib = load_library()
+    n = len(engines)
+    arr = (ctypes.c_void_p * n)(*[e._ctx for e in engines])
+    a, b = _f64(pc_contam), _f64(pc_intended)
+    ms = ctypes.c_float()
+    rc = lib.vb2_llk_time_device_many(arr, n, warmup_launches, launches, a.ctypes.data, b.ctypes.data, float(alpha),
+                                      ctypes.byref(ms))
     if rc != VB2_OK:
         raise VB2Error(rc, lib.vb2_last_error(engines[0]._ctx).decode())
     return float(ms.value)
