@@ -140,6 +140,12 @@ int vb2_llk_get_info(const vb2_llk_ctx *ctx, vb2_llk_info *info);
 int vb2_llk_eval(vb2_llk_ctx *ctx, const double *pc_contam, const double *pc_intended, double alpha,
                  double *llk_out);
 
+/* The same evaluation split in two, so that one host thread can drive several contexts (marker shards
+ * on several GPUs) concurrently: begin on every context, then end on every context and add the
+ * partial sums in context order.  One evaluation may be pending per context.                    */
+int vb2_llk_eval_begin(vb2_llk_ctx *ctx, const double *pc_contam, const double *pc_intended, double alpha);
+int vb2_llk_eval_end(vb2_llk_ctx *ctx, double *llk_out);
+
 /* n evaluations of the same sample in ONE pass (e.g. all Nelder-Mead candidates of a step):
  * pc_contam / pc_intended are [n][n_pc] row-major, alphas and llk_out are [n].               */
 int vb2_llk_eval_batch(vb2_llk_ctx *ctx, int n, const double *pc_contam, const double *pc_intended,

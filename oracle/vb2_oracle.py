@@ -207,14 +207,22 @@ def sanity_check(panel: Panel, viewer: Viewer) -> bool:
     return viewer.effective_num_site > 1000 and viewer.effective_num_site > n * 0.1
 
 
+_NUM = __import__("re").compile(r"\s*([-+]?(?:\d+\.?\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?))")
+
+
 def read_known_af(path: str) -> Dict[str, Dict[int, float]]:
+    """ContaminationEstimator.cpp:461-487: `ss >> chr >> pos >> pos >> ref >> alt >> AF` with ref/alt single
+    chars.  Stream semantics matter: after a multi-allelic ALT ("A,G") the extraction of AF starts at ",G",
+    fails, and (C++11) stores 0 -- the reference really uses AF = 0 for those rows."""
     out: Dict[str, Dict[int, float]] = {}
     with open(path) as f:
-        for line in f:                                 # cpp:461-487: chr x pos ref alt AF
-            tok = line.split()
-            if len(tok) < 6:
+        for line in f:
+            tok = line.split(None, 3)
+            if len(tok) < 4:
                 continue
-            out.setdefault(tok[0], {})[int(tok[2])] = float(tok[5])
+            rest = tok[3].lstrip()[1:].lstrip()[1:]        # drop the ref char, then the alt char
+            m = _NUM.match(rest)
+            out.setdefault(tok[0], {})[int(tok[2])] = float(m.group(1)) if m else 0.0
     return out
 
 

@@ -88,3 +88,26 @@ def test_oracle_matches_reference_binary(tmp_path):
         assert mine["alpha"] == opt["alpha"] and mine["evals"] == opt["evals"]
         assert mine["pc_contam"] == opt["pc_contam"] and mine["pc_intended"] == opt["pc_intended"]
         assert mine["llk1"] == opt["llk1"] and mine["llk0"] == opt["llk0"]
+
+
+@pytest.mark.skipif(not vo.ref_available(), reason="oracle/_ref/vb2_ref not built (no /root/reference here)")
+def test_known_af_stream_semantics_match_reference_binary(tmp_path):
+    """--KnownAF rows with a multi-allelic ALT ("A,G") make the reference's `ss >> alt >> AF` fail and use
+    AF = 0 (ContaminationEstimator.cpp:476-484); the oracle's reader must do the same."""
+    rows = []
+    with open(HAPMAP + ".bed") as f:
+        for i, line in enumerate(f):
+            c, _, p, r, a = line.split()[:5]
+            alt = a + ",T" if i % 7 == 0 else a
+            rows.append("%s\t%d\t%s\t%s\t%s\t%r\n" % (c, int(p) - 1, p, r, alt, 0.05 + 0.009 * (i % 100)))
+    af = tmp_path / "af.txt"
+    af.write_text("".join(rows))
+    pts = tmp_path / "pts.txt"
+    pts.write_text("0 0 0 0 0.03\n0 0 0 0 0.3\n")
+    recs = vo.run_ref(["--DisableSanityCheck", "--PileupFile", RESULT_PILEUP, "--SVDPrefix", HAPMAP, "--NumPC", "2",
+                       "--KnownAF", str(af), "--Output", str(tmp_path / "o"), "--EvalPoints", str(pts)])
+    p = vo.problem_from_files(HAPMAP, RESULT_PILEUP, 2, disable_sanity=True, known_af_path=str(af))
+    assert (p.known_af == 0).sum() > 0
+    assert [r["llk"] for r in recs if r["phase"] == "eval"] == [p.compute_mix_llks([0, 0], [0, 0], a) for a in (0.03, 0.3)]
+    opt = [r for r in recs if r["phase"] == "optimize"][0]
+    assert p.optimize()["alpha"] == opt["alpha"]

@@ -3,6 +3,7 @@
 Only what that one path needs lives here:
   csrc/        hand-written sm_100a kernel + C ABI (libvb2llk.so) + the C++ host side / CLI
   engine.py    ctypes binding of the C ABI (what tests and bench.py call)
+  host.py      ctypes binding of the C++ host side (readers, parser, Nelder-Mead) + the CLI path
   problem.py   the flat image of the reference's estimator data the ABI takes
   panels.py    bundled SVD panels, text <-> packed
   synth.py     synthetic contaminated pileups (BASELINE.json configs)

@@ -1,0 +1,579 @@
+// estimator.cpp -- see estimator.h.  Host logic of the likelihood path with the reference's control
+// flow (ContaminationEstimator.cpp / ContaminationEstimator.h); the per-marker, per-read arithmetic
+// lives in llk_engine.cu and is reached only through the C ABI.
+#include "estimator.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <sstream>
+#include <stdexcept>
+
+namespace vb2 {
+
+// ---- statgen/Error.cpp:26-79 ---------------------------------------------------------------------
+void notice(const char *msg, ...) {
+  va_list ap;
+  va_start(ap, msg);
+  fprintf(stderr, "NOTICE - ");
+  vfprintf(stderr, msg, ap);
+  fprintf(stderr, "\n");
+  va_end(ap);
+}
+void warning(const char *msg, ...) {
+  va_list ap;
+  va_start(ap, msg);
+  fprintf(stderr, "\n\aWARNING - \n");
+  vfprintf(stderr, msg, ap);
+  fprintf(stderr, "\n");
+  va_end(ap);
+}
+void error(const char *msg, ...) {
+  va_list ap;
+  va_start(ap, msg);
+  fprintf(stderr, "\nFATAL ERROR - \n");
+  vfprintf(stderr, msg, ap);
+  fprintf(stderr, "\n\n");
+  va_end(ap);
+  throw std::runtime_error("FATAL ERROR");  // the reference throws pexception here
+}
+
+namespace {
+
+// ContaminationEstimator.cpp:10-24
+struct PhaseTimer {
+  std::string name;
+  std::chrono::steady_clock::time_point start;
+  explicit PhaseTimer(const std::string &phaseName) : name(phaseName), start(std::chrono::steady_clock::now()) {
+    notice("  Starting phase: %s", name.c_str());
+  }
+  ~PhaseTimer() {
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    notice("  Finished phase: %s  [%.3f seconds]", name.c_str(), secs);
+  }
+};
+
+// InputFile::readLine returns -1 when EOF arrives before '\n' (statgen/InputFile.h:302-309), so the
+// reference's `while (fin.readLine(line)==0)` loops drop an unterminated last line.  Same here.
+bool read_terminated_lines(const std::string &path, std::vector<std::string> &lines) {
+  std::ifstream fin(path, std::ios::binary);
+  if (!fin.is_open()) return false;
+  std::string all((std::istreambuf_iterator<char>(fin)), std::istreambuf_iterator<char>());
+  size_t beg = 0;
+  for (;;) {
+    size_t nl = all.find('\n', beg);
+    if (nl == std::string::npos) break;
+    lines.emplace_back(all, beg, nl - beg);
+    beg = nl + 1;
+  }
+  return true;
+}
+
+[[noreturn]] void open_failed(const std::string &path) {
+  std::cerr << "Open file:" << path << "\t failed, exit!";
+  exit(EXIT_FAILURE);
+}
+
+}  // namespace
+
+// ---- FullLLKFunc ---------------------------------------------------------------------------------
+double ContaminationEstimator::FullLLKFunc::InvLogit(double x) {
+  double e = exp(x);
+  return e / (1. + e);
+}
+double ContaminationEstimator::FullLLKFunc::Logit(double x) { return log(x / (1. - x)); }
+
+double ContaminationEstimator::FullLLKFunc::ComputeMixLLKs(const std::vector<double> &tPC1,
+                                                           const std::vector<double> &tPC2, double alpha) {
+  ContaminationEstimator &E = *ptr;
+  if (E.engines.empty()) error("ComputeMixLLKs called before the engine was created");
+  auto t0 = std::chrono::steady_clock::now();
+  ++evalCount;
+  // every marker shard (one per GPU) evaluates concurrently; partial sums are added in shard order
+  for (vb2_llk_ctx *c : E.engines)
+    if (vb2_llk_eval_begin(c, tPC1.data(), tPC2.data(), alpha) != VB2_OK) error("GPU engine: %s", vb2_last_error(c));
+  double sumLLK = 0;
+  for (vb2_llk_ctx *c : E.engines) {
+    double part = 0;
+    if (vb2_llk_eval_end(c, &part) != VB2_OK) error("GPU engine: %s", vb2_last_error(c));
+    sumLLK += part;
+  }
+  E.engineSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return sumLLK;
+}
+
+int ContaminationEstimator::FullLLKFunc::Initialize() {
+  globalPC = fixPC = globalPC2 = fixPC2 = ptr->PC[1];  // only the intended sample has pre-defined PCs
+  globalAlpha = fixAlpha = ptr->alpha;
+  llk1 = (0 - ComputeMixLLKs(fixPC, fixPC2, fixAlpha));
+  for (int k = 0; k < ptr->numPC; ++k) ptr->PC[0][k] = 0.01;
+  for (int k = 0; k < ptr->numPC; ++k) ptr->PC[1][k] = 0.01;
+  ptr->alpha = 0.03;
+  return 0;
+}
+
+int ContaminationEstimator::FullLLKFunc::CalculateLLK0() {
+  llk0 = (0 - ComputeMixLLKs(globalPC, globalPC, 0));
+  return 0;
+}
+
+double ContaminationEstimator::FullLLKFunc::Evaluate(const std::vector<double> &v) {
+  double smLLK = 0;
+  const int numPC = ptr->numPC;
+  if (!ptr->isHeter) {
+    if (ptr->isPCFixed) {
+      double tmpAlpha = InvLogit(v[0]);
+      smLLK = 0 - ComputeMixLLKs(fixPC, fixPC2, tmpAlpha);
+      if (smLLK < llk1) {
+        llk1 = smLLK;
+        globalAlpha = tmpAlpha;
+      }
+    } else if (ptr->isAlphaFixed) {
+      std::vector<double> tmpPC(v.begin(), v.begin() + numPC);
+      smLLK = 0 - ComputeMixLLKs(tmpPC, tmpPC, fixAlpha);
+      if (smLLK < llk1) {
+        llk1 = smLLK;
+        globalPC = tmpPC;
+        globalPC2 = tmpPC;
+      }
+    } else {
+      std::vector<double> tmpPC(v.begin(), v.begin() + numPC);
+      double tmpAlpha = InvLogit(v[numPC]);
+      smLLK = 0 - ComputeMixLLKs(tmpPC, tmpPC, tmpAlpha);
+      if (smLLK < llk1) {
+        llk1 = smLLK;
+        globalPC = tmpPC;
+        globalPC2 = tmpPC;
+        globalAlpha = tmpAlpha;
+      }
+    }
+  } else {  // contamination source from a different population
+    if (ptr->isPCFixed) {  // only fixed for the intended sample
+      std::vector<double> tmpPC(v.begin(), v.begin() + numPC);
+      double tmpAlpha = InvLogit(v[numPC]);
+      smLLK = 0 - ComputeMixLLKs(tmpPC, fixPC2, tmpAlpha);
+      if (smLLK < llk1) {
+        llk1 = smLLK;
+        globalPC = tmpPC;
+        globalAlpha = tmpAlpha;
+      }
+    } else if (ptr->isAlphaFixed) {
+      std::vector<double> tmpPC(numPC, 0.), tmpPC2(numPC, 0.);
+      for (int k = 0; k < (int)v.size(); ++k) {
+        if (k < numPC) tmpPC[k] = v[k];
+        else if (k < numPC * 2) tmpPC2[k - numPC] = v[k];
+        else error("Simplex Vector dimension error!");
+      }
+      smLLK = 0 - ComputeMixLLKs(tmpPC, tmpPC2, fixAlpha);
+      if (smLLK < llk1) {
+        llk1 = smLLK;
+        globalPC = tmpPC;
+        globalPC2 = tmpPC2;
+      }
+    } else {
+      std::vector<double> tmpPC(numPC, 0.), tmpPC2(numPC, 0.);
+      double tmpAlpha = 0.;
+      for (int k = 0; k < (int)v.size(); ++k) {
+        if (k < numPC) tmpPC[k] = v[k];
+        else if (k < numPC * 2) tmpPC2[k - numPC] = v[k];
+        else if (k == numPC * 2) tmpAlpha = InvLogit(v[k]);
+        else error("Simplex Vector dimension error!");
+      }
+      smLLK = (0 - ComputeMixLLKs(tmpPC, tmpPC2, tmpAlpha));
+      if (smLLK < llk1) {
+        llk1 = smLLK;
+        globalPC = tmpPC;
+        globalPC2 = tmpPC2;
+        globalAlpha = tmpAlpha;
+      }
+    }
+  }
+  if (ptr->verbose)
+    notice("ContaminatingSamplePC1:%f\tContaminatingSamplePC2:%f\tIntendedSamplePC1:%f\tIntendedSamplePC2:%f\tFREEMIX(Alpha):%f\tllk:%f",
+           globalPC[0], numPC > 1 ? globalPC[1] : 0., globalPC2[0], numPC > 1 ? globalPC2[1] : 0., globalAlpha, llk1);
+  return smLLK;
+}
+
+// ---- ContaminationEstimator -------------------------------------------------------------------------
+ContaminationEstimator::ContaminationEstimator(int nPC, const char *bedFile, int nThread, double ep)
+    : numPC(nPC), numThread(nThread), epsilon(ep), PC(2, std::vector<double>(nPC, 0.)) {
+  fn.ptr = this;
+  fn.fixPC.assign(nPC, 0.);
+  fn.fixPC2.assign(nPC, 0.);
+  fn.globalPC = fn.fixPC;
+  fn.globalPC2 = fn.fixPC2;
+  std::cerr << "Initialize from FullLLKFunc(int dim, ContaminationEstimator* contPtr)" << std::endl;  // h:114
+  ReadChooseBed(std::string(bedFile));
+  alpha = 0.5;
+  NumMarker = 0;
+}
+
+ContaminationEstimator::~ContaminationEstimator() { DestroyEngines(); }
+
+void ContaminationEstimator::BuildResolvedMarkers() {
+  resolvedMarkers.resize(NumMarker);
+  for (size_t i = 0; i < NumMarker; ++i) {
+    const std::string &chr = PosVec[i].first;
+    int pos = PosVec[i].second;
+    ResolvedMarker &rm = resolvedMarkers[i];
+    rm.altBase = 0;
+    rm.knownAFValue = 0.0;
+    auto chrIt = viewer.posIndex.find(chr);
+    if (chrIt == viewer.posIndex.end()) { rm.baseInfoIndex = -1; continue; }
+    auto posIt = chrIt->second.find(pos);
+    if (posIt == chrIt->second.end()) { rm.baseInfoIndex = -1; continue; }
+    rm.baseInfoIndex = posIt->second;
+    rm.altBase = ChooseBed[chr][pos].second;
+    if (isAFknown) rm.knownAFValue = knownAF[chr][pos];
+  }
+}
+
+void ContaminationEstimator::CreateEngines() {
+  DestroyEngines();
+  if (PosVec.size() < NumMarker || means.size() < NumMarker)
+    error("SVD files disagree: %u rows in .UD, %d in .bed, %d in .mu", NumMarker, (int)PosVec.size(), (int)means.size());
+  std::vector<double> ud((size_t)NumMarker * numPC);
+  std::vector<int32_t> idx(NumMarker);
+  std::vector<char> alt(NumMarker);
+  std::vector<double> kaf;
+  if (isAFknown) kaf.resize(NumMarker);
+  for (size_t i = 0; i < NumMarker; ++i) {
+    for (int k = 0; k < numPC; ++k) ud[i * numPC + k] = UD[i][k];
+    idx[i] = resolvedMarkers[i].baseInfoIndex;
+    alt[i] = resolvedMarkers[i].altBase;
+    if (isAFknown) kaf[i] = resolvedMarkers[i].knownAFValue;
+  }
+  vb2_llk_desc d;
+  memset(&d, 0, sizeof(d));
+  d.struct_size = sizeof(d);
+  d.n_marker = NumMarker;
+  d.n_pc = (uint32_t)numPC;
+  d.ud_stride = (uint32_t)numPC;
+  d.ud = ud.data();
+  d.means = means.data();
+  d.base_info_index = idx.data();
+  d.alt_base = alt.data();
+  d.known_af = isAFknown ? kaf.data() : nullptr;
+  d.info_offset = viewer.infoOffset.data();
+  d.bases = viewer.bases.data();
+  d.quals = viewer.quals.data();
+  d.sanity_disabled = isSanityCheckDisabled ? 1 : 0;
+  d.avg_depth = viewer.avgDepth;
+  d.sd_depth = viewer.sdDepth;
+  d.panel_dtype = panelFp64 ? VB2_PANEL_FP64 : VB2_PANEL_FP32;
+  d.shard_count = (uint32_t)numGPU;
+  for (int g = 0; g < numGPU; ++g) {
+    d.shard_rank = (uint32_t)g;
+    d.device = firstDevice + g;
+    vb2_llk_ctx *c = nullptr;
+    if (vb2_llk_create(&d, &c) != VB2_OK) {
+      std::string why = vb2_last_error(nullptr);
+      DestroyEngines();
+      error("cannot create the GPU likelihood engine on device %d: %s", d.device, why.c_str());
+    }
+    engines.push_back(c);
+  }
+  vb2_llk_info info;
+  info.struct_size = sizeof(info);
+  uint64_t markers = 0, reads = 0;
+  for (vb2_llk_ctx *c : engines)
+    if (vb2_llk_get_info(c, &info) == VB2_OK) { markers += info.markers_used; reads += info.reads_used; }
+  notice("GPU likelihood engine: %d device(s), %llu markers / %llu reads resident in HBM", numGPU,
+         (unsigned long long)markers, (unsigned long long)reads);
+}
+
+void ContaminationEstimator::DestroyEngines() {
+  for (vb2_llk_ctx *c : engines) vb2_llk_destroy(c);
+  engines.clear();
+}
+
+int ContaminationEstimator::OptimizeLLK(const std::string &OutputPrefix) {
+  AmoebaMinimizer myMinimizer;
+  BuildResolvedMarkers();
+  {
+    PhaseTimer t("Flatten pileup into HBM");
+    CreateEngines();
+  }
+  {
+    PhaseTimer t("Initialize likelihood");
+    fn.Initialize();
+  }
+  if (!isHeter) {
+    if (isPCFixed) {
+      std::cout << "Estimation from OptimizeHomoFixedPC:" << std::endl;
+      PhaseTimer t("OptimizeHomoFixedPC");
+      OptimizeHomoFixedPC(myMinimizer);
+    } else if (isAlphaFixed) {
+      PhaseTimer t("OptimizeHomoFixedAlpha");
+      OptimizeHomoFixedAlpha(myMinimizer);
+    } else {
+      std::cout << "Estimation from OptimizeHomo:" << std::endl;
+      PhaseTimer t("OptimizeHomo");
+      OptimizeHomo(myMinimizer);
+    }
+  } else {  // contamination source from a different population
+    if (isPCFixed) {
+      std::cout << "Estimation from OptimizeHeterFixedPC:" << std::endl;
+      PhaseTimer t("OptimizeHeterFixedPC");
+      OptimizeHeterFixedPC(myMinimizer);
+    } else if (isAlphaFixed) {
+      std::cout << "Estimation from OptimizeHeterFixedAlpha:" << std::endl;
+      {
+        PhaseTimer t("OptimizeHomoFixedAlpha (initial)");
+        isHeter = false;
+        OptimizeHomoFixedAlpha(myMinimizer);
+        PC[1] = PC[0];
+        fn.globalPC2 = fn.globalPC;
+        isHeter = true;
+      }
+      {
+        PhaseTimer t("OptimizeHeterFixedAlpha");
+        OptimizeHeterFixedAlpha(myMinimizer);
+      }
+    } else {
+      std::cout << "Estimation from OptimizeHeter:" << std::endl;
+      {
+        PhaseTimer t("OptimizeHomo (initial)");
+        isHeter = false;
+        OptimizeHomo(myMinimizer);
+        PC[1] = PC[0];
+        fn.globalPC2 = fn.globalPC;
+        isHeter = true;
+      }
+      {
+        PhaseTimer t("OptimizeHeter");
+        OptimizeHeter(myMinimizer);
+      }
+    }
+    if (fn.globalAlpha >= 0.5) {  // cpp:146-149: only PC1 and PC2 are swapped
+      std::swap(fn.globalPC[0], fn.globalPC2[0]);
+      if (numPC > 1) std::swap(fn.globalPC[1], fn.globalPC2[1]);
+    }
+  }
+  {
+    PhaseTimer t("Calculate null-model LLK");
+    fn.CalculateLLK0();
+  }
+  std::cout << "Contaminating Sample ";
+  for (int i = 0; i < numPC; ++i) std::cout << "PC" << i + 1 << ":" << fn.globalPC[i] << "\t";
+  std::cout << std::endl;
+  std::cout << "Intended Sample ";
+  for (int i = 0; i < numPC; ++i) std::cout << "PC" << i + 1 << ":" << fn.globalPC2[i] << "\t";
+  std::cout << std::endl;
+  std::cout << "FREEMIX(Alpha):" << (fn.globalAlpha < 0.5 ? fn.globalAlpha : (1 - fn.globalAlpha)) << std::endl;
+
+  std::string fileName(OutputPrefix + ".Ancestry");
+  std::ofstream fout(fileName);
+  if (!fout.is_open()) error("Open file %s failed!", fileName.c_str());
+  fout << "PC\tContaminatingSample\tIntendedSample" << std::endl;
+  for (int i = 0; i < numPC; ++i) fout << i + 1 << "\t" << fn.globalPC[i] << "\t" << fn.globalPC2[i] << std::endl;
+  fout.close();
+  if (!fout) error("Errors detected when writing to file %s !", fileName.c_str());
+  notice("Likelihood evaluations: %ld, %.3f ms inside the GPU engine (%.1f us per evaluation)", fn.evalCount,
+         engineSeconds * 1e3, fn.evalCount ? engineSeconds * 1e6 / fn.evalCount : 0.0);
+  return 0;
+}
+
+bool ContaminationEstimator::OptimizeHeter(AmoebaMinimizer &myMinimizer) {
+  std::vector<double> startingPoint(numPC * 2 + 1);
+  for (int i = 0; i < numPC * 2; ++i) startingPoint[i] = i < numPC ? PC[0][i] : PC[1][i - numPC];
+  startingPoint[numPC * 2] = FullLLKFunc::Logit(alpha);
+  if (verbose) {
+    std::cerr << "Start point:";
+    for (int i = 0; i < numPC * 2; ++i) std::cerr << startingPoint[i] << "\t";
+    std::cerr << "and alpha:\t" << alpha << std::endl;
+  }
+  myMinimizer.func = &fn;
+  myMinimizer.Reset(numPC * 2 + 1);
+  myMinimizer.point = startingPoint;
+  double ret = myMinimizer.Minimize(epsilon);
+  alpha = FullLLKFunc::InvLogit(myMinimizer.point[numPC * 2]);
+  for (int i = 0; i < numPC; ++i) PC[0][i] = myMinimizer.point[i];
+  for (int i = numPC; i < numPC * 2; ++i) PC[1][i - numPC] = myMinimizer.point[i];
+  return ret != std::numeric_limits<double>::max();
+}
+
+bool ContaminationEstimator::OptimizeHeterFixedAlpha(AmoebaMinimizer &myMinimizer) {
+  std::vector<double> startingPoint(numPC * 2);
+  for (int i = 0; i < numPC * 2; ++i) startingPoint[i] = i < numPC ? PC[0][i] : PC[1][i - numPC];
+  if (verbose) {
+    std::cerr << "Start point:";
+    for (int i = 0; i < numPC * 2; ++i) std::cerr << startingPoint[i] << "\t";
+  }
+  myMinimizer.func = &fn;
+  myMinimizer.Reset(numPC * 2);
+  myMinimizer.point = startingPoint;
+  myMinimizer.Minimize(epsilon);
+  for (int i = 0; i < numPC; ++i) PC[0][i] = myMinimizer.point[i];
+  for (int i = numPC; i < numPC * 2; ++i) PC[1][i - numPC] = myMinimizer.point[i];
+  return true;  // fixAlpha usually converges well
+}
+
+bool ContaminationEstimator::OptimizeHeterFixedPC(AmoebaMinimizer &myMinimizer) { return OptimizeHomo(myMinimizer); }
+
+bool ContaminationEstimator::OptimizeHomo(AmoebaMinimizer &myMinimizer) {
+  std::vector<double> startingPoint(numPC + 1);
+  for (int i = 0; i < numPC; ++i) startingPoint[i] = PC[0][i];
+  startingPoint[numPC] = FullLLKFunc::Logit(alpha);
+  if (verbose) {
+    std::cerr << "Start point:";
+    for (int i = 0; i < numPC; ++i) std::cerr << startingPoint[i] << "\t";
+    std::cerr << "and alpha:\t" << alpha << std::endl;
+  }
+  myMinimizer.func = &fn;
+  myMinimizer.Reset(numPC + 1);
+  myMinimizer.point = startingPoint;
+  double ret = myMinimizer.Minimize(epsilon);
+  alpha = FullLLKFunc::InvLogit(myMinimizer.point[numPC]);
+  for (int i = 0; i < numPC; ++i) PC[0][i] = myMinimizer.point[i];
+  return ret != std::numeric_limits<double>::max();
+}
+
+bool ContaminationEstimator::OptimizeHomoFixedAlpha(AmoebaMinimizer &myMinimizer) {
+  std::vector<double> startingPoint(numPC);
+  for (int i = 0; i < numPC; ++i) startingPoint[i] = PC[0][i];
+  if (verbose) {
+    std::cerr << "Start point:";
+    for (int i = 0; i < numPC; ++i) std::cerr << startingPoint[i] << "\t";
+  }
+  myMinimizer.func = &fn;
+  myMinimizer.Reset(numPC);
+  myMinimizer.point = startingPoint;
+  myMinimizer.Minimize(epsilon);
+  for (int i = 0; i < numPC; ++i) PC[0][i] = myMinimizer.point[i];
+  return true;  // fixAlpha usually converges well
+}
+
+bool ContaminationEstimator::OptimizeHomoFixedPC(AmoebaMinimizer &myMinimizer) {
+  std::vector<double> startingPoint(1);
+  startingPoint[0] = FullLLKFunc::Logit(alpha);
+  if (verbose) {
+    std::cerr << "Start point";
+    std::cerr << "alpha:\t" << alpha << std::endl;
+  }
+  myMinimizer.func = &fn;
+  myMinimizer.Reset(1);
+  myMinimizer.point = startingPoint;
+  double ret = myMinimizer.Minimize(epsilon);
+  alpha = FullLLKFunc::InvLogit(myMinimizer.point[0]);
+  return ret != std::numeric_limits<double>::max();
+}
+
+int ContaminationEstimator::ReadSVDMatrix(const std::string &UDpath, const std::string &, const std::string &Mean) {
+  ReadMatrixUD(UDpath);
+  ReadMean(Mean);
+  return 0;
+}
+
+int ContaminationEstimator::ReadMatrixUD(const std::string &path) {
+  std::vector<std::string> lines;
+  if (!read_terminated_lines(path, lines)) open_failed(path);
+  std::vector<double> tmpUD(numPC, 0);
+  UD.reserve(lines.size());
+  for (const std::string &line : lines) {
+    std::stringstream ss(line);
+    int index = 0;
+    while (index < numPC && ss >> tmpUD[index]) index++;
+    if (index < numPC) {  // cpp:358-363
+      warning("--NumPC should be less than or equal to the number of PCs in SVD files provided by --SVDPrefix! (Expected:%d vs Observed:%d)", numPC, index);
+      warning("--NumPC only permits as large as 4 PCs when using SVD files in ${verifybamID}/resource/ directory!");
+      warning("You can always prepare you own SVD files with arbitrary number of PCs with --RefVCF enabled.");
+      exit(EXIT_FAILURE);
+    }
+    UD.push_back(tmpUD);
+    NumMarker++;
+  }
+  return 0;
+}
+
+int ContaminationEstimator::ReadChooseBed(const std::string &path) {
+  std::vector<std::string> lines;
+  if (!read_terminated_lines(path, lines)) open_failed(path);
+  std::string chr;
+  int pos(0);
+  char ref(0), alt(0);
+  for (const std::string &line : lines) {
+    std::stringstream ss(line);
+    ss >> chr >> pos >> pos;
+    ss >> ref >> alt;  // single chars: ALT "G,T" is read as 'G' (cpp:417,429)
+    PosVec.push_back(std::make_pair(chr, pos));
+    ChooseBed[chr][pos] = std::make_pair(ref, alt);
+  }
+  return 0;
+}
+
+int ContaminationEstimator::ReadMean(const std::string &path) {
+  std::vector<std::string> lines;
+  if (!read_terminated_lines(path, lines)) open_failed(path);
+  double mu(0);
+  std::string snpName;
+  for (const std::string &line : lines) {
+    std::stringstream ss(line);
+    ss >> snpName;
+    ss >> mu;
+    means.push_back(mu);
+  }
+  return 0;
+}
+
+int ContaminationEstimator::ReadAF(const std::string &path) {
+  std::ifstream fin(path);
+  std::string line, chr;
+  uint32_t pos(0);
+  double AF(0);
+  char ref(0), alt(0);
+  if (!fin.is_open()) open_failed(path);
+  while (std::getline(fin, line)) {
+    std::stringstream ss(line);
+    ss >> chr;
+    ss >> pos >> pos;
+    ss >> ref >> alt;
+    ss >> AF;
+    knownAF[chr][pos] = AF;
+  }
+  return 0;
+}
+
+int ContaminationEstimator::ReadPileup(const std::string &pileupFile) {
+  viewer = SimplePileupViewer();
+  viewer.ReadPileup(pileupFile, ChooseBed);
+  isPileupInput = true;
+  return 0;
+}
+
+bool ContaminationEstimator::IsSanityCheckOK() {
+  notice("Number of marker in Reference Matrix:%d", NumMarker);
+  notice("Number of marker shared with input file:%d", viewer.GetNumMarker());
+  auto depth_at = [&](size_t i, int &depth) -> bool {
+    auto chrIt = viewer.posIndex.find(PosVec[i].first);
+    if (chrIt == viewer.posIndex.end()) return false;
+    auto posIt = chrIt->second.find(PosVec[i].second);
+    if (posIt == chrIt->second.end()) return false;
+    depth = (int)viewer.DepthOf(posIt->second);
+    return true;
+  };
+  int tmpDepth = 0;
+  for (size_t i = 0; i < NumMarker; ++i)
+    if (depth_at(i, tmpDepth)) viewer.sdDepth += tmpDepth * tmpDepth;  // (int multiply, as in the reference)
+  viewer.sdDepth = sqrt(viewer.sdDepth / viewer.effectiveNumSite - viewer.avgDepth * viewer.avgDepth);
+  viewer.effectiveNumSite = 0;
+  for (size_t i = 0; i < NumMarker; ++i) {
+    if (!depth_at(i, tmpDepth)) continue;
+    if (tmpDepth == 0 || tmpDepth < (viewer.avgDepth - 3 * viewer.sdDepth) ||
+        tmpDepth > (viewer.avgDepth + 3 * viewer.sdDepth))
+      continue;
+    viewer.effectiveNumSite++;
+  }
+  notice("Mean Depth:%f", viewer.avgDepth);
+  notice("SD Depth:%f", viewer.sdDepth);
+  notice("%d SNP markers remained after sanity check.", viewer.GetNumMarker());
+  return viewer.GetNumMarker() > 1000 && viewer.GetNumMarker() > (NumMarker * 0.1);
+}
+
+}  // namespace vb2

@@ -455,6 +455,9 @@ struct vb2_llk_ctx {
   uint32_t *h_slots = nullptr, *d_slots = nullptr;
   uint32_t many_n = 0, many_grid_x = 0, many_kc = 1, many_buf_bytes = 0;  // last staged eval_many launch
   unsigned long long seq = 0;
+  int pending_n = 0;                 // evaluations launched by eval_begin and not yet collected
+  bool pending_host_reduce = false;
+  unsigned long long pending_seq = 0;
   double spin_timeout_ms = 20000.0;
   std::string err;
 };
@@ -820,22 +823,36 @@ int vb2_llk_get_info(const vb2_llk_ctx *ctx, vb2_llk_info *info) {
   return VB2_OK;
 }
 
-int vb2_llk_eval_batch(vb2_llk_ctx *ctx, int n, const double *pc_contam, const double *pc_intended,
-                       const double *alphas, double *llk_out) {
+static int begin_batch(vb2_llk_ctx *ctx, int n, const double *pc_contam, const double *pc_intended,
+                       const double *alphas) {
   if (!ctx) return set_err(nullptr, VB2_ERR_INVALID, "null context");
-  if (!llk_out) return set_err(ctx, VB2_ERR_INVALID, "null output pointer");
+  if (ctx->pending_n) return set_err(ctx, VB2_ERR_INVALID, "an evaluation is already pending on this context");
   if (n <= 0 || n > VB2_MAX_BATCH) return set_err(ctx, VB2_ERR_INVALID, "batch size out of range");
-  const uint32_t gx = ctx->S.grid_x;
   const bool host_reduce = n <= kMaxArgJobs && ctx->rounds.size() <= (size_t)kMaxArgRounds;
   unsigned long long seq = 0;
   int rc = launch_batch(ctx, n, pc_contam, pc_intended, alphas, host_reduce ? Reduce::kHost : Reduce::kDevice,
                         nullptr, true, &seq);
   if (rc) return rc;
+  ctx->pending_n = n;
+  ctx->pending_host_reduce = host_reduce;
+  ctx->pending_seq = seq;
+  return VB2_OK;
+}
+
+static int end_batch(vb2_llk_ctx *ctx, double *llk_out) {
+  if (!ctx) return set_err(nullptr, VB2_ERR_INVALID, "null context");
+  if (!llk_out) return set_err(ctx, VB2_ERR_INVALID, "null output pointer");
+  const int n = ctx->pending_n;
+  if (!n) return set_err(ctx, VB2_ERR_INVALID, "no evaluation pending on this context");
+  ctx->pending_n = 0;
+  const uint32_t gx = ctx->S.grid_x;
   if (gx == 0) {  // no usable marker: the reference's empty sum (h:231, :313)
     for (int j = 0; j < n; ++j) llk_out[j] = 0.0;
     return VB2_OK;
   }
-  if ((rc = wait_mailbox(ctx, host_reduce ? (uint32_t)n * gx : (uint32_t)n, seq))) return rc;
+  const bool host_reduce = ctx->pending_host_reduce;
+  int rc = wait_mailbox(ctx, host_reduce ? (uint32_t)n * gx : (uint32_t)n, ctx->pending_seq);
+  if (rc) return rc;
   volatile Slot *mb = ctx->h_mbox;
   if (host_reduce) {
     // Same fixed order as the device-side reduction (lane-strided sums, then a butterfly), so both
@@ -858,10 +875,24 @@ int vb2_llk_eval_batch(vb2_llk_ctx *ctx, int n, const double *pc_contam, const d
   return VB2_OK;
 }
 
+int vb2_llk_eval_batch(vb2_llk_ctx *ctx, int n, const double *pc_contam, const double *pc_intended,
+                       const double *alphas, double *llk_out) {
+  if (ctx && !llk_out) return set_err(ctx, VB2_ERR_INVALID, "null output pointer");
+  int rc = begin_batch(ctx, n, pc_contam, pc_intended, alphas);
+  if (rc) return rc;
+  return end_batch(ctx, llk_out);
+}
+
 int vb2_llk_eval(vb2_llk_ctx *ctx, const double *pc_contam, const double *pc_intended, double alpha,
                  double *llk_out) {
   return vb2_llk_eval_batch(ctx, 1, pc_contam, pc_intended, &alpha, llk_out);
 }
+
+int vb2_llk_eval_begin(vb2_llk_ctx *ctx, const double *pc_contam, const double *pc_intended, double alpha) {
+  return begin_batch(ctx, 1, pc_contam, pc_intended, &alpha);
+}
+
+int vb2_llk_eval_end(vb2_llk_ctx *ctx, double *llk_out) { return end_batch(ctx, llk_out); }
 
 int vb2_llk_eval_batch_device(vb2_llk_ctx *ctx, int n, const double *pc_contam, const double *pc_intended,
                               const double *alphas, double *d_llk_out) {

@@ -1,0 +1,254 @@
+// main.cpp -- command line of the B200 contamination-likelihood engine, flag-compatible with the
+// reference for the likelihood path (main.cpp:56-414 of the reference): same option names, same
+// defaults, same <out>.selfSM / <out>.Ancestry / <out>.Pileup files, same stdout lines.
+//   --BamFile needs htslib (absent here): give --PileupFile instead.
+//   --RefVCF (SVD panel construction) is a separate offline workload and is not built.
+// Engine-only options: --NumGPU n (marker shards over devices 0..n-1), --Device d, --PanelFP64.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "estimator.h"
+
+using namespace vb2;
+
+namespace {
+
+struct Options {
+  std::string UDPath = "Empty", MeanPath = "Empty", BedPath = "Empty", BamFile = "Empty", RefPath = "Empty";
+  std::string outputPrefix = "result", PileupFile = "Empty", SVDPrefix = "Empty", knownAF = "Empty";
+  std::string RefVCF = "Empty", fixPC = "Empty";
+  double fixAlpha = -1., epsilon = 1e-8;  // main.cpp:76
+  bool withinAncestry = false, outputPileup = false, verbose = false, disableSanityCheck = false;
+  int seed = 12345, nPC = 2, nthread = 4;  // main.cpp:79
+  int numGPU = 1, device = 0;
+  bool panelFp64 = false;
+};
+
+bool ieq(const std::string &a, const char *b) {
+  size_t n = strlen(b);
+  if (a.size() != n) return false;
+  for (size_t i = 0; i < n; ++i)
+    if (tolower((unsigned char)a[i]) != tolower((unsigned char)b[i])) return false;
+  return true;
+}
+
+void usage() {
+  fprintf(stderr,
+          "Options (likelihood path of VerifyBamID2):\n"
+          "  --SVDPrefix [String]   SVD files prefix (.UD, .mu, .bed)            | --UDPath --MeanPath --BedPath\n"
+          "  --PileupFile [String]  pileup of the sample (samtools mpileup format)\n"
+          "  --Reference [String]   reference FASTA (required by the reference CLI; unused with --PileupFile)\n"
+          "  --Output [String]      prefix of output files [result]\n"
+          "  --NumPC [Int] (2)  --NumThread [Int] (4, host side only)  --Seed [Int] (ignored)  --Epsilon [Double] (1e-8)\n"
+          "  --WithinAncestry  --FixPC a:b:...  --FixAlpha x  --KnownAF file  --DisableSanityCheck\n"
+          "  --OutputPileup  --Verbose\n"
+          "  --NumGPU [Int] (1)  --Device [Int] (0)  --PanelFP64     (engine options)\n");
+}
+
+// libStatGen-style long options: "--Name value", booleans are presence flags (params.cpp:114-185)
+bool parse(int argc, char **argv, Options &o) {
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a.size() < 3 || a[0] != '-' || a[1] != '-') {
+      fprintf(stderr, "Command line parameter %s (#%d) ignored\n", a.c_str(), i);
+      continue;
+    }
+    std::string name = a.substr(2);
+    auto value = [&](std::string &dst) {
+      if (i + 1 >= argc) { fprintf(stderr, "missing value for --%s\n", name.c_str()); exit(1); }
+      dst = argv[++i];
+    };
+    auto ivalue = [&](int &dst) { std::string s; value(s); dst = atoi(s.c_str()); };
+    auto dvalue = [&](double &dst) { std::string s; value(s); dst = atof(s.c_str()); };
+    if (ieq(name, "help")) { usage(); exit(1); }
+    else if (ieq(name, "BamFile")) value(o.BamFile);
+    else if (ieq(name, "PileupFile")) value(o.PileupFile);
+    else if (ieq(name, "Reference")) value(o.RefPath);
+    else if (ieq(name, "SVDPrefix")) value(o.SVDPrefix);
+    else if (ieq(name, "Output")) value(o.outputPrefix);
+    else if (ieq(name, "WithinAncestry")) o.withinAncestry = true;
+    else if (ieq(name, "DisableSanityCheck")) o.disableSanityCheck = true;
+    else if (ieq(name, "NumPC")) ivalue(o.nPC);
+    else if (ieq(name, "FixPC")) value(o.fixPC);
+    else if (ieq(name, "FixAlpha")) dvalue(o.fixAlpha);
+    else if (ieq(name, "KnownAF")) value(o.knownAF);
+    else if (ieq(name, "NumThread")) ivalue(o.nthread);
+    else if (ieq(name, "Seed")) ivalue(o.seed);
+    else if (ieq(name, "Epsilon")) dvalue(o.epsilon);
+    else if (ieq(name, "OutputPileup")) o.outputPileup = true;
+    else if (ieq(name, "Verbose")) o.verbose = true;
+    else if (ieq(name, "RefVCF")) value(o.RefVCF);
+    else if (ieq(name, "UDPath")) value(o.UDPath);
+    else if (ieq(name, "MeanPath")) value(o.MeanPath);
+    else if (ieq(name, "BedPath")) value(o.BedPath);
+    else if (ieq(name, "NumGPU")) ivalue(o.numGPU);
+    else if (ieq(name, "Device")) ivalue(o.device);
+    else if (ieq(name, "PanelFP64")) o.panelFp64 = true;
+    else fprintf(stderr, "Command line parameter %s (#%d) ignored\n", a.c_str(), i);
+  }
+  return true;
+}
+
+struct PhaseTimer {  // main.cpp:40-54
+  std::string name;
+  std::chrono::steady_clock::time_point start;
+  explicit PhaseTimer(const std::string &n) : name(n), start(std::chrono::steady_clock::now()) {
+    notice("Starting phase: %s", name.c_str());
+  }
+  ~PhaseTimer() {
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    notice("Finished phase: %s  [%.3f seconds]", name.c_str(), secs);
+  }
+};
+
+int execute(int argc, char **argv) {
+  Options o;
+  parse(argc, argv, o);
+
+  if (o.RefVCF != "Empty") {
+    error("--RefVCF (SVD panel construction) is not part of this engine; build the panel with the reference tool");
+  }
+  if (o.SVDPrefix == "Empty") {  // main.cpp:214-231
+    if (o.UDPath == "Empty") error("--UDPath is required when --RefVCF is absent");
+    if (o.MeanPath == "Empty") error("--MeanPath is required when --RefVCF is absent");
+    if (o.BedPath == "Empty") error("--BedPath is required when --RefVCF is absent");
+  } else {
+    o.UDPath = o.SVDPrefix + ".UD";
+    o.MeanPath = o.SVDPrefix + ".mu";
+    o.BedPath = o.SVDPrefix + ".bed";
+  }
+  std::string PCPath = o.UDPath.substr(0, o.UDPath.size() - 3) + ".V";
+  if (o.RefPath == "Empty") error("--Reference is required");  // main.cpp:263-266
+  if (o.BamFile != "Empty") {
+    error("--BamFile needs htslib, which this build does not link. Produce a pileup "
+          "(samtools mpileup, or --OutputPileup of the reference) and pass it with --PileupFile");
+  } else if (o.PileupFile == "Empty") {
+    error("--BamFile or --PileupFile is required");
+  }
+  if (o.numGPU < 1) error("--NumGPU must be at least 1");
+
+  // main.cpp:283-319
+  ContaminationEstimator Estimator(o.nPC, o.BedPath.c_str(), o.nthread, o.epsilon);
+  Estimator.verbose = o.verbose;
+  Estimator.seed = o.seed;
+  Estimator.isHeter = !o.withinAncestry;
+  Estimator.isSanityCheckDisabled = o.disableSanityCheck;
+  Estimator.numGPU = o.numGPU;
+  Estimator.firstDevice = o.device;
+  Estimator.panelFp64 = o.panelFp64;
+  if (o.fixPC != "Empty") {
+    notice("you specified --fixPC, this will overide dynamic estimation of PCs");
+    notice("parsing the PCs");
+    std::stringstream ss(o.fixPC);
+    std::string token;
+    std::vector<double> tmpPC;
+    while (std::getline(ss, token, ':')) tmpPC.push_back(atof(token.c_str()));
+    if ((int)tmpPC.size() > o.nPC)
+      warning("parameter --fixPC provided larger dimension than parameter --numPC(default value 2) and hence will be truncated");
+    if ((int)tmpPC.size() < o.nPC)
+      error("parameter --fixPC provided smaller dimension than parameter --numPC(default value 2)");
+    for (int i = 0; i < o.nPC; ++i) Estimator.PC[1][i] = tmpPC[i];
+    Estimator.isPCFixed = true;
+  } else if (fabs(o.fixAlpha + 1.) > std::numeric_limits<double>::epsilon()) {
+    notice("you specified --fixAlpha, this will overide dynamic estimation of alpha");
+    Estimator.alpha = o.fixAlpha;
+    Estimator.isAlphaFixed = true;
+  }
+  if (o.knownAF != "Empty") {
+    Estimator.isAFknown = true;
+    Estimator.isPCFixed = true;
+    Estimator.isHeter = false;  // under --knownAF we assume the WithinAncestry model
+    Estimator.ReadAF(o.knownAF);
+  }
+  {
+    PhaseTimer t("Load SVD reference data");
+    Estimator.ReadSVDMatrix(o.UDPath, PCPath, o.MeanPath);
+  }
+  {
+    PhaseTimer t("Read pileup");
+    Estimator.ReadPileup(o.PileupFile);
+  }
+
+  if (o.outputPileup) {  // main.cpp:336-369
+    std::string fileName(o.outputPrefix + ".Pileup");
+    std::ofstream fout(fileName);
+    if (!fout.is_open()) error("Open file %s failed!", fileName.c_str());
+    for (auto &item : Estimator.PosVec) {
+      auto chrIt = Estimator.viewer.posIndex.find(item.first);
+      if (chrIt == Estimator.viewer.posIndex.end()) continue;
+      auto posIt = chrIt->second.find(item.second);
+      if (posIt == chrIt->second.end()) continue;
+      const int32_t b = posIt->second;
+      const size_t depth = Estimator.viewer.DepthOf(b);
+      if (depth > 0) {
+        fout << item.first << "\t" << item.second << "\t" << Estimator.ChooseBed[item.first][item.second].first << "\t"
+             << depth << "\t";
+        fout.write(Estimator.viewer.bases.data() + Estimator.viewer.infoOffset[b], (std::streamsize)depth);
+        fout << "\t";
+        fout.write(Estimator.viewer.quals.data() + Estimator.viewer.infoOffset[b], (std::streamsize)depth);
+        fout << std::endl;
+      }
+    }
+    fout.close();
+    if (!fout) error("Errors detected when writing to file %s !", fileName.c_str());
+  }
+
+  if (!o.disableSanityCheck) {  // main.cpp:371-379
+    PhaseTimer t("Marker sanity check");
+    if (Estimator.IsSanityCheckOK()) notice("Passing Marker Sanity Check...");
+    else {
+      warning("Insufficient Available markers, check input bam depth distribution in output pileup file after specifying --OutputPileup");
+      exit(EXIT_FAILURE);
+    }
+  }
+  {
+    PhaseTimer t("Optimize likelihood");
+    Estimator.OptimizeLLK(o.outputPrefix);
+  }
+  {  // vb1-compatible result, main.cpp:386-411
+    const char *headers =
+        "#SEQ_ID\tRG\tCHIP_ID\t#SNPS\t#READS\tAVG_DP\tFREEMIX\tFREELK1\tFREELK0\tFREE_RH\tFREE_RA\tCHIPMIX\tCHIPLK1\tCHIPLK0\tCHIP_RH\tCHIP_RA\tDPREF\tRDPHET\tRDPALT";
+    std::string fileName(o.outputPrefix + ".selfSM");
+    std::ofstream fout(fileName);
+    if (!fout.is_open()) error("Open file %s failed!", fileName.c_str());
+    fout << headers << std::endl;
+    fout << Estimator.viewer.SEQ_SM << "\tNA\tNA\t" << Estimator.NumMarker << "\t";
+    if (Estimator.isPileupInput) fout << "NA";
+    else fout << Estimator.viewer.numBases;
+    fout << "\t" << Estimator.viewer.avgDepth << "\t"
+         << ((Estimator.fn.globalAlpha < 0.5) ? Estimator.fn.globalAlpha : (1.f - Estimator.fn.globalAlpha)) << "\t"
+         << -Estimator.fn.llk1 << "\t" << -Estimator.fn.llk0 << "\t"
+         << "NA\tNA\t"
+         << "NA\tNA\tNA\tNA\tNA\t"
+         << "NA\tNA\tNA" << std::endl;
+    fout.close();
+    if (!fout) error("Errors detected when writing to file %s !", fileName.c_str());
+  }
+  notice("Success!");
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  fprintf(stderr, "VerifyBamID2 contamination-likelihood engine for NVIDIA B200 (sm_100a).\n");
+  fprintf(stderr, " Same model, options and outputs as VerifyBamID2 (Zhang & Kang) on the --PileupFile path.\n\n");
+  try {
+    return execute(argc, argv);
+  } catch (std::exception &e) {  // main.cpp:438-455
+    std::string errorMsg = "Exiting due to ERROR:\n\t";
+    errorMsg += e.what();
+    std::cerr << errorMsg << std::endl;
+    return -1;
+  }
+}

@@ -32,7 +32,7 @@ _STATUS = {1: "VB2_ERR_INVALID", 2: "VB2_ERR_NO_DEVICE", 3: "VB2_ERR_CUDA", 4: "
 
 # every symbol include/vb2_llk.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_create", "vb2_llk_destroy", "vb2_llk_get_info",
-               "vb2_llk_eval", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many",
+               "vb2_llk_eval", "vb2_llk_eval_begin", "vb2_llk_eval_end", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many",
                "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free",
                "vb2_llk_time_device", "vb2_llk_time_device_many", "vb2_llk_time_host")
 
@@ -110,6 +110,10 @@ def load_library() -> ctypes.CDLL:
     lib.vb2_llk_eval.restype = ctypes.c_int
     lib.vb2_llk_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
                                  ctypes.POINTER(ctypes.c_double)]
+    lib.vb2_llk_eval_begin.restype = ctypes.c_int
+    lib.vb2_llk_eval_begin.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double]
+    lib.vb2_llk_eval_end.restype = ctypes.c_int
+    lib.vb2_llk_eval_end.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
     for name in ("vb2_llk_eval_batch", "vb2_llk_eval_batch_device"):
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
@@ -252,6 +256,18 @@ class LLKEngine:
             raise ValueError("PC vectors must have n_pc=%d entries" % self.n_pc)
         out = ctypes.c_double()
         self._check(self._lib.vb2_llk_eval(self._ctx, a.ctypes.data, b.ctypes.data, float(alpha), ctypes.byref(out)))
+        return float(out.value)
+
+    def eval_begin(self, pc_contam: Sequence[float], pc_intended: Sequence[float], alpha: float) -> None:
+        """Launch one evaluation without waiting (see eval_end): lets one thread drive several shards."""
+        a, b = _f64(pc_contam), _f64(pc_intended)
+        if a.size != self.n_pc or b.size != self.n_pc:
+            raise ValueError("PC vectors must have n_pc=%d entries" % self.n_pc)
+        self._check(self._lib.vb2_llk_eval_begin(self._ctx, a.ctypes.data, b.ctypes.data, float(alpha)))
+
+    def eval_end(self) -> float:
+        out = ctypes.c_double()
+        self._check(self._lib.vb2_llk_eval_end(self._ctx, ctypes.byref(out)))
         return float(out.value)
 
     def eval_batch(self, pc_contam, pc_intended, alphas) -> np.ndarray:
