@@ -107,20 +107,27 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own CPU implementation on this host's cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(sample, evals: int, warmup: int, threads: int):
-    """Time `evals` evaluations of the whole workload on the CPU.  Returns (seconds, kind, reads_used)."""
+def cpu_reference_run(sample, evals: int, warmup: int, threads: int, converge: bool = False):
+    """Time `evals` evaluations of the whole workload on the CPU.  Returns (seconds, kind, reads_used, conv)
+    where conv (when asked for) compares the wall-clock to converged alpha of the C++ GPU CLI and of the
+    reference binary on the same panel + pileup text files."""
     from oracle import vb2_oracle as vo  # checker / baseline only -- never on the product path
     p = sample.problem
+    conv = None
     if vo.ref_available():
         from verifybamid_b200 import panels
         with tempfile.TemporaryDirectory() as td:
             prefix = panels.write_text_panel(sample.panel, os.path.join(td, "panel"))
             pile = sample.write_pileup(os.path.join(td, "sample.pileup"))
             recs = vo.run_ref(["--SVDPrefix", prefix, "--PileupFile", pile, "--NumPC", str(N_PC), "--NumThread",
-                               str(threads), "--NoOptimize", "--BenchEvals", str(evals), "--BenchWarmup", str(warmup),
-                               "--Output", os.path.join(td, "o")])
+                               str(threads), "--BenchEvals", str(evals), "--BenchWarmup", str(warmup),
+                               "--Output", os.path.join(td, "o")] + ([] if converge else ["--NoOptimize"]))
+            if converge:
+                conv = {"reference": converge_reference(recs, threads), "ours": converge_ours(prefix, pile, td)}
+                conv["abs_diff_alpha"] = abs(conv["ours"]["alpha"] - conv["reference"]["alpha"])
+                conv["abs_diff_pc_max"] = max(abs(a - b) for a, b in zip(conv["ours"]["pcs"], conv["reference"]["pcs"]))
         b = [r for r in recs if r["phase"] == "bench"][0]
-        return float(b["seconds"]), "reference", int(b["reads_used"])
+        return float(b["seconds"]), "reference", int(b["reads_used"]), conv
     ora = vo.Problem(p.ud, p.means, p.base_info_index, p.alt_base, p.info_offset, p.bases, p.quals, None,
                      p.sanity_disabled, p.avg_depth, p.sd_depth, threads)
     for _ in range(warmup):
@@ -128,7 +135,34 @@ def cpu_reference_run(sample, evals: int, warmup: int, threads: int):
     t0 = time.perf_counter()
     for i in range(evals):
         ora.compute_mix_llks([0.01 + 1e-6 * i] + [0.01] * (N_PC - 1), [0.01] * N_PC, 0.03)
-    return time.perf_counter() - t0, "port", ora.used_counts()[1]
+    return time.perf_counter() - t0, "port", ora.used_counts()[1], conv
+
+
+def converge_reference(recs, threads):
+    o = [r for r in recs if r["phase"] == "optimize"][0]
+    load = [r for r in recs if r["phase"] == "load"][0]
+    return {"optimize_s": o["optimize_s"], "evals": o["evals"], "threads": threads, "alpha": o["alpha"],
+            "pcs": o["pc_contam"] + o["pc_intended"], "read_panel_s": load["panel_s"], "read_pileup_s": load["pileup_s"]}
+
+
+def converge_ours(prefix, pile, td):
+    """Wall-clock to converged alpha through the product CLI (C++ host + GPU engine)."""
+    import re
+    from verifybamid_b200 import host
+    out = os.path.join(td, "gpu")
+    t0 = time.perf_counter()
+    cp = subprocess.run([host.CLI_PATH, "--SVDPrefix", prefix, "--PileupFile", pile, "--Reference", "x", "--NumPC",
+                         str(N_PC), "--Output", out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, check=True)
+    wall = time.perf_counter() - t0
+    phase = dict(re.findall(r"Finished phase: (.*?)  \[([0-9.]+) seconds\]", cp.stderr))
+    m = re.search(r"Likelihood evaluations: (\d+), ([0-9.]+) ms inside the GPU engine", cp.stderr)
+    rows = [l.split("\t") for l in open(out + ".Ancestry").read().splitlines()[1:]]
+    sm = open(out + ".selfSM").read().splitlines()[1].split("\t")
+    return {"optimize_s": float(phase.get("Optimize likelihood", "nan")), "evals": int(m.group(1)),
+            "engine_ms": float(m.group(2)), "flatten_upload_s": float(phase.get("  Flatten pileup into HBM", phase.get("Flatten pileup into HBM", "nan"))),
+            "read_panel_s": float(phase.get("Load SVD reference data", "nan")), "read_pileup_s": float(phase.get("Read pileup", "nan")),
+            "process_wall_s": wall, "alpha": float(sm[6]), "pcs": [float(r[1]) for r in rows] + [float(r[2]) for r in rows],
+            "note": "alpha/PCs as printed (6 significant digits)"}
 
 
 def run_reference_arm(args):
@@ -137,7 +171,7 @@ def run_reference_arm(args):
         return
     sample = make_workload()
     threads = os.cpu_count() or 1
-    secs, kind, reads = cpu_reference_run(sample, args.steps, args.warmup, threads)
+    secs, kind, reads, _ = cpu_reference_run(sample, args.steps, args.warmup, threads)
     ms = secs / args.steps * 1e3
     value = reads / (secs / args.steps)
     cpu = {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
@@ -158,6 +192,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import verifybamid_b200 as vb
+    from verifybamid_b200.distributed import allreduce_partials
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,10 +225,10 @@ def run_ours(args):
     pc_a = np.full((1, k), 0.01); pc_b = np.full((1, k), 0.01); al = np.array([0.03])
 
     def step(i: int):
+        # rank-local kernel on this rank's marker shard, then ONE allreduce of the scalar partial
         pc_a[0, 0] = 0.01 + 1e-7 * (i % 1000)
         engines[i % copies].eval_batch_device(pc_a, pc_b, al, d_out.data_ptr())
-        if world > 1:
-            dist.all_reduce(d_out)
+        allreduce_partials(d_out)
 
     def barrier():
         torch.cuda.synchronize()
@@ -286,7 +321,7 @@ def run_ours(args):
         def e2e_step(i: int) -> float:
             host_pc[0, 0] = 0.01 + 1e-7 * (i % 1000)
             engines[i % copies].eval_batch_device(host_pc, pc_b, al, d_out.data_ptr())
-            dist.all_reduce(d_out)
+            allreduce_partials(d_out)
             host_out.copy_(d_out, non_blocking=False)
             return float(host_out[0])
         for i in range(args.warmup):
@@ -313,10 +348,11 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n_eval = 100
-        secs, kind, reads = cpu_reference_run(sample, n_eval, 3, threads)
+        secs, kind, reads, conv = cpu_reference_run(sample, n_eval, 3, threads, converge=True)
         cpu = {"value": reads / (secs / n_eval), "unit": UNIT, "cores": threads, "kind": kind,
                "sample": "%d full evaluations of the same workload (%d reads each), %d OpenMP threads; %.2f ms/eval"
-                         % (n_eval, reads, threads, secs / n_eval * 1e3)}
+                         % (n_eval, reads, threads, secs / n_eval * 1e3),
+               "wall_clock_to_converged_alpha": conv}
 
     for e in engines:
         e.close()

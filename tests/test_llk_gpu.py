@@ -211,3 +211,15 @@ def test_timing_helpers_run_the_real_kernel(sample10k):
     finally:
         for e in engines:
             e.close()
+
+
+def test_sharded_llk_single_rank_is_the_whole_sample(sample10k):
+    """verifybamid_b200.distributed.ShardedLLK with world = 1 (no process group): same bits as the plain engine."""
+    from verifybamid_b200.distributed import ShardedLLK
+    s = ShardedLLK(sample10k.problem, device=0, rank=0, world=1)
+    try:
+        with vb.LLKEngine(sample10k.problem) as eng:
+            for pt in POINTS[:3]:
+                assert s.compute_mix_llks(*pt) == eng.compute_mix_llks(*pt)
+    finally:
+        s.close()

@@ -206,45 +206,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
 llk_kernel(const __grid_constant__ LaunchArgs A) {
   extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][n_buf][buf_bytes]
   __shared__ double s_e[256];
-  __shared__ JobParams s_job;
-  __shared__ SampleDev s_sample;
-  __shared__ vb2::Round s_rounds[kMaxArgRounds];
   __shared__ double s_red[kMaxWarps];
   __shared__ __align__(8) uint64_t s_bar[kMaxWarps][2];
-  __shared__ int s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_warps = blockDim.x >> 5;
   const uint32_t job = blockIdx.y;
 
   // ---- per-CTA set-up --------------------------------------------------------------------------
-  // ARGS kernels read everything from the constant bank, so a warp can arm its own mbarrier and fire
-  // its first TMA bulk copy before the CTA-wide barrier that publishes the Phred table: the HBM
-  // latency of the blob overlaps the set-up.
+  // Sample descriptor, round table and job parameters are read in place with warp-uniform loads --
+  // from the constant bank (ARGS) or from HBM through L1 (generic) -- so a warp can arm its own
+  // mbarrier and fire its first TMA bulk copy before the single CTA-wide barrier that publishes the
+  // Phred table: the HBM latency of the blob overlaps the set-up.
   if (lane == 0) {
     mbar_init(&s_bar[warp][0], 1);
     mbar_init(&s_bar[warp][1], 1);
     mbar_fence_init();
   }
   __syncwarp();
-  if constexpr (!ARGS) {
-    if (threadIdx.x < sizeof(SampleDev) / 8) {
-      reinterpret_cast<uint64_t *>(&s_sample)[threadIdx.x] =
-          reinterpret_cast<const uint64_t *>(A.samples ? A.samples + job : &A.sample)[threadIdx.x];
-    } else if (threadIdx.x >= 64 && threadIdx.x < 64 + sizeof(JobParams) / 8) {
-      reinterpret_cast<double *>(&s_job)[threadIdx.x - 64] =
-          reinterpret_cast<const double *>(A.jobs_dev + job)[threadIdx.x - 64];
-    }
-    __syncthreads();
-    if (s_sample.n_rounds <= kMaxArgRounds && threadIdx.x < s_sample.n_rounds * (sizeof(vb2::Round) / 8))
-      reinterpret_cast<uint64_t *>(s_rounds)[threadIdx.x] =
-          reinterpret_cast<const uint64_t *>(s_sample.rounds)[threadIdx.x];
-    __syncthreads();
-  }
-  const SampleDev &S = ARGS ? A.sample : s_sample;
-  const JobParams &J = ARGS ? A.jobs[job] : s_job;
+  const SampleDev &S = (ARGS || !A.samples) ? A.sample : A.samples[job];
+  const JobParams &J = ARGS ? A.jobs[job] : A.jobs_dev[job];
+  const vb2::Round *rounds_tab = ARGS ? A.rounds : S.rounds;
   const bool active_cta = blockIdx.x < S.grid_x;  // eval_many: a sample may need fewer CTAs than the grid has
-  const bool rounds_cached = ARGS || S.n_rounds <= kMaxArgRounds;
 
   const uint32_t bin = blockIdx.x * vb2::kBinsPerCta + (warp & 3);
   const uint32_t kc = A.kc;
@@ -253,10 +236,7 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   const uint32_t n_buf = A.n_buf, buf_bytes = S.buf_bytes, off_words = S.off_words;
   uint8_t *mybuf = s_buf + (size_t)warp * n_buf * buf_bytes;
 
-  auto get_round = [&](uint32_t r) -> vb2::Round {
-    if constexpr (ARGS) return A.rounds[r];
-    else return rounds_cached ? s_rounds[r] : S.rounds[r];
-  };
+  auto get_round = [&](uint32_t r) -> vb2::Round { return rounds_tab[r]; };
   // The warp walks a sequence of (round, chunk) items; `cur` is being consumed, `nxt` is the next one
   // to fetch.  Both cursors keep their round descriptor in registers.  Warp kk = warp/4 serves the
   // rounds kk, 2kc-1-kk, 2kc+kk, 4kc-1-kk, ... (a snake over groups of kc rounds): rounds are sorted
@@ -385,30 +365,29 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   for (int o = 16; o; o >>= 1) vsum += __shfl_xor_sync(0xFFFFFFFFu, vsum, o);
   if (lane == 0) s_red[warp] = vsum;
   __syncthreads();
-  if (!active_cta) return;
+  if (!active_cta || warp != 0) return;  // warp 0 finishes alone: no other warp waits for the grid-level work
+  double cta = 0.0;
+  for (int w = 0; w < n_warps; ++w) cta += s_red[w];  // (every lane computes the same sum)
   if constexpr (HOST_REDUCE) {
-    if (threadIdx.x == 0) {
-      double cta = 0.0;
-      for (int w = 0; w < n_warps; ++w) cta += s_red[w];
+    if (lane == 0) {
       Slot *slot = A.mbox + (size_t)job * S.grid_x + blockIdx.x;
       *reinterpret_cast<ulonglong2 *>(slot) = make_ulonglong2((unsigned long long)__double_as_longlong(cta), A.seq);
     }
   } else {
     const uint32_t pslot = A.slots ? A.slots[job] : job;
-    if (threadIdx.x == 0) {
-      double cta = 0.0;
-      for (int w = 0; w < n_warps; ++w) cta += s_red[w];
-      S.partials[(size_t)pslot * S.grid_x + blockIdx.x] = cta;
+    const uint32_t grid_x = S.grid_x;
+    double *part = S.partials + (size_t)pslot * grid_x;
+    unsigned int ticket = 0;
+    if (lane == 0) {
+      part[blockIdx.x] = cta;
       __threadfence();
-      const unsigned int t = atomicAdd(S.tickets + pslot, 1u);
-      s_last = (t == S.grid_x - 1);
+      ticket = atomicAdd(S.tickets + pslot, 1u);
     }
-    __syncthreads();
-    if (s_last && warp == 0) {
+    ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+    if (ticket == grid_x - 1) {  // this CTA arrived last: add the partials in a fixed order
       __threadfence();
-      const double *part = S.partials + (size_t)pslot * S.grid_x;
       double s = 0.0;
-      for (uint32_t i = lane; i < S.grid_x; i += 32) s += __ldcg(part + i);
+      for (uint32_t i = lane; i < grid_x; i += 32) s += __ldcg(part + i);
 #pragma unroll
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
       if (lane == 0) {
@@ -576,7 +555,7 @@ Geometry geometry(const vb2_llk_ctx *ctx, bool throughput) {
   g.kc = std::max(1u, S.conc_rounds);
   g.n_buf = S.n_buf;
   if (throughput && g.kc > 1) {
-    g.kc = (g.kc + 1) / 2;
+    g.kc = 1;  // measured on B200: 4-warp CTAs (six co-resident per SM), every warp walks all its rounds
     if (const char *t = getenv("VB2_LLK_TPUT_KC")) g.kc = (uint32_t)std::min<int>(std::max(1, atoi(t)), (int)S.conc_rounds);
     g.n_buf = g.kc < S.n_rounds || S.n_buf == 2 ? 2u : 1u;
   }
