@@ -163,6 +163,11 @@ int vb2_llk_eval_batch_device(vb2_llk_ctx *ctx, int n, const double *pc_contam, 
 int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
                       const double *alphas, double *llk_out);
 
+/* Same, asynchronous, results left in DEVICE memory (d_llk_out[n], on ctxs[0]'s stream): the marker-shard
+ * partial sums of n evaluations ready for ONE all-reduce.                                        */
+int vb2_llk_eval_many_device(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
+                             const double *alphas, double *d_llk_out);
+
 /* Block until everything queued on the context's stream has finished. */
 int vb2_llk_sync(vb2_llk_ctx *ctx);
 

@@ -491,6 +491,14 @@ void fill_job(JobParams *J, uint32_t n_pc, const double *pc1, const double *pc2,
   }
 }
 
+// Pinned + device staging for parameter sets that do not fit in the kernel arguments (allocated on first use).
+int ensure_job_staging(vb2_llk_ctx *ctx) {
+  if (ctx->h_jobs) return VB2_OK;
+  VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_jobs, sizeof(JobParams) * VB2_MAX_BATCH, cudaHostAllocDefault));
+  VB2_CUDA(ctx, cudaMalloc(&ctx->d_jobs, sizeof(JobParams) * VB2_MAX_BATCH));
+  return VB2_OK;
+}
+
 // Device-side reduction scratch: one row of grid_x partials + one ticket per concurrent job.
 int ensure_slots(vb2_llk_ctx *ctx, uint32_t need) {
   if (need <= ctx->slots) return VB2_OK;
@@ -597,6 +605,8 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
     for (int j = 0; j < n; ++j) fill_job(&A.jobs[j], k, pc1 + (size_t)j * k, pc2 + (size_t)j * k, alphas[j]);
   } else {
     // the pinned staging buffer may still be read by the previous batch's copy
+    int rcs = ensure_job_staging(ctx);
+    if (rcs) return rcs;
     VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int j = 0; j < n; ++j) fill_job(&ctx->h_jobs[j], k, pc1 + (size_t)j * k, pc2 + (size_t)j * k, alphas[j]);
     VB2_CUDA(ctx, cudaMemcpyAsync(ctx->d_jobs, ctx->h_jobs, (size_t)n * sizeof(JobParams), cudaMemcpyHostToDevice,
@@ -748,8 +758,6 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_mbox, sizeof(Slot) * ctx->mbox_slots, cudaHostAllocMapped));
   memset(ctx->h_mbox, 0, sizeof(Slot) * ctx->mbox_slots);
   VB2_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->d_mbox, ctx->h_mbox, 0));
-  VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_jobs, sizeof(JobParams) * VB2_MAX_BATCH, cudaHostAllocDefault));
-  VB2_CUDA(ctx, cudaMalloc(&ctx->d_jobs, sizeof(JobParams) * VB2_MAX_BATCH));
   VB2_CUDA(ctx, cudaMalloc(&ctx->d_out, sizeof(double) * VB2_MAX_BATCH));
   VB2_CUDA(ctx, cudaMalloc(&ctx->d_sample, sizeof(SampleDev)));
   if ((rc = ensure_slots(ctx, 8))) return rc;
@@ -898,6 +906,10 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
     VB2_CUDA(lead, cudaHostAlloc((void **)&lead->h_slots, sizeof(uint32_t) * VB2_MAX_BATCH, cudaHostAllocDefault));
     VB2_CUDA(lead, cudaMalloc(&lead->d_slots, sizeof(uint32_t) * VB2_MAX_BATCH));
   }
+  {
+    int rcs = ensure_job_staging(lead);
+    if (rcs) return rcs;
+  }
   VB2_CUDA(lead, cudaStreamSynchronize(lead->stream));  // staging buffers are free again
   const uint32_t k = lead->S.n_pc;
   // slot of job j inside its sample = number of earlier jobs on the same context
@@ -942,7 +954,7 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
 }
 
 // eval_many, step 2: one launch over whatever stage_many staged last (generic kernel, device reduction).
-static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq_out) {
+static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq_out, double *d_out = nullptr) {
   if (!lead->many_n) return set_err(lead, VB2_ERR_INVALID, "internal: nothing staged");
   LaunchArgs A;
   memset(&A, 0, sizeof(A));
@@ -950,7 +962,7 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
   A.slots = lead->d_slots;
   A.jobs_dev = lead->d_jobs;
   A.n_jobs = lead->many_n;
-  A.d_out = lead->d_out;
+  A.d_out = d_out ? d_out : lead->d_out;
   A.kc = lead->many_kc;
   A.n_buf = 2;
   if (to_mailbox) {
@@ -980,6 +992,20 @@ int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
   if ((rc = wait_mailbox(lead, (uint32_t)n, seq))) return rc;
   for (int j = 0; j < n; ++j) llk_out[j] = lead->h_mbox[j].val;
   return VB2_OK;
+}
+
+int vb2_llk_eval_many_device(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
+                             const double *alphas, double *d_llk_out) {
+  if (!d_llk_out) return set_err(ctxs && n > 0 ? ctxs[0] : nullptr, VB2_ERR_INVALID, "null device output pointer");
+  bool nothing = false;
+  int rc = stage_many(ctxs, n, pc_contam, pc_intended, alphas, &nothing);
+  if (rc) return rc;
+  vb2_llk_ctx *lead = ctxs[0];
+  if (nothing) {
+    VB2_CUDA(lead, cudaMemsetAsync(d_llk_out, 0, sizeof(double) * n, lead->stream));
+    return VB2_OK;
+  }
+  return fire_many(lead, false, nullptr, d_llk_out);
 }
 
 int vb2_llk_time_device_many(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup_launches, int launches,

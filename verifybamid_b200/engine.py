@@ -32,7 +32,7 @@ _STATUS = {1: "VB2_ERR_INVALID", 2: "VB2_ERR_NO_DEVICE", 3: "VB2_ERR_CUDA", 4: "
 
 # every symbol include/vb2_llk.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_create", "vb2_llk_destroy", "vb2_llk_get_info",
-               "vb2_llk_eval", "vb2_llk_eval_begin", "vb2_llk_eval_end", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many",
+               "vb2_llk_eval", "vb2_llk_eval_begin", "vb2_llk_eval_end", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many", "vb2_llk_eval_many_device",
                "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free",
                "vb2_llk_time_device", "vb2_llk_time_device_many", "vb2_llk_time_host")
 
@@ -121,6 +121,8 @@ def load_library() -> ctypes.CDLL:
     lib.vb2_llk_eval_many.restype = ctypes.c_int
     lib.vb2_llk_eval_many.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_void_p]
+    lib.vb2_llk_eval_many_device.restype = ctypes.c_int
+    lib.vb2_llk_eval_many_device.argtypes = lib.vb2_llk_eval_many.argtypes
     lib.vb2_llk_sync.restype = ctypes.c_int
     lib.vb2_llk_sync.argtypes = [ctypes.c_void_p]
     lib.vb2_llk_time_device.restype = ctypes.c_int
@@ -310,6 +312,19 @@ def eval_many(engines: List[LLKEngine], pc_contam, pc_intended, alphas) -> np.nd
     if rc != VB2_OK:
         raise VB2Error(rc, lib.vb2_last_error(engines[0]._ctx).decode())
     return out
+
+
+def eval_many_device(engines: List[LLKEngine], pc_contam, pc_intended, alphas, d_out_ptr: int) -> None:
+    """Asynchronous eval_many: results stay in device memory at `d_out_ptr` (len(engines) doubles)."""
+    n = len(engines)
+    k = engines[0].n_pc
+    al = _f64(alphas).ravel()
+    a, b = _f64(pc_contam, (n, k)), _f64(pc_intended, (n, k))
+    arr = (ctypes.c_void_p * n)(*[e._ctx for e in engines])
+    lib = load_library()
+    rc = lib.vb2_llk_eval_many_device(arr, n, a.ctypes.data, b.ctypes.data, al.ctypes.data, ctypes.c_void_p(d_out_ptr))
+    if rc != VB2_OK:
+        raise VB2Error(rc, lib.vb2_last_error(engines[0]._ctx).decode())
 
 
 def time_device(engines: List[LLKEngine], warmup: int, steps: int, pc_contam, pc_intended, alpha: float) -> float:
