@@ -217,6 +217,10 @@ def run_ours(args):
     info = probe.info()
     copies = max(2, int(np.ceil(2.0 * L2_BYTES / max(1, info["device_bytes"]))))
     copies = min(copies, 256)
+    if world > 1:                               # shards differ slightly in size: every rank must agree
+        c = torch.tensor([copies], dtype=torch.int64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX)
+        copies = int(c.item())
     engines = [probe] + [vb.LLKEngine(p, device=local, shard_rank=rank, shard_count=world, stream=stream.cuda_stream)
                          for _ in range(copies - 1)]
     reads_total = p.used_counts()[1]           # whole sample, all shards

@@ -626,12 +626,13 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
   return VB2_OK;
 }
 
-int init_device_tables(vb2_llk_ctx *ctx) {
+// Phred table + kernel attributes of the CURRENT device (idempotent; the stream may be the default one).
+int init_device_tables(vb2_llk_ctx *ctx, cudaStream_t stream) {
   double phred[256];
   vb2::build_phred_table(phred);
   for (int q = vb2::kNumQual; q < 256; ++q) phred[q] = 1.0;
-  VB2_CUDA(ctx, cudaMemcpyToSymbolAsync(g_phred, phred, sizeof(phred), 0, cudaMemcpyHostToDevice, ctx->stream));
-  VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  VB2_CUDA(ctx, cudaMemcpyToSymbolAsync(g_phred, phred, sizeof(phred), 0, cudaMemcpyHostToDevice, stream));
+  VB2_CUDA(ctx, cudaStreamSynchronize(stream));
   const int smem_max = 200 * 1024;
   VB2_CUDA(ctx, cudaFuncSetAttribute(llk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   VB2_CUDA(ctx, cudaFuncSetAttribute(llk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
@@ -655,6 +656,18 @@ int vb2_device_count(void) {
     return 0;
   }
   return n;
+}
+
+int vb2_llk_warmup(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_err(nullptr, VB2_ERR_NO_DEVICE, "no CUDA device available (this engine has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return set_err(nullptr, VB2_ERR_NO_DEVICE, "device out of range");
+  VB2_CUDA(nullptr, cudaSetDevice(device));
+  VB2_CUDA(nullptr, cudaFree(0));  // context creation
+  return init_device_tables(nullptr, cudaStreamPerThread);  // module load
 }
 
 const char *vb2_last_error(const vb2_llk_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
@@ -701,7 +714,7 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   }
   ctx->spin = !(desc->flags & VB2_FLAG_NO_SPIN);
   if (const char *t = getenv("VB2_LLK_SPIN_TIMEOUT_MS")) ctx->spin_timeout_ms = atof(t);
-  int rc = init_device_tables(ctx);
+  int rc = init_device_tables(ctx, ctx->stream);
   if (rc) return rc;
 
   // ---- flatten on the host ----------------------------------------------------------------------

@@ -5,7 +5,11 @@
 #include <cctype>
 #include <cmath>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
+#include <thread>
 
 namespace vb2 {
 
@@ -29,6 +33,23 @@ inline int clamp_qual(char qc) {
   if (q < 0) q = 0;
   else if (q > 93) q = 93;
   return q;
+}
+
+// Run fn(begin, end, chunk) over [0, n) on up to 8 host threads; chunk boundaries depend only on n and the
+// thread count, and every caller combines per-chunk results in chunk order, so the output is deterministic.
+template <typename F>
+void parallel_chunks(size_t n, unsigned n_threads, F fn, size_t min_n = 4096) {
+  if (n_threads <= 1 || n < min_n) {
+    fn((size_t)0, n, 0u);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t per = (n + n_threads - 1) / n_threads;
+  for (unsigned t = 0; t < n_threads; ++t) {
+    const size_t b = std::min(n, (size_t)t * per), e = std::min(n, b + per);
+    pool.emplace_back([=, &fn]() { fn(b, e, t); });
+  }
+  for (auto &th : pool) th.join();
 }
 
 struct MarkerTmp {
@@ -66,6 +87,14 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
   PackedSample &P = *out;
   P = PackedSample();
   P.n_pc = d.n_pc;
+  const bool timing = getenv("VB2_LLK_PACK_TIMING") != nullptr;
+  auto tick = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "pack: %-28s %.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+    tick = now;
+  };
   P.known_af = d.known_af != nullptr;
 
   // Per-(class, q, g) single-read emission A_bc[g] = E[g]*e + N[g]*(1-e)
@@ -83,44 +112,58 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
   }
 
   // ---- 1. skip rules (h:238-249) and per-marker class counts ---------------------------------
+  unsigned n_threads = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  if (const char *t = getenv("VB2_LLK_PACK_THREADS")) n_threads = (unsigned)std::max(1, atoi(t));
+  std::vector<std::vector<MarkerTmp>> used_parts(n_threads);
+  std::vector<const char *> part_err(n_threads, nullptr);
+  parallel_chunks(d.n_marker, n_threads, [&](size_t i0, size_t i1, unsigned t) {
+    std::vector<MarkerTmp> &mine = used_parts[t];
+    mine.reserve(i1 - i0);
+    for (size_t i = i0; i < i1; ++i) {
+      const int32_t idx = d.base_info_index[i];
+      if (idx < 0) continue;
+      const int64_t beg = d.info_offset[idx], end = d.info_offset[idx + 1];
+      if (end < beg) { part_err[t] = "info_offset is not non-decreasing"; return; }
+      const size_t size = (size_t)(end - beg);
+      if (size == 0) continue;
+      if (!d.sanity_disabled &&
+          (size < (d.avg_depth - 3 * d.sd_depth) || size > (d.avg_depth + 3 * d.sd_depth)))
+        continue;
+      if (!d.bases || !d.quals) { part_err[t] = "null bases/quals with non-empty markers"; return; }
+      MarkerTmp m{(uint32_t)i, beg, end, 0, 0};
+      const char alt = d.alt_base[i];
+      for (int64_t j = beg; j < end; ++j) {
+        const int bc = classify_base(d.bases[j], alt);
+        if (bc == 0) ++m.n_ref;
+        else if (bc == 1) ++m.n_alt;
+      }
+      mine.push_back(m);
+    }
+  });
+  for (const char *e : part_err)
+    if (e) return fail(e);
   std::vector<MarkerTmp> used;
   used.reserve(d.n_marker);
-  for (uint32_t i = 0; i < d.n_marker; ++i) {
-    const int32_t idx = d.base_info_index[i];
-    if (idx < 0) continue;
-    const int64_t beg = d.info_offset[idx], end = d.info_offset[idx + 1];
-    if (end < beg) return fail("info_offset is not non-decreasing");
-    const size_t size = (size_t)(end - beg);
-    if (size == 0) continue;
-    if (!d.sanity_disabled &&
-        (size < (d.avg_depth - 3 * d.sd_depth) || size > (d.avg_depth + 3 * d.sd_depth)))
-      continue;
-    if (!d.bases || !d.quals) return fail("null bases/quals with non-empty markers");
-    MarkerTmp m{i, beg, end, 0, 0};
-    const char alt = d.alt_base[i];
-    for (int64_t j = beg; j < end; ++j) {
-      const int bc = classify_base(d.bases[j], alt);
-      if (bc == 0) ++m.n_ref;
-      else if (bc == 1) ++m.n_alt;
-    }
-    used.push_back(m);
-  }
+  for (auto &part : used_parts) used.insert(used.end(), part.begin(), part.end());
+  used_parts.clear();
 
+  lap("1 skip rules + class counts");
   // ---- 2. order markers so that the 32 lanes of a warp run the same trip counts --------------
   // A warp executes max(ref words) + max(alt words) over its lanes, so markers are grouped by alt
   // words and, inside a group, ordered by ref words -- alternating direction from group to group so
   // that the slice straddling a group boundary mixes similar ref depths.
   auto words_of = [](uint32_t n) { return (n + kReadsPerWord - 1) / kReadsPerWord; };
+  // one key per marker: alt words (descending), then ref words (descending, or ascending in odd alt
+  // groups); ties keep panel order because `used` is in panel order and the sort is stable
+  std::vector<uint64_t> keys(used.size());
+  for (size_t u = 0; u < used.size(); ++u) {
+    const uint64_t wa = words_of(used[u].n_alt), wr = words_of(used[u].n_ref);
+    keys[u] = ((0xFFFFFull - wa) << 24) | ((wa & 1u) ? wr : 0xFFFFFull - wr);
+  }
   std::vector<uint32_t> order(used.size());
   std::iota(order.begin(), order.end(), 0u);
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-    const uint32_t wa_a = words_of(used[a].n_alt), wa_b = words_of(used[b].n_alt);
-    if (wa_a != wa_b) return wa_a > wa_b;
-    const uint32_t wr_a = words_of(used[a].n_ref), wr_b = words_of(used[b].n_ref);
-    if (wr_a != wr_b) return (wa_a & 1u) ? wr_a < wr_b : wr_a > wr_b;
-    return used[a].panel_row < used[b].panel_row;
-  });
-
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+  lap("2 sort markers");
   // ---- 3. cut into 32-marker slices, heaviest first; slice s belongs to shard s % shard_count ----
   const size_t total_slices = (order.size() + kSliceMarkers - 1) / kSliceMarkers;
   struct SliceGeom { uint32_t wr, wa; size_t first; };
@@ -142,6 +185,7 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
   P.n_slices = (uint32_t)geom.size();
   P.marker_index.assign((size_t)P.n_slices * kSliceMarkers, 0xFFFFFFFFu);
 
+  lap("3 slices");
   // ---- 4. blob layout ------------------------------------------------------------------------------
   BlobLayout &L = P.layout;
   L.panel_elem = cfg.panel_fp64 ? 8u : 4u;
@@ -176,9 +220,13 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
   P.conc_rounds = std::max(1u, std::min((uint32_t)P.rounds.size(), kMaxConcRounds));
   P.blob.assign((size_t)total_bytes, 0xFF);  // 0xFF = pad byte everywhere a read is not written
 
+  lap("4-5 layout, rounds, alloc");
   // ---- 6. fill ------------------------------------------------------------------------------------
-  long double other_sum = 0.0L;
-  for (uint32_t j = 0; j < P.n_slices; ++j) {
+  struct SliceTotals { long double other = 0.0L; uint64_t used = 0, streamed = 0, folded = 0; uint32_t markers = 0; };
+  std::vector<SliceTotals> totals(P.n_slices);
+  parallel_chunks(P.n_slices, n_threads, [&](size_t j0, size_t j1, unsigned) {
+  for (uint32_t j = (uint32_t)j0; j < (uint32_t)j1; ++j) {
+    SliceTotals &T = totals[j];
     const Round &R = P.rounds[j / P.n_bins];
     const uint32_t bin = bin_of(P.n_slices, P.n_bins, j);
     uint8_t *blob = P.blob.data() + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
@@ -227,8 +275,8 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
         const int bc = classify_base(d.bases[jj], alt);
         const int q = clamp_qual(d.quals[jj]);
         if (bc == 2) {
-          other_sum += (long double)log_other[q];
-          ++P.reads_folded;
+          T.other += (long double)log_other[q];
+          ++T.folded;
           continue;
         }
         uint32_t r, t0;
@@ -236,16 +284,23 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
         else         { r = ia++; t0 = wr; for (int g = 0; g < 3; ++g) dg[g] *= a_alt[q][g]; }
         // row t = t0 + r/4 of lane l; little-endian: byte b of the word = bits 8b..8b+7
         wbytes[((size_t)(t0 + r / kReadsPerWord) * kSliceMarkers + l) * 4 + (r % kReadsPerWord)] = (uint8_t)q;
-        ++P.reads_streamed;
+        ++T.streamed;
       }
       for (int g = 0; g < 3; ++g) reinterpret_cast<double *>(blob + L.off_diag)[g * kSliceMarkers + l] = dg[g];
-      P.reads_used += (uint64_t)(m.end - m.beg);
-      ++P.n_used;
+      T.used += (uint64_t)(m.end - m.beg);
+      ++T.markers;
     }
     uint32_t hdr[4] = {wr, wa, n_valid, full_ref | (full_alt << 16)};
     std::memcpy(blob, hdr, sizeof(hdr));
   }
+  }, 64);
+  long double other_sum = 0.0L;
+  for (const SliceTotals &T : totals) {  // slice order: the same sum whatever the thread count
+    other_sum += T.other;
+    P.reads_used += T.used; P.reads_streamed += T.streamed; P.reads_folded += T.folded; P.n_used += T.markers;
+  }
   P.log_other_const = (double)other_sum;
+  lap("6 fill blobs");
   return VB2_OK;
 }
 

@@ -15,6 +15,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "estimator.h"
@@ -137,6 +138,15 @@ int execute(int argc, char **argv) {
   }
   if (o.numGPU < 1) error("--NumGPU must be at least 1");
 
+  // CUDA context creation and kernel loading take 0.3-0.5 s in a fresh process: do them on helper threads
+  // while this thread reads the panel and the pileup.  Failures are reported when the engine is created.
+  std::vector<std::thread> warm;
+  for (int g = 0; g < o.numGPU; ++g) warm.emplace_back([=]() { vb2_llk_warmup(o.device + g); });
+  struct Joiner {
+    std::vector<std::thread> &t;
+    ~Joiner() { for (auto &x : t) if (x.joinable()) x.join(); }
+  } joiner{warm};
+
   // main.cpp:283-319
   ContaminationEstimator Estimator(o.nPC, o.BedPath.c_str(), o.nthread, o.epsilon);
   Estimator.verbose = o.verbose;
@@ -211,6 +221,7 @@ int execute(int argc, char **argv) {
       exit(EXIT_FAILURE);
     }
   }
+  for (auto &x : warm) x.join();
   {
     PhaseTimer t("Optimize likelihood");
     Estimator.OptimizeLLK(o.outputPrefix);

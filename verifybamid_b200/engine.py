@@ -31,7 +31,7 @@ VB2_MAX_BATCH = 4096
 _STATUS = {1: "VB2_ERR_INVALID", 2: "VB2_ERR_NO_DEVICE", 3: "VB2_ERR_CUDA", 4: "VB2_ERR_NOMEM", 5: "VB2_ERR_TIMEOUT"}
 
 # every symbol include/vb2_llk.h declares (tests check the library exports exactly these)
-ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_create", "vb2_llk_destroy", "vb2_llk_get_info",
+ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_warmup", "vb2_llk_create", "vb2_llk_destroy", "vb2_llk_get_info",
                "vb2_llk_eval", "vb2_llk_eval_begin", "vb2_llk_eval_end", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many", "vb2_llk_eval_many_device",
                "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free",
                "vb2_llk_time_device", "vb2_llk_time_device_many", "vb2_llk_time_host")
