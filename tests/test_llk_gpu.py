@@ -223,3 +223,44 @@ def test_sharded_llk_single_rank_is_the_whole_sample(sample10k):
                 assert s.compute_mix_llks(*pt) == eng.compute_mix_llks(*pt)
     finally:
         s.close()
+
+
+def test_abi_misuse_is_reported_not_crashed(sample10k):
+    import ctypes
+    lib = vb.load_library()
+    with vb.LLKEngine(sample10k.problem) as eng:
+        out = ctypes.c_double()
+        assert lib.vb2_llk_eval_end(eng._ctx, ctypes.byref(out)) == 1          # nothing pending
+        eng.eval_begin([0.01, 0.01], [0.01, 0.01], 0.03)
+        with pytest.raises(vb.VB2Error):
+            eng.eval_begin([0.01, 0.01], [0.01, 0.01], 0.03)                   # one evaluation per context at a time
+        assert eng.eval_end() == eng.compute_mix_llks([0.01, 0.01], [0.01, 0.01], 0.03)
+        with pytest.raises(vb.VB2Error):
+            eng.eval_batch(np.zeros((0, 2)), np.zeros((0, 2)), np.zeros(0))    # empty batch
+        assert b"pending" in lib.vb2_last_error(eng._ctx) or b"batch" in lib.vb2_last_error(eng._ctx)
+    with pytest.raises(vb.VB2Error) as ei:
+        vb.LLKEngine(sample10k.problem, device=99)
+    assert ei.value.code == 2
+    with pytest.raises(vb.VB2Error):
+        vb.LLKEngine(sample10k.problem, shard_rank=3, shard_count=2)
+
+
+def test_sixteen_pcs_and_multi_chunk_stage():
+    """VB2_MAX_PC principal components: the fixed part of a blob grows, so even 30x reads need several stages."""
+    rng = np.random.default_rng(12)
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    s = synth.make_sample(panel, n_pc=4, depth=30.0, alpha=0.03, seed=2, n_markers=4000)
+    p = s.problem
+    ud16 = np.concatenate([p.ud, rng.normal(0, 1.0, (p.n_marker, 12))], axis=1)
+    q = vb.PileupProblem(ud16, p.means, p.base_info_index, p.alt_base, p.info_offset, p.bases, p.quals, None,
+                         p.sanity_disabled, p.avg_depth, p.sd_depth)
+    ora = to_oracle(q)
+    pc1 = rng.normal(0, 0.01, 16); pc2 = rng.normal(0, 0.01, 16)
+    with vb.LLKEngine(q, panel_dtype=vb.VB2_PANEL_FP64) as eng:
+        for a in (0.02, 0.4):
+            assert rel(eng.compute_mix_llks(pc1, pc2, a), ora.compute_mix_llks(pc1, pc2, a)) <= REL_FP64
+        two = eng.eval_batch(np.stack([pc1, pc2]), np.stack([pc2, pc1]), np.array([0.02, 0.4]))
+        assert two[0] == eng.compute_mix_llks(pc1, pc2, 0.02) and two[1] == eng.compute_mix_llks(pc2, pc1, 0.4)
+    with pytest.raises(vb.VB2Error):
+        vb.LLKEngine(vb.PileupProblem(np.zeros((p.n_marker, 17)), p.means, p.base_info_index, p.alt_base, p.info_offset,
+                                      p.bases, p.quals))
