@@ -211,7 +211,8 @@ typedef struct vb2_packed_view {
   double log_other_const;
   const uint8_t *blob;          /* [blob_bytes]; bin b's blob of round r at
                                    base_r + (b - first_bin_r) * stride_r;
-                                   16-byte header = u32 ref_rows, alt_rows, n_valid,
+                                   16-byte header = u32 ref_rows, alt_rows,
+                                   n_valid | tail_ref << 8 | tail_alt << 12,
                                    full_ref_rows | full_alt_rows << 16                       */
   const uint32_t *rounds;       /* [n_rounds][6]: base lo, base hi, stride, first_bin, count, rows */
   const uint32_t *marker_index; /* [n_slices*32] panel row per (slice, lane), 0xFFFFFFFF pad;

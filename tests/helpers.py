@@ -87,7 +87,8 @@ def emulate_packed_llk(pk: dict, pc1, pc2, alpha: float, min_af=5e-5, max_af=0.9
         af = np.clip(af, min_af, max_af)
         return np.stack([(1 - af) * (1 - af), 2 * af * (1 - af), af * af])
     for _, _, blob in iter_blobs(pk):
-        wr, wa, n_valid, full = blob[:16].view(np.uint32)
+        wr, wa, nv_tails, full = blob[:16].view(np.uint32)
+        n_valid, tail_ref, tail_alt = int(nv_tails) & 0xFF, (int(nv_tails) >> 8) & 0xF, (int(nv_tails) >> 12) & 0xF
         if pk["known_af"]:
             af1 = af2 = blob[pk["off_kaf"]:pk["off_kaf"] + 256].view(np.float64)
         else:
@@ -102,6 +103,11 @@ def emulate_packed_llk(pk: dict, pc1, pc2, alpha: float, min_af=5e-5, max_af=0.9
         fr, fa = int(full) & 0xFFFF, int(full) >> 16
         assert fr <= wr and fa <= wa
         assert not (byts[:fr, :n_valid] == 0xFF).any() and not (byts[wr:wr + fa, :n_valid] == 0xFF).any()
+        # ... and a uniform tail holds exactly tail_x reads (then fillers) in the row after the full rows, in every valid lane
+        for tail, row in ((tail_ref, fr), (tail_alt, wr + fa)):
+            if tail:
+                assert 1 <= tail <= 3 and row == (wr - 1 if row == fr else wr + wa - 1)
+                assert not (byts[row, :n_valid, :tail] == 0xFF).any() and (byts[row, :n_valid, tail:] == 0xFF).all()
         acc = np.ones((6, 32))
         for sect, lo, hi in (("ref", 0, wr), ("alt", wr, wr + wa)):
             q = byts[lo:hi].transpose(1, 0, 2).reshape(32, -1)      # [lane, reads]

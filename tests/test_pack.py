@@ -26,7 +26,8 @@ def test_pack_counts_and_layout():
     # padding lanes are marked and carry no reads
     assert (pk["marker_index"][13:] == 0xFFFFFFFF).all()
     (_, _, blob), = list(iter_blobs(pk))
-    wr, wa, n_valid, _ = blob[:16].view(np.uint32)
+    wr, wa, nv, _ = blob[:16].view(np.uint32)
+    n_valid = int(nv) & 0xFF
     assert n_valid == 13 and blob.size == pk["off_words"] + (wr + wa) * 128 == pk["rounds"][0]["stride"]
     byts = blob[pk["off_words"]:]
     assert ((byts <= 93) | (byts == 0xFF)).all()

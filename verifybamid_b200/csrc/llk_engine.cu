@@ -142,6 +142,30 @@ __device__ __forceinline__ void eat_word_full(uint32_t w, const double *s_e, con
   }
 }
 
+// The ragged last word of a run when every lane holds the same number n (1..3) of reads in it: the
+// first n bytes are reads in all lanes, so no byte has to be inspected.
+template <bool ALT>
+__device__ __forceinline__ void eat_word_tail(uint32_t w, uint32_t n, const double *s_e, const double (&c0)[kNumPairs],
+                                              const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
+  const double e0 = s_e[w & 0xFFu];
+  if (n == 1) {
+#pragma unroll
+    for (int p = 0; p < kNumPairs; ++p) acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(c1[p], e0, c0[p]);
+    return;
+  }
+  const double e1 = s_e[(w >> 8) & 0xFFu];
+  if (n == 2) {
+#pragma unroll
+    for (int p = 0; p < kNumPairs; ++p)
+      acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(c1[p], e0, c0[p]) * fma(c1[p], e1, c0[p]);
+    return;
+  }
+  const double e2 = s_e[(w >> 16) & 0xFFu];
+#pragma unroll
+  for (int p = 0; p < kNumPairs; ++p)
+    acc[ALT ? (kNumPairs - 1 - p) : p] *= (fma(c1[p], e0, c0[p]) * fma(c1[p], e1, c0[p])) * fma(c1[p], e2, c0[p]);
+}
+
 // A word that may carry 0xFF filler bytes (the last word of a lane's ref or alt section).
 template <bool ALT>
 __device__ __forceinline__ void eat_word_checked(uint32_t w, const double *s_e, const double (&c0)[kNumPairs],
@@ -157,14 +181,19 @@ __device__ __forceinline__ void eat_word_checked(uint32_t w, const double *s_e, 
   }
 }
 
-// n_full rows in which every lane holds four real reads, then n_ragged rows that may hold fillers.
+// n_full rows in which every lane holds four real reads, then n_ragged rows that may hold fillers; when
+// `tail` is 1..3 the (single) ragged row holds exactly that many reads in every lane.
 template <bool ALT>
-__device__ __forceinline__ void eat_rows(const uint32_t *rows, uint32_t n_full, uint32_t n_ragged, const double *s_e,
-                                         const double (&c0)[kNumPairs], const double (&c1)[kNumPairs],
-                                         double (&acc)[kNumPairs]) {
+__device__ __forceinline__ void eat_rows(const uint32_t *rows, uint32_t n_full, uint32_t n_ragged, uint32_t tail,
+                                         const double *s_e, const double (&c0)[kNumPairs],
+                                         const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
   uint32_t t = 0;
 #pragma unroll 1
   for (; t < n_full; ++t) eat_word_full<ALT>(rows[t * 32], s_e, c0, c1, acc);
+  if (tail && n_ragged == 1) {
+    eat_word_tail<ALT>(rows[t * 32], tail, s_e, c0, c1, acc);
+    return;
+  }
 #pragma unroll 1
   for (; t < n_full + n_ragged; ++t) eat_word_checked<ALT>(rows[t * 32], s_e, c0, c1, acc);
 }
@@ -301,7 +330,7 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
       c1[p] = J.c1[p];
     }
     double acc[kNumPairs], ldiag = 0.;
-    uint32_t wr = 0, wa = 0, n_valid = 0, fr = 0, fa = 0;
+    uint32_t wr = 0, wa = 0, n_valid = 0, fr = 0, fa = 0, tails = 0;
     while (cur.r < n_rounds) {
       if (n_buf == 2 && nxt.r < n_rounds) {
         __syncwarp();  // every lane finished reading the buffer about to be overwritten
@@ -315,7 +344,7 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
       if (cur.c == 0) {
         // ---- (i) header, allele frequencies, genotype priors, diagonal pairs ----------------------
         const uint4 hdr = *reinterpret_cast<const uint4 *>(buf);
-        wr = hdr.x; wa = hdr.y; n_valid = hdr.z; fr = hdr.w & 0xFFFFu; fa = hdr.w >> 16;
+        wr = hdr.x; wa = hdr.y; n_valid = hdr.z & 0xFFu; tails = hdr.z >> 8; fr = hdr.w & 0xFFFFu; fa = hdr.w >> 16;
         double af1, af2;
         if (S.known_af) {
           af1 = af2 = reinterpret_cast<const double *>(buf + S.off_kaf)[lane];  // h:251-252
@@ -344,8 +373,10 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
         auto clampu = [&](uint32_t x) { return x < t_lo ? t_lo : (x > t_hi ? t_hi : x); };
         const uint32_t a0 = clampu(fr), a1 = clampu(wr), a2 = clampu(wr + fa);
         if (t_hi > t_lo) {
-          eat_rows<false>(rows, a0 - t_lo, a1 - a0, s_e, c0, c1, acc);
-          eat_rows<true>(rows + (size_t)(a1 - t_lo) * 32, a2 - a1, t_hi - a2, s_e, c0, c1, acc);
+          // (a uniform tail is only used when its row lies in this chunk together with the run's end)
+          eat_rows<false>(rows, a0 - t_lo, a1 - a0, a1 == wr ? (tails & 0xFu) : 0u, s_e, c0, c1, acc);
+          eat_rows<true>(rows + (size_t)(a1 - t_lo) * 32, a2 - a1, t_hi - a2, t_hi == wr + wa ? ((tails >> 4) & 0xFu) : 0u,
+                         s_e, c0, c1, acc);
         }
       }
       if (cur.c + 1 == cur.n_ch) {

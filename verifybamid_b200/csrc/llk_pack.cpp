@@ -153,12 +153,14 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
   // words and, inside a group, ordered by ref words -- alternating direction from group to group so
   // that the slice straddling a group boundary mixes similar ref depths.
   auto words_of = [](uint32_t n) { return (n + kReadsPerWord - 1) / kReadsPerWord; };
-  // one key per marker: alt words (descending), then ref words (descending, or ascending in odd alt
-  // groups); ties keep panel order because `used` is in panel order and the sort is stable
+  // one key per marker: alt READS (descending), then ref READS (descending, or ascending in odd alt
+  // groups); ties keep panel order because `used` is in panel order and the sort is stable.  Sorting by
+  // exact read counts (word counts follow monotonically) makes most slices hold 32 markers with the SAME
+  // (n_ref, n_alt), so the ragged last word of a run has the same number of reads in every lane.
   std::vector<uint64_t> keys(used.size());
   for (size_t u = 0; u < used.size(); ++u) {
-    const uint64_t wa = words_of(used[u].n_alt), wr = words_of(used[u].n_ref);
-    keys[u] = ((0xFFFFFull - wa) << 24) | ((wa & 1u) ? wr : 0xFFFFFull - wr);
+    const uint64_t na = std::min<uint64_t>(used[u].n_alt, 0xFFFFFFull), nr = std::min<uint64_t>(used[u].n_ref, 0xFFFFFFull);
+    keys[u] = ((0xFFFFFFull - na) << 24) | ((na & 1u) ? nr : 0xFFFFFFull - nr);
   }
   std::vector<uint32_t> order(used.size());
   std::iota(order.begin(), order.end(), 0u);
@@ -232,6 +234,8 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
     uint8_t *blob = P.blob.data() + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
     const uint32_t wr = geom[j].wr, wa = geom[j].wa;
     uint32_t n_valid = 0, full_ref = wr, full_alt = wa;  // leading rows with four real reads in EVERY lane
+    uint32_t nref0 = 0xFFFFFFFFu, nalt0 = 0xFFFFFFFFu;   // read counts if identical in every valid lane
+    bool same_ref = true, same_alt = true;
     // neutral values for padding lanes
     for (uint32_t l = 0; l < (uint32_t)kSliceMarkers; ++l) {
       if (P.known_af) {
@@ -253,6 +257,9 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
       const MarkerTmp &m = used[order[o]];
       full_ref = std::min(full_ref, m.n_ref / kReadsPerWord);
       full_alt = std::min(full_alt, m.n_alt / kReadsPerWord);
+      if (nref0 == 0xFFFFFFFFu) { nref0 = m.n_ref; nalt0 = m.n_alt; }
+      same_ref = same_ref && m.n_ref == nref0;
+      same_alt = same_alt && m.n_alt == nalt0;
       P.marker_index[(size_t)j * kSliceMarkers + l] = m.panel_row;
       if (P.known_af) {
         reinterpret_cast<double *>(blob + L.off_kaf)[l] = d.known_af[m.panel_row];
@@ -290,7 +297,10 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
       T.used += (uint64_t)(m.end - m.beg);
       ++T.markers;
     }
-    uint32_t hdr[4] = {wr, wa, n_valid, full_ref | (full_alt << 16)};
+    // uniform ragged tail: every valid lane holds exactly `tail` (1..3) reads in the one row after the full rows
+    const uint32_t tail_ref = (same_ref && n_valid && wr == full_ref + 1) ? nref0 % kReadsPerWord : 0u;
+    const uint32_t tail_alt = (same_alt && n_valid && wa == full_alt + 1) ? nalt0 % kReadsPerWord : 0u;
+    uint32_t hdr[4] = {wr, wa, n_valid | (tail_ref << 8) | (tail_alt << 12), full_ref | (full_alt << 16)};
     std::memcpy(blob, hdr, sizeof(hdr));
   }
   }, 64);

@@ -75,9 +75,11 @@ struct PackedSample {
   double log_other_const = 0.0;
   BlobLayout layout;
   std::vector<Round> rounds;
-  // Blob header (16 bytes): u32 wr (ref word rows), u32 wa (alt word rows), u32 n_valid (lanes
-  // 0..n_valid-1 hold markers), u32 full_ref | full_alt << 16 (leading ref / alt rows in which every
-  // valid lane has four real reads: the kernel streams those without looking for filler bytes).
+  // Blob header (16 bytes): u32 wr (ref word rows), u32 wa (alt word rows),
+  // u32 n_valid | tail_ref << 8 | tail_alt << 12 (lanes 0..n_valid-1 hold markers; tail_x = 1..3 when the single
+  // row after the full rows holds exactly that many reads in EVERY valid lane, 0 = unknown / mixed),
+  // u32 full_ref | full_alt << 16 (leading ref / alt rows in which every valid lane has four real reads:
+  // the kernel streams those -- and uniform tails -- without looking for filler bytes).
   std::vector<uint8_t> blob;          // the whole image
   std::vector<uint32_t> marker_index; // [n_slices*32] panel row per (slice, lane); slice j (heaviest
                                       // first) is the blob of round j / n_bins, bin bin_of(j)
