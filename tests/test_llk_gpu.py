@@ -264,3 +264,17 @@ def test_sixteen_pcs_and_multi_chunk_stage():
     with pytest.raises(vb.VB2Error):
         vb.LLKEngine(vb.PileupProblem(np.zeros((p.n_marker, 17)), p.means, p.base_info_index, p.alt_base, p.info_offset,
                                       p.bases, p.quals))
+
+
+def test_runtime_layout_kernel_equals_specialised_kernel(sample10k, monkeypatch):
+    """NumPC 2/4 with an fp32 panel runs a kernel instantiation with compile-time blob offsets; forcing the
+    runtime-layout instantiation on the same sample must give the same bits."""
+    with vb.LLKEngine(sample10k.problem) as eng:
+        fast = [eng.compute_mix_llks(*pt) for pt in POINTS]
+        fast_batch = eng.eval_batch(np.array([p[0] for p in POINTS]), np.array([p[1] for p in POINTS]),
+                                    np.array([p[2] for p in POINTS])).tolist()
+    monkeypatch.setenv("VB2_LLK_NO_SPEC", "1")
+    with vb.LLKEngine(sample10k.problem) as eng:
+        assert [eng.compute_mix_llks(*pt) for pt in POINTS] == fast
+        assert eng.eval_batch(np.array([p[0] for p in POINTS]), np.array([p[1] for p in POINTS]),
+                              np.array([p[2] for p in POINTS])).tolist() == fast_batch == fast

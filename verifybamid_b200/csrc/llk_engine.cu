@@ -25,6 +25,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "llk_pack.h"
@@ -207,32 +208,118 @@ __device__ __forceinline__ void initial_gf(double af, double min_af, double max_
   gf[2] = __dmul_rn(af, af);
 }
 
-template <typename PanelT>
-__device__ __forceinline__ void marker_af(const uint8_t *blob, const SampleDev &S, const JobParams &J, int lane,
+// Blob layout as the kernel sees it.  FixedLayout<NPC>: the common case (fp32 panel, default AF clamps,
+// no --KnownAF, NumPC = NPC) with every offset a compile-time constant and the PC loop unrolled;
+// RuntimeLayout: anything else, loaded once per warp from the sample descriptor.
+template <int NPC>
+struct FixedLayout {
+  static constexpr bool kFixed = true;
+  static constexpr uint32_t n_pc = NPC, off_ud = vb2::kBlobHeaderBytes, off_mu = off_ud + NPC * 128u,
+                            off_diag = off_mu + 128u, off_words = off_diag + 768u, off_kaf = 0u;
+  static constexpr bool panel_fp64 = false, known_af = false;
+  static constexpr double min_af = 0.00005, max_af = 0.99995;  // h:94-95
+  __device__ __forceinline__ explicit FixedLayout(const SampleDev &) {}
+};
+struct RuntimeLayout {
+  static constexpr bool kFixed = false;
+  uint32_t n_pc, off_ud, off_mu, off_kaf, off_diag, off_words;
+  bool panel_fp64, known_af;
+  double min_af, max_af;
+  __device__ __forceinline__ explicit RuntimeLayout(const SampleDev &S)
+      : n_pc(S.n_pc), off_ud(S.off_ud), off_mu(S.off_mu), off_kaf(S.off_kaf), off_diag(S.off_diag),
+        off_words(S.off_words), panel_fp64(S.panel_fp64 != 0), known_af(S.known_af != 0), min_af(S.min_af),
+        max_af(S.max_af) {}
+};
+
+template <typename PanelT, typename Layout>
+__device__ __forceinline__ void marker_af(const uint8_t *blob, const Layout &Y, const JobParams &J, int lane,
                                           double &af1, double &af2) {
   // h:251-267: AF = (sum_k UD[i][k]*PC[k] + means[i]) / 2, accumulated in k order in fp64.
-  const PanelT *ud = reinterpret_cast<const PanelT *>(blob + S.off_ud);
-  const PanelT *mu = reinterpret_cast<const PanelT *>(blob + S.off_mu);
+  const PanelT *ud = reinterpret_cast<const PanelT *>(blob + Y.off_ud);
+  const PanelT *mu = reinterpret_cast<const PanelT *>(blob + Y.off_mu);
   double a1 = 0., a2 = 0.;
-  for (uint32_t k = 0; k < S.n_pc; ++k) {
-    const double u = (double)ud[k * 32 + lane];
-    a1 = __dadd_rn(a1, __dmul_rn(u, J.pc1[k]));
-    a2 = __dadd_rn(a2, __dmul_rn(u, J.pc2[k]));
+  if constexpr (Layout::kFixed) {
+#pragma unroll
+    for (uint32_t k = 0; k < Layout::n_pc; ++k) {
+      const double u = (double)ud[k * 32 + lane];
+      a1 = __dadd_rn(a1, __dmul_rn(u, J.pc1[k]));
+      a2 = __dadd_rn(a2, __dmul_rn(u, J.pc2[k]));
+    }
+  } else {
+    for (uint32_t k = 0; k < Y.n_pc; ++k) {
+      const double u = (double)ud[k * 32 + lane];
+      a1 = __dadd_rn(a1, __dmul_rn(u, J.pc1[k]));
+      a2 = __dadd_rn(a2, __dmul_rn(u, J.pc2[k]));
+    }
   }
   const double m = (double)mu[lane];
   af1 = (a1 + m) * 0.5;
   af2 = (a2 + m) * 0.5;
 }
 
+// (i) header, allele frequencies, genotype priors, diagonal pairs of the slice whose chunk 0 sits at `buf`
+struct SliceHeader {
+  uint32_t wr, wa, n_valid, fr, fa, tails;
+};
+template <typename Layout>
+__device__ __forceinline__ void slice_begin(const uint8_t *buf, const Layout &Y, const JobParams &J, int lane,
+                                            SliceHeader &H, double (&acc)[kNumPairs], double &ldiag) {
+  const uint4 hdr = *reinterpret_cast<const uint4 *>(buf);
+  H.wr = hdr.x; H.wa = hdr.y; H.n_valid = hdr.z & 0xFFu; H.tails = hdr.z >> 8; H.fr = hdr.w & 0xFFFFu; H.fa = hdr.w >> 16;
+  double af1, af2;
+  if (Y.known_af) {
+    af1 = af2 = reinterpret_cast<const double *>(buf + Y.off_kaf)[lane];  // h:251-252
+  } else if (Y.panel_fp64) {
+    marker_af<double>(buf, Y, J, lane, af1, af2);
+  } else {
+    marker_af<float>(buf, Y, J, lane, af1, af2);
+  }
+  double gf[3], gf2[3];
+  initial_gf(af1, Y.min_af, Y.max_af, gf);   // contaminating sample
+  initial_gf(af2, Y.min_af, Y.max_af, gf2);  // intended sample
+  const double *dg = reinterpret_cast<const double *>(buf + Y.off_diag);
+  ldiag = dg[lane] * (gf[0] * gf2[0]) + dg[32 + lane] * (gf[1] * gf2[1]) + dg[64 + lane] * (gf[2] * gf2[2]);
+  // h:307-311 weights GF[g1]*GF2[g2]: start each running product at its weight, so the marginal is just
+  // ldiag + sum(acc) at the end
+#pragma unroll
+  for (int p = 0; p < kNumPairs; ++p) acc[p] = gf[pair_g1(p)] * gf2[pair_g2(p)];
+}
+
+// (ii) the word rows [t_lo, t_hi) of the slice, stored from `rows` on (this lane's column): ref rows first,
+// then alt rows; rows [0,fr) and [wr, wr+fa) are filler-free in every lane.
+__device__ __forceinline__ void slice_rows(const uint32_t *rows, uint32_t t_lo, uint32_t t_hi, const SliceHeader &H,
+                                           const double *s_e, const double (&c0)[kNumPairs],
+                                           const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
+  if (t_hi > H.wr + H.wa) t_hi = H.wr + H.wa;
+  if (t_hi <= t_lo) return;
+  auto clampu = [&](uint32_t x) { return x < t_lo ? t_lo : (x > t_hi ? t_hi : x); };
+  const uint32_t a0 = clampu(H.fr), a1 = clampu(H.wr), a2 = clampu(H.wr + H.fa);
+  // (a uniform tail is only used when its row lies in this window together with the run's end)
+  eat_rows<false>(rows, a0 - t_lo, a1 - a0, a1 == H.wr ? (H.tails & 0xFu) : 0u, s_e, c0, c1, acc);
+  eat_rows<true>(rows + (size_t)(a1 - t_lo) * 32, a2 - a1, t_hi - a2, t_hi == H.wr + H.wa ? ((H.tails >> 4) & 0xFu) : 0u,
+                 s_e, c0, c1, acc);
+}
+
+// (iii) marginal over the nine genotype pairs, log.  h:307-311: markerLK = sum exp(acc)*GF[g1]*GF2[g2]; the
+// running products carry their weights and the diagonal pairs were folded into ldiag.
+__device__ __forceinline__ double slice_end(const SliceHeader &H, int lane, const double (&acc)[kNumPairs], double ldiag) {
+  const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));
+  return ((uint32_t)lane < H.n_valid && L > 0) ? log(L) : 0.0;
+}
+
 // One persistent CTA per SM.  Warp w issues on SM sub-partition w % 4 and owns bin
-// blockIdx.x*4 + w%4; it serves rounds w/4, w/4 + conc_rounds, ... of that bin.
+// blockIdx.x*4 + w%4; warp kk = w/4 serves the rounds kk, 2kc-1-kk, 2kc+kk, ... of that bin (a snake over
+// groups of kc rounds: rounds are sorted heaviest first, so every warp gets about the same work).
 //   ARGS         sample, round table and job parameters are read from the kernel arguments
-//                (constant bank, uniform addresses); otherwise they are staged from HBM.
+//                (constant bank, uniform addresses); otherwise from HBM through L1.
 //   HOST_REDUCE  every CTA publishes {partial, seq} into the host-mapped mailbox and the host adds
-//                them in CTA order; otherwise the last CTA to finish adds the partials on the device.
-template <bool ARGS, bool HOST_REDUCE>
+//                them in a fixed order; otherwise the last CTA to finish adds the partials on the device.
+//   NPC          2 or 4: FixedLayout<NPC> (fp32 panel, default clamps, no known AF); 0: RuntimeLayout.
+//   CHUNKED      blobs may be deeper than one shared-memory stage and are streamed in chunks.
+template <bool ARGS, bool HOST_REDUCE, int NPC, bool CHUNKED>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 llk_kernel(const __grid_constant__ LaunchArgs A) {
+  using Layout = typename std::conditional<NPC != 0, FixedLayout<NPC>, RuntimeLayout>::type;
   extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][n_buf][buf_bytes]
   __shared__ double s_e[256];
   __shared__ double s_red[kMaxWarps];
@@ -243,10 +330,9 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   const uint32_t job = blockIdx.y;
 
   // ---- per-CTA set-up --------------------------------------------------------------------------
-  // Sample descriptor, round table and job parameters are read in place with warp-uniform loads --
-  // from the constant bank (ARGS) or from HBM through L1 (generic) -- so a warp can arm its own
-  // mbarrier and fire its first TMA bulk copy before the single CTA-wide barrier that publishes the
-  // Phred table: the HBM latency of the blob overlaps the set-up.
+  // Sample descriptor, round table and job parameters are read in place with warp-uniform loads, so a
+  // warp can arm its own mbarrier and fire its first TMA bulk copy before the single CTA-wide barrier
+  // that publishes the Phred table: the HBM latency of the blob overlaps the set-up.
   if (lane == 0) {
     mbar_init(&s_bar[warp][0], 1);
     mbar_init(&s_bar[warp][1], 1);
@@ -257,66 +343,67 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   const JobParams &J = ARGS ? A.jobs[job] : A.jobs_dev[job];
   const vb2::Round *rounds_tab = ARGS ? A.rounds : S.rounds;
   const bool active_cta = blockIdx.x < S.grid_x;  // eval_many: a sample may need fewer CTAs than the grid has
+  const Layout Y(S);
 
   const uint32_t bin = blockIdx.x * vb2::kBinsPerCta + (warp & 3);
-  const uint32_t kc = A.kc;
-  const uint32_t n_rounds = active_cta ? S.n_rounds : 0u;
+  const uint32_t kc = A.kc, kk = (uint32_t)(warp >> 2);
+  const uint32_t n_rounds = (active_cta && kk < kc) ? S.n_rounds : 0u;
   const uint32_t chunk_rows = S.chunk_rows;
-  const uint32_t n_buf = A.n_buf, buf_bytes = S.buf_bytes, off_words = S.off_words;
+  const uint32_t n_buf = A.n_buf, buf_bytes = S.buf_bytes;
+  const uint8_t *blob_base = S.blob;
   uint8_t *mybuf = s_buf + (size_t)warp * n_buf * buf_bytes;
 
-  auto get_round = [&](uint32_t r) -> vb2::Round { return rounds_tab[r]; };
-  // The warp walks a sequence of (round, chunk) items; `cur` is being consumed, `nxt` is the next one
-  // to fetch.  Both cursors keep their round descriptor in registers.  Warp kk = warp/4 serves the
-  // rounds kk, 2kc-1-kk, 2kc+kk, 4kc-1-kk, ... (a snake over groups of kc rounds): rounds are sorted
-  // heaviest first, so pairing the heaviest with the lightest gives every warp about the same work.
-  struct Cursor {
-    uint32_t r, c, n_ch, rows;
+  // An item = one TMA bulk copy = one blob (CHUNKED: one chunk of a blob).
+  struct Item {
+    uint32_t r, c, n_ch, rows;  // round, chunk, chunks of this blob, word rows of this blob
     const uint8_t *src;
   };
-  const uint32_t kk = (uint32_t)(warp >> 2);
   auto snake_next = [&](uint32_t r) -> uint32_t {  // the round this warp serves after round r
-    const uint32_t g = r / kc, i = r - g * kc;     // group, position inside it
+    const uint32_t g = r / kc, i = r - g * kc;
     return (g + 1) * kc + (kc - 1 - i);
   };
-  auto seek = [&](Cursor &k, uint32_t r) {  // first round at or after r (in this warp's order) with a blob for this bin
+  auto seek = [&](Item &k, uint32_t r) {  // first round at or after r (in this warp's order) with a blob for this bin
     k.c = 0;
     while (r < n_rounds) {
-      const vb2::Round R = get_round(r);
+      const vb2::Round R = rounds_tab[r];
       if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
         k.rows = R.rows;
-        k.n_ch = R.rows <= chunk_rows ? 1u : (R.rows + chunk_rows - 1) / chunk_rows;
-        k.src = S.blob + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
+        k.n_ch = (!CHUNKED || R.rows <= chunk_rows) ? 1u : (R.rows + chunk_rows - 1) / chunk_rows;
+        k.src = blob_base + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
         break;
       }
       r = snake_next(r);
     }
     k.r = r;
   };
-  auto step = [&](Cursor &k) {
-    if (k.c + 1 < k.n_ch) ++k.c;
+  auto step = [&](Item &k) {
+    if (CHUNKED && k.c + 1 < k.n_ch) ++k.c;
     else seek(k, snake_next(k.r));
   };
-  // TMA: chunk 0 = header + panel + diag + the first chunk_rows word rows; chunk c >= 1 = the next rows
-  auto issue = [&](const Cursor &k, uint32_t b) {
-    uint32_t off = 0, n = k.rows < chunk_rows ? k.rows : chunk_rows, bytes = off_words + n * 128u;
-    if (k.c) {
-      off = off_words + k.c * chunk_rows * 128u;
-      n = k.rows - k.c * chunk_rows;
+  // chunk 0 = header + panel + diag + the first chunk_rows word rows; chunk c >= 1 = the next rows
+  auto issue = [&](const Item &k, uint32_t b) {
+    uint32_t off = 0, bytes;
+    if (!CHUNKED) {
+      bytes = Y.off_words + k.rows * 128u;
+    } else if (k.c == 0) {
+      bytes = Y.off_words + (k.rows < chunk_rows ? k.rows : chunk_rows) * 128u;
+    } else {
+      off = Y.off_words + k.c * chunk_rows * 128u;
+      const uint32_t n = k.rows - k.c * chunk_rows;
       bytes = (n < chunk_rows ? n : chunk_rows) * 128u;
     }
     mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
     bulk_g2s(mybuf + (size_t)b * buf_bytes, k.src + off, bytes, &s_bar[warp][b]);
   };
-  Cursor cur, nxt;
-  cur.r = n_rounds; cur.c = 0; cur.n_ch = 1; cur.rows = 0; cur.src = nullptr;
-  if (kk < kc) seek(cur, kk);
-  nxt = cur;
+  Item cur, nxt;
+  nxt.r = n_rounds; nxt.c = 0; nxt.n_ch = 1; nxt.rows = 0; nxt.src = nullptr;
+  if (n_rounds) seek(nxt, kk);
+  cur = nxt;
   uint32_t ib = 0, cb = 0, parity = 0;
-  if (nxt.r < n_rounds) {
-    if (lane == 0) issue(nxt, ib);
-    step(nxt);
-    ib ^= (n_buf - 1);
+  if (cur.r < n_rounds) {
+    if (lane == 0) issue(cur, 0);
+    step(nxt);  // nxt = the item after cur
+    ib = n_buf - 1;
   }
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_e[i] = g_phred[i];
   __syncthreads();
@@ -330,63 +417,29 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
       c1[p] = J.c1[p];
     }
     double acc[kNumPairs], ldiag = 0.;
-    uint32_t wr = 0, wa = 0, n_valid = 0, fr = 0, fa = 0, tails = 0;
+    SliceHeader H{0, 0, 0, 0, 0, 0};
     while (cur.r < n_rounds) {
-      if (n_buf == 2 && nxt.r < n_rounds) {
+      const Item upcoming = nxt;  // fetched while `cur` is consumed (needs the second buffer)
+      if (n_buf == 2 && upcoming.r < n_rounds) {
         __syncwarp();  // every lane finished reading the buffer about to be overwritten
-        if (lane == 0) issue(nxt, ib);
+        if (lane == 0) issue(upcoming, ib);
         step(nxt);
         ib ^= 1u;
       }
       mbar_wait(&s_bar[warp][cb], (parity >> cb) & 1u);
       parity ^= 1u << cb;
       const uint8_t *buf = mybuf + (size_t)cb * buf_bytes;
-      if (cur.c == 0) {
-        // ---- (i) header, allele frequencies, genotype priors, diagonal pairs ----------------------
-        const uint4 hdr = *reinterpret_cast<const uint4 *>(buf);
-        wr = hdr.x; wa = hdr.y; n_valid = hdr.z & 0xFFu; tails = hdr.z >> 8; fr = hdr.w & 0xFFFFu; fa = hdr.w >> 16;
-        double af1, af2;
-        if (S.known_af) {
-          af1 = af2 = reinterpret_cast<const double *>(buf + S.off_kaf)[lane];  // h:251-252
-        } else if (S.panel_fp64) {
-          marker_af<double>(buf, S, J, lane, af1, af2);
-        } else {
-          marker_af<float>(buf, S, J, lane, af1, af2);
-        }
-        double gf[3], gf2[3];
-        initial_gf(af1, S.min_af, S.max_af, gf);   // contaminating sample
-        initial_gf(af2, S.min_af, S.max_af, gf2);  // intended sample
-        const double *dg = reinterpret_cast<const double *>(buf + S.off_diag);
-        ldiag = dg[lane] * (gf[0] * gf2[0]) + dg[32 + lane] * (gf[1] * gf2[1]) + dg[64 + lane] * (gf[2] * gf2[2]);
-        // h:307-311 weights GF[g1]*GF2[g2]: start each running product at its weight, so the marginal
-        // is just ldiag + sum(acc) at the end
-#pragma unroll
-        for (int p = 0; p < kNumPairs; ++p) acc[p] = gf[pair_g1(p)] * gf2[pair_g2(p)];
-      }
-      // ---- (ii) stream this chunk's word rows: ref rows first, then alt rows --------------------
-      // rows [0,fr) and [wr, wr+fa) are filler-free in every lane; the rest may hold 0xFF fillers
-      {
+      if (!CHUNKED || cur.c == 0) slice_begin(buf, Y, J, lane, H, acc, ldiag);
+      if (!CHUNKED) {
+        slice_rows(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, 0u, H.wr + H.wa, H, s_e, c0, c1, acc);
+        vsum += slice_end(H, lane, acc, ldiag);
+      } else {
         const uint32_t t_lo = cur.c * chunk_rows;
-        uint32_t t_hi = t_lo + chunk_rows;
-        if (t_hi > wr + wa) t_hi = wr + wa;
-        const uint32_t *rows = reinterpret_cast<const uint32_t *>(buf + (cur.c == 0 ? off_words : 0u)) + lane;
-        auto clampu = [&](uint32_t x) { return x < t_lo ? t_lo : (x > t_hi ? t_hi : x); };
-        const uint32_t a0 = clampu(fr), a1 = clampu(wr), a2 = clampu(wr + fa);
-        if (t_hi > t_lo) {
-          // (a uniform tail is only used when its row lies in this chunk together with the run's end)
-          eat_rows<false>(rows, a0 - t_lo, a1 - a0, a1 == wr ? (tails & 0xFu) : 0u, s_e, c0, c1, acc);
-          eat_rows<true>(rows + (size_t)(a1 - t_lo) * 32, a2 - a1, t_hi - a2, t_hi == wr + wa ? ((tails >> 4) & 0xFu) : 0u,
-                         s_e, c0, c1, acc);
-        }
+        slice_rows(reinterpret_cast<const uint32_t *>(buf + (cur.c == 0 ? Y.off_words : 0u)) + lane, t_lo,
+                   t_lo + chunk_rows, H, s_e, c0, c1, acc);
+        if (cur.c + 1 == cur.n_ch) vsum += slice_end(H, lane, acc, ldiag);
       }
-      if (cur.c + 1 == cur.n_ch) {
-        // ---- (iii) marginal over the nine genotype pairs, log -------------------------------------
-        // h:307-311: markerLK = sum_{g1,g2} exp(acc)*GF[g1]*GF2[g2]; the running products carry their
-        // weights and the diagonal pairs were folded into ldiag.
-        const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));
-        if ((uint32_t)lane < n_valid && L > 0) vsum += log(L);
-      }
-      step(cur);
+      cur = upcoming;  // (with one buffer there is exactly one item per warp, and upcoming.r == n_rounds)
       if (n_buf == 2) cb ^= 1u;
     }
   }
@@ -433,6 +486,24 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   }
 }
 
+// Pick the instantiation for a launch.  spec = 2 / 4 when every sample of the launch has the FixedLayout<spec>
+// shape, else 0; chunked = some blob is deeper than its shared-memory stage.
+template <bool ARGS, bool HOST_REDUCE>
+void launch_llk(dim3 grid, dim3 block, uint32_t smem, cudaStream_t stream, const LaunchArgs &A, int spec, bool chunked) {
+  if (chunked) llk_kernel<ARGS, HOST_REDUCE, 0, true><<<grid, block, smem, stream>>>(A);
+  else if (spec == 2) llk_kernel<ARGS, HOST_REDUCE, 2, false><<<grid, block, smem, stream>>>(A);
+  else if (spec == 4) llk_kernel<ARGS, HOST_REDUCE, 4, false><<<grid, block, smem, stream>>>(A);
+  else llk_kernel<ARGS, HOST_REDUCE, 0, false><<<grid, block, smem, stream>>>(A);
+}
+template <bool ARGS, bool HOST_REDUCE>
+cudaError_t set_smem_limit(int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(llk_kernel<ARGS, HOST_REDUCE, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_kernel<ARGS, HOST_REDUCE, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_kernel<ARGS, HOST_REDUCE, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_kernel<ARGS, HOST_REDUCE, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return e;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -454,6 +525,8 @@ struct vb2_llk_ctx {
   uint32_t slots = 0;
   uint32_t smem_bytes = 0;
   uint32_t block_threads = 0;
+  int spec = 0;          // 2 / 4: FixedLayout<spec> applies to this sample, else 0
+  bool chunked = false;  // some blob is deeper than one shared-memory stage
   std::vector<vb2::Round> rounds;  // host copy (kernel arguments)
   Slot *h_mbox = nullptr, *d_mbox = nullptr;
   uint32_t mbox_slots = 0;
@@ -464,6 +537,8 @@ struct vb2_llk_ctx {
   SampleDev *h_many = nullptr, *d_many = nullptr;
   uint32_t *h_slots = nullptr, *d_slots = nullptr;
   uint32_t many_n = 0, many_grid_x = 0, many_kc = 1, many_buf_bytes = 0;  // last staged eval_many launch
+  int many_spec = 0;
+  bool many_chunked = false;
   unsigned long long seq = 0;
   int pending_n = 0;                 // evaluations launched by eval_begin and not yet collected
   bool pending_host_reduce = false;
@@ -650,9 +725,9 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
     if (seq_out) *seq_out = A.seq;
   }
   dim3 grid(ctx->S.grid_x, (unsigned)n, 1), block(g.threads, 1, 1);
-  if (mode == Reduce::kHost) llk_kernel<true, true><<<grid, block, g.smem, ctx->stream>>>(A);
-  else if (args) llk_kernel<true, false><<<grid, block, g.smem, ctx->stream>>>(A);
-  else llk_kernel<false, false><<<grid, block, g.smem, ctx->stream>>>(A);
+  if (mode == Reduce::kHost) launch_llk<true, true>(grid, block, g.smem, ctx->stream, A, ctx->spec, ctx->chunked);
+  else if (args) launch_llk<true, false>(grid, block, g.smem, ctx->stream, A, ctx->spec, ctx->chunked);
+  else launch_llk<false, false>(grid, block, g.smem, ctx->stream, A, ctx->spec, ctx->chunked);
   VB2_CUDA(ctx, cudaGetLastError());
   return VB2_OK;
 }
@@ -665,9 +740,9 @@ int init_device_tables(vb2_llk_ctx *ctx, cudaStream_t stream) {
   VB2_CUDA(ctx, cudaMemcpyToSymbolAsync(g_phred, phred, sizeof(phred), 0, cudaMemcpyHostToDevice, stream));
   VB2_CUDA(ctx, cudaStreamSynchronize(stream));
   const int smem_max = 200 * 1024;
-  VB2_CUDA(ctx, cudaFuncSetAttribute(llk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-  VB2_CUDA(ctx, cudaFuncSetAttribute(llk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-  VB2_CUDA(ctx, cudaFuncSetAttribute(llk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  VB2_CUDA(ctx, (set_smem_limit<true, true>(smem_max)));
+  VB2_CUDA(ctx, (set_smem_limit<true, false>(smem_max)));
+  VB2_CUDA(ctx, (set_smem_limit<false, false>(smem_max)));
   return VB2_OK;
 }
 
@@ -791,6 +866,10 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   if (const char *t = getenv("VB2_LLK_STAGE_WORDS")) cap_rows = (uint32_t)std::max(1, atoi(t));
   S.chunk_rows = std::max(1u, std::min(std::max(max_rows, 1u), cap_rows));
   S.buf_bytes = S.off_words + S.chunk_rows * 128u;
+  ctx->chunked = max_rows > S.chunk_rows;
+  const bool default_clamps = S.min_af == 0.00005 && S.max_af == 0.99995;
+  ctx->spec = (!cfg.panel_fp64 && !P.known_af && default_clamps && (P.n_pc == 2 || P.n_pc == 4)) ? (int)P.n_pc : 0;
+  if (getenv("VB2_LLK_NO_SPEC")) ctx->spec = 0;  // (tests: force the runtime-layout kernel)
   const bool one_item_per_warp = S.n_rounds <= S.conc_rounds && max_rows <= S.chunk_rows;
   S.n_buf = one_item_per_warp ? 1u : 2u;
   ctx->block_threads = 128u * std::max(1u, S.conc_rounds);
@@ -968,11 +1047,14 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
     if (rc) return set_err(lead, rc, c->err);
     lead->h_slots[j] = slot;
   }
-  bool any = false;
+  bool any = false, chunked = false;
+  int spec = ctxs[0]->spec;
   uint32_t grid_x = 0, kc = 1, buf_bytes = 0;
   for (int j = 0; j < n; ++j) {
     vb2_llk_ctx *c = ctxs[j];
     lead->h_many[j] = c->S;
+    chunked = chunked || c->chunked;
+    if (c->spec != spec) spec = 0;
     // the launch uses the largest geometry; every sample indexes shared memory with its own buf_bytes
     const Geometry g = geometry(c, true);
     grid_x = std::max(grid_x, c->S.grid_x);
@@ -994,6 +1076,8 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
   lead->many_grid_x = grid_x;
   lead->many_kc = kc;
   lead->many_buf_bytes = buf_bytes;
+  lead->many_spec = spec;
+  lead->many_chunked = chunked;
   return VB2_OK;
 }
 
@@ -1015,7 +1099,8 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
     if (seq_out) *seq_out = A.seq;
   }
   dim3 grid(lead->many_grid_x, lead->many_n, 1), block(128u * lead->many_kc, 1, 1);
-  llk_kernel<false, false><<<grid, block, 4u * lead->many_kc * 2u * lead->many_buf_bytes, lead->stream>>>(A);
+  launch_llk<false, false>(grid, block, 4u * lead->many_kc * 2u * lead->many_buf_bytes, lead->stream, A, lead->many_spec,
+                           lead->many_chunked);
   VB2_CUDA(lead, cudaGetLastError());
   return VB2_OK;
 }
