@@ -356,13 +356,12 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   // An item = one TMA bulk copy = one blob (CHUNKED: one chunk of a blob).
   struct Item {
     uint32_t r, c, n_ch, rows;  // round, chunk, chunks of this blob, word rows of this blob
+    uint32_t odd;               // parity of the round's group (r / kc) & 1
     const uint8_t *src;
   };
-  auto snake_next = [&](uint32_t r) -> uint32_t {  // the round this warp serves after round r
-    const uint32_t g = r / kc, i = r - g * kc;
-    return (g + 1) * kc + (kc - 1 - i);
-  };
-  auto seek = [&](Item &k, uint32_t r) {  // first round at or after r (in this warp's order) with a blob for this bin
+  // the round this warp serves after a round of an even / odd group: kk -> 2kc-1-kk -> 2kc+kk -> ...
+  const uint32_t d_even = 2u * kc - 1u - 2u * kk, d_odd = 2u * kk + 1u;
+  auto seek = [&](Item &k, uint32_t r, uint32_t odd) {  // first round from r on (this warp's order) with a blob for this bin
     k.c = 0;
     while (r < n_rounds) {
       const vb2::Round R = rounds_tab[r];
@@ -372,13 +371,15 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
         k.src = blob_base + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
         break;
       }
-      r = snake_next(r);
+      r += odd ? d_odd : d_even;
+      odd ^= 1u;
     }
     k.r = r;
+    k.odd = odd;
   };
   auto step = [&](Item &k) {
     if (CHUNKED && k.c + 1 < k.n_ch) ++k.c;
-    else seek(k, snake_next(k.r));
+    else seek(k, k.r + (k.odd ? d_odd : d_even), k.odd ^ 1u);
   };
   // chunk 0 = header + panel + diag + the first chunk_rows word rows; chunk c >= 1 = the next rows
   auto issue = [&](const Item &k, uint32_t b) {
@@ -396,8 +397,8 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
     bulk_g2s(mybuf + (size_t)b * buf_bytes, k.src + off, bytes, &s_bar[warp][b]);
   };
   Item cur, nxt;
-  nxt.r = n_rounds; nxt.c = 0; nxt.n_ch = 1; nxt.rows = 0; nxt.src = nullptr;
-  if (n_rounds) seek(nxt, kk);
+  nxt.r = n_rounds; nxt.c = 0; nxt.n_ch = 1; nxt.rows = 0; nxt.odd = 0; nxt.src = nullptr;
+  if (n_rounds) seek(nxt, kk, 0u);
   cur = nxt;
   uint32_t ib = 0, cb = 0, parity = 0;
   if (cur.r < n_rounds) {
