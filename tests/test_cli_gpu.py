@@ -149,3 +149,30 @@ def test_marker_shards_over_two_gpus(synthetic10k):
                  "--NumGPU", str(n)], str(td))
         outs.append(read_ancestry(out + ".Ancestry"))
     assert np.abs(outs[0] - outs[1]).max() <= TOL
+
+
+def test_cohort_mode_equals_one_sample_at_a_time(tmp_path):
+    """--PileupList (BASELINE configs[3] shape, scaled down): five samples optimised in lock-step, one launch per
+    simplex step for the whole cohort, must write exactly the files five separate runs write."""
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    prefix = None
+    lines, singles = [], []
+    for i, (depth, alpha, nm) in enumerate([(30.0, 0.02, 5000), (12.0, 0.10, 5000), (45.0, 0.005, 5000),
+                                            (20.0, 0.3, 5000), (30.0, 0.02, 5000)]):
+        s = synth.make_sample(panel, n_pc=2, depth=depth, alpha=alpha, seed=50 + i, n_markers=nm)
+        if prefix is None:
+            prefix = panels.write_text_panel(s.panel, str(tmp_path / "panel"))
+        pile = s.write_pileup(str(tmp_path / ("s%d.pileup" % i)))
+        lines.append("%s\t%s\n" % (pile, tmp_path / ("cohort%d" % i)))
+        singles.append((pile, str(tmp_path / ("single%d" % i))))
+    lst = tmp_path / "cohort.list"
+    lst.write_text("".join(lines))
+    cp = run_cli(["--PileupList", str(lst), "--SVDPrefix", prefix, "--Reference", "x", "--NumPC", "2"], str(tmp_path))
+    table = [l.split("\t") for l in cp.stdout.splitlines() if l and not l.startswith("#")]
+    assert len(table) == 5 and all(row[-1] == "OK" for row in table)
+    assert "launches" in cp.stderr
+    for i, (pile, out) in enumerate(singles):
+        run_cli(["--PileupFile", pile, "--SVDPrefix", prefix, "--Reference", "x", "--NumPC", "2", "--Output", out],
+                str(tmp_path))
+        for ext in (".Ancestry", ".selfSM"):
+            assert open(out + ext).read() == open(str(tmp_path / ("cohort%d" % i)) + ext).read(), (i, ext)

@@ -107,3 +107,24 @@ def test_nelder_mead_gives_up_after_cycle_max():
         return float((-1) ** calls[0] * (1 + calls[0] % 7))
     r, _, cyc = host.amoeba_minimize(noisy, [0.0, 0.0], 1e-8)
     assert r == np.finfo(np.float64).max and cyc > 50000      # MathGenMin.cpp:380-383
+
+
+def test_cohort_lock_step_keeps_every_trajectory():
+    """Cohort mode: samples optimise concurrently, the coordinator serves all pending requests with one launch;
+    each sample must land exactly where it lands alone, and the launch count is the longest sample's eval count."""
+    def rosen(v):
+        return float(sum(100.0 * (v[i + 1] - v[i] ** 2) ** 2 + (1 - v[i]) ** 2 for i in range(len(v) - 1)) + (v[0] - 0.3) ** 2)
+    n, dim = 7, 3
+    starts = np.array([[0.01 + 0.02 * i] * dim for i in range(n)])
+    launches, pts, fmin, cyc = host.cohort_selftest(rosen, starts, 1e-8)
+    evals = []
+    for i in range(n):
+        count = [0]
+        def f_i(v, i=i):
+            count[0] += 1
+            return rosen(v - 0.1 * i)
+        r, p, c = host.amoeba_minimize(f_i, starts[i], 1e-8)
+        assert r == fmin[i] and p.tolist() == pts[i].tolist() and c == cyc[i]
+        evals.append(count[0])
+    assert launches == max(evals)            # one launch per lock-step round, samples drop out as they converge
+    assert len(set(evals)) > 1               # (the samples really need different numbers of steps)

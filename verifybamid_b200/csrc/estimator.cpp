@@ -3,6 +3,8 @@
 // lives in llk_engine.cu and is reached only through the C ABI.
 #include "estimator.h"
 
+#include "cohort.h"
+
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -95,6 +97,11 @@ double ContaminationEstimator::FullLLKFunc::ComputeMixLLKs(const std::vector<dou
   if (E.engines.empty()) error("ComputeMixLLKs called before the engine was created");
   auto t0 = std::chrono::steady_clock::now();
   ++evalCount;
+  if (E.cohort) {  // lock-step with the other samples of the cohort: one launch evaluates all of them
+    const double llk = E.cohort->Evaluate(E.cohortIndex, E.engines[0], tPC1.data(), tPC2.data(), alpha);
+    E.engineSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return llk;
+  }
   // every marker shard (one per GPU) evaluates concurrently; partial sums are added in shard order
   for (vb2_llk_ctx *c : E.engines)
     if (vb2_llk_eval_begin(c, tPC1.data(), tPC2.data(), alpha) != VB2_OK) error("GPU engine: %s", vb2_last_error(c));
@@ -214,6 +221,21 @@ ContaminationEstimator::ContaminationEstimator(int nPC, const char *bedFile, int
   NumMarker = 0;
 }
 
+ContaminationEstimator::ContaminationEstimator(int nPC, const ContaminationEstimator &panel, int nThread, double ep)
+    : numPC(nPC), numThread(nThread), epsilon(ep), PC(2, std::vector<double>(nPC, 0.)) {
+  fn.ptr = this;
+  fn.fixPC.assign(nPC, 0.);
+  fn.fixPC2.assign(nPC, 0.);
+  fn.globalPC = fn.fixPC;
+  fn.globalPC2 = fn.fixPC2;
+  alpha = 0.5;
+  NumMarker = panel.NumMarker;
+  UD = panel.UD;
+  means = panel.means;
+  ChooseBed = panel.ChooseBed;
+  PosVec = panel.PosVec;
+}
+
 ContaminationEstimator::~ContaminationEstimator() { DestroyEngines(); }
 
 void ContaminationEstimator::BuildResolvedMarkers() {
@@ -306,24 +328,24 @@ int ContaminationEstimator::OptimizeLLK(const std::string &OutputPrefix) {
   }
   if (!isHeter) {
     if (isPCFixed) {
-      std::cout << "Estimation from OptimizeHomoFixedPC:" << std::endl;
+      if (!quiet) std::cout << "Estimation from OptimizeHomoFixedPC:" << std::endl;
       PhaseTimer t("OptimizeHomoFixedPC");
       OptimizeHomoFixedPC(myMinimizer);
     } else if (isAlphaFixed) {
       PhaseTimer t("OptimizeHomoFixedAlpha");
       OptimizeHomoFixedAlpha(myMinimizer);
     } else {
-      std::cout << "Estimation from OptimizeHomo:" << std::endl;
+      if (!quiet) std::cout << "Estimation from OptimizeHomo:" << std::endl;
       PhaseTimer t("OptimizeHomo");
       OptimizeHomo(myMinimizer);
     }
   } else {  // contamination source from a different population
     if (isPCFixed) {
-      std::cout << "Estimation from OptimizeHeterFixedPC:" << std::endl;
+      if (!quiet) std::cout << "Estimation from OptimizeHeterFixedPC:" << std::endl;
       PhaseTimer t("OptimizeHeterFixedPC");
       OptimizeHeterFixedPC(myMinimizer);
     } else if (isAlphaFixed) {
-      std::cout << "Estimation from OptimizeHeterFixedAlpha:" << std::endl;
+      if (!quiet) std::cout << "Estimation from OptimizeHeterFixedAlpha:" << std::endl;
       {
         PhaseTimer t("OptimizeHomoFixedAlpha (initial)");
         isHeter = false;
@@ -337,7 +359,7 @@ int ContaminationEstimator::OptimizeLLK(const std::string &OutputPrefix) {
         OptimizeHeterFixedAlpha(myMinimizer);
       }
     } else {
-      std::cout << "Estimation from OptimizeHeter:" << std::endl;
+      if (!quiet) std::cout << "Estimation from OptimizeHeter:" << std::endl;
       {
         PhaseTimer t("OptimizeHomo (initial)");
         isHeter = false;
@@ -360,13 +382,15 @@ int ContaminationEstimator::OptimizeLLK(const std::string &OutputPrefix) {
     PhaseTimer t("Calculate null-model LLK");
     fn.CalculateLLK0();
   }
-  std::cout << "Contaminating Sample ";
-  for (int i = 0; i < numPC; ++i) std::cout << "PC" << i + 1 << ":" << fn.globalPC[i] << "\t";
-  std::cout << std::endl;
-  std::cout << "Intended Sample ";
-  for (int i = 0; i < numPC; ++i) std::cout << "PC" << i + 1 << ":" << fn.globalPC2[i] << "\t";
-  std::cout << std::endl;
-  std::cout << "FREEMIX(Alpha):" << (fn.globalAlpha < 0.5 ? fn.globalAlpha : (1 - fn.globalAlpha)) << std::endl;
+  if (!quiet) {
+    std::cout << "Contaminating Sample ";
+    for (int i = 0; i < numPC; ++i) std::cout << "PC" << i + 1 << ":" << fn.globalPC[i] << "\t";
+    std::cout << std::endl;
+    std::cout << "Intended Sample ";
+    for (int i = 0; i < numPC; ++i) std::cout << "PC" << i + 1 << ":" << fn.globalPC2[i] << "\t";
+    std::cout << std::endl;
+    std::cout << "FREEMIX(Alpha):" << (fn.globalAlpha < 0.5 ? fn.globalAlpha : (1 - fn.globalAlpha)) << std::endl;
+  }
 
   std::string fileName(OutputPrefix + ".Ancestry");
   std::ofstream fout(fileName);

@@ -17,6 +17,8 @@
 
 namespace vb2 {
 
+class CohortCoordinator;  // cohort.h: lock-step evaluation of many samples in one launch
+
 void notice(const char *msg, ...);   // statgen/Error.cpp:70-79
 void warning(const char *msg, ...);  // statgen/Error.cpp:42-53
 [[noreturn]] void error(const char *msg, ...);  // statgen/Error.cpp:26-40: prints and throws
@@ -31,6 +33,9 @@ class ContaminationEstimator {
   int numGPU = 1;           // marker shards, one per device 0..numGPU-1
   int firstDevice = 0;
   bool panelFp64 = false;   // keep UD/mu in fp64 in HBM
+  bool quiet = false;       // cohort mode: no per-sample lines on stdout
+  CohortCoordinator *cohort = nullptr;  // cohort mode: evaluations go through the coordinator
+  int cohortIndex = -1;
 
   // ContaminationEstimator.h:76-443
   class FullLLKFunc : public VectorFunc {
@@ -69,6 +74,10 @@ class ContaminationEstimator {
   std::vector<ResolvedMarker> resolvedMarkers;
 
   ContaminationEstimator(int nPC, const char *bedFile, int nThread, double ep);  // cpp:38-51
+  // cohort mode: share an already parsed panel (.UD/.mu/.bed) instead of reading the files again
+  ContaminationEstimator(int nPC, const ContaminationEstimator &panel, int nThread, double ep);
+  ContaminationEstimator(const ContaminationEstimator &) = delete;
+  ContaminationEstimator &operator=(const ContaminationEstimator &) = delete;
   ~ContaminationEstimator();
 
   int ReadSVDMatrix(const std::string &UDpath, const std::string &PCpath, const std::string &Mean);  // cpp:334-340

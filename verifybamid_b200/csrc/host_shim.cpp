@@ -6,7 +6,11 @@
 #include <exception>
 #include <string>
 
+#include <thread>
+#include <vector>
+
 #include "amoeba.h"
+#include "cohort.h"
 #include "estimator.h"
 
 using namespace vb2;
@@ -97,6 +101,51 @@ int vb2_host_copy(void *h, int32_t *base_info_index, char *alt_base, double *kno
     memcpy(quals, E.viewer.quals.data(), E.viewer.quals.size());
   }
   return 0;
+}
+
+// Lock-step logic of cohort mode without a GPU: n samples, sample i minimises (over dim variables, from
+// start[i*dim..]) the callback fn(user, x, dim) shifted by i -- f_i(x) = fn(x - 0.1*i) -- with AmoebaMinimizer on
+// its own thread, every function value served by one CohortCoordinator whose launcher calls fn on the host.
+// out_point[n*dim], out_fmin[n], out_cycles[n]; returns the number of coordinator launches (< 0 on error).
+long vb2_host_cohort_selftest(double (*fn)(void *, const double *, int), void *user, int n, int dim, const double *start,
+                              double ftol, double *out_point, double *out_fmin, long *out_cycles) {
+  CohortCoordinator::Launcher launcher = [&](vb2_llk_ctx *const *ctxs, int m, const double *a, const double *,
+                                             const double *al, double *out) -> int {
+    for (int j = 0; j < m; ++j) {
+      const int i = (int)(intptr_t)ctxs[j] - 1;  // the "context" carries the sample number
+      std::vector<double> x(a + (size_t)j * dim, a + (size_t)(j + 1) * dim);
+      for (double &v : x) v -= 0.1 * i;
+      out[j] = fn(user, x.data(), dim) + 0.0 * al[j];
+    }
+    return VB2_OK;
+  };
+  CohortCoordinator C(n, dim, launcher);
+  struct Via : VectorFunc {
+    CohortCoordinator *c;
+    int i;
+    double Evaluate(const std::vector<double> &v) override {
+      return c->Evaluate(i, (vb2_llk_ctx *)(intptr_t)(i + 1), v.data(), v.data(), 0.0);
+    }
+  };
+  std::thread coord([&]() { C.Run(); });
+  std::vector<std::thread> workers;
+  for (int i = 0; i < n; ++i)
+    workers.emplace_back([&, i]() {
+      Via f;
+      f.c = &C;
+      f.i = i;
+      AmoebaMinimizer m;
+      m.func = &f;
+      m.Reset(dim);
+      m.point.assign(start + (size_t)i * dim, start + (size_t)(i + 1) * dim);
+      out_fmin[i] = m.Minimize(ftol);
+      for (int d = 0; d < dim; ++d) out_point[(size_t)i * dim + d] = m.point[d];
+      out_cycles[i] = m.cycleCount;
+      C.Finish(i);
+    });
+  for (auto &w : workers) w.join();
+  coord.join();
+  return C.error.empty() ? C.launches : -1;
 }
 
 void vb2_host_free(void *h) {

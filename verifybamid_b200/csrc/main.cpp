@@ -3,7 +3,8 @@
 // defaults, same <out>.selfSM / <out>.Ancestry / <out>.Pileup files, same stdout lines.
 //   --BamFile needs htslib (absent here): give --PileupFile instead.
 //   --RefVCF (SVD panel construction) is a separate offline workload and is not built.
-// Engine-only options: --NumGPU n (marker shards over devices 0..n-1), --Device d, --PanelFP64.
+// Engine-only options: --NumGPU n (marker shards over devices 0..n-1), --Device d, --PanelFP64,
+// --PileupList file (cohort mode: many samples on one panel, evaluated in lock-step, see cohort.h).
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -12,12 +13,15 @@
 #include <fstream>
 #include <iostream>
 #include <limits>
+#include <memory>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
 
+#include "cohort.h"
 #include "estimator.h"
 
 using namespace vb2;
@@ -27,7 +31,7 @@ namespace {
 struct Options {
   std::string UDPath = "Empty", MeanPath = "Empty", BedPath = "Empty", BamFile = "Empty", RefPath = "Empty";
   std::string outputPrefix = "result", PileupFile = "Empty", SVDPrefix = "Empty", knownAF = "Empty";
-  std::string RefVCF = "Empty", fixPC = "Empty";
+  std::string RefVCF = "Empty", fixPC = "Empty", PileupList = "Empty";
   double fixAlpha = -1., epsilon = 1e-8;  // main.cpp:76
   bool withinAncestry = false, outputPileup = false, verbose = false, disableSanityCheck = false;
   int seed = 12345, nPC = 2, nthread = 4;  // main.cpp:79
@@ -53,7 +57,10 @@ void usage() {
           "  --NumPC [Int] (2)  --NumThread [Int] (4, host side only)  --Seed [Int] (ignored)  --Epsilon [Double] (1e-8)\n"
           "  --WithinAncestry  --FixPC a:b:...  --FixAlpha x  --KnownAF file  --DisableSanityCheck\n"
           "  --OutputPileup  --Verbose\n"
-          "  --NumGPU [Int] (1)  --Device [Int] (0)  --PanelFP64     (engine options)\n");
+          "  --NumGPU [Int] (1)  --Device [Int] (0)  --PanelFP64     (engine options)\n"
+          "  --PileupList [String]  cohort mode: one '<pileup> [<output prefix>]' per line, all samples on the same\n"
+          "                         panel, evaluated in lock-step (one launch per simplex step for the whole cohort;\n"
+          "                         with --NumGPU n the samples are spread over n devices)\n");
 }
 
 // libStatGen-style long options: "--Name value", booleans are presence flags (params.cpp:114-185)
@@ -95,6 +102,7 @@ bool parse(int argc, char **argv, Options &o) {
     else if (ieq(name, "NumGPU")) ivalue(o.numGPU);
     else if (ieq(name, "Device")) ivalue(o.device);
     else if (ieq(name, "PanelFP64")) o.panelFp64 = true;
+    else if (ieq(name, "PileupList")) value(o.PileupList);
     else fprintf(stderr, "Command line parameter %s (#%d) ignored\n", a.c_str(), i);
   }
   return true;
@@ -111,6 +119,152 @@ struct PhaseTimer {  // main.cpp:40-54
     notice("Finished phase: %s  [%.3f seconds]", name.c_str(), secs);
   }
 };
+
+// main.cpp:285-319: model flags
+void configure_model(ContaminationEstimator &Estimator, const Options &o, bool chatty) {
+  Estimator.verbose = o.verbose;
+  Estimator.seed = o.seed;
+  Estimator.isHeter = !o.withinAncestry;
+  Estimator.isSanityCheckDisabled = o.disableSanityCheck;
+  Estimator.panelFp64 = o.panelFp64;
+  if (o.fixPC != "Empty") {
+    if (chatty) {
+      notice("you specified --fixPC, this will overide dynamic estimation of PCs");
+      notice("parsing the PCs");
+    }
+    std::stringstream ss(o.fixPC);
+    std::string token;
+    std::vector<double> tmpPC;
+    while (std::getline(ss, token, ':')) tmpPC.push_back(atof(token.c_str()));
+    if ((int)tmpPC.size() > o.nPC && chatty)
+      warning("parameter --fixPC provided larger dimension than parameter --numPC(default value 2) and hence will be truncated");
+    if ((int)tmpPC.size() < o.nPC)
+      error("parameter --fixPC provided smaller dimension than parameter --numPC(default value 2)");
+    for (int i = 0; i < o.nPC; ++i) Estimator.PC[1][i] = tmpPC[i];
+    Estimator.isPCFixed = true;
+  } else if (fabs(o.fixAlpha + 1.) > std::numeric_limits<double>::epsilon()) {
+    if (chatty) notice("you specified --fixAlpha, this will overide dynamic estimation of alpha");
+    Estimator.alpha = o.fixAlpha;
+    Estimator.isAlphaFixed = true;
+  }
+  if (o.knownAF != "Empty") {
+    Estimator.isAFknown = true;
+    Estimator.isPCFixed = true;
+    Estimator.isHeter = false;  // under --knownAF we assume the WithinAncestry model
+    Estimator.ReadAF(o.knownAF);
+  }
+}
+
+// vb1-compatible result, main.cpp:386-411
+void write_selfsm(ContaminationEstimator &Estimator, const std::string &outputPrefix) {
+  const char *headers =
+      "#SEQ_ID\tRG\tCHIP_ID\t#SNPS\t#READS\tAVG_DP\tFREEMIX\tFREELK1\tFREELK0\tFREE_RH\tFREE_RA\tCHIPMIX\tCHIPLK1\tCHIPLK0\tCHIP_RH\tCHIP_RA\tDPREF\tRDPHET\tRDPALT";
+  std::string fileName(outputPrefix + ".selfSM");
+  std::ofstream fout(fileName);
+  if (!fout.is_open()) error("Open file %s failed!", fileName.c_str());
+  fout << headers << std::endl;
+  fout << Estimator.viewer.SEQ_SM << "\tNA\tNA\t" << Estimator.NumMarker << "\t";
+  if (Estimator.isPileupInput) fout << "NA";
+  else fout << Estimator.viewer.numBases;
+  fout << "\t" << Estimator.viewer.avgDepth << "\t"
+       << ((Estimator.fn.globalAlpha < 0.5) ? Estimator.fn.globalAlpha : (1.f - Estimator.fn.globalAlpha)) << "\t"
+       << -Estimator.fn.llk1 << "\t" << -Estimator.fn.llk0 << "\t"
+       << "NA\tNA\t"
+       << "NA\tNA\tNA\tNA\tNA\t"
+       << "NA\tNA\tNA" << std::endl;
+  fout.close();
+  if (!fout) error("Errors detected when writing to file %s !", fileName.c_str());
+}
+
+// Cohort mode (--PileupList): every sample optimises on its own host thread with the reference's sequential
+// Nelder-Mead; one coordinator per GPU turns the samples' concurrent likelihood requests into one launch.
+int run_cohort(const Options &o, const std::string &UDPath, const std::string &PCPath, const std::string &MeanPath,
+               const std::string &BedPath) {
+  struct Sample {
+    std::string pileup, prefix, err;
+    std::unique_ptr<ContaminationEstimator> E;
+    int device = 0, local = 0;
+    bool ok = false;
+  };
+  std::vector<Sample> samples;
+  {
+    std::ifstream fin(o.PileupList);
+    if (!fin.is_open()) error("Open file %s failed!", o.PileupList.c_str());
+    std::string line;
+    while (std::getline(fin, line)) {
+      std::stringstream ss(line);
+      Sample smp;
+      if (!(ss >> smp.pileup)) continue;
+      if (!(ss >> smp.prefix)) smp.prefix = o.outputPrefix + "." + std::to_string(samples.size());
+      samples.push_back(std::move(smp));
+    }
+  }
+  if (samples.empty()) error("--PileupList %s names no pileup", o.PileupList.c_str());
+  notice("Cohort mode: %d samples on %d GPU(s)", (int)samples.size(), o.numGPU);
+
+  ContaminationEstimator panel(o.nPC, BedPath.c_str(), o.nthread, o.epsilon);
+  {
+    PhaseTimer t("Load SVD reference data");
+    panel.ReadSVDMatrix(UDPath, PCPath, MeanPath);
+  }
+  std::vector<int> per_device(o.numGPU, 0);
+  for (size_t i = 0; i < samples.size(); ++i) {
+    samples[i].device = o.device + (int)(i % o.numGPU);
+    samples[i].local = per_device[i % o.numGPU]++;
+  }
+  std::vector<std::unique_ptr<CohortCoordinator>> coord;
+  for (int d = 0; d < o.numGPU; ++d) coord.emplace_back(new CohortCoordinator(per_device[d], o.nPC));
+
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> workers, coordinators;
+  for (int d = 0; d < o.numGPU; ++d)
+    if (per_device[d]) coordinators.emplace_back([&, d]() { coord[d]->Run(); });
+  for (size_t i = 0; i < samples.size(); ++i)
+    workers.emplace_back([&, i]() {
+      Sample &smp = samples[i];
+      CohortCoordinator &C = *coord[smp.device - o.device];
+      try {
+        smp.E.reset(new ContaminationEstimator(o.nPC, panel, o.nthread, o.epsilon));
+        ContaminationEstimator &E = *smp.E;
+        configure_model(E, o, false);
+        E.quiet = true;
+        E.numGPU = 1;
+        E.firstDevice = smp.device;
+        E.cohort = &C;
+        E.cohortIndex = smp.local;
+        E.ReadPileup(smp.pileup);
+        if (!o.disableSanityCheck && !E.IsSanityCheckOK())
+          throw std::runtime_error("Insufficient Available markers (sanity check)");
+        E.OptimizeLLK(smp.prefix);
+        write_selfsm(E, smp.prefix);
+        smp.ok = true;
+      } catch (std::exception &e) {
+        smp.err = e.what();
+      }
+      C.Finish(smp.local);
+    });
+  for (auto &w : workers) w.join();
+  for (auto &c : coordinators) c.join();
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+  long launches = 0, evals = 0;
+  for (auto &c : coord) { launches += c->launches; evals += c->evaluations; }
+  std::cout << "#SAMPLE\tOUTPUT\tFREEMIX\tFREELK1\tFREELK0\tSTATUS" << std::endl;
+  int failed = 0;
+  for (auto &smp : samples) {
+    if (smp.ok) {
+      auto &fn = smp.E->fn;
+      std::cout << smp.pileup << "\t" << smp.prefix << "\t" << (fn.globalAlpha < 0.5 ? fn.globalAlpha : (1 - fn.globalAlpha))
+                << "\t" << -fn.llk1 << "\t" << -fn.llk0 << "\tOK" << std::endl;
+    } else {
+      ++failed;
+      std::cout << smp.pileup << "\t" << smp.prefix << "\tNA\tNA\tNA\tFAILED: " << smp.err << std::endl;
+    }
+  }
+  notice("Cohort: %d samples, %ld likelihood evaluations in %ld launches (%.1f per launch), %.3f s", (int)samples.size(),
+         evals, launches, launches ? (double)evals / launches : 0.0, secs);
+  return failed ? 1 : 0;
+}
 
 int execute(int argc, char **argv) {
   Options o;
@@ -133,7 +287,7 @@ int execute(int argc, char **argv) {
   if (o.BamFile != "Empty") {
     error("--BamFile needs htslib, which this build does not link. Produce a pileup "
           "(samtools mpileup, or --OutputPileup of the reference) and pass it with --PileupFile");
-  } else if (o.PileupFile == "Empty") {
+  } else if (o.PileupFile == "Empty" && o.PileupList == "Empty") {
     error("--BamFile or --PileupFile is required");
   }
   if (o.numGPU < 1) error("--NumGPU must be at least 1");
@@ -147,39 +301,16 @@ int execute(int argc, char **argv) {
     ~Joiner() { for (auto &x : t) if (x.joinable()) x.join(); }
   } joiner{warm};
 
+  if (o.PileupList != "Empty") {
+    for (auto &x : warm) x.join();
+    return run_cohort(o, o.UDPath, PCPath, o.MeanPath, o.BedPath);
+  }
+
   // main.cpp:283-319
   ContaminationEstimator Estimator(o.nPC, o.BedPath.c_str(), o.nthread, o.epsilon);
-  Estimator.verbose = o.verbose;
-  Estimator.seed = o.seed;
-  Estimator.isHeter = !o.withinAncestry;
-  Estimator.isSanityCheckDisabled = o.disableSanityCheck;
   Estimator.numGPU = o.numGPU;
   Estimator.firstDevice = o.device;
-  Estimator.panelFp64 = o.panelFp64;
-  if (o.fixPC != "Empty") {
-    notice("you specified --fixPC, this will overide dynamic estimation of PCs");
-    notice("parsing the PCs");
-    std::stringstream ss(o.fixPC);
-    std::string token;
-    std::vector<double> tmpPC;
-    while (std::getline(ss, token, ':')) tmpPC.push_back(atof(token.c_str()));
-    if ((int)tmpPC.size() > o.nPC)
-      warning("parameter --fixPC provided larger dimension than parameter --numPC(default value 2) and hence will be truncated");
-    if ((int)tmpPC.size() < o.nPC)
-      error("parameter --fixPC provided smaller dimension than parameter --numPC(default value 2)");
-    for (int i = 0; i < o.nPC; ++i) Estimator.PC[1][i] = tmpPC[i];
-    Estimator.isPCFixed = true;
-  } else if (fabs(o.fixAlpha + 1.) > std::numeric_limits<double>::epsilon()) {
-    notice("you specified --fixAlpha, this will overide dynamic estimation of alpha");
-    Estimator.alpha = o.fixAlpha;
-    Estimator.isAlphaFixed = true;
-  }
-  if (o.knownAF != "Empty") {
-    Estimator.isAFknown = true;
-    Estimator.isPCFixed = true;
-    Estimator.isHeter = false;  // under --knownAF we assume the WithinAncestry model
-    Estimator.ReadAF(o.knownAF);
-  }
+  configure_model(Estimator, o, true);
   {
     PhaseTimer t("Load SVD reference data");
     Estimator.ReadSVDMatrix(o.UDPath, PCPath, o.MeanPath);
@@ -226,25 +357,7 @@ int execute(int argc, char **argv) {
     PhaseTimer t("Optimize likelihood");
     Estimator.OptimizeLLK(o.outputPrefix);
   }
-  {  // vb1-compatible result, main.cpp:386-411
-    const char *headers =
-        "#SEQ_ID\tRG\tCHIP_ID\t#SNPS\t#READS\tAVG_DP\tFREEMIX\tFREELK1\tFREELK0\tFREE_RH\tFREE_RA\tCHIPMIX\tCHIPLK1\tCHIPLK0\tCHIP_RH\tCHIP_RA\tDPREF\tRDPHET\tRDPALT";
-    std::string fileName(o.outputPrefix + ".selfSM");
-    std::ofstream fout(fileName);
-    if (!fout.is_open()) error("Open file %s failed!", fileName.c_str());
-    fout << headers << std::endl;
-    fout << Estimator.viewer.SEQ_SM << "\tNA\tNA\t" << Estimator.NumMarker << "\t";
-    if (Estimator.isPileupInput) fout << "NA";
-    else fout << Estimator.viewer.numBases;
-    fout << "\t" << Estimator.viewer.avgDepth << "\t"
-         << ((Estimator.fn.globalAlpha < 0.5) ? Estimator.fn.globalAlpha : (1.f - Estimator.fn.globalAlpha)) << "\t"
-         << -Estimator.fn.llk1 << "\t" << -Estimator.fn.llk0 << "\t"
-         << "NA\tNA\t"
-         << "NA\tNA\tNA\tNA\tNA\t"
-         << "NA\tNA\tNA" << std::endl;
-    fout.close();
-    if (!fout) error("Errors detected when writing to file %s !", fileName.c_str());
-  }
+  write_selfsm(Estimator, o.outputPrefix);
   notice("Success!");
   return 0;
 }

@@ -40,6 +40,9 @@ def load_library() -> ctypes.CDLL:
                                          ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int)]
         lib.vb2_host_copy.restype = ctypes.c_int
         lib.vb2_host_copy.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 8
+        lib.vb2_host_cohort_selftest.restype = ctypes.c_long
+        lib.vb2_host_cohort_selftest.argtypes = [_CB, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         lib.vb2_host_free.restype = None
         lib.vb2_host_free.argtypes = [ctypes.c_void_p]
         _lib = lib
@@ -54,6 +57,19 @@ def amoeba_minimize(fn: Callable[[np.ndarray], float], start: Sequence[float], f
     cyc = ctypes.c_long()
     r = lib.vb2_host_amoeba_minimize(cb, None, pt.size, pt.ctypes.data, float(ftol), ctypes.byref(cyc))
     return float(r), pt, int(cyc.value)
+
+
+def cohort_selftest(fn: Callable[[np.ndarray], float], starts: np.ndarray, ftol: float = 1e-8):
+    """n samples minimise f_i(x) = fn(x - 0.1 i) concurrently through one CohortCoordinator (host launcher).
+    Returns (launches, points[n, dim], fmin[n], cycles[n])."""
+    lib = load_library()
+    st = np.ascontiguousarray(starts, dtype=np.float64)
+    n, dim = st.shape
+    pts = np.empty((n, dim)); fmin = np.empty(n); cyc = np.empty(n, dtype=np.int64)
+    cb = _CB(lambda user, v, k: float(fn(np.ctypeslib.as_array(v, shape=(k,)).copy())))
+    launches = lib.vb2_host_cohort_selftest(cb, None, n, dim, st.ctypes.data, float(ftol), pts.ctypes.data, fmin.ctypes.data,
+                                            cyc.ctypes.data)
+    return int(launches), pts, fmin, cyc
 
 
 def load_problem(svd_prefix: str, pileup: str, n_pc: int = 2, disable_sanity: bool = False,
