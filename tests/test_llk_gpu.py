@@ -69,6 +69,20 @@ def test_four_pcs(sample10k):
                        ora.compute_mix_llks(pc, list(s.pc_intended), 0.03)) <= REL_FP64
 
 
+def test_low_quality_reads_match_oracle():
+    """Phred 0..12: e up to 1.0, where the pair products F(ea)F(eb) = C0 + C1(ea+eb) + C2 ea eb cancel the most."""
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    s = synth.make_sample(panel, n_pc=2, depth=25.0, alpha=0.05, seed=21, n_markers=4000, q_lo=0, q_hi=12)
+    ora = to_oracle(s.problem)
+    with vb.LLKEngine(s.problem, panel_dtype=vb.VB2_PANEL_FP64) as eng:
+        for pc1, pc2, a in POINTS + [([0.01, 0.01], [0.01, 0.01], 1e-6)]:
+            assert rel(eng.compute_mix_llks(pc1, pc2, a), ora.compute_mix_llks(pc1, pc2, a)) <= REL_FP64
+        got = eng.eval_batch(np.array([p[0] for p in POINTS]), np.array([p[1] for p in POINTS]),
+                             np.array([p[2] for p in POINTS]))
+        for g, (pc1, pc2, a) in zip(got, POINTS):
+            assert rel(g, ora.compute_mix_llks(pc1, pc2, a)) <= REL_FP64
+
+
 def test_bit_reproducible_and_batch_equals_single(sample10k):
     with vb.LLKEngine(sample10k.problem) as eng:
         single = [eng.compute_mix_llks(*pt) for pt in POINTS]
@@ -81,6 +95,17 @@ def test_bit_reproducible_and_batch_equals_single(sample10k):
         rep = 5
         big = eng.eval_batch(np.tile(pc1, (rep, 1)), np.tile(pc2, (rep, 1)), np.tile(al, rep))
         assert big.tolist() == single * rep
+
+
+def test_launch_geometry_does_not_change_the_bits(sample10k, monkeypatch):
+    """One evaluation per launch runs 4*kc warps per CTA (kc rounds of a bin in flight at once); whatever kc, the
+    marginals of a bin are multiplied up in the same order, so the result is the same to the bit."""
+    with vb.LLKEngine(sample10k.problem) as eng:
+        want = [eng.compute_mix_llks(*pt) for pt in POINTS]
+    for kc in ("1", "2", "3"):
+        monkeypatch.setenv("VB2_LLK_LAT_KC", kc)
+        with vb.LLKEngine(sample10k.problem) as eng:
+            assert [eng.compute_mix_llks(*pt) for pt in POINTS] == want, kc
 
 
 def test_stream_sync_wait_mode(sample10k):

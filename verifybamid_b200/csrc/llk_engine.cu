@@ -33,7 +33,8 @@
 
 namespace {
 
-constexpr int kMaxWarps = 4 * vb2::kMaxConcRounds;  // 24 warps: 6 per SM sub-partition
+constexpr int kMaxConcRounds = 4;            // rounds a CTA runs concurrently in the latency geometry
+constexpr int kMaxWarps = 4 * kMaxConcRounds;  // 16 warps (4 per SM sub-partition): 128 registers per thread
 constexpr int kMaxThreads = kMaxWarps * 32;
 constexpr int kMaxArgJobs = 4;    // evaluations whose parameters travel in the kernel arguments
 constexpr int kMaxArgRounds = 16; // round-table entries that travel in the kernel arguments
@@ -129,55 +130,95 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                : "memory");
 }
 
-// Four reads (one word) of one lane, all four bytes real reads.  ALT = alt-allele reads.
+// ---------------------------------------------------------------------------------------------
+// (ii) the read stream
+// ---------------------------------------------------------------------------------------------
+// For a ref-class read with Phred error e the emission of genotype pair p is F_p(e) = c0_p + c1_p e.
+// Two reads are eaten at once through the symmetric functions of their errors,
+//     F_p(ea) F_p(eb) = C0_p + C1_p (ea + eb) + C2_p ea eb,     C0 = c0^2, C1 = c0 c1, C2 = c1^2,
+// so a word of four reads costs 4 shared instructions (two sums, two products) plus, per pair,
+// 4 DFMA + 2 DMUL: 40 fp64 instructions instead of the 48 of four separate F_p(e) factors.
+struct Quad {
+  double C0[kNumPairs], C1[kNumPairs], C2[kNumPairs];
+};
+
+// Four reads of one lane.  ALT = alt-allele reads: acc[5-p] takes what a ref read gives acc[p].
+// Written breadth-first (all pairs advance together) so that dependent instructions sit >= 6 apart.
 template <bool ALT>
-__device__ __forceinline__ void eat_word_full(uint32_t w, const double *s_e, const double (&c0)[kNumPairs],
-                                              const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
-  const double e0 = s_e[w & 0xFFu], e1 = s_e[(w >> 8) & 0xFFu], e2 = s_e[(w >> 16) & 0xFFu], e3 = s_e[w >> 24];
+__device__ __forceinline__ void eat4(double e0, double e1, double e2, double e3, const Quad &Q,
+                                     double (&acc)[kNumPairs]) {
+  const double s01 = e0 + e1, t01 = e0 * e1, s23 = e2 + e3, t23 = e2 * e3;
+  double g[kNumPairs], h[kNumPairs];
 #pragma unroll
   for (int p = 0; p < kNumPairs; ++p) {
-    // (F(e0)*F(e1)) * (F(e2)*F(e3)): same multiply count as a chain, one link on the accumulator
-    const double f01 = fma(c1[p], e0, c0[p]) * fma(c1[p], e1, c0[p]);
-    const double f23 = fma(c1[p], e2, c0[p]) * fma(c1[p], e3, c0[p]);
-    acc[ALT ? (kNumPairs - 1 - p) : p] *= f01 * f23;
+    g[p] = fma(Q.C1[p], s01, Q.C0[p]);
+    h[p] = fma(Q.C1[p], s23, Q.C0[p]);
   }
+#pragma unroll
+  for (int p = 0; p < kNumPairs; ++p) {
+    g[p] = fma(Q.C2[p], t01, g[p]);
+    h[p] = fma(Q.C2[p], t23, h[p]);
+  }
+#pragma unroll
+  for (int p = 0; p < kNumPairs; ++p) g[p] *= h[p];
+#pragma unroll
+  for (int p = 0; p < kNumPairs; ++p) acc[ALT ? (kNumPairs - 1 - p) : p] *= g[p];
+}
+
+// n rows in which every lane holds four real reads; `col` = this lane's column of the first row.  The
+// word and the four table look-ups of row t+1 are issued before the arithmetic of row t.
+template <bool ALT>
+__device__ __forceinline__ void eat_full_rows(const uint32_t *col, uint32_t n, const double *s_e, const Quad &Q,
+                                              double (&acc)[kNumPairs]) {
+  if (n == 0) return;
+  uint32_t w = col[0];
+  double e0 = s_e[w & 0xFFu], e1 = s_e[(w >> 8) & 0xFFu], e2 = s_e[(w >> 16) & 0xFFu], e3 = s_e[w >> 24];
+#pragma unroll 1
+  for (uint32_t t = 1; t < n; ++t) {
+    w = col[t * 32];
+    const double n0 = s_e[w & 0xFFu], n1 = s_e[(w >> 8) & 0xFFu], n2 = s_e[(w >> 16) & 0xFFu], n3 = s_e[w >> 24];
+    eat4<ALT>(e0, e1, e2, e3, Q, acc);
+    e0 = n0; e1 = n1; e2 = n2; e3 = n3;
+  }
+  eat4<ALT>(e0, e1, e2, e3, Q, acc);
 }
 
 // The ragged last word of a run when every lane holds the same number n (1..3) of reads in it: the
-// first n bytes are reads in all lanes, so no byte has to be inspected.
+// first n bytes are reads in all lanes, so no byte has to be inspected.  lin = {c0[6], c1[6]} (shared memory).
 template <bool ALT>
-__device__ __forceinline__ void eat_word_tail(uint32_t w, uint32_t n, const double *s_e, const double (&c0)[kNumPairs],
-                                              const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
+__device__ __forceinline__ void eat_word_tail(uint32_t w, uint32_t n, const double *s_e, const double *lin,
+                                              const Quad &Q, double (&acc)[kNumPairs]) {
   const double e0 = s_e[w & 0xFFu];
   if (n == 1) {
 #pragma unroll
-    for (int p = 0; p < kNumPairs; ++p) acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(c1[p], e0, c0[p]);
+    for (int p = 0; p < kNumPairs; ++p) acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(lin[kNumPairs + p], e0, lin[p]);
     return;
   }
   const double e1 = s_e[(w >> 8) & 0xFFu];
+  const double s = e0 + e1, t = e0 * e1;
   if (n == 2) {
 #pragma unroll
     for (int p = 0; p < kNumPairs; ++p)
-      acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(c1[p], e0, c0[p]) * fma(c1[p], e1, c0[p]);
+      acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(Q.C2[p], t, fma(Q.C1[p], s, Q.C0[p]));
     return;
   }
   const double e2 = s_e[(w >> 16) & 0xFFu];
 #pragma unroll
   for (int p = 0; p < kNumPairs; ++p)
-    acc[ALT ? (kNumPairs - 1 - p) : p] *= (fma(c1[p], e0, c0[p]) * fma(c1[p], e1, c0[p])) * fma(c1[p], e2, c0[p]);
+    acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(Q.C2[p], t, fma(Q.C1[p], s, Q.C0[p])) * fma(lin[kNumPairs + p], e2, lin[p]);
 }
 
-// A word that may carry 0xFF filler bytes (the last word of a lane's ref or alt section).
+// A word that may carry 0xFF filler bytes (the last words of a lane whose run is shorter than its slice's).
 template <bool ALT>
-__device__ __forceinline__ void eat_word_checked(uint32_t w, const double *s_e, const double (&c0)[kNumPairs],
-                                                 const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
+__device__ __forceinline__ void eat_word_checked(uint32_t w, const double *s_e, const double *lin,
+                                                 double (&acc)[kNumPairs]) {
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     const uint32_t q = (w >> (8 * b)) & 0xFFu;
     if (q != 0xFFu) {
       const double e = s_e[q];
 #pragma unroll
-      for (int p = 0; p < kNumPairs; ++p) acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(c1[p], e, c0[p]);
+      for (int p = 0; p < kNumPairs; ++p) acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(lin[kNumPairs + p], e, lin[p]);
     }
   }
 }
@@ -185,20 +226,23 @@ __device__ __forceinline__ void eat_word_checked(uint32_t w, const double *s_e, 
 // n_full rows in which every lane holds four real reads, then n_ragged rows that may hold fillers; when
 // `tail` is 1..3 the (single) ragged row holds exactly that many reads in every lane.
 template <bool ALT>
-__device__ __forceinline__ void eat_rows(const uint32_t *rows, uint32_t n_full, uint32_t n_ragged, uint32_t tail,
-                                         const double *s_e, const double (&c0)[kNumPairs],
-                                         const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
-  uint32_t t = 0;
-#pragma unroll 1
-  for (; t < n_full; ++t) eat_word_full<ALT>(rows[t * 32], s_e, c0, c1, acc);
+__device__ __forceinline__ void eat_rows(const uint32_t *col, uint32_t n_full, uint32_t n_ragged, uint32_t tail,
+                                         const double *s_e, const double *lin, const Quad &Q,
+                                         double (&acc)[kNumPairs]) {
+  eat_full_rows<ALT>(col, n_full, s_e, Q, acc);
+  if (n_ragged == 0) return;
+  col += (size_t)n_full * 32;
   if (tail && n_ragged == 1) {
-    eat_word_tail<ALT>(rows[t * 32], tail, s_e, c0, c1, acc);
+    eat_word_tail<ALT>(col[0], tail, s_e, lin, Q, acc);
     return;
   }
 #pragma unroll 1
-  for (; t < n_full + n_ragged; ++t) eat_word_checked<ALT>(rows[t * 32], s_e, c0, c1, acc);
+  for (uint32_t t = 0; t < n_ragged; ++t) eat_word_checked<ALT>(col[t * 32], s_e, lin, acc);
 }
 
+// ---------------------------------------------------------------------------------------------
+// (i) per-marker set-up
+// ---------------------------------------------------------------------------------------------
 // ContaminationEstimator.h:186-192 with the reference's comparison order (NaN passes through).
 __device__ __forceinline__ void initial_gf(double af, double min_af, double max_af, double (&gf)[3]) {
   if (af < min_af) af = min_af;
@@ -231,33 +275,47 @@ struct RuntimeLayout {
         max_af(S.max_af) {}
 };
 
-template <typename PanelT, typename Layout>
-__device__ __forceinline__ void marker_af(const uint8_t *blob, const Layout &Y, const JobParams &J, int lane,
-                                          double &af1, double &af2) {
-  // h:251-267: AF = (sum_k UD[i][k]*PC[k] + means[i]) / 2, accumulated in k order in fp64.
-  const PanelT *ud = reinterpret_cast<const PanelT *>(blob + Y.off_ud);
-  const PanelT *mu = reinterpret_cast<const PanelT *>(blob + Y.off_mu);
-  double a1 = 0., a2 = 0.;
-  if constexpr (Layout::kFixed) {
-#pragma unroll
-    for (uint32_t k = 0; k < Layout::n_pc; ++k) {
-      const double u = (double)ud[k * 32 + lane];
-      a1 = __dadd_rn(a1, __dmul_rn(u, J.pc1[k]));
-      a2 = __dadd_rn(a2, __dmul_rn(u, J.pc2[k]));
-    }
-  } else {
+// h:251-267: AF = (sum_k UD[i][k]*PC[k] + means[i]) / 2.
+//   fp64 panel: the reference's operation order exactly (products and sums rounded separately, k ascending,
+//               the mean added last), so AF is the reference's bit for bit;
+//   fp32 panel: the stored panel is already a rounded copy, so the sum runs as one FMA chain from the mean.
+template <typename Layout>
+__device__ __forceinline__ void marker_af(const uint8_t *blob, const Layout &Y, const double *pc1, const double *pc2,
+                                          int lane, double &af1, double &af2) {
+  if (Y.panel_fp64) {
+    const double *ud = reinterpret_cast<const double *>(blob + Y.off_ud);
+    double a1 = 0., a2 = 0.;
     for (uint32_t k = 0; k < Y.n_pc; ++k) {
-      const double u = (double)ud[k * 32 + lane];
-      a1 = __dadd_rn(a1, __dmul_rn(u, J.pc1[k]));
-      a2 = __dadd_rn(a2, __dmul_rn(u, J.pc2[k]));
+      const double u = ud[k * 32 + lane];
+      a1 = __dadd_rn(a1, __dmul_rn(u, pc1[k]));
+      a2 = __dadd_rn(a2, __dmul_rn(u, pc2[k]));
     }
+    const double m = reinterpret_cast<const double *>(blob + Y.off_mu)[lane];
+    af1 = (a1 + m) * 0.5;
+    af2 = (a2 + m) * 0.5;
+  } else {
+    const float *ud = reinterpret_cast<const float *>(blob + Y.off_ud);
+    double a1 = (double)reinterpret_cast<const float *>(blob + Y.off_mu)[lane], a2 = a1;
+    if constexpr (Layout::kFixed) {
+#pragma unroll
+      for (uint32_t k = 0; k < Layout::n_pc; ++k) {
+        const double u = (double)ud[k * 32 + lane];
+        a1 = fma(u, pc1[k], a1);
+        a2 = fma(u, pc2[k], a2);
+      }
+    } else {
+      for (uint32_t k = 0; k < Y.n_pc; ++k) {
+        const double u = (double)ud[k * 32 + lane];
+        a1 = fma(u, pc1[k], a1);
+        a2 = fma(u, pc2[k], a2);
+      }
+    }
+    af1 = a1 * 0.5;
+    af2 = a2 * 0.5;
   }
-  const double m = (double)mu[lane];
-  af1 = (a1 + m) * 0.5;
-  af2 = (a2 + m) * 0.5;
 }
 
-// (i) header, allele frequencies, genotype priors, diagonal pairs of the slice whose chunk 0 sits at `buf`
+// header, allele frequencies, genotype priors, diagonal pairs of the slice whose chunk 0 sits at `buf`
 struct SliceHeader {
   uint32_t wr, wa, n_valid, fr, fa, tails;
 };
@@ -269,10 +327,8 @@ __device__ __forceinline__ void slice_begin(const uint8_t *buf, const Layout &Y,
   double af1, af2;
   if (Y.known_af) {
     af1 = af2 = reinterpret_cast<const double *>(buf + Y.off_kaf)[lane];  // h:251-252
-  } else if (Y.panel_fp64) {
-    marker_af<double>(buf, Y, J, lane, af1, af2);
   } else {
-    marker_af<float>(buf, Y, J, lane, af1, af2);
+    marker_af(buf, Y, J.pc1, J.pc2, lane, af1, af2);
   }
   double gf[3], gf2[3];
   initial_gf(af1, Y.min_af, Y.max_af, gf);   // contaminating sample
@@ -285,31 +341,31 @@ __device__ __forceinline__ void slice_begin(const uint8_t *buf, const Layout &Y,
   for (int p = 0; p < kNumPairs; ++p) acc[p] = gf[pair_g1(p)] * gf2[pair_g2(p)];
 }
 
-// (ii) the word rows [t_lo, t_hi) of the slice, stored from `rows` on (this lane's column): ref rows first,
+// the word rows [t_lo, t_hi) of the slice, stored from `col` on (this lane's column): ref rows first,
 // then alt rows; rows [0,fr) and [wr, wr+fa) are filler-free in every lane.
-__device__ __forceinline__ void slice_rows(const uint32_t *rows, uint32_t t_lo, uint32_t t_hi, const SliceHeader &H,
-                                           const double *s_e, const double (&c0)[kNumPairs],
-                                           const double (&c1)[kNumPairs], double (&acc)[kNumPairs]) {
+__device__ __forceinline__ void slice_rows(const uint32_t *col, uint32_t t_lo, uint32_t t_hi, const SliceHeader &H,
+                                           const double *s_e, const double *lin, const Quad &Q,
+                                           double (&acc)[kNumPairs]) {
   if (t_hi > H.wr + H.wa) t_hi = H.wr + H.wa;
   if (t_hi <= t_lo) return;
   auto clampu = [&](uint32_t x) { return x < t_lo ? t_lo : (x > t_hi ? t_hi : x); };
   const uint32_t a0 = clampu(H.fr), a1 = clampu(H.wr), a2 = clampu(H.wr + H.fa);
   // (a uniform tail is only used when its row lies in this window together with the run's end)
-  eat_rows<false>(rows, a0 - t_lo, a1 - a0, a1 == H.wr ? (H.tails & 0xFu) : 0u, s_e, c0, c1, acc);
-  eat_rows<true>(rows + (size_t)(a1 - t_lo) * 32, a2 - a1, t_hi - a2, t_hi == H.wr + H.wa ? ((H.tails >> 4) & 0xFu) : 0u,
-                 s_e, c0, c1, acc);
+  eat_rows<false>(col, a0 - t_lo, a1 - a0, a1 == H.wr ? (H.tails & 0xFu) : 0u, s_e, lin, Q, acc);
+  eat_rows<true>(col + (size_t)(a1 - t_lo) * 32, a2 - a1, t_hi - a2, t_hi == H.wr + H.wa ? ((H.tails >> 4) & 0xFu) : 0u,
+                 s_e, lin, Q, acc);
 }
 
-// (iii) marginal over the nine genotype pairs, log.  h:307-311: markerLK = sum exp(acc)*GF[g1]*GF2[g2]; the
-// running products carry their weights and the diagonal pairs were folded into ldiag.
-__device__ __forceinline__ double slice_end(const SliceHeader &H, int lane, const double (&acc)[kNumPairs], double ldiag) {
-  const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));
-  return ((uint32_t)lane < H.n_valid && L > 0) ? log(L) : 0.0;
-}
-
-// One persistent CTA per SM.  Warp w issues on SM sub-partition w % 4 and owns bin
-// blockIdx.x*4 + w%4; warp kk = w/4 serves the rounds kk, 2kc-1-kk, 2kc+kk, ... of that bin (a snake over
-// groups of kc rounds: rounds are sorted heaviest first, so every warp gets about the same work).
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+// Warp w issues on SM sub-partition w % 4 and owns bin blockIdx.x*4 + w%4; warp kk = w/4 serves the rounds
+// kk, 2kc-1-kk, 2kc+kk, ... of that bin (a snake over groups of kc rounds: rounds are sorted heaviest first,
+// so every warp gets about the same work).  Two launch geometries:
+//   latency     one evaluation per launch: one CTA per SM with 4*kc warps (kc <= 4), all TMA copies of a
+//               bin's first kc rounds in flight at once;
+//   throughput  many evaluations per launch (gridDim.y = evaluation): kc = 1, four-warp CTAs, four of them
+//               co-resident per SM, every warp walks all rounds of its bin behind a double-buffered TMA pipeline.
 //   ARGS         sample, round table and job parameters are read from the kernel arguments
 //                (constant bank, uniform addresses); otherwise from HBM through L1.
 //   HOST_REDUCE  every CTA publishes {partial, seq} into the host-mapped mailbox and the host adds
@@ -322,6 +378,7 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   using Layout = typename std::conditional<NPC != 0, FixedLayout<NPC>, RuntimeLayout>::type;
   extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][n_buf][buf_bytes]
   __shared__ double s_e[256];
+  __shared__ __align__(16) JobParams s_job;
   __shared__ double s_red[kMaxWarps];
   __shared__ __align__(8) uint64_t s_bar[kMaxWarps][2];
 
@@ -330,9 +387,9 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   const uint32_t job = blockIdx.y;
 
   // ---- per-CTA set-up --------------------------------------------------------------------------
-  // Sample descriptor, round table and job parameters are read in place with warp-uniform loads, so a
-  // warp can arm its own mbarrier and fire its first TMA bulk copy before the single CTA-wide barrier
-  // that publishes the Phred table: the HBM latency of the blob overlaps the set-up.
+  // A warp arms its own mbarrier and fires its first TMA bulk copy before the single CTA-wide barrier
+  // that publishes the Phred table and the evaluation's parameters: the HBM latency of the first blob
+  // overlaps the set-up.
   if (lane == 0) {
     mbar_init(&s_bar[warp][0], 1);
     mbar_init(&s_bar[warp][1], 1);
@@ -340,7 +397,6 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   }
   __syncwarp();
   const SampleDev &S = (ARGS || !A.samples) ? A.sample : A.samples[job];
-  const JobParams &J = ARGS ? A.jobs[job] : A.jobs_dev[job];
   const vb2::Round *rounds_tab = ARGS ? A.rounds : S.rounds;
   const bool active_cta = blockIdx.x < S.grid_x;  // eval_many: a sample may need fewer CTAs than the grid has
   const Layout Y(S);
@@ -353,106 +409,176 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   const uint8_t *blob_base = S.blob;
   uint8_t *mybuf = s_buf + (size_t)warp * n_buf * buf_bytes;
 
-  // An item = one TMA bulk copy = one blob (CHUNKED: one chunk of a blob).
-  struct Item {
-    uint32_t r, c, n_ch, rows;  // round, chunk, chunks of this blob, word rows of this blob
-    uint32_t odd;               // parity of the round's group (r / kc) & 1
-    const uint8_t *src;
-  };
-  // the round this warp serves after a round of an even / odd group: kk -> 2kc-1-kk -> 2kc+kk -> ...
-  const uint32_t d_even = 2u * kc - 1u - 2u * kk, d_odd = 2u * kk + 1u;
-  auto seek = [&](Item &k, uint32_t r, uint32_t odd) {  // first round from r on (this warp's order) with a blob for this bin
-    k.c = 0;
-    while (r < n_rounds) {
-      const vb2::Round R = rounds_tab[r];
-      if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
-        k.rows = R.rows;
-        k.n_ch = (!CHUNKED || R.rows <= chunk_rows) ? 1u : (R.rows + chunk_rows - 1) / chunk_rows;
-        k.src = blob_base + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
-        break;
+  // This warp's blobs.  Lane i of the item table holds round rbase + i: whether this warp serves it and this
+  // bin owns a blob in it, and where that blob is (all blobs of a round have one stride, so the address is
+  // arithmetic on the round table -- no per-blob descriptor is ever loaded).
+  uint32_t rbase = 0, mask = 0, it_off16 = 0, it_rows = 0;
+  auto load_table = [&]() {
+    const uint32_t r = rbase + (uint32_t)lane;
+    bool mine = false;
+    if (r < n_rounds) {
+      const uint32_t m = r % (2u * kc);
+      if (m == kk || m == 2u * kc - 1u - kk) {
+        const vb2::Round R = rounds_tab[r];
+        if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
+          mine = true;
+          it_off16 = (uint32_t)((R.base + (uint64_t)(bin - R.first_bin) * R.stride) >> 4);
+          it_rows = R.rows;
+        }
       }
-      r += odd ? d_odd : d_even;
-      odd ^= 1u;
     }
-    k.r = r;
-    k.odd = odd;
+    mask = __ballot_sync(0xFFFFFFFFu, mine);
   };
-  auto step = [&](Item &k) {
-    if (CHUNKED && k.c + 1 < k.n_ch) ++k.c;
-    else seek(k, k.r + (k.odd ? d_odd : d_even), k.odd ^ 1u);
+  // A stage = one TMA bulk copy = one blob (CHUNKED: one chunk of a blob).
+  struct Stage {
+    uint32_t off16, rows, c, n_ch, r;
+    bool valid;
+  };
+  uint32_t q_off16 = 0, q_rows = 0, q_c = 0, q_nch = 0, q_r = 0;  // the issue cursor's current blob
+  auto advance = [&](Stage &s) {                           // s = the next stage in this warp's order
+    if (CHUNKED && q_c + 1 < q_nch) {
+      ++q_c;
+    } else {
+      while (mask == 0) {
+        rbase += 32;
+        if (rbase >= n_rounds) {
+          s.valid = false;
+          return;
+        }
+        load_table();
+      }
+      const int i = __ffs((int)mask) - 1;
+      mask &= mask - 1u;
+      q_off16 = __shfl_sync(0xFFFFFFFFu, it_off16, i);
+      q_rows = __shfl_sync(0xFFFFFFFFu, it_rows, i);
+      q_r = rbase + (uint32_t)i;
+      q_c = 0;
+      q_nch = (!CHUNKED || q_rows <= chunk_rows) ? 1u : (q_rows + chunk_rows - 1) / chunk_rows;
+    }
+    s.off16 = q_off16; s.rows = q_rows; s.c = q_c; s.n_ch = q_nch; s.r = q_r; s.valid = true;
   };
   // chunk 0 = header + panel + diag + the first chunk_rows word rows; chunk c >= 1 = the next rows
-  auto issue = [&](const Item &k, uint32_t b) {
+  auto issue = [&](const Stage &s, uint32_t b) {
     uint32_t off = 0, bytes;
     if (!CHUNKED) {
-      bytes = Y.off_words + k.rows * 128u;
-    } else if (k.c == 0) {
-      bytes = Y.off_words + (k.rows < chunk_rows ? k.rows : chunk_rows) * 128u;
+      bytes = Y.off_words + s.rows * 128u;
+    } else if (s.c == 0) {
+      bytes = Y.off_words + (s.rows < chunk_rows ? s.rows : chunk_rows) * 128u;
     } else {
-      off = Y.off_words + k.c * chunk_rows * 128u;
-      const uint32_t n = k.rows - k.c * chunk_rows;
+      off = Y.off_words + s.c * chunk_rows * 128u;
+      const uint32_t n = s.rows - s.c * chunk_rows;
       bytes = (n < chunk_rows ? n : chunk_rows) * 128u;
     }
     mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
-    bulk_g2s(mybuf + (size_t)b * buf_bytes, k.src + off, bytes, &s_bar[warp][b]);
+    bulk_g2s(mybuf + (size_t)b * buf_bytes, blob_base + ((uint64_t)s.off16 << 4) + off, bytes, &s_bar[warp][b]);
   };
-  Item cur, nxt;
-  nxt.r = n_rounds; nxt.c = 0; nxt.n_ch = 1; nxt.rows = 0; nxt.odd = 0; nxt.src = nullptr;
-  if (n_rounds) seek(nxt, kk, 0u);
-  cur = nxt;
+  Stage cur, nxt;
+  cur.valid = nxt.valid = false;
+  if (n_rounds) {
+    load_table();
+    advance(cur);
+  }
   uint32_t ib = 0, cb = 0, parity = 0;
-  if (cur.r < n_rounds) {
+  if (cur.valid) {
     if (lane == 0) issue(cur, 0);
-    step(nxt);  // nxt = the item after cur
+    advance(nxt);  // nxt = the stage after cur
     ib = n_buf - 1;
   }
+  // kc > 1: the marginals of a bin's slices meet in shared memory, [round][bin of the CTA][lane] (see below)
+  double *s_L = reinterpret_cast<double *>(s_buf + (size_t)n_warps * n_buf * buf_bytes);
+  const uint32_t n_rounds_cta = active_cta ? S.n_rounds : 0u;
+  if (kc > 1)
+    for (uint32_t i = threadIdx.x; i < n_rounds_cta * 128u; i += blockDim.x) s_L[i] = 1.0;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_e[i] = g_phred[i];
+  {
+    const double *src = reinterpret_cast<const double *>(ARGS ? &A.jobs[job] : &A.jobs_dev[job]);
+    double *dst = reinterpret_cast<double *>(&s_job);
+    for (int i = threadIdx.x; i < (int)(sizeof(JobParams) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+  }
   __syncthreads();
 
-  double vsum = 0.0;
-  if (cur.r < n_rounds) {
-    double c0[kNumPairs], c1[kNumPairs];
+  // Sum over a BIN's markers of log(marginal), kept per lane as log(prod * 2^esum) + vsum: the marginals of the
+  // bin's slices are multiplied up in round order (exponent split off after every factor) and ONE log per
+  // lane is taken at the end.  kc == 1: the bin's only warp does that as it goes.  kc > 1: the bin's warps
+  // leave their marginals in shared memory and warp (bin % 4) multiplies them up after the CTA barrier --
+  // the same factors in the same order, so both launch geometries return the same bits.
+  double vsum = 0.0, prod = 1.0;
+  int esum = 0;
+  auto combine = [&](double Lv) {  // Lv = marginal of one marker of this lane, or 1.0 (no marker / skipped)
+    if (Lv > 1e-280) prod *= Lv;
+    else vsum += log(Lv);  // (sub)normal marginal of a very deep marker: no exponent tricks
+    const int hi = __double2hiint(prod);  // prod in [1e-280, 2): positive and normal
+    esum += (hi >> 20) - 1023;
+    prod = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(prod));
+  };
+  if (cur.valid) {
+    const double *lin = s_job.c0;  // c0[6] then c1[6] (contiguous in JobParams)
+    Quad Q;
 #pragma unroll
     for (int p = 0; p < kNumPairs; ++p) {
-      c0[p] = J.c0[p];
-      c1[p] = J.c1[p];
+      const double c0 = s_job.c0[p], c1 = s_job.c1[p];
+      Q.C0[p] = c0 * c0;
+      Q.C1[p] = c0 * c1;
+      Q.C2[p] = c1 * c1;
     }
     double acc[kNumPairs], ldiag = 0.;
     SliceHeader H{0, 0, 0, 0, 0, 0};
-    while (cur.r < n_rounds) {
-      const Item upcoming = nxt;  // fetched while `cur` is consumed (needs the second buffer)
-      if (n_buf == 2 && upcoming.r < n_rounds) {
+    while (cur.valid) {
+      const Stage upcoming = nxt;  // fetched while `cur` is consumed (needs the second buffer)
+      if (n_buf == 2 && upcoming.valid) {
         __syncwarp();  // every lane finished reading the buffer about to be overwritten
         if (lane == 0) issue(upcoming, ib);
-        step(nxt);
+        advance(nxt);
         ib ^= 1u;
       }
       mbar_wait(&s_bar[warp][cb], (parity >> cb) & 1u);
       parity ^= 1u << cb;
       const uint8_t *buf = mybuf + (size_t)cb * buf_bytes;
-      if (!CHUNKED || cur.c == 0) slice_begin(buf, Y, J, lane, H, acc, ldiag);
+      if (!CHUNKED || cur.c == 0) slice_begin(buf, Y, s_job, lane, H, acc, ldiag);
+      bool last = true;
       if (!CHUNKED) {
-        slice_rows(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, 0u, H.wr + H.wa, H, s_e, c0, c1, acc);
-        vsum += slice_end(H, lane, acc, ldiag);
+        const uint32_t *col = reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane;
+        eat_rows<false>(col, H.fr, H.wr - H.fr, H.tails & 0xFu, s_e, lin, Q, acc);
+        eat_rows<true>(col + (size_t)H.wr * 32, H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, s_e, lin, Q, acc);
       } else {
         const uint32_t t_lo = cur.c * chunk_rows;
         slice_rows(reinterpret_cast<const uint32_t *>(buf + (cur.c == 0 ? Y.off_words : 0u)) + lane, t_lo,
-                   t_lo + chunk_rows, H, s_e, c0, c1, acc);
-        if (cur.c + 1 == cur.n_ch) vsum += slice_end(H, lane, acc, ldiag);
+                   t_lo + chunk_rows, H, s_e, lin, Q, acc);
+        last = cur.c + 1 == cur.n_ch;
       }
-      cur = upcoming;  // (with one buffer there is exactly one item per warp, and upcoming.r == n_rounds)
-      if (n_buf == 2) cb ^= 1u;
+      if (last) {
+        // h:307-311: markerLK = sum over the nine pairs (the running products carry their weights, the
+        // diagonal pairs were folded into ldiag); markers with markerLK <= 0 (or NaN) are skipped (h:310)
+        const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));
+        const double Lv = ((uint32_t)lane < H.n_valid && L > 0) ? L : 1.0;
+        if (kc == 1) combine(Lv);
+        else s_L[(cur.r * 4u + (uint32_t)(warp & 3)) * 32u + lane] = Lv;
+      }
+      if (n_buf == 2) {
+        cb ^= 1u;
+      } else if (upcoming.valid) {  // one buffer only: fetch the next stage now (serial)
+        __syncwarp();
+        if (lane == 0) issue(upcoming, 0);
+        advance(nxt);
+      }
+      cur = upcoming;
     }
   }
+  if (kc > 1) {
+    __syncthreads();       // every marginal of the CTA's four bins is in shared memory
+    if (warp >= 4) return;
+    for (uint32_t r = 0; r < n_rounds_cta; ++r) combine(s_L[(r * 4u + (uint32_t)warp) * 32u + lane]);
+  }
+  vsum += log(prod) + (double)esum * 0.693147180559945309417232121458;
 
-  // ---- fixed-order reduction: warp shuffle tree -> CTA -> (host | last CTA) --------------------
+  // ---- fixed-order reduction: warp shuffle tree -> the CTA's four bins -> (host | last CTA) ---------
 #pragma unroll
   for (int o = 16; o; o >>= 1) vsum += __shfl_xor_sync(0xFFFFFFFFu, vsum, o);
   if (lane == 0) s_red[warp] = vsum;
-  __syncthreads();
+  if (kc > 1) asm volatile("bar.sync 1, 128;" ::: "memory");  // (only warps 0..3 are still here)
+  else __syncthreads();
   if (!active_cta || warp != 0) return;  // warp 0 finishes alone: no other warp waits for the grid-level work
-  double cta = 0.0;
-  for (int w = 0; w < n_warps; ++w) cta += s_red[w];  // (every lane computes the same sum)
+  const double cta = ((s_red[0] + s_red[1]) + s_red[2]) + s_red[3];  // (every lane computes the same sum)
   if constexpr (HOST_REDUCE) {
     if (lane == 0) {
       Slot *slot = A.mbox + (size_t)job * S.grid_x + blockIdx.x;
@@ -658,24 +784,26 @@ int wait_mailbox(vb2_llk_ctx *ctx, uint32_t n_slots, unsigned long long seq) {
 
 enum class Reduce { kHost, kDevice };
 
-// Launch geometry.  One evaluation per launch: every warp serves one round (lowest latency).  Several
-// evaluations per launch: half as many warps per CTA, two CTAs co-resident per SM, so one CTA's data
-// wait and reduction tail hide behind the other's arithmetic (highest throughput).
+// Launch geometry.  One evaluation per launch: up to kMaxConcRounds rounds of a bin in flight at once
+// (4 warps per round).  Several evaluations per launch: four-warp CTAs, four co-resident per SM, every warp
+// walks all rounds of its bin, so one CTA's data wait and reduction tail hide behind the others' arithmetic.
 struct Geometry {
   uint32_t kc, n_buf, threads, smem;
 };
+uint32_t env_kc(const char *name, uint32_t dflt) {
+  if (const char *t = getenv(name)) return (uint32_t)std::min<int>(std::max(1, atoi(t)), kMaxConcRounds);
+  return dflt;
+}
+constexpr uint32_t kMaxMeetRounds = 64;  // kc > 1 keeps n_rounds KiB of marginals in shared memory
 Geometry geometry(const vb2_llk_ctx *ctx, bool throughput) {
   Geometry g;
   const SampleDev &S = ctx->S;
-  g.kc = std::max(1u, S.conc_rounds);
-  g.n_buf = S.n_buf;
-  if (throughput && g.kc > 1) {
-    g.kc = 1;  // measured on B200: 4-warp CTAs (six co-resident per SM), every warp walks all its rounds
-    if (const char *t = getenv("VB2_LLK_TPUT_KC")) g.kc = (uint32_t)std::min<int>(std::max(1, atoi(t)), (int)S.conc_rounds);
-    g.n_buf = g.kc < S.n_rounds || S.n_buf == 2 ? 2u : 1u;
-  }
+  const uint32_t want = throughput ? 1u : env_kc("VB2_LLK_LAT_KC", (uint32_t)kMaxConcRounds);
+  g.kc = std::max(1u, std::min(want, S.n_rounds));
+  if (S.n_rounds > kMaxMeetRounds) g.kc = 1;
+  g.n_buf = (g.kc < S.n_rounds || ctx->chunked) ? 2u : 1u;
   g.threads = 128u * g.kc;
-  g.smem = 4u * g.kc * g.n_buf * S.buf_bytes;
+  g.smem = 4u * g.kc * g.n_buf * S.buf_bytes + (g.kc > 1 ? S.n_rounds * 1024u : 0u);
   return g;
 }
 
@@ -871,10 +999,12 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   const bool default_clamps = S.min_af == 0.00005 && S.max_af == 0.99995;
   ctx->spec = (!cfg.panel_fp64 && !P.known_af && default_clamps && (P.n_pc == 2 || P.n_pc == 4)) ? (int)P.n_pc : 0;
   if (getenv("VB2_LLK_NO_SPEC")) ctx->spec = 0;  // (tests: force the runtime-layout kernel)
-  const bool one_item_per_warp = S.n_rounds <= S.conc_rounds && max_rows <= S.chunk_rows;
-  S.n_buf = one_item_per_warp ? 1u : 2u;
-  ctx->block_threads = 128u * std::max(1u, S.conc_rounds);
-  ctx->smem_bytes = (ctx->block_threads / 32u) * S.n_buf * S.buf_bytes;
+  S.n_buf = 2u;
+  {
+    const Geometry g = geometry(ctx, false);  // the one-evaluation launch (the larger CTA of the two geometries)
+    ctx->block_threads = g.threads;
+    ctx->smem_bytes = g.smem;
+  }
   if (ctx->smem_bytes > 200u * 1024u) return set_err(ctx, VB2_ERR_INVALID, "shared-memory stage too large (n_pc too big?)");
 
   // ---- result plumbing ---------------------------------------------------------------------------
