@@ -40,6 +40,7 @@ constexpr int kMaxArgJobs = 4;    // evaluations whose parameters travel in the 
 constexpr int kMaxArgRounds = 16; // round-table entries that travel in the kernel arguments
 constexpr int kNumPairs = 6;      // off-diagonal genotype pairs
 constexpr uint32_t kChunkTargetBytes = 4096;  // shared-memory stage per warp
+constexpr double kLn2 = 0.693147180559945309417232121458;
 
 // Pair p = (g1 contaminant, g2 intended): 0:(0,1) 1:(0,2) 2:(1,0) 3:(1,2) 4:(2,0) 5:(2,1).
 // The alt-allele emission is the ref-allele one with g -> 2-g (COND_LK, h:164-177), and
@@ -57,7 +58,7 @@ struct JobParams {  // one evaluation (352 bytes)
 struct SampleDev {  // one sample resident in HBM (see llk_pack.h for the blob/round layout)
   const uint8_t *blob;
   const vb2::Round *rounds;  // [n_rounds] in HBM
-  double *partials;          // [slots][grid_x]   (device-side reduction only)
+  double *partials;          // [slots][4*grid_x] (device-side reduction only; llk_kernel uses [slots][grid_x] of it)
   unsigned int *tickets;     // [slots]
   double log_other_const, min_af, max_af;
   uint32_t n_rounds, n_bins, grid_x, conc_rounds;
@@ -87,7 +88,10 @@ struct LaunchArgs {
   uint32_t n_jobs;
   uint32_t kc;     // rounds a CTA runs concurrently in THIS launch (it has 4*kc warps)
   uint32_t n_buf;  // shared-memory stages per warp in THIS launch (1 or 2)
+  uint32_t n_bins_max;   // llk_stream_kernel: bins per evaluation in this launch (tasks = n_jobs * n_bins_max)
+  uint32_t stage_bytes;  // llk_stream_kernel: bytes per shared-memory stage (largest buf_bytes of the launch)
   uint32_t pad_;
+  unsigned int *queue;   // llk_stream_kernel: next task to hand out; zero between launches (llk_reduce_kernel rewinds it)
   vb2::Round rounds[kMaxArgRounds];  // ARGS kernels: sample.rounds[0..n_rounds)
   JobParams jobs[kMaxArgJobs];       // ARGS kernels: parameters of job blockIdx.y
 };
@@ -569,7 +573,7 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
     if (warp >= 4) return;
     for (uint32_t r = 0; r < n_rounds_cta; ++r) combine(s_L[(r * 4u + (uint32_t)warp) * 32u + lane]);
   }
-  vsum += log(prod) + (double)esum * 0.693147180559945309417232121458;
+  vsum += fma((double)esum, kLn2, log(prod));
 
   // ---- fixed-order reduction: warp shuffle tree -> the CTA's four bins -> (host | last CTA) ---------
 #pragma unroll
@@ -613,6 +617,277 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// the many-evaluations kernel (throughput geometry)
+// ---------------------------------------------------------------------------------------------
+// A launch of n evaluations is n * n_bins TASKS: task (j, b) = every round of bin b for evaluation j.  The grid
+// is persistent -- four-warp CTAs, four co-resident per SM, 128 registers per thread -- and after one barrier
+// that publishes the Phred table the warps never meet again: each warp pulls tasks from a queue in HBM (its
+// first task is its own index, the rest come from an atomic counter whose next value is fetched one task
+// ahead), walks the task's blobs behind a double-buffered TMA pipeline that runs across task boundaries, and
+// leaves the task's sum in partials[j][b].  Which warp ran a task never shows in the result:
+// llk_reduce_kernel, launched behind it, adds every evaluation's partials in the fixed order llk_kernel and
+// the host use.  Everything the pipeline's issue side knows lives in shared memory (WarpCtl), so the read
+// loops keep the registers.
+struct WarpCtl {
+  const uint8_t *blob;     // the issue cursor's task: sample image, round table, sizes
+  const vb2::Round *tab;
+  uint32_t next_task, job, bin, n_rounds, chunk_rows, off_words;
+  uint32_t first;          // no stage of the cursor's task has been issued yet
+  uint32_t rbase, mask;    // item table: entry i = round rbase + i; mask = entries not yet issued
+  uint32_t off16, rows, c, nch;  // the blob being issued (CHUNKED: chunk c of nch)
+  uint32_t done;           // queue exhausted
+  uint32_t it_off16[32], it_rows[32];
+  struct StageDesc {
+    uint32_t job, bin, first, c, n_ch, chunk_rows;
+  } st[2];                 // what sits (or is landing) in each of the warp's two buffers
+};
+
+template <bool ARGS, int NPC, bool CHUNKED>
+__global__ void __launch_bounds__(128, 4)
+llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
+  using Layout = typename std::conditional<NPC != 0, FixedLayout<NPC>, RuntimeLayout>::type;
+  extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][2][stage_bytes]
+  __shared__ double s_e[256];
+  __shared__ __align__(16) JobParams s_job[4];       // the evaluation each warp is working on
+  __shared__ __align__(8) uint64_t s_bar[4][2];
+  __shared__ __align__(16) WarpCtl s_ctl[4];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    mbar_init(&s_bar[warp][0], 1);
+    mbar_init(&s_bar[warp][1], 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_e[i] = g_phred[i];
+  __syncthreads();  // the only CTA-wide barrier
+
+  const uint32_t stage_bytes = A.stage_bytes;
+  uint8_t *mybuf = s_buf + (size_t)warp * 2u * stage_bytes;
+  WarpCtl &W = s_ctl[warp];
+
+  // ---- task queue ------------------------------------------------------------------------------
+  uint32_t fetched = 0;  // (lane 0) the task after W.next_task; the atomic is in flight while a task runs
+  auto fetch = [&]() {
+    if (lane == 0) fetched = atomicAdd(A.queue, 1u) + gridDim.x * 4u;
+  };
+  if (lane == 0) {
+    W.next_task = blockIdx.x * 4u + (uint32_t)warp;
+    W.n_rounds = 0; W.first = 0; W.rbase = 0; W.mask = 0; W.c = 0; W.nch = 0; W.done = 0;
+  }
+  fetch();
+  __syncwarp();
+
+  // v = this lane's share of task (job, bin): xor-shuffle tree over the lanes -> partials[job][bin]
+  auto store_partial = [&](uint32_t job, uint32_t bin, double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) {
+      const SampleDev &S = (ARGS || !A.samples) ? A.sample : A.samples[job];
+      const uint32_t pslot = A.slots ? A.slots[job] : job;
+      S.partials[(size_t)pslot * (4u * S.grid_x) + bin] = v;
+    }
+  };
+
+  // ---- issue side: put the next stage (blob, or chunk of a blob) of this warp's task sequence into buffer b.
+  // Every lane runs it with the same values (the state is read from and written back to shared memory); returns
+  // false when the queue is exhausted.
+  auto produce = [&](uint32_t b) -> bool {
+    if (W.done) return false;
+    uint32_t c = W.c, nch = W.nch, mask = W.mask, rbase = W.rbase, n_rounds = W.n_rounds, bin = W.bin;
+    uint32_t first = W.first, off16 = W.off16, rows = W.rows;
+    const uint32_t n_bins_max = A.n_bins_max, n_tasks = A.n_jobs * n_bins_max;
+    if (CHUNKED && c + 1 < nch) {
+      ++c;
+    } else {
+      while (mask == 0) {
+        rbase += 32;
+        if (rbase >= n_rounds) {  // the task's table is exhausted: take the next task
+          if (first) store_partial(W.job, bin, 0.0);  // (it had no blob at all: an empty bin still reports in)
+          first = 0;
+          n_rounds = 0;
+          const uint32_t t = W.next_task;
+          if (t >= n_tasks) {
+            __syncwarp();
+            if (lane == 0) W.done = 1;
+            __syncwarp();
+            return false;
+          }
+          const uint32_t nt = __shfl_sync(0xFFFFFFFFu, fetched, 0);
+          fetch();
+          const uint32_t job = t / n_bins_max;
+          bin = t - job * n_bins_max;
+          const SampleDev &S = (ARGS || !A.samples) ? A.sample : A.samples[job];
+          const bool active = bin < 4u * S.grid_x;  // eval_many: a sample may have fewer bins than the launch
+          __syncwarp();
+          if (lane == 0) {
+            W.next_task = nt;
+            W.job = job;
+            W.bin = bin;
+            if (active) {
+              W.blob = S.blob;
+              W.tab = ARGS ? A.rounds : S.rounds;
+              W.chunk_rows = S.chunk_rows;
+              W.off_words = S.off_words;
+            }
+          }
+          __syncwarp();
+          if (!active) continue;
+          n_rounds = S.n_rounds;
+          first = 1;
+          rbase = 0;
+        }
+        // item table of rounds [rbase, rbase + 32): lane i looks at round rbase + i
+        const uint32_t r = rbase + (uint32_t)lane;
+        bool mine = false;
+        if (r < n_rounds) {
+          const vb2::Round R = W.tab[r];
+          if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
+            mine = true;
+            W.it_off16[lane] = (uint32_t)((R.base + (uint64_t)(bin - R.first_bin) * R.stride) >> 4);
+            W.it_rows[lane] = R.rows;
+          }
+        }
+        mask = __ballot_sync(0xFFFFFFFFu, mine);
+      }
+      const int i = __ffs((int)mask) - 1;
+      mask &= mask - 1u;
+      off16 = W.it_off16[i];
+      rows = W.it_rows[i];
+      c = 0;
+      const uint32_t chunk_rows = W.chunk_rows;
+      nch = (!CHUNKED || rows <= chunk_rows) ? 1u : (rows + chunk_rows - 1) / chunk_rows;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      // chunk 0 = header + panel + diag + the first chunk_rows word rows; chunk c >= 1 = the next rows
+      const uint32_t chunk_rows = W.chunk_rows;
+      uint32_t off_words = W.off_words;
+      if constexpr (Layout::kFixed) off_words = Layout::off_words;
+      uint32_t off = 0, bytes;
+      if (!CHUNKED) {
+        bytes = off_words + rows * 128u;
+      } else if (c == 0) {
+        bytes = off_words + (rows < chunk_rows ? rows : chunk_rows) * 128u;
+      } else {
+        off = off_words + c * chunk_rows * 128u;
+        const uint32_t n = rows - c * chunk_rows;
+        bytes = (n < chunk_rows ? n : chunk_rows) * 128u;
+      }
+      mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
+      bulk_g2s(mybuf + (size_t)b * stage_bytes, W.blob + ((uint64_t)off16 << 4) + off, bytes, &s_bar[warp][b]);
+      WarpCtl::StageDesc &D = W.st[b];
+      D.job = W.job; D.bin = bin; D.first = (first && c == 0) ? 1u : 0u; D.c = c; D.n_ch = nch; D.chunk_rows = chunk_rows;
+      W.c = c; W.nch = nch; W.mask = mask; W.rbase = rbase; W.n_rounds = n_rounds; W.first = 0;
+      W.off16 = off16; W.rows = rows;
+    }
+    __syncwarp();
+    return true;
+  };
+
+  // ---- consume ------------------------------------------------------------------------------------
+  uint32_t in_flight = 0, ib = 0, cb = 0, parity = 0;
+  if (produce(0)) {
+    in_flight = 1;
+    ib = 1;
+    if (produce(1)) {
+      in_flight = 2;
+      ib = 0;
+    }
+  }
+  double vsum = 0.0, prod = 1.0;  // the running task: sum of log(marginal) = log(prod * 2^esum) + vsum
+  int esum = 0;
+  auto combine = [&](double Lv) {
+    if (Lv > 1e-280) prod *= Lv;
+    else vsum += log(Lv);
+    const int hi = __double2hiint(prod);
+    esum += (hi >> 20) - 1023;
+    prod = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(prod));
+  };
+  auto task_value = [&]() { return vsum + fma((double)esum, kLn2, log(prod)); };
+  bool have_task = false;
+  uint32_t c_job = 0, c_bin = 0;
+  const JobParams &J = s_job[warp];
+  const double *lin = J.c0;  // c0[6] then c1[6] (contiguous in JobParams)
+  Layout Y(A.sample);
+  Quad Q;
+  double acc[kNumPairs], ldiag = 0.;
+  SliceHeader H{0, 0, 0, 0, 0, 0};
+  while (in_flight) {
+    const WarpCtl::StageDesc D = W.st[cb];
+    if (D.first) {  // a new task: close the previous one, load this evaluation's parameters
+      if (have_task) store_partial(c_job, c_bin, task_value());
+      have_task = true;
+      c_job = D.job;
+      c_bin = D.bin;
+      vsum = 0.0; prod = 1.0; esum = 0;
+      const double *src = reinterpret_cast<const double *>(ARGS ? &A.jobs[c_job] : &A.jobs_dev[c_job]);
+      double *dst = reinterpret_cast<double *>(&s_job[warp]);
+      __syncwarp();
+      for (int i = lane; i < (int)(sizeof(JobParams) / sizeof(double)); i += 32) dst[i] = src[i];
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < kNumPairs; ++p) {
+        const double c0 = J.c0[p], c1 = J.c1[p];
+        Q.C0[p] = c0 * c0;
+        Q.C1[p] = c0 * c1;
+        Q.C2[p] = c1 * c1;
+      }
+      if (!Layout::kFixed) Y = Layout((ARGS || !A.samples) ? A.sample : A.samples[c_job]);
+    }
+    mbar_wait(&s_bar[warp][cb], (parity >> cb) & 1u);
+    parity ^= 1u << cb;
+    const uint8_t *buf = mybuf + (size_t)cb * stage_bytes;
+    if (!CHUNKED || D.c == 0) slice_begin(buf, Y, J, lane, H, acc, ldiag);
+    bool last = true;
+    if (!CHUNKED) {
+      const uint32_t *col = reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane;
+      eat_rows<false>(col, H.fr, H.wr - H.fr, H.tails & 0xFu, s_e, lin, Q, acc);
+      eat_rows<true>(col + (size_t)H.wr * 32, H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, s_e, lin, Q, acc);
+    } else {
+      const uint32_t t_lo = D.c * D.chunk_rows;
+      slice_rows(reinterpret_cast<const uint32_t *>(buf + (D.c == 0 ? Y.off_words : 0u)) + lane, t_lo,
+                 t_lo + D.chunk_rows, H, s_e, lin, Q, acc);
+      last = D.c + 1 == D.n_ch;
+    }
+    if (last) {  // h:307-311, as in llk_kernel
+      const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));
+      combine(((uint32_t)lane < H.n_valid && L > 0) ? L : 1.0);
+    }
+    // the buffer just read is free: refill it (every lane passed the __syncwarp inside produce() only after
+    // its last read of the buffer)
+    --in_flight;
+    if (produce(cb)) ++in_flight;
+    cb ^= 1u;
+  }
+  if (have_task) store_partial(c_job, c_bin, task_value());
+  if (lane == 0 && fetched == 0xFFFFFFFFu) __threadfence();  // (retires the atomic still in flight)
+}
+
+// Behind llk_stream_kernel on the same stream: evaluation j's partials -> d_out[j] / mailbox slot j, in the fixed
+// order of llk_kernel (the four bins of a CTA, those lane-strided over the CTAs, then a tree); rewinds the queue.
+__global__ void __launch_bounds__(32, 1) llk_reduce_kernel(const __grid_constant__ LaunchArgs A) {
+  const uint32_t job = blockIdx.x, lane = threadIdx.x;
+  const SampleDev &S = !A.samples ? A.sample : A.samples[job];
+  const uint32_t pslot = A.slots ? A.slots[job] : job;
+  const uint32_t grid_x = S.grid_x;
+  const double *part = S.partials + (size_t)pslot * (4u * grid_x);
+  double s = 0.0;
+  for (uint32_t c = lane; c < grid_x; c += 32) {
+    const double p0 = part[4u * c], p1 = part[4u * c + 1], p2 = part[4u * c + 2], p3 = part[4u * c + 3];
+    s += ((p0 + p1) + p2) + p3;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if (lane == 0) {
+    const double out = s + S.log_other_const;
+    if (A.d_out) A.d_out[job] = out;
+    if (A.mbox)
+      *reinterpret_cast<ulonglong2 *>(A.mbox + job) = make_ulonglong2((unsigned long long)__double_as_longlong(out), A.seq);
+    if (job == 0) A.queue[0] = 0u;
+  }
+}
+
 // Pick the instantiation for a launch.  spec = 2 / 4 when every sample of the launch has the FixedLayout<spec>
 // shape, else 0; chunked = some blob is deeper than its shared-memory stage.
 template <bool ARGS, bool HOST_REDUCE>
@@ -621,6 +896,23 @@ void launch_llk(dim3 grid, dim3 block, uint32_t smem, cudaStream_t stream, const
   else if (spec == 2) llk_kernel<ARGS, HOST_REDUCE, 2, false><<<grid, block, smem, stream>>>(A);
   else if (spec == 4) llk_kernel<ARGS, HOST_REDUCE, 4, false><<<grid, block, smem, stream>>>(A);
   else llk_kernel<ARGS, HOST_REDUCE, 0, false><<<grid, block, smem, stream>>>(A);
+}
+template <bool ARGS>
+void launch_stream(dim3 grid, uint32_t smem, cudaStream_t stream, const LaunchArgs &A, int spec, bool chunked) {
+  const dim3 block(128, 1, 1);
+  if (chunked) llk_stream_kernel<ARGS, 0, true><<<grid, block, smem, stream>>>(A);
+  else if (spec == 2) llk_stream_kernel<ARGS, 2, false><<<grid, block, smem, stream>>>(A);
+  else if (spec == 4) llk_stream_kernel<ARGS, 4, false><<<grid, block, smem, stream>>>(A);
+  else llk_stream_kernel<ARGS, 0, false><<<grid, block, smem, stream>>>(A);
+  llk_reduce_kernel<<<dim3(A.n_jobs, 1, 1), dim3(32, 1, 1), 0, stream>>>(A);
+}
+template <bool ARGS>
+cudaError_t set_stream_smem_limit(int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(llk_stream_kernel<ARGS, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<ARGS, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<ARGS, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<ARGS, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return e;
 }
 template <bool ARGS, bool HOST_REDUCE>
 cudaError_t set_smem_limit(int bytes) {
@@ -660,6 +952,7 @@ struct vb2_llk_ctx {
   JobParams *h_jobs = nullptr;  // pinned staging [VB2_MAX_BATCH]
   JobParams *d_jobs = nullptr;
   double *d_out = nullptr;      // [VB2_MAX_BATCH]
+  unsigned int *d_queue = nullptr;  // llk_stream_kernel task queue {next task, warps done}
   // eval_many staging (owned by the leading context)
   SampleDev *h_many = nullptr, *d_many = nullptr;
   uint32_t *h_slots = nullptr, *d_slots = nullptr;
@@ -732,7 +1025,7 @@ int ensure_job_staging(vb2_llk_ctx *ctx) {
   return VB2_OK;
 }
 
-// Device-side reduction scratch: one row of grid_x partials + one ticket per concurrent job.
+// Device-side reduction scratch: one row of n_bins = 4*grid_x partials + one ticket per concurrent job.
 int ensure_slots(vb2_llk_ctx *ctx, uint32_t need) {
   if (need <= ctx->slots) return VB2_OK;
   uint32_t n = ctx->slots ? ctx->slots : 8;
@@ -741,7 +1034,7 @@ int ensure_slots(vb2_llk_ctx *ctx, uint32_t need) {
   double *partials = nullptr;
   unsigned int *tickets = nullptr;
   const size_t gx = ctx->S.grid_x ? ctx->S.grid_x : 1;
-  VB2_CUDA(ctx, cudaMalloc(&partials, (size_t)n * gx * sizeof(double)));
+  VB2_CUDA(ctx, cudaMalloc(&partials, (size_t)n * gx * vb2::kBinsPerCta * sizeof(double)));
   VB2_CUDA(ctx, cudaMalloc(&tickets, (size_t)n * sizeof(unsigned int)));
   VB2_CUDA(ctx, cudaMemsetAsync(tickets, 0, (size_t)n * sizeof(unsigned int), ctx->stream));
   if (ctx->S.partials) cudaFree(ctx->S.partials);
@@ -807,6 +1100,11 @@ Geometry geometry(const vb2_llk_ctx *ctx, bool throughput) {
   return g;
 }
 
+// CTAs of an llk_stream_kernel launch: four per SM (128 threads x 128 registers), never more than the tasks need.
+uint32_t stream_grid(int sm_count, uint32_t n_tasks) {
+  return std::max(1u, std::min(4u * (uint32_t)std::max(1, sm_count), (n_tasks + 3u) / 4u));
+}
+
 // Launch n evaluations of ONE sample.
 //   Reduce::kHost    n <= kMaxArgJobs: per-CTA partials go to mailbox slots [j*grid_x + cta]
 //   Reduce::kDevice  the last CTA of job j writes d_out[j] (if given) and mailbox slot [j] (if to_mailbox)
@@ -819,7 +1117,8 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
   VB2_CUDA(ctx, cudaSetDevice(ctx->device));
   const uint32_t k = ctx->S.n_pc;
   const bool args = n <= kMaxArgJobs && ctx->rounds.size() <= (size_t)kMaxArgRounds;
-  if (mode == Reduce::kHost && !args) return set_err(ctx, VB2_ERR_INVALID, "internal: host reduction needs ARGS");
+  if (mode == Reduce::kHost && (!args || n != 1))
+    return set_err(ctx, VB2_ERR_INVALID, "internal: host reduction is for one evaluation with ARGS");
   if (mode == Reduce::kDevice) {
     int rc = ensure_slots(ctx, (uint32_t)n);
     if (rc) return rc;
@@ -832,6 +1131,9 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
   A.seq = 0;
   A.n_jobs = (uint32_t)n;
   A.pad_ = 0;
+  A.n_bins_max = vb2::kBinsPerCta * ctx->S.grid_x;
+  A.stage_bytes = ctx->S.buf_bytes;
+  A.queue = ctx->d_queue;
   const Geometry g = geometry(ctx, n > 1);
   A.kc = g.kc;
   A.n_buf = g.n_buf;
@@ -853,6 +1155,13 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
     A.seq = ++ctx->seq;
     if (seq_out) *seq_out = A.seq;
   }
+  if (n > 1) {  // several evaluations: the persistent task-queue kernel
+    const dim3 sgrid(stream_grid(ctx->sm_count, (uint32_t)n * A.n_bins_max), 1, 1);
+    if (args) launch_stream<true>(sgrid, 8u * A.stage_bytes, ctx->stream, A, ctx->spec, ctx->chunked);
+    else launch_stream<false>(sgrid, 8u * A.stage_bytes, ctx->stream, A, ctx->spec, ctx->chunked);
+    VB2_CUDA(ctx, cudaGetLastError());
+    return VB2_OK;
+  }
   dim3 grid(ctx->S.grid_x, (unsigned)n, 1), block(g.threads, 1, 1);
   if (mode == Reduce::kHost) launch_llk<true, true>(grid, block, g.smem, ctx->stream, A, ctx->spec, ctx->chunked);
   else if (args) launch_llk<true, false>(grid, block, g.smem, ctx->stream, A, ctx->spec, ctx->chunked);
@@ -872,6 +1181,8 @@ int init_device_tables(vb2_llk_ctx *ctx, cudaStream_t stream) {
   VB2_CUDA(ctx, (set_smem_limit<true, true>(smem_max)));
   VB2_CUDA(ctx, (set_smem_limit<true, false>(smem_max)));
   VB2_CUDA(ctx, (set_smem_limit<false, false>(smem_max)));
+  VB2_CUDA(ctx, (set_stream_smem_limit<true>(smem_max)));
+  VB2_CUDA(ctx, (set_stream_smem_limit<false>(smem_max)));
   return VB2_OK;
 }
 
@@ -917,6 +1228,7 @@ void vb2_llk_destroy(vb2_llk_ctx *ctx) {
   if (ctx->d_sample) cudaFree(ctx->d_sample);
   if (ctx->d_jobs) cudaFree(ctx->d_jobs);
   if (ctx->d_out) cudaFree(ctx->d_out);
+  if (ctx->d_queue) cudaFree(ctx->d_queue);
   if (ctx->d_many) cudaFree(ctx->d_many);
   if (ctx->d_slots) cudaFree(ctx->d_slots);
   if (ctx->h_mbox) cudaFreeHost(ctx->h_mbox);
@@ -1013,6 +1325,8 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   memset(ctx->h_mbox, 0, sizeof(Slot) * ctx->mbox_slots);
   VB2_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->d_mbox, ctx->h_mbox, 0));
   VB2_CUDA(ctx, cudaMalloc(&ctx->d_out, sizeof(double) * VB2_MAX_BATCH));
+  VB2_CUDA(ctx, cudaMalloc(&ctx->d_queue, 2 * sizeof(unsigned int)));
+  VB2_CUDA(ctx, cudaMemsetAsync(ctx->d_queue, 0, 2 * sizeof(unsigned int), ctx->stream));
   VB2_CUDA(ctx, cudaMalloc(&ctx->d_sample, sizeof(SampleDev)));
   if ((rc = ensure_slots(ctx, 8))) return rc;
   VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1069,7 +1383,7 @@ static int begin_batch(vb2_llk_ctx *ctx, int n, const double *pc_contam, const d
   if (!ctx) return set_err(nullptr, VB2_ERR_INVALID, "null context");
   if (ctx->pending_n) return set_err(ctx, VB2_ERR_INVALID, "an evaluation is already pending on this context");
   if (n <= 0 || n > VB2_MAX_BATCH) return set_err(ctx, VB2_ERR_INVALID, "batch size out of range");
-  const bool host_reduce = n <= kMaxArgJobs && ctx->rounds.size() <= (size_t)kMaxArgRounds;
+  const bool host_reduce = n == 1 && ctx->rounds.size() <= (size_t)kMaxArgRounds;
   unsigned long long seq = 0;
   int rc = launch_batch(ctx, n, pc_contam, pc_intended, alphas, host_reduce ? Reduce::kHost : Reduce::kDevice,
                         nullptr, true, &seq);
@@ -1229,9 +1543,11 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
     A.seq = ++lead->seq;
     if (seq_out) *seq_out = A.seq;
   }
-  dim3 grid(lead->many_grid_x, lead->many_n, 1), block(128u * lead->many_kc, 1, 1);
-  launch_llk<false, false>(grid, block, 4u * lead->many_kc * 2u * lead->many_buf_bytes, lead->stream, A, lead->many_spec,
-                           lead->many_chunked);
+  A.n_bins_max = vb2::kBinsPerCta * lead->many_grid_x;
+  A.stage_bytes = lead->many_buf_bytes;
+  A.queue = lead->d_queue;
+  const dim3 grid(stream_grid(lead->sm_count, lead->many_n * A.n_bins_max), 1, 1);
+  launch_stream<false>(grid, 8u * A.stage_bytes, lead->stream, A, lead->many_spec, lead->many_chunked);
   VB2_CUDA(lead, cudaGetLastError());
   return VB2_OK;
 }
