@@ -172,6 +172,17 @@ int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
 int vb2_llk_eval_many_device(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
                              const double *alphas, double *d_llk_out);
 
+/* Evaluation session: for the several hundred DEPENDENT evaluations of one sample that a simplex search makes
+ * (AmoebaMinimizer::Minimize, MathGenMin.cpp:326-423).  vb2_llk_session_begin launches one resident kernel that
+ * keeps the whole sample in shared memory; until vb2_llk_session_end, vb2_llk_eval / _eval_begin / _eval_end on this
+ * context ring a host-mapped doorbell instead of launching (same results, bit for bit, at about half the latency).
+ * Rules: the sample must fit on chip (VB2_ERR_INVALID otherwise -- keep calling vb2_llk_eval without a session);
+ * the resident kernel owns every SM of its device, so work of OTHER contexts on that device waits until the session
+ * ends or has been idle for VB2_LLK_SESSION_IDLE_MS (default 200 ms; the kernel then leaves by itself and the next
+ * evaluation brings it back); any batched call on this context ends the session.                              */
+int vb2_llk_session_begin(vb2_llk_ctx *ctx);
+int vb2_llk_session_end(vb2_llk_ctx *ctx);
+
 /* Block until everything queued on the context's stream has finished. */
 int vb2_llk_sync(vb2_llk_ctx *ctx);
 
@@ -192,6 +203,15 @@ int vb2_llk_time_device_many(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup_lau
                              const double *pc_contam, const double *pc_intended, double alpha, float *elapsed_ms);
 int vb2_llk_time_host(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup, int steps, const double *pc_contam,
                       const double *pc_intended, double alpha, double *elapsed_s, double *last_llk);
+
+/* vb2_llk_trace: ONE vb2_llk_eval with the kernel's stage clock on.  stamps[cta][VB2_TRACE_SLOTS]:
+ * SM clock (cycles) of the CTA's first thread at 0 entry, 1 tables published, 2 warp 0's last blob landed,
+ * 3 warp 0 out of the read loop, 4 all marginals in shared memory, 5 CTA partial ready, 6 partial published;
+ * slots 8 / 9 = the GPU's global timer (ns) at entry / exit; 7, 10..14 = finer points of the prologue and the
+ * epilogue (see llk_kernel).  *n_ctas = CTAs of the launch (<= max_ctas).                                      */
+#define VB2_TRACE_SLOTS 16
+int vb2_llk_trace(vb2_llk_ctx *ctx, const double *pc_contam, const double *pc_intended, double alpha,
+                  unsigned long long *stamps, uint32_t max_ctas, uint32_t *n_ctas, double *llk_out);
 
 /* ---- diagnostics (host only, no CUDA call): the flattened image vb2_llk_create uploads ------
  * Lets CPU-only tests check the flatten (skip rules, classification, folding, slice layout,

@@ -108,6 +108,44 @@ def test_launch_geometry_does_not_change_the_bits(sample10k, monkeypatch):
             assert [eng.compute_mix_llks(*pt) for pt in POINTS] == want, kc
 
 
+def test_session_resident_kernel_returns_the_same_bits(sample10k, monkeypatch):
+    """vb2_llk_session_begin: one resident kernel, the sample in shared memory, evaluations through a doorbell."""
+    import time
+    monkeypatch.setenv("VB2_LLK_SESSION_IDLE_MS", "20")
+    with vb.LLKEngine(sample10k.problem) as eng:
+        want = [eng.compute_mix_llks(*pt) for pt in POINTS]
+        eng.session_begin()
+        eng.session_begin()                                            # idempotent
+        assert [eng.compute_mix_llks(*pt) for pt in POINTS] == want
+        eng.eval_begin(*POINTS[1])                                     # the split call rings the doorbell too
+        assert eng.eval_end() == want[1]
+        time.sleep(0.2)                                                # idle watchdog: the kernel has left by now ...
+        assert [eng.compute_mix_llks(*pt) for pt in POINTS] == want    # ... and the next doorbell brings it back
+        pc1 = np.array([pt[0] for pt in POINTS]); pc2 = np.array([pt[1] for pt in POINTS])
+        al = np.array([pt[2] for pt in POINTS])
+        assert eng.eval_batch(pc1, pc2, al).tolist() == want           # a batched call ends the session
+        assert eng.compute_mix_llks(*POINTS[0]) == want[0]             # (launch per evaluation again)
+        eng.session_begin()
+        assert eng.compute_mix_llks(*POINTS[2]) == want[2]
+        eng.session_end()
+        eng.session_end()                                              # idempotent
+        assert eng.compute_mix_llks(*POINTS[3]) == want[3]
+
+
+def test_session_on_reference_fixture_and_unsupported_shapes(monkeypatch):
+    with vb.LLKEngine(to_product(golden_problem(RESULT_PILEUP)), panel_dtype=vb.VB2_PANEL_FP64) as eng:
+        eng.session_begin()
+        for (pc1, pc2, a), want in zip(KAT_POINTS, KAT_RESULT):
+            assert rel(eng.compute_mix_llks(pc1, pc2, a), want) <= REL_FP64
+        eng.session_end()
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    deep = synth.make_sample(panel, n_pc=2, depth=200.0, alpha=0.02, seed=3, n_markers=600)
+    with vb.LLKEngine(deep.problem) as eng:                            # blobs deeper than one stage: no session
+        with pytest.raises(vb.VB2Error):
+            eng.session_begin()
+        assert np.isfinite(eng.compute_mix_llks(*POINTS[0]))
+
+
 def test_stream_sync_wait_mode(sample10k):
     with vb.LLKEngine(sample10k.problem, spin=False) as a, vb.LLKEngine(sample10k.problem, spin=True) as b:
         for pt in POINTS[:3]:

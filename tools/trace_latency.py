@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Stage timeline of the one-evaluation kernel on the bench workload (vb2_llk_trace).  Run on a GPU box."""
+import sys, os
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+import verifybamid_b200 as vb
+
+s = bench.make_workload()
+with vb.LLKEngine(s.problem) as eng:
+    for _ in range(20):
+        eng.compute_mix_llks([0.01, 0.01], [0.01, 0.01], 0.03)
+    rows = []
+    for rep in range(5):
+        llk, st = eng.trace([0.01 + 1e-7 * rep, 0.01], [0.01, 0.01], 0.03)
+        st = st.astype(np.int64)
+        order = [7, 11, 1, 2, 3, 15, 4, 12, 14, 5, 6]
+        cyc = st[:, order] - st[:, 0:1]
+        g0 = st[:, 8] - st[:, 8].min()
+        g1 = st[:, 9] - st[:, 8].min()
+        print("rep %d: global start skew max %d ns, last exit %d ns after first entry" % (rep, g0.max(), g1.max()))
+        names = ["first TMA issued", "tables requested", "tables (barrier)", "blob landed", "warp 0 loop done",
+                 "last warp loop done", "barrier passed (*)", "combined", "bin sum stored", "partial ready", "published"]
+        if rep < 4:
+            continue
+        for k, nme in enumerate(names):
+            c = cyc[:, k]
+            print("   %-18s cycles since CTA entry: min %6d  median %6d  max %6d" % (nme, c.min(), np.median(c), c.max()))
+    print("info", eng.info())

@@ -40,6 +40,8 @@ constexpr int kMaxArgJobs = 4;    // evaluations whose parameters travel in the 
 constexpr int kMaxArgRounds = 16; // round-table entries that travel in the kernel arguments
 constexpr int kNumPairs = 6;      // off-diagonal genotype pairs
 constexpr uint32_t kChunkTargetBytes = 4096;  // shared-memory stage per warp
+constexpr int kTraceSlots = 16;
+constexpr int kPhredArgs = 96;  // Phred errors 0..93 (+2 pad) that travel in the kernel arguments
 constexpr double kLn2 = 0.693147180559945309417232121458;
 
 // Pair p = (g1 contaminant, g2 intended): 0:(0,1) 1:(0,2) 2:(1,0) 3:(1,2) 4:(2,0) 5:(2,1).
@@ -65,7 +67,7 @@ struct SampleDev {  // one sample resident in HBM (see llk_pack.h for the blob/r
   uint32_t n_pc, panel_fp64, known_af, n_buf;
   uint32_t off_ud, off_mu, off_kaf, off_diag, off_words;
   uint32_t chunk_rows;  // word rows per shared-memory stage
-  uint32_t buf_bytes;   // off_words + chunk_rows * 128
+  uint32_t buf_bytes;   // off_words + (chunk_rows + 1) * 128
   uint32_t pad_;
 };
 static_assert(sizeof(SampleDev) % 8 == 0 && sizeof(SampleDev) <= 8 * 32, "SampleDev copy loop");
@@ -91,15 +93,19 @@ struct LaunchArgs {
   uint32_t n_bins_max;   // llk_stream_kernel: bins per evaluation in this launch (tasks = n_jobs * n_bins_max)
   uint32_t stage_bytes;  // llk_stream_kernel: bytes per shared-memory stage (largest buf_bytes of the launch)
   uint32_t pad_;
+  unsigned long long *trace;  // llk_kernel: [grid_x][kTraceSlots] clock stamps of thread 0 (diagnostics; usually null)
   unsigned int *queue;   // llk_stream_kernel: next task to hand out; zero between launches (llk_reduce_kernel rewinds it)
+  double phred[kPhredArgs];          // 10^(-q/10), q = 0..93, exactly as the host computes it (h:65-74)
   vb2::Round rounds[kMaxArgRounds];  // ARGS kernels: sample.rounds[0..n_rounds)
   JobParams jobs[kMaxArgJobs];       // ARGS kernels: parameters of job blockIdx.y
 };
 static_assert(sizeof(LaunchArgs) <= 4000, "kernel arguments must stay below 4 KiB");
 
-// 10^(-q/10) for q = 0..93 exactly as the host computes it (ContaminationEstimator.h:65-74);
-// entries 94..255 are 1.0 (the 0xFF filler byte indexes 255).  One copy per device, L2-resident.
-__device__ double g_phred[256];
+// 10^(-q/10), q = 0..93, travels in the kernel arguments (LaunchArgs::phred) exactly as the host computes it
+// (ContaminationEstimator.h:65-74); entries 94..255 of the shared-memory copy are 1.0 (a 0xFF filler byte indexes 255).
+// The per-CTA copy every kernel reads: at file scope, so that a look-up is ONE instruction,
+// LDS.64 [byte offset register + constant].
+__shared__ double s_e[256];
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
@@ -142,6 +148,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 //     F_p(ea) F_p(eb) = C0_p + C1_p (ea + eb) + C2_p ea eb,     C0 = c0^2, C1 = c0 c1, C2 = c1^2,
 // so a word of four reads costs 4 shared instructions (two sums, two products) plus, per pair,
 // 4 DFMA + 2 DMUL: 40 fp64 instructions instead of the 48 of four separate F_p(e) factors.
+// log of a (sub)normal marginal: never on the hot path, kept out of line so its code is not fetched
+__device__ __noinline__ double cold_log(double x) { return log(x); }
+
 struct Quad {
   double C0[kNumPairs], C1[kNumPairs], C2[kNumPairs];
 };
@@ -170,28 +179,29 @@ __device__ __forceinline__ void eat4(double e0, double e1, double e2, double e3,
 }
 
 // n rows in which every lane holds four real reads; `col` = this lane's column of the first row.  The
-// word and the four table look-ups of row t+1 are issued before the arithmetic of row t.
+// word and the four table look-ups of row t+1 are issued before the arithmetic of row t -- also after the last
+// row: the loop reads one row past the run (the next run, or the 128-byte pad every stage buffer ends with) and
+// drops what it read, which keeps the loop free of a peeled copy.
 template <bool ALT>
-__device__ __forceinline__ void eat_full_rows(const uint32_t *col, uint32_t n, const double *s_e, const Quad &Q,
+__device__ __forceinline__ void eat_full_rows(const uint32_t *col, uint32_t n, const Quad &Q,
                                               double (&acc)[kNumPairs]) {
   if (n == 0) return;
   uint32_t w = col[0];
   double e0 = s_e[w & 0xFFu], e1 = s_e[(w >> 8) & 0xFFu], e2 = s_e[(w >> 16) & 0xFFu], e3 = s_e[w >> 24];
 #pragma unroll 1
-  for (uint32_t t = 1; t < n; ++t) {
+  for (uint32_t t = 1; t <= n; ++t) {
     w = col[t * 32];
     const double n0 = s_e[w & 0xFFu], n1 = s_e[(w >> 8) & 0xFFu], n2 = s_e[(w >> 16) & 0xFFu], n3 = s_e[w >> 24];
     eat4<ALT>(e0, e1, e2, e3, Q, acc);
     e0 = n0; e1 = n1; e2 = n2; e3 = n3;
   }
-  eat4<ALT>(e0, e1, e2, e3, Q, acc);
 }
 
 // The ragged last word of a run when every lane holds the same number n (1..3) of reads in it: the
 // first n bytes are reads in all lanes, so no byte has to be inspected.  lin = {c0[6], c1[6]} (shared memory).
 template <bool ALT>
-__device__ __forceinline__ void eat_word_tail(uint32_t w, uint32_t n, const double *s_e, const double *lin,
-                                              const Quad &Q, double (&acc)[kNumPairs]) {
+__device__ __forceinline__ void eat_word_tail(uint32_t w, uint32_t n, const double *lin, const Quad &Q,
+                                              double (&acc)[kNumPairs]) {
   const double e0 = s_e[w & 0xFFu];
   if (n == 1) {
 #pragma unroll
@@ -212,36 +222,62 @@ __device__ __forceinline__ void eat_word_tail(uint32_t w, uint32_t n, const doub
     acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(Q.C2[p], t, fma(Q.C1[p], s, Q.C0[p])) * fma(lin[kNumPairs + p], e2, lin[p]);
 }
 
-// A word that may carry 0xFF filler bytes (the last words of a lane whose run is shorter than its slice's).
+// Rows that may carry 0xFF filler bytes (the last words of a lane whose run is shorter than its slice's),
+// read by read: acc *= F_p(e) = c0_p + c1_p e.
 template <bool ALT>
-__device__ __forceinline__ void eat_word_checked(uint32_t w, const double *s_e, const double *lin,
-                                                 double (&acc)[kNumPairs]) {
+__device__ __forceinline__ void eat_checked(const uint32_t *col, uint32_t n_rows, const double *lin,
+                                            double (&acc)[kNumPairs]) {
+#pragma unroll 1
+  for (uint32_t t = 0; t < n_rows; ++t) {
+    uint32_t w = col[t * 32];
+#pragma unroll 1
+    for (uint32_t b = 0; b < 4; ++b, w >>= 8) {
+      const uint32_t q = w & 0xFFu;
+      if (q != 0xFFu) {
+        const double e = s_e[q];
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const uint32_t q = (w >> (8 * b)) & 0xFFu;
-    if (q != 0xFFu) {
-      const double e = s_e[q];
-#pragma unroll
-      for (int p = 0; p < kNumPairs; ++p) acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(lin[kNumPairs + p], e, lin[p]);
+        for (int p = 0; p < kNumPairs; ++p) acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(lin[kNumPairs + p], e, lin[p]);
+      }
     }
   }
 }
 
-// n_full rows in which every lane holds four real reads, then n_ragged rows that may hold fillers; when
-// `tail` is 1..3 the (single) ragged row holds exactly that many reads in every lane.
+// One run (the ref-allele or the alt-allele reads of the slice): n_full rows in which every lane holds four real
+// reads, then n_ragged rows that may hold fillers; when `tail` is 1..3 the (single) ragged row holds exactly
+// that many reads in every lane.
 template <bool ALT>
 __device__ __forceinline__ void eat_rows(const uint32_t *col, uint32_t n_full, uint32_t n_ragged, uint32_t tail,
-                                         const double *s_e, const double *lin, const Quad &Q,
-                                         double (&acc)[kNumPairs]) {
-  eat_full_rows<ALT>(col, n_full, s_e, Q, acc);
+                                         const double *lin, const Quad &Q, double (&acc)[kNumPairs]) {
+  eat_full_rows<ALT>(col, n_full, Q, acc);
   if (n_ragged == 0) return;
   col += (size_t)n_full * 32;
-  if (tail && n_ragged == 1) {
-    eat_word_tail<ALT>(col[0], tail, s_e, lin, Q, acc);
-    return;
-  }
+  if (tail && n_ragged == 1) eat_word_tail<ALT>(col[0], tail, lin, Q, acc);
+  else eat_checked<ALT>(col, n_ragged, lin, acc);
+}
+
+// Both runs of a slice.  MERGED = false: two copies of the code (ref, alt) with the accumulators renamed at
+// compile time.  MERGED = true: ONE copy run twice with the accumulators reversed in between (acc[p] <-> acc[5-p]
+// is exactly what turns a ref read into an alt read) -- half the instructions to fetch, which is what bounds a
+// launch that evaluates once: its code arrives cold from L2 at about five cycles per instruction.
+template <bool MERGED>
+__device__ __forceinline__ void eat_runs(const uint32_t *col, uint32_t fr, uint32_t rr, uint32_t tr, uint32_t fa,
+                                         uint32_t ra, uint32_t ta, const double *lin, const Quad &Q,
+                                         double (&acc)[kNumPairs]) {
+  if constexpr (!MERGED) {
+    eat_rows<false>(col, fr, rr, tr, lin, Q, acc);
+    eat_rows<true>(col + (size_t)(fr + rr) * 32, fa, ra, ta, lin, Q, acc);
+  } else {
 #pragma unroll 1
-  for (uint32_t t = 0; t < n_ragged; ++t) eat_word_checked<ALT>(col[t * 32], s_e, lin, acc);
+    for (int cls = 0; cls < 2; ++cls) {
+      eat_rows<false>(col, fr, rr, tr, lin, Q, acc);
+      col += (size_t)(fr + rr) * 32;
+      fr = fa; rr = ra; tr = ta;
+      double t;
+      t = acc[0]; acc[0] = acc[5]; acc[5] = t;
+      t = acc[1]; acc[1] = acc[4]; acc[4] = t;
+      t = acc[2]; acc[2] = acc[3]; acc[3] = t;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -347,17 +383,16 @@ __device__ __forceinline__ void slice_begin(const uint8_t *buf, const Layout &Y,
 
 // the word rows [t_lo, t_hi) of the slice, stored from `col` on (this lane's column): ref rows first,
 // then alt rows; rows [0,fr) and [wr, wr+fa) are filler-free in every lane.
+template <bool MERGED>
 __device__ __forceinline__ void slice_rows(const uint32_t *col, uint32_t t_lo, uint32_t t_hi, const SliceHeader &H,
-                                           const double *s_e, const double *lin, const Quad &Q,
-                                           double (&acc)[kNumPairs]) {
+                                           const double *lin, const Quad &Q, double (&acc)[kNumPairs]) {
   if (t_hi > H.wr + H.wa) t_hi = H.wr + H.wa;
-  if (t_hi <= t_lo) return;
+  if (t_hi < t_lo) t_hi = t_lo;
   auto clampu = [&](uint32_t x) { return x < t_lo ? t_lo : (x > t_hi ? t_hi : x); };
   const uint32_t a0 = clampu(H.fr), a1 = clampu(H.wr), a2 = clampu(H.wr + H.fa);
   // (a uniform tail is only used when its row lies in this window together with the run's end)
-  eat_rows<false>(col, a0 - t_lo, a1 - a0, a1 == H.wr ? (H.tails & 0xFu) : 0u, s_e, lin, Q, acc);
-  eat_rows<true>(col + (size_t)(a1 - t_lo) * 32, a2 - a1, t_hi - a2, t_hi == H.wr + H.wa ? ((H.tails >> 4) & 0xFu) : 0u,
-                 s_e, lin, Q, acc);
+  eat_runs<MERGED>(col, a0 - t_lo, a1 - a0, a1 == H.wr ? (H.tails & 0xFu) : 0u, a2 - a1, t_hi - a2,
+                   t_hi == H.wr + H.wa ? ((H.tails >> 4) & 0xFu) : 0u, lin, Q, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -380,51 +415,109 @@ template <bool ARGS, bool HOST_REDUCE, int NPC, bool CHUNKED>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 llk_kernel(const __grid_constant__ LaunchArgs A) {
   using Layout = typename std::conditional<NPC != 0, FixedLayout<NPC>, RuntimeLayout>::type;
-  extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][n_buf][buf_bytes]
-  __shared__ double s_e[256];
+  extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][n_buf][buf_bytes], then (kc > 1) the marginals
   __shared__ __align__(16) JobParams s_job;
-  __shared__ double s_red[kMaxWarps];
+  __shared__ double s_red[4];
   __shared__ __align__(8) uint64_t s_bar[kMaxWarps][2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_warps = blockDim.x >> 5;
   const uint32_t job = blockIdx.y;
+  auto stamp = [&](int k) {  // diagnostics: SM clock of thread 0 at stage k (slot 8/9: global timer at entry/exit)
+    if (A.trace && threadIdx.x == 0) {
+      A.trace[blockIdx.x * kTraceSlots + k] = (unsigned long long)clock64();
+      if (k == 0 || k == 6) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        A.trace[blockIdx.x * kTraceSlots + (k == 0 ? 8 : 9)] = g;
+      }
+    }
+  };
+  stamp(0);
 
   // ---- per-CTA set-up --------------------------------------------------------------------------
-  // A warp arms its own mbarrier and fires its first TMA bulk copy before the single CTA-wide barrier
-  // that publishes the Phred table and the evaluation's parameters: the HBM latency of the first blob
-  // overlaps the set-up.
-  if (lane == 0) {
-    mbar_init(&s_bar[warp][0], 1);
-    mbar_init(&s_bar[warp][1], 1);
-    mbar_fence_init();
-  }
-  __syncwarp();
+  // The code of a launch arrives cold from L2 (about five cycles per instruction), so the order is: arm the
+  // warp's mbarriers and fire the TMA bulk copy of its first blob with as few instructions as possible, then
+  // publish the tables, then look for the second blob -- all of it under the HBM latency of the first.
   const SampleDev &S = (ARGS || !A.samples) ? A.sample : A.samples[job];
   const vb2::Round *rounds_tab = ARGS ? A.rounds : S.rounds;
   const bool active_cta = blockIdx.x < S.grid_x;  // eval_many: a sample may need fewer CTAs than the grid has
   const Layout Y(S);
-
   const uint32_t bin = blockIdx.x * vb2::kBinsPerCta + (warp & 3);
   const uint32_t kc = A.kc, kk = (uint32_t)(warp >> 2);
-  const uint32_t n_rounds = (active_cta && kk < kc) ? S.n_rounds : 0u;
+  const uint32_t n_rounds = active_cta ? S.n_rounds : 0u;
   const uint32_t chunk_rows = S.chunk_rows;
   const uint32_t n_buf = A.n_buf, buf_bytes = S.buf_bytes;
   const uint8_t *blob_base = S.blob;
   uint8_t *mybuf = s_buf + (size_t)warp * n_buf * buf_bytes;
 
-  // This warp's blobs.  Lane i of the item table holds round rbase + i: whether this warp serves it and this
-  // bin owns a blob in it, and where that blob is (all blobs of a round have one stride, so the address is
-  // arithmetic on the round table -- no per-blob descriptor is ever loaded).
+  // A stage = one TMA bulk copy = one blob (CHUNKED: one chunk of a blob).
+  struct Stage {
+    uint32_t off16, rows, c, n_ch, r;
+    bool valid;
+  };
+  // chunk 0 = header + panel + diag + the first chunk_rows word rows; chunk c >= 1 = the next rows
+  auto issue = [&](const Stage &s, uint32_t b) {
+    uint32_t off = 0, bytes;
+    if (!CHUNKED) {
+      bytes = Y.off_words + s.rows * 128u;
+    } else if (s.c == 0) {
+      bytes = Y.off_words + (s.rows < chunk_rows ? s.rows : chunk_rows) * 128u;
+    } else {
+      off = Y.off_words + s.c * chunk_rows * 128u;
+      const uint32_t n = s.rows - s.c * chunk_rows;
+      bytes = (n < chunk_rows ? n : chunk_rows) * 128u;
+    }
+    mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
+    bulk_g2s(mybuf + (size_t)b * buf_bytes, blob_base + ((uint64_t)s.off16 << 4) + off, bytes, &s_bar[warp][b]);
+  };
+  // Warp kk of a bin serves the rounds kk, 2kc-1-kk, 2kc+kk, ...: its first blob is the one of round kk.
+  Stage cur, nxt;
+  cur.valid = nxt.valid = false;
+  if (kk < n_rounds) {
+    const vb2::Round R = rounds_tab[kk];
+    if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
+      cur.off16 = (uint32_t)((R.base + (uint64_t)(bin - R.first_bin) * R.stride) >> 4);
+      cur.rows = R.rows;
+      cur.c = 0;
+      cur.n_ch = (!CHUNKED || R.rows <= chunk_rows) ? 1u : (R.rows + chunk_rows - 1) / chunk_rows;
+      cur.r = kk;
+      cur.valid = true;
+    }
+  }
+  if (lane == 0) {
+    mbar_init(&s_bar[warp][0], 1);
+    mbar_init(&s_bar[warp][1], 1);
+    mbar_fence_init();
+    if (cur.valid) issue(cur, 0);
+  }
+  __syncwarp();
+  stamp(7);
+
+  // tables: Phred errors (kernel arguments -> shared memory), this evaluation's parameters, neutral marginals
+  if (threadIdx.x < 256) s_e[threadIdx.x] = threadIdx.x < (uint32_t)kPhredArgs ? A.phred[threadIdx.x] : 1.0;
+  if (blockDim.x < 256 && threadIdx.x < 128) s_e[threadIdx.x + 128] = 1.0;
+  if (threadIdx.x < sizeof(JobParams) / sizeof(double))
+    reinterpret_cast<double *>(&s_job)[threadIdx.x] =
+        reinterpret_cast<const double *>(ARGS ? &A.jobs[job] : &A.jobs_dev[job])[threadIdx.x];
+  // kc > 1: the marginals of a bin's slices meet in shared memory, [round][bin of the CTA][lane] (see below)
+  double *s_L = reinterpret_cast<double *>(s_buf + (size_t)(blockDim.x >> 5) * n_buf * buf_bytes);
+  if (kc > 1) {
+#pragma unroll 1
+    for (uint32_t i = threadIdx.x; i < n_rounds * 128u; i += blockDim.x) s_L[i] = 1.0;
+  }
+
+  // The rest of this warp's blobs: lane i of the item table holds round rbase + i -- whether this warp serves it
+  // and this bin owns a blob in it, and where that blob is (all blobs of a round have one stride, so the address
+  // is arithmetic on the round table; no per-blob descriptor is ever loaded).
   uint32_t rbase = 0, mask = 0, it_off16 = 0, it_rows = 0;
   auto load_table = [&]() {
     const uint32_t r = rbase + (uint32_t)lane;
     bool mine = false;
-    if (r < n_rounds) {
+    if (r < n_rounds && r != kk) {
       const uint32_t m = r % (2u * kc);
       if (m == kk || m == 2u * kc - 1u - kk) {
         const vb2::Round R = rounds_tab[r];
-        if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
+        if (bin - R.first_bin < R.count) {
           mine = true;
           it_off16 = (uint32_t)((R.base + (uint64_t)(bin - R.first_bin) * R.stride) >> 4);
           it_rows = R.rows;
@@ -433,13 +526,8 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
     }
     mask = __ballot_sync(0xFFFFFFFFu, mine);
   };
-  // A stage = one TMA bulk copy = one blob (CHUNKED: one chunk of a blob).
-  struct Stage {
-    uint32_t off16, rows, c, n_ch, r;
-    bool valid;
-  };
-  uint32_t q_off16 = 0, q_rows = 0, q_c = 0, q_nch = 0, q_r = 0;  // the issue cursor's current blob
-  auto advance = [&](Stage &s) {                           // s = the next stage in this warp's order
+  uint32_t q_off16 = cur.off16, q_rows = cur.rows, q_c = cur.c, q_nch = cur.n_ch, q_r = cur.r;  // the issue cursor's blob
+  auto advance = [&](Stage &s) {  // s = the next stage in this warp's order
     if (CHUNKED && q_c + 1 < q_nch) {
       ++q_c;
     } else {
@@ -461,45 +549,14 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
     }
     s.off16 = q_off16; s.rows = q_rows; s.c = q_c; s.n_ch = q_nch; s.r = q_r; s.valid = true;
   };
-  // chunk 0 = header + panel + diag + the first chunk_rows word rows; chunk c >= 1 = the next rows
-  auto issue = [&](const Stage &s, uint32_t b) {
-    uint32_t off = 0, bytes;
-    if (!CHUNKED) {
-      bytes = Y.off_words + s.rows * 128u;
-    } else if (s.c == 0) {
-      bytes = Y.off_words + (s.rows < chunk_rows ? s.rows : chunk_rows) * 128u;
-    } else {
-      off = Y.off_words + s.c * chunk_rows * 128u;
-      const uint32_t n = s.rows - s.c * chunk_rows;
-      bytes = (n < chunk_rows ? n : chunk_rows) * 128u;
-    }
-    mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
-    bulk_g2s(mybuf + (size_t)b * buf_bytes, blob_base + ((uint64_t)s.off16 << 4) + off, bytes, &s_bar[warp][b]);
-  };
-  Stage cur, nxt;
-  cur.valid = nxt.valid = false;
-  if (n_rounds) {
+  uint32_t ib = n_buf - 1, cb = 0, parity = 0;
+  if (cur.valid && (CHUNKED || 2u * kc - 1u - kk < n_rounds)) {  // (otherwise round kk was this warp's only one)
     load_table();
-    advance(cur);
+    advance(nxt);
   }
-  uint32_t ib = 0, cb = 0, parity = 0;
-  if (cur.valid) {
-    if (lane == 0) issue(cur, 0);
-    advance(nxt);  // nxt = the stage after cur
-    ib = n_buf - 1;
-  }
-  // kc > 1: the marginals of a bin's slices meet in shared memory, [round][bin of the CTA][lane] (see below)
-  double *s_L = reinterpret_cast<double *>(s_buf + (size_t)n_warps * n_buf * buf_bytes);
-  const uint32_t n_rounds_cta = active_cta ? S.n_rounds : 0u;
-  if (kc > 1)
-    for (uint32_t i = threadIdx.x; i < n_rounds_cta * 128u; i += blockDim.x) s_L[i] = 1.0;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_e[i] = g_phred[i];
-  {
-    const double *src = reinterpret_cast<const double *>(ARGS ? &A.jobs[job] : &A.jobs_dev[job]);
-    double *dst = reinterpret_cast<double *>(&s_job);
-    for (int i = threadIdx.x; i < (int)(sizeof(JobParams) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
-  }
+  stamp(11);
   __syncthreads();
+  stamp(1);
 
   // Sum over a BIN's markers of log(marginal), kept per lane as log(prod * 2^esum) + vsum: the marginals of the
   // bin's slices are multiplied up in round order (exponent split off after every factor) and ONE log per
@@ -510,7 +567,7 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
   int esum = 0;
   auto combine = [&](double Lv) {  // Lv = marginal of one marker of this lane, or 1.0 (no marker / skipped)
     if (Lv > 1e-280) prod *= Lv;
-    else vsum += log(Lv);  // (sub)normal marginal of a very deep marker: no exponent tricks
+    else vsum += cold_log(Lv);  // (sub)normal marginal of a very deep marker: no exponent tricks
     const int hi = __double2hiint(prod);  // prod in [1e-280, 2): positive and normal
     esum += (hi >> 20) - 1023;
     prod = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(prod));
@@ -527,27 +584,28 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
     }
     double acc[kNumPairs], ldiag = 0.;
     SliceHeader H{0, 0, 0, 0, 0, 0};
+#pragma unroll 1
     while (cur.valid) {
-      const Stage upcoming = nxt;  // fetched while `cur` is consumed (needs the second buffer)
-      if (n_buf == 2 && upcoming.valid) {
-        __syncwarp();  // every lane finished reading the buffer about to be overwritten
+      const Stage upcoming = nxt;  // fetched while `cur` is consumed (the host gives two buffers whenever a
+      if (upcoming.valid) {        // warp can have more than one stage)
+        __syncwarp();              // every lane finished reading the buffer about to be overwritten
         if (lane == 0) issue(upcoming, ib);
         advance(nxt);
         ib ^= 1u;
       }
       mbar_wait(&s_bar[warp][cb], (parity >> cb) & 1u);
       parity ^= 1u << cb;
+      stamp(2);
       const uint8_t *buf = mybuf + (size_t)cb * buf_bytes;
       if (!CHUNKED || cur.c == 0) slice_begin(buf, Y, s_job, lane, H, acc, ldiag);
       bool last = true;
       if (!CHUNKED) {
-        const uint32_t *col = reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane;
-        eat_rows<false>(col, H.fr, H.wr - H.fr, H.tails & 0xFu, s_e, lin, Q, acc);
-        eat_rows<true>(col + (size_t)H.wr * 32, H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, s_e, lin, Q, acc);
+        eat_runs<true>(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, H.fr, H.wr - H.fr, H.tails & 0xFu,
+                       H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, lin, Q, acc);
       } else {
         const uint32_t t_lo = cur.c * chunk_rows;
-        slice_rows(reinterpret_cast<const uint32_t *>(buf + (cur.c == 0 ? Y.off_words : 0u)) + lane, t_lo,
-                   t_lo + chunk_rows, H, s_e, lin, Q, acc);
+        slice_rows<true>(reinterpret_cast<const uint32_t *>(buf + (cur.c == 0 ? Y.off_words : 0u)) + lane, t_lo,
+                         t_lo + chunk_rows, H, lin, Q, acc);
         last = cur.c + 1 == cur.n_ch;
       }
       if (last) {
@@ -558,36 +616,39 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
         if (kc == 1) combine(Lv);
         else s_L[(cur.r * 4u + (uint32_t)(warp & 3)) * 32u + lane] = Lv;
       }
-      if (n_buf == 2) {
-        cb ^= 1u;
-      } else if (upcoming.valid) {  // one buffer only: fetch the next stage now (serial)
-        __syncwarp();
-        if (lane == 0) issue(upcoming, 0);
-        advance(nxt);
-      }
+      cb ^= n_buf - 1u;
       cur = upcoming;
     }
   }
+  stamp(3);
+  if (A.trace && lane == 0)  // diagnostics: when the CTA's last warp left the read loop
+    atomicMax(A.trace + blockIdx.x * kTraceSlots + 15, (unsigned long long)clock64());
   if (kc > 1) {
-    __syncthreads();       // every marginal of the CTA's four bins is in shared memory
+    __syncthreads();  // every marginal of the CTA's four bins is in shared memory
+    stamp(4);
     if (warp >= 4) return;
-    for (uint32_t r = 0; r < n_rounds_cta; ++r) combine(s_L[(r * 4u + (uint32_t)warp) * 32u + lane]);
+    vsum = 0.0; prod = 1.0; esum = 0;
+#pragma unroll 1
+    for (uint32_t r = 0; r < n_rounds; ++r) combine(s_L[(r * 4u + (uint32_t)warp) * 32u + lane]);
   }
+  stamp(12);
   vsum += fma((double)esum, kLn2, log(prod));
-
-  // ---- fixed-order reduction: warp shuffle tree -> the CTA's four bins -> (host | last CTA) ---------
+  // ---- fixed-order reduction: warp shuffle tree -> the CTA's four bins -> (host | last CTA) -----
 #pragma unroll
   for (int o = 16; o; o >>= 1) vsum += __shfl_xor_sync(0xFFFFFFFFu, vsum, o);
   if (lane == 0) s_red[warp] = vsum;
+  stamp(14);
   if (kc > 1) asm volatile("bar.sync 1, 128;" ::: "memory");  // (only warps 0..3 are still here)
   else __syncthreads();
   if (!active_cta || warp != 0) return;  // warp 0 finishes alone: no other warp waits for the grid-level work
   const double cta = ((s_red[0] + s_red[1]) + s_red[2]) + s_red[3];  // (every lane computes the same sum)
+  stamp(5);
   if constexpr (HOST_REDUCE) {
     if (lane == 0) {
       Slot *slot = A.mbox + (size_t)job * S.grid_x + blockIdx.x;
       *reinterpret_cast<ulonglong2 *>(slot) = make_ulonglong2((unsigned long long)__double_as_longlong(cta), A.seq);
     }
+    stamp(6);
   } else {
     const uint32_t pslot = A.slots ? A.slots[job] : job;
     const uint32_t grid_x = S.grid_x;
@@ -643,12 +704,14 @@ struct WarpCtl {
   } st[2];                 // what sits (or is landing) in each of the warp's two buffers
 };
 
+#ifndef VB2_STREAM_CTAS_PER_SM
+#define VB2_STREAM_CTAS_PER_SM 4
+#endif
 template <bool ARGS, int NPC, bool CHUNKED>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, VB2_STREAM_CTAS_PER_SM)
 llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
   using Layout = typename std::conditional<NPC != 0, FixedLayout<NPC>, RuntimeLayout>::type;
   extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][2][stage_bytes]
-  __shared__ double s_e[256];
   __shared__ __align__(16) JobParams s_job[4];       // the evaluation each warp is working on
   __shared__ __align__(8) uint64_t s_bar[4][2];
   __shared__ __align__(16) WarpCtl s_ctl[4];
@@ -659,7 +722,7 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
     mbar_init(&s_bar[warp][1], 1);
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_e[i] = g_phred[i];
+  for (int i = threadIdx.x; i < 256; i += 128) s_e[i] = i < kPhredArgs ? A.phred[i] : 1.0;
   __syncthreads();  // the only CTA-wide barrier
 
   const uint32_t stage_bytes = A.stage_bytes;
@@ -799,7 +862,7 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
   int esum = 0;
   auto combine = [&](double Lv) {
     if (Lv > 1e-280) prod *= Lv;
-    else vsum += log(Lv);
+    else vsum += cold_log(Lv);
     const int hi = __double2hiint(prod);
     esum += (hi >> 20) - 1023;
     prod = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(prod));
@@ -841,13 +904,12 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
     if (!CHUNKED || D.c == 0) slice_begin(buf, Y, J, lane, H, acc, ldiag);
     bool last = true;
     if (!CHUNKED) {
-      const uint32_t *col = reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane;
-      eat_rows<false>(col, H.fr, H.wr - H.fr, H.tails & 0xFu, s_e, lin, Q, acc);
-      eat_rows<true>(col + (size_t)H.wr * 32, H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, s_e, lin, Q, acc);
+      eat_runs<false>(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, H.fr, H.wr - H.fr, H.tails & 0xFu,
+                      H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, lin, Q, acc);
     } else {
       const uint32_t t_lo = D.c * D.chunk_rows;
-      slice_rows(reinterpret_cast<const uint32_t *>(buf + (D.c == 0 ? Y.off_words : 0u)) + lane, t_lo,
-                 t_lo + D.chunk_rows, H, s_e, lin, Q, acc);
+      slice_rows<false>(reinterpret_cast<const uint32_t *>(buf + (D.c == 0 ? Y.off_words : 0u)) + lane, t_lo,
+                 t_lo + D.chunk_rows, H, lin, Q, acc);
       last = D.c + 1 == D.n_ch;
     }
     if (last) {  // h:307-311, as in llk_kernel
@@ -885,6 +947,181 @@ __global__ void __launch_bounds__(32, 1) llk_reduce_kernel(const __grid_constant
     if (A.mbox)
       *reinterpret_cast<ulonglong2 *>(A.mbox + job) = make_ulonglong2((unsigned long long)__double_as_longlong(out), A.seq);
     if (job == 0) A.queue[0] = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the evaluation session: a resident kernel with the sample in shared memory
+// ---------------------------------------------------------------------------------------------
+// The simplex search evaluates ONE sample several hundred times, each evaluation waiting for the previous
+// result, so a launch per evaluation pays the launch path of the part (~8 us from cudaLaunchKernel to a
+// host-visible result for an empty kernel) every time.  A session launches llk_session_kernel ONCE: one CTA per
+// SM, the geometry of llk_kernel, but every warp keeps ALL its blobs in shared memory (a 100k x 30x sample is
+// ~50 KB per SM) and the CTA then serves evaluations until told to stop:
+//   doorbell   host-mapped chunks {payload, seq}: the host writes the evaluation's coefficients and PCs and
+//              stamps every 16-byte chunk with the sequence number; warp 0 polls all chunks with one coalesced
+//              load (one PCIe round trip) until every chunk carries the number it waits for;
+//   compute    slice_begin / eat_runs / the marginals' meeting exactly as in llk_kernel (same bits), with no
+//              HBM or L2 traffic at all;
+//   answer     {CTA partial, seq} into the host mailbox; the host adds the partials in llk_kernel's order.
+// The kernel leaves on the exit doorbell, or by itself after idle_cycles without a doorbell (so a host that
+// went away cannot leave the GPU spinning); the host notices and relaunches.
+constexpr int kMaxBellChunks = 12 + 2 * VB2_MAX_PC;  // c0[6], c1[6], pc_contam[k], pc_intended[k]
+constexpr int kMaxSessionItems = 4;                  // blobs a warp may hold resident
+constexpr unsigned long long kBellExit = ~0ull;
+
+struct __align__(16) BellChunk {
+  double payload;
+  unsigned long long seq;
+};
+
+struct SessionArgs {
+  SampleDev sample;
+  const BellChunk *bell;  // device view of the host-mapped doorbell
+  Slot *mbox;             // device view of the host mailbox: slot [cta]
+  unsigned long long first_seq, idle_cycles;
+  uint32_t kc, n_items, n_chunks, pad_;
+  double phred[kPhredArgs];
+  vb2::Round rounds[kMaxArgRounds];
+};
+
+template <int NPC>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+llk_session_kernel(const __grid_constant__ SessionArgs A) {
+  using Layout = typename std::conditional<NPC != 0, FixedLayout<NPC>, RuntimeLayout>::type;
+  extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][n_items][buf_bytes], then the marginals
+  __shared__ __align__(16) JobParams s_job;
+  __shared__ double s_red[4];
+  __shared__ __align__(8) uint64_t s_bar[kMaxWarps];
+  __shared__ uint32_t s_item_r[kMaxWarps][kMaxSessionItems];
+  __shared__ uint32_t s_stop;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const SampleDev &S = A.sample;
+  const Layout Y(S);
+  const uint32_t bin = blockIdx.x * vb2::kBinsPerCta + (warp & 3);
+  const uint32_t kc = A.kc, kk = (uint32_t)(warp >> 2);
+  const uint32_t n_rounds = S.n_rounds, buf_bytes = S.buf_bytes;
+  uint8_t *mybuf = s_buf + (size_t)warp * A.n_items * buf_bytes;
+  double *s_L = reinterpret_cast<double *>(s_buf + (size_t)(blockDim.x >> 5) * A.n_items * buf_bytes);
+
+  // ---- once: fetch this warp's blobs (rounds kk, 2kc-1-kk, 2kc+kk, ... in which the bin owns one) -----
+  if (lane == 0) {
+    mbar_init(&s_bar[warp], 1);
+    mbar_fence_init();
+    uint32_t n = 0, bytes_total = 0;
+    uint32_t r = kk, odd = 0;
+    while (r < n_rounds && n < (uint32_t)kMaxSessionItems) {
+      const vb2::Round R = A.rounds[r];
+      if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
+        bytes_total += Y.off_words + R.rows * 128u;
+        s_item_r[warp][n++] = r;
+      }
+      r += odd ? 2u * kk + 1u : 2u * kc - 1u - 2u * kk;
+      odd ^= 1u;
+    }
+    for (uint32_t j = n; j < (uint32_t)kMaxSessionItems; ++j) s_item_r[warp][j] = 0xFFFFFFFFu;
+    if (n) {
+      mbar_arrive_expect_tx(&s_bar[warp], bytes_total);
+      for (uint32_t j = 0; j < n; ++j) {
+        const vb2::Round R = A.rounds[s_item_r[warp][j]];
+        bulk_g2s(mybuf + (size_t)j * buf_bytes, S.blob + R.base + (uint64_t)(bin - R.first_bin) * R.stride,
+                 Y.off_words + R.rows * 128u, &s_bar[warp]);
+      }
+    }
+  }
+  if (threadIdx.x < 256) s_e[threadIdx.x] = threadIdx.x < (uint32_t)kPhredArgs ? A.phred[threadIdx.x] : 1.0;
+  if (blockDim.x < 256 && threadIdx.x < 128) s_e[threadIdx.x + 128] = 1.0;
+  if (threadIdx.x == 0) s_stop = 0u;
+#pragma unroll 1
+  for (uint32_t i = threadIdx.x; i < n_rounds * 128u; i += blockDim.x) s_L[i] = 1.0;  // neutral marginals
+  __syncwarp();
+  uint32_t n_items = 0;
+  while (n_items < (uint32_t)kMaxSessionItems && s_item_r[warp][n_items] != 0xFFFFFFFFu) ++n_items;
+  if (n_items) mbar_wait(&s_bar[warp], 0u);  // resident from here on
+
+  unsigned long long expected = A.first_seq;
+#pragma unroll 1
+  for (;;) {
+    // ---- doorbell ----------------------------------------------------------------------------------
+    if (warp == 0) {
+      const unsigned long long t_idle = (unsigned long long)clock64();
+      const uint32_t n_chunks = A.n_chunks;
+      uint32_t stop = 0;
+      for (;;) {
+        bool ok = true, bye = false;
+#pragma unroll
+        for (uint32_t base = 0; base < (uint32_t)kMaxBellChunks; base += 32) {
+          const uint32_t i = base + (uint32_t)lane;
+          if (i < n_chunks) {
+            unsigned long long pay, seq;
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(pay), "=l"(seq) : "l"(A.bell + i) : "memory");
+            bye = bye || seq == kBellExit;
+            ok = ok && seq == expected;
+            if (seq == expected) {
+              const uint32_t k = S.n_pc;  // chunk -> JobParams: c0[6], c1[6], pc1[k] (at 12), pc2[k] (at 12 + VB2_MAX_PC)
+              const uint32_t idx = i < 12u ? i : (i < 12u + k ? i : i - k + (uint32_t)VB2_MAX_PC);
+              reinterpret_cast<double *>(&s_job)[idx] = __longlong_as_double((long long)pay);
+            }
+          }
+        }
+        if (__any_sync(0xFFFFFFFFu, bye)) { stop = 1; break; }
+        if (__all_sync(0xFFFFFFFFu, ok)) break;
+        if ((unsigned long long)clock64() - t_idle > A.idle_cycles) { stop = 1; break; }
+      }
+      if (lane == 0 && stop) s_stop = 1u;
+    }
+    __syncthreads();  // parameters (or the stop flag) published
+    if (s_stop) return;
+
+    // ---- the evaluation: every resident slice of this warp -------------------------------------------
+    if (n_items) {
+      const double *lin = s_job.c0;
+      Quad Q;
+#pragma unroll
+      for (int p = 0; p < kNumPairs; ++p) {
+        const double c0 = s_job.c0[p], c1 = s_job.c1[p];
+        Q.C0[p] = c0 * c0;
+        Q.C1[p] = c0 * c1;
+        Q.C2[p] = c1 * c1;
+      }
+#pragma unroll 1
+      for (uint32_t j = 0; j < n_items; ++j) {
+        const uint8_t *buf = mybuf + (size_t)j * buf_bytes;
+        double acc[kNumPairs], ldiag = 0.;
+        SliceHeader H{0, 0, 0, 0, 0, 0};
+        slice_begin(buf, Y, s_job, lane, H, acc, ldiag);
+        eat_runs<true>(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, H.fr, H.wr - H.fr, H.tails & 0xFu,
+                       H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, lin, Q, acc);
+        const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));  // h:307-311
+        s_L[(s_item_r[warp][j] * 4u + (uint32_t)(warp & 3)) * 32u + lane] = ((uint32_t)lane < H.n_valid && L > 0) ? L : 1.0;
+      }
+    }
+    __syncthreads();  // every marginal of the CTA's four bins is in shared memory
+    if (warp < 4) {
+      double vsum = 0.0, prod = 1.0;
+      int esum = 0;
+#pragma unroll 1
+      for (uint32_t r = 0; r < n_rounds; ++r) {  // the same factors in the same order as llk_kernel
+        const double Lv = s_L[(r * 4u + (uint32_t)warp) * 32u + lane];
+        if (Lv > 1e-280) prod *= Lv;
+        else vsum += cold_log(Lv);
+        const int hi = __double2hiint(prod);
+        esum += (hi >> 20) - 1023;
+        prod = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(prod));
+      }
+      vsum += fma((double)esum, kLn2, log(prod));
+#pragma unroll
+      for (int o = 16; o; o >>= 1) vsum += __shfl_xor_sync(0xFFFFFFFFu, vsum, o);
+      if (lane == 0) s_red[warp] = vsum;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 0 && lane == 0) {
+        const double cta = ((s_red[0] + s_red[1]) + s_red[2]) + s_red[3];
+        *reinterpret_cast<ulonglong2 *>(A.mbox + blockIdx.x) =
+            make_ulonglong2((unsigned long long)__double_as_longlong(cta), expected);
+      }
+    }
+    ++expected;
   }
 }
 
@@ -952,7 +1189,14 @@ struct vb2_llk_ctx {
   JobParams *h_jobs = nullptr;  // pinned staging [VB2_MAX_BATCH]
   JobParams *d_jobs = nullptr;
   double *d_out = nullptr;      // [VB2_MAX_BATCH]
-  unsigned int *d_queue = nullptr;  // llk_stream_kernel task queue {next task, warps done}
+  unsigned int *d_queue = nullptr;  // llk_stream_kernel task queue
+  unsigned long long *d_trace = nullptr;  // vb2_llk_trace: [grid_x][kTraceSlots]
+  bool trace_on = false;
+  // evaluation session (llk_session_kernel resident on the device)
+  BellChunk *h_bell = nullptr, *d_bell = nullptr;  // host-mapped doorbell
+  bool session_active = false;
+  uint32_t session_relaunches = 0;
+  double clock_khz = 0.0, session_idle_ms = 200.0;
   // eval_many staging (owned by the leading context)
   SampleDev *h_many = nullptr, *d_many = nullptr;
   uint32_t *h_slots = nullptr, *d_slots = nullptr;
@@ -983,6 +1227,10 @@ int set_err(vb2_llk_ctx *ctx, int code, const std::string &msg) {
                      std::string(#call) + ": " + cudaGetErrorString(e_));                           \
     }                                                                                               \
   } while (0)
+
+int session_launch(vb2_llk_ctx *ctx, unsigned long long first_seq);
+void session_stop(vb2_llk_ctx *ctx);
+void fill_phred(LaunchArgs *A);
 
 template <typename T>
 int upload(vb2_llk_ctx *ctx, const std::vector<T> &h, const T **d, bool count_bytes = true) {
@@ -1061,18 +1309,103 @@ int wait_mailbox(vb2_llk_ctx *ctx, uint32_t n_slots, unsigned long long seq) {
   auto t0 = std::chrono::steady_clock::now();
   uint32_t i = 0;
   while (i < n_slots) {
-    if (mb[i].seq == seq) { ++i; continue; }
+    if (mb[i].seq == seq) {
+      // the device's writes invalidated these lines in the host's caches: once the first slot is in, ask for all
+      // the others at once instead of missing on them one after the other (4 slots per 64-byte line)
+      if (i == 0)
+        for (uint32_t j = 4; j < n_slots; j += 4) __builtin_prefetch((const void *)(ctx->h_mbox + j), 0, 0);
+      ++i;
+      continue;
+    }
     if ((++spins & 0xFFFFu) == 0) {
       cudaError_t q = cudaStreamQuery(ctx->stream);
       if (q != cudaSuccess && q != cudaErrorNotReady)
         return set_err(ctx, VB2_ERR_CUDA, std::string("llk_kernel: ") + cudaGetErrorString(q));
-      if (q == cudaSuccess && mb[i].seq != seq)
+      if (q == cudaSuccess && mb[i].seq != seq) {
+        if (ctx->session_active) {  // the resident kernel left on its idle watchdog: bring it back for this doorbell
+          ++ctx->session_relaunches;
+          int rc = session_launch(ctx, seq);
+          if (rc) return rc;
+          continue;
+        }
         return set_err(ctx, VB2_ERR_CUDA, "kernel finished without publishing its result");
+      }
       double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       if (ms > ctx->spin_timeout_ms) return set_err(ctx, VB2_ERR_TIMEOUT, "timed out waiting for the device");
     }
   }
   return VB2_OK;
+}
+
+// ---- evaluation session (llk_session_kernel) ---------------------------------------------------------------
+template <int NPC>
+cudaError_t session_smem_limit(int bytes) {
+  return cudaFuncSetAttribute(llk_session_kernel<NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+struct SessionGeometry {
+  uint32_t kc, n_items, smem;
+  bool ok;
+};
+SessionGeometry session_geometry(const vb2_llk_ctx *ctx) {
+  SessionGeometry g{1, 1, 0, false};
+  const SampleDev &S = ctx->S;
+  if (S.grid_x == 0 || ctx->chunked || ctx->rounds.size() > (size_t)kMaxArgRounds) return g;
+  g.kc = std::max(1u, std::min((uint32_t)kMaxConcRounds, S.n_rounds));
+  g.n_items = (S.n_rounds + g.kc - 1) / g.kc;
+  g.smem = 4u * g.kc * g.n_items * S.buf_bytes + S.n_rounds * 1024u;
+  g.ok = g.n_items <= (uint32_t)kMaxSessionItems && g.smem <= 200u * 1024u;
+  return g;
+}
+// (re)launch the resident kernel; it serves sequence numbers from ctx->seq + 1 - pending on
+int session_launch(vb2_llk_ctx *ctx, unsigned long long first_seq) {
+  const SessionGeometry g = session_geometry(ctx);
+  if (!g.ok) return set_err(ctx, VB2_ERR_INVALID, "this sample cannot be held resident in shared memory");
+  SessionArgs A;
+  memset(&A, 0, sizeof(A));
+  A.sample = ctx->S;
+  A.bell = ctx->d_bell;
+  A.mbox = ctx->d_mbox;
+  A.first_seq = first_seq;
+  A.idle_cycles = (unsigned long long)(ctx->session_idle_ms * ctx->clock_khz);
+  A.kc = g.kc;
+  A.n_items = g.n_items;
+  A.n_chunks = 12u + 2u * ctx->S.n_pc;
+  LaunchArgs tmp;
+  fill_phred(&tmp);
+  memcpy(A.phred, tmp.phred, sizeof(A.phred));
+  memcpy(A.rounds, ctx->rounds.data(), ctx->rounds.size() * sizeof(vb2::Round));
+  const dim3 grid(ctx->S.grid_x, 1, 1), block(128u * g.kc, 1, 1);
+  if (ctx->spec == 2) llk_session_kernel<2><<<grid, block, g.smem, ctx->stream>>>(A);
+  else if (ctx->spec == 4) llk_session_kernel<4><<<grid, block, g.smem, ctx->stream>>>(A);
+  else llk_session_kernel<0><<<grid, block, g.smem, ctx->stream>>>(A);
+  VB2_CUDA(ctx, cudaGetLastError());
+  return VB2_OK;
+}
+// ring the doorbell for sequence number `seq`: every chunk's payload first, its stamp after it (x86 keeps the
+// order of the two stores; the device reads a chunk with one 16-byte load)
+void session_ring(vb2_llk_ctx *ctx, const JobParams &J, unsigned long long seq) {
+  const uint32_t k = ctx->S.n_pc;
+  volatile BellChunk *bell = ctx->h_bell;
+  auto put = [&](uint32_t i, double v) {
+    bell[i].payload = v;
+    __atomic_store_n(&ctx->h_bell[i].seq, seq, __ATOMIC_RELEASE);
+  };
+  for (uint32_t p = 0; p < (uint32_t)kNumPairs; ++p) {
+    put(p, J.c0[p]);
+    put(kNumPairs + p, J.c1[p]);
+  }
+  for (uint32_t j = 0; j < k; ++j) {
+    put(12u + j, J.pc1[j]);
+    put(12u + k + j, J.pc2[j]);
+  }
+}
+// stop the resident kernel (exit doorbell) and wait for it; no-op without a session
+void session_stop(vb2_llk_ctx *ctx) {
+  if (!ctx || !ctx->session_active) return;
+  __atomic_store_n(&ctx->h_bell[0].seq, kBellExit, __ATOMIC_RELEASE);
+  cudaStreamSynchronize(ctx->stream);
+  __atomic_store_n(&ctx->h_bell[0].seq, 0ull, __ATOMIC_RELEASE);
+  ctx->session_active = false;
 }
 
 enum class Reduce { kHost, kDevice };
@@ -1102,7 +1435,18 @@ Geometry geometry(const vb2_llk_ctx *ctx, bool throughput) {
 
 // CTAs of an llk_stream_kernel launch: four per SM (128 threads x 128 registers), never more than the tasks need.
 uint32_t stream_grid(int sm_count, uint32_t n_tasks) {
-  return std::max(1u, std::min(4u * (uint32_t)std::max(1, sm_count), (n_tasks + 3u) / 4u));
+  return std::max(1u, std::min((uint32_t)VB2_STREAM_CTAS_PER_SM * (uint32_t)std::max(1, sm_count), (n_tasks + 3u) / 4u));
+}
+
+void fill_phred(LaunchArgs *A) {
+  static double table[kPhredArgs];
+  static bool ready = false;
+  if (!ready) {
+    vb2::build_phred_table(table);
+    for (int q = vb2::kNumQual; q < kPhredArgs; ++q) table[q] = 1.0;
+    ready = true;
+  }
+  memcpy(A->phred, table, sizeof(table));
 }
 
 // Launch n evaluations of ONE sample.
@@ -1115,6 +1459,7 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
   if (!pc1 || !pc2 || !alphas) return set_err(ctx, VB2_ERR_INVALID, "null parameter array");
   if (ctx->S.grid_x == 0) return VB2_OK;  // no usable marker: handled by the callers
   VB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  session_stop(ctx);  // (any other launch on this context ends its evaluation session)
   const uint32_t k = ctx->S.n_pc;
   const bool args = n <= kMaxArgJobs && ctx->rounds.size() <= (size_t)kMaxArgRounds;
   if (mode == Reduce::kHost && (!args || n != 1))
@@ -1134,6 +1479,8 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
   A.n_bins_max = vb2::kBinsPerCta * ctx->S.grid_x;
   A.stage_bytes = ctx->S.buf_bytes;
   A.queue = ctx->d_queue;
+  A.trace = ctx->trace_on ? ctx->d_trace : nullptr;
+  fill_phred(&A);
   const Geometry g = geometry(ctx, n > 1);
   A.kc = g.kc;
   A.n_buf = g.n_buf;
@@ -1172,17 +1519,15 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
 
 // Phred table + kernel attributes of the CURRENT device (idempotent; the stream may be the default one).
 int init_device_tables(vb2_llk_ctx *ctx, cudaStream_t stream) {
-  double phred[256];
-  vb2::build_phred_table(phred);
-  for (int q = vb2::kNumQual; q < 256; ++q) phred[q] = 1.0;
-  VB2_CUDA(ctx, cudaMemcpyToSymbolAsync(g_phred, phred, sizeof(phred), 0, cudaMemcpyHostToDevice, stream));
-  VB2_CUDA(ctx, cudaStreamSynchronize(stream));
   const int smem_max = 200 * 1024;
   VB2_CUDA(ctx, (set_smem_limit<true, true>(smem_max)));
   VB2_CUDA(ctx, (set_smem_limit<true, false>(smem_max)));
   VB2_CUDA(ctx, (set_smem_limit<false, false>(smem_max)));
   VB2_CUDA(ctx, (set_stream_smem_limit<true>(smem_max)));
   VB2_CUDA(ctx, (set_stream_smem_limit<false>(smem_max)));
+  VB2_CUDA(ctx, (session_smem_limit<0>(smem_max)));
+  VB2_CUDA(ctx, (session_smem_limit<2>(smem_max)));
+  VB2_CUDA(ctx, (session_smem_limit<4>(smem_max)));
   return VB2_OK;
 }
 
@@ -1221,6 +1566,7 @@ const char *vb2_last_error(const vb2_llk_ctx *ctx) { return ctx ? ctx->err.c_str
 void vb2_llk_destroy(vb2_llk_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  session_stop(ctx);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (void *p : ctx->allocs) cudaFree(p);
   if (ctx->S.partials) cudaFree(ctx->S.partials);
@@ -1229,6 +1575,8 @@ void vb2_llk_destroy(vb2_llk_ctx *ctx) {
   if (ctx->d_jobs) cudaFree(ctx->d_jobs);
   if (ctx->d_out) cudaFree(ctx->d_out);
   if (ctx->d_queue) cudaFree(ctx->d_queue);
+  if (ctx->d_trace) cudaFree(ctx->d_trace);
+  if (ctx->h_bell) cudaFreeHost(ctx->h_bell);
   if (ctx->d_many) cudaFree(ctx->d_many);
   if (ctx->d_slots) cudaFree(ctx->d_slots);
   if (ctx->h_mbox) cudaFreeHost(ctx->h_mbox);
@@ -1253,6 +1601,12 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   if (prop.major < 10)
     return set_err(ctx, VB2_ERR_NO_DEVICE, std::string("device is not Blackwell (sm_100a) : ") + prop.name);
   ctx->sm_count = prop.multiProcessorCount;
+  {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    ctx->clock_khz = khz > 0 ? (double)khz : 1.9e6;
+    if (const char *t = getenv("VB2_LLK_SESSION_IDLE_MS")) ctx->session_idle_ms = std::max(1.0, atof(t));
+  }
   if (desc->stream) {
     ctx->stream = static_cast<cudaStream_t>(desc->stream);
   } else {
@@ -1306,7 +1660,7 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   uint32_t cap_rows = kChunkTargetBytes > S.off_words + 4u * 128u ? (kChunkTargetBytes - S.off_words) / 128u : 4u;
   if (const char *t = getenv("VB2_LLK_STAGE_WORDS")) cap_rows = (uint32_t)std::max(1, atoi(t));
   S.chunk_rows = std::max(1u, std::min(std::max(max_rows, 1u), cap_rows));
-  S.buf_bytes = S.off_words + S.chunk_rows * 128u;
+  S.buf_bytes = S.off_words + S.chunk_rows * 128u + 128u;  // (+ one row: the read loop looks one row ahead)
   ctx->chunked = max_rows > S.chunk_rows;
   const bool default_clamps = S.min_af == 0.00005 && S.max_af == 0.99995;
   ctx->spec = (!cfg.panel_fp64 && !P.known_af && default_clamps && (P.n_pc == 2 || P.n_pc == 4)) ? (int)P.n_pc : 0;
@@ -1383,6 +1737,16 @@ static int begin_batch(vb2_llk_ctx *ctx, int n, const double *pc_contam, const d
   if (!ctx) return set_err(nullptr, VB2_ERR_INVALID, "null context");
   if (ctx->pending_n) return set_err(ctx, VB2_ERR_INVALID, "an evaluation is already pending on this context");
   if (n <= 0 || n > VB2_MAX_BATCH) return set_err(ctx, VB2_ERR_INVALID, "batch size out of range");
+  if (ctx->session_active && n == 1 && ctx->S.grid_x) {  // ring the resident kernel's doorbell: no launch
+    JobParams J;
+    fill_job(&J, ctx->S.n_pc, pc_contam, pc_intended, alphas[0]);
+    const unsigned long long s = ++ctx->seq;
+    session_ring(ctx, J, s);
+    ctx->pending_n = 1;
+    ctx->pending_host_reduce = true;
+    ctx->pending_seq = s;
+    return VB2_OK;
+  }
   const bool host_reduce = n == 1 && ctx->rounds.size() <= (size_t)kMaxArgRounds;
   unsigned long long seq = 0;
   int rc = launch_batch(ctx, n, pc_contam, pc_intended, alphas, host_reduce ? Reduce::kHost : Reduce::kDevice,
@@ -1484,6 +1848,7 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
   for (int j = 0; j < n; ++j) {
     vb2_llk_ctx *c = ctxs[j];
     if (!c) return set_err(lead, VB2_ERR_INVALID, "null context in list");
+    session_stop(c);
     if (c->device != lead->device) return set_err(lead, VB2_ERR_INVALID, "contexts live on different devices");
     if (c->S.n_pc != k) return set_err(lead, VB2_ERR_INVALID, "contexts differ in n_pc");
     uint32_t slot = 0;
@@ -1531,6 +1896,8 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
   if (!lead->many_n) return set_err(lead, VB2_ERR_INVALID, "internal: nothing staged");
   LaunchArgs A;
   memset(&A, 0, sizeof(A));
+  A.trace = nullptr;
+  fill_phred(&A);
   A.samples = lead->d_many;
   A.slots = lead->d_slots;
   A.jobs_dev = lead->d_jobs;
@@ -1648,7 +2015,8 @@ int vb2_llk_time_host(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup, int steps
   if (!ctxs || n_ctx <= 0 || !ctxs[0] || steps <= 0 || !elapsed_s) return set_err(nullptr, VB2_ERR_INVALID, "bad argument");
   vb2_llk_ctx *lead = ctxs[0];
   std::vector<double> pc1(pc_contam, pc_contam + lead->S.n_pc);
-  double llk = 0.0;
+  double llk = 0.0, t_launch = 0.0, t_wait = 0.0;
+  const bool breakdown = getenv("VB2_LLK_HOST_TIMING") != nullptr;
   std::chrono::steady_clock::time_point t0;
   for (int i = -warmup; i < steps; ++i) {
     if (i == 0) {
@@ -1656,11 +2024,80 @@ int vb2_llk_time_host(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup, int steps
       t0 = std::chrono::steady_clock::now();
     }
     pc1[0] = pc_contam[0] + 1e-7 * ((i + warmup) % 1000);
-    int rc = vb2_llk_eval(ctxs[(i + warmup) % n_ctx], pc1.data(), pc_intended, alpha, &llk);
-    if (rc) return rc;
+    vb2_llk_ctx *c = ctxs[(i + warmup) % n_ctx];
+    if (!breakdown) {
+      int rc = vb2_llk_eval(c, pc1.data(), pc_intended, alpha, &llk);
+      if (rc) return rc;
+    } else {  // VB2_LLK_HOST_TIMING: the same two halves, timed separately
+      auto a = std::chrono::steady_clock::now();
+      int rc = vb2_llk_eval_begin(c, pc1.data(), pc_intended, alpha);
+      auto b = std::chrono::steady_clock::now();
+      if (rc == VB2_OK) rc = vb2_llk_eval_end(c, &llk);
+      auto d = std::chrono::steady_clock::now();
+      if (rc) return rc;
+      if (i >= 0) {
+        t_launch += std::chrono::duration<double>(b - a).count();
+        t_wait += std::chrono::duration<double>(d - b).count();
+      }
+    }
   }
   *elapsed_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (breakdown)
+    fprintf(stderr, "vb2_llk_time_host: %d steps, launch %.2f us + wait %.2f us per step (args %zu bytes)\n", steps,
+            t_launch / steps * 1e6, t_wait / steps * 1e6, sizeof(LaunchArgs));
   if (last_llk) *last_llk = llk;
+  return VB2_OK;
+}
+
+int vb2_llk_session_begin(vb2_llk_ctx *ctx) {
+  if (!ctx) return set_err(nullptr, VB2_ERR_INVALID, "null context");
+  if (ctx->session_active) return VB2_OK;
+  if (ctx->pending_n) return set_err(ctx, VB2_ERR_INVALID, "an evaluation is pending on this context");
+  if (!ctx->spin) return set_err(ctx, VB2_ERR_INVALID, "a session needs the polling wait mode (VB2_FLAG_NO_SPIN is set)");
+  if (!session_geometry(ctx).ok)
+    return set_err(ctx, VB2_ERR_INVALID, "this sample cannot be held resident in shared memory (too deep or too large)");
+  VB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->h_bell) {
+    VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_bell, sizeof(BellChunk) * kMaxBellChunks, cudaHostAllocMapped));
+    memset(ctx->h_bell, 0, sizeof(BellChunk) * kMaxBellChunks);
+    VB2_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->d_bell, ctx->h_bell, 0));
+  }
+  int rc = session_launch(ctx, ctx->seq + 1);
+  if (rc) return rc;
+  ctx->session_active = true;
+  return VB2_OK;
+}
+
+int vb2_llk_session_end(vb2_llk_ctx *ctx) {
+  if (!ctx) return set_err(nullptr, VB2_ERR_INVALID, "null context");
+  if (ctx->pending_n) return set_err(ctx, VB2_ERR_INVALID, "an evaluation is pending on this context");
+  VB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  session_stop(ctx);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(ctx, VB2_ERR_CUDA, std::string("llk_session_kernel: ") + cudaGetErrorString(e));
+  return VB2_OK;
+}
+
+int vb2_llk_trace(vb2_llk_ctx *ctx, const double *pc_contam, const double *pc_intended, double alpha,
+                  unsigned long long *stamps, uint32_t max_ctas, uint32_t *n_ctas, double *llk_out) {
+  if (!ctx || !stamps || !n_ctas) return set_err(ctx, VB2_ERR_INVALID, "null argument");
+  const uint32_t gx = ctx->S.grid_x;
+  *n_ctas = gx;
+  if (gx == 0 || gx > max_ctas) return set_err(ctx, VB2_ERR_INVALID, "stamp buffer too small (or no usable marker)");
+  VB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  session_stop(ctx);
+  const size_t bytes = (size_t)gx * kTraceSlots * sizeof(unsigned long long);
+  if (!ctx->d_trace) VB2_CUDA(ctx, cudaMalloc(&ctx->d_trace, bytes));
+  VB2_CUDA(ctx, cudaMemsetAsync(ctx->d_trace, 0, bytes, ctx->stream));
+  VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->trace_on = true;
+  double llk = 0.0;
+  int rc = vb2_llk_eval(ctx, pc_contam, pc_intended, alpha, &llk);
+  ctx->trace_on = false;
+  if (rc) return rc;
+  if (llk_out) *llk_out = llk;
+  VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  VB2_CUDA(ctx, cudaMemcpy(stamps, ctx->d_trace, bytes, cudaMemcpyDeviceToHost));
   return VB2_OK;
 }
 

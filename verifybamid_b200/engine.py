@@ -19,7 +19,7 @@ import numpy as np
 from .problem import PileupProblem
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libvb2llk.so")
+LIB_PATH = os.environ.get("VB2_LLK_LIBRARY") or os.path.join(PKG_DIR, "libvb2llk.so")  # (override: A/B builds)
 
 VB2_OK = 0
 VB2_PANEL_FP32 = 0
@@ -34,7 +34,8 @@ _STATUS = {1: "VB2_ERR_INVALID", 2: "VB2_ERR_NO_DEVICE", 3: "VB2_ERR_CUDA", 4: "
 ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_warmup", "vb2_llk_create", "vb2_llk_destroy", "vb2_llk_get_info",
                "vb2_llk_eval", "vb2_llk_eval_begin", "vb2_llk_eval_end", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many", "vb2_llk_eval_many_device",
                "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free",
-               "vb2_llk_time_device", "vb2_llk_time_device_many", "vb2_llk_time_host")
+               "vb2_llk_time_device", "vb2_llk_time_device_many", "vb2_llk_time_host", "vb2_llk_trace",
+               "vb2_llk_session_begin", "vb2_llk_session_end")
 
 
 class VB2Error(RuntimeError):
@@ -123,6 +124,14 @@ def load_library() -> ctypes.CDLL:
                                       ctypes.c_void_p, ctypes.c_void_p]
     lib.vb2_llk_eval_many_device.restype = ctypes.c_int
     lib.vb2_llk_eval_many_device.argtypes = lib.vb2_llk_eval_many.argtypes
+    if hasattr(lib, "vb2_llk_trace"):  # (absent from older A/B builds loaded through VB2_LLK_LIBRARY)
+        lib.vb2_llk_trace.restype = ctypes.c_int
+        lib.vb2_llk_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
+                                      ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_double)]
+    for name in ("vb2_llk_session_begin", "vb2_llk_session_end"):
+        if hasattr(lib, name):
+            getattr(lib, name).restype = ctypes.c_int
+            getattr(lib, name).argtypes = [ctypes.c_void_p]
     lib.vb2_llk_sync.restype = ctypes.c_int
     lib.vb2_llk_sync.argtypes = [ctypes.c_void_p]
     lib.vb2_llk_time_device.restype = ctypes.c_int
@@ -291,6 +300,24 @@ class LLKEngine:
 
     def sync(self) -> None:
         self._check(self._lib.vb2_llk_sync(self._ctx))
+
+    def session_begin(self) -> None:
+        """Resident kernel with the sample in shared memory: compute_mix_llks rings a doorbell until session_end()."""
+        self._check(self._lib.vb2_llk_session_begin(self._ctx))
+
+    def session_end(self) -> None:
+        self._check(self._lib.vb2_llk_session_end(self._ctx))
+
+    def trace(self, pc_contam, pc_intended, alpha: float):
+        """One evaluation with the kernel's stage clock on: (llk, stamps[cta][VB2_TRACE_SLOTS]) (include/vb2_llk.h)."""
+        a = np.ascontiguousarray(pc_contam, dtype=np.float64)
+        b = np.ascontiguousarray(pc_intended, dtype=np.float64)
+        stamps = np.zeros((1024, 16), dtype=np.uint64)
+        n = ctypes.c_uint32()
+        llk = ctypes.c_double()
+        self._check(self._lib.vb2_llk_trace(self._ctx, a.ctypes.data, b.ctypes.data, float(alpha), stamps.ctypes.data,
+                                            1024, ctypes.byref(n), ctypes.byref(llk)))
+        return llk.value, stamps[:n.value]
 
     def info(self) -> dict:
         i = _Info()
