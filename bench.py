@@ -14,8 +14,10 @@ Keys of the JSON line (rank 0):
   value     marker-reads/s with everything resident in HBM, device-timed (CUDA events on the launching
             stream) over K back-to-back steps that rotate through enough resident copies of the sample
             to exceed L2, so every step streams from HBM;
-  e2e       the same metric through the public call with HOST parameter buffers: each step copies the
-            step's inputs (2k+1 doubles) to the device and reads the scalar result back;
+  e2e       the same metric through the public call (vb2_llk_eval) with HOST parameter buffers, every step moving
+            its inputs (2k+1 doubles) to the device and its scalar result back, inside an evaluation session
+            (resident kernel, sample in shared memory) -- the way the simplex search calls it; the figure for one
+            launch per evaluation is reported beside it;
   roofline  algorithmic bytes (SURVEY 8d: 2*R + 4*(k+2)*M') / measured kernel time vs measured HBM peak;
   cpu_baseline  the reference's own CPU implementation (oracle/_ref, else the C port) on this host.
 """
@@ -266,7 +268,7 @@ def run_ours(args):
         barrier()
         if world == 1:
             dev_ms = timed_steps(args.steps, args.warmup)
-            launches = args.steps // copies + (1 if args.steps % copies else 0)
+            launches = 2 * (args.steps // copies + (1 if args.steps % copies else 0))  # stream kernel + reduce kernel
         else:
             # `copies` steps per launch on every rank (its marker shard of each resident copy), then ONE
             # NCCL allreduce of the `copies` partial sums
@@ -289,7 +291,7 @@ def run_ours(args):
             ev1.record(stream)
             barrier()
             dev_ms = ev0.elapsed_time(ev1)
-            launches = full + (1 if rem else 0)
+            launches = 2 * (full + (1 if rem else 0))  # stream kernel + reduce kernel per launch_steps()
         keep_busy(0.5)                      # clocks under the same load, for the sampler
         barrier()
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -309,17 +311,24 @@ def run_ours(args):
     kern_us = (dev_ms / args.steps) * 1e3       # per evaluation (N>1: includes the allreduce share)
     achieved = alg_bytes / (kern_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "llk_kernel",
+                "traffic": None, "peak_source": peak_src, "kernel": "llk_stream_kernel",
                 "evaluations_per_launch": copies,
                 "us_per_evaluation": kern_us, "us_per_evaluation_one_launch_each": one_ms * 1e3,
                 "algorithmic_bytes_per_evaluation": alg_bytes, "device_bytes_per_evaluation": info["device_bytes"],
-                "note": "co-bound by FP64 issue rate: 12 fp64 ops per streamed read -> >= 2.5 us per evaluation "
-                        "at 64 DFMA/clk/SM (DESIGN.md)"}
+                "note": "co-bound by the FP64 pipe: 10 fp64 instructions per streamed read + ~40 per marker -> >= 2.2 us per "
+                        "evaluation at 64 lanes/clk/SM (DESIGN.md section 4)"}
 
     # ---- e2e: the public C-ABI call with HOST buffers; every step moves the step's inputs (2k+1 doubles)
     # to the device and the scalar result back to the host ------------------------------------------------
     if world == 1:
-        e2e_s, last = vb.time_host(engines, args.warmup, args.steps, start_pc, start_pc, 0.03)
+        # (a) the call as the simplex search makes it: several hundred dependent evaluations of ONE sample inside an
+        #     evaluation session (vb2_llk_session_begin: resident kernel, the sample in shared memory, host-mapped
+        #     doorbell in, host mailbox out).  Every step still moves its 2k+1 doubles in and its scalar out.
+        engines[0].session_begin()
+        e2e_s, last = vb.time_host(engines[:1], args.warmup, args.steps, start_pc, start_pc, 0.03)
+        engines[0].session_end()
+        # (b) one launch per evaluation (no session), rotating through the resident copies (HBM-cold every step)
+        cold_s, last_cold = vb.time_host(engines, args.warmup, args.steps, start_pc, start_pc, 0.03)
         # the same call through the Python binding (interpreter + ctypes overhead included)
         t0 = time.perf_counter()
         for i in range(200):
@@ -345,13 +354,16 @@ def run_ours(args):
         barrier()
         e2e_s = time.perf_counter() - t0
         py_us = None
+        cold_s = None
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e = {"value": reads_total / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": (2 * k + 1) * 8,
            "d2h_bytes_per_step": 8, "us_per_step": e2e_s / args.steps * 1e6, "last_llk": last,
-           "caller": "C loop over vb2_llk_eval (host buffers)" if world == 1 else "python: kernel + NCCL allreduce + D2H",
+           "caller": ("C loop over vb2_llk_eval (host buffers) inside an evaluation session: resident kernel, sample in "
+                      "shared memory, host-mapped doorbell/mailbox") if world == 1 else "python: kernel + NCCL allreduce + D2H",
+           "us_per_step_one_launch_per_evaluation": (cold_s / args.steps * 1e6) if cold_s else None,
            "python_binding_us_per_step": py_us}
 
     # ---- cpu baseline beside it (rank 0, N=1 only) --------------------------------------------

@@ -52,28 +52,17 @@ def job_coefficients(alpha: float):
     return pairs, np.array(c0), np.array(c1)
 
 
-def bin_of(n_slices: int, n_bins: int, j: int) -> int:
-    """The dealing rule of llk_pack.cpp (bin_of)."""
-    r, i = divmod(j, n_bins)
-    rem = n_slices % n_bins
-    n_short = n_bins - rem
-    if (r + 1) * n_bins > n_slices:
-        return n_short + i
-    if i < n_short:
-        return n_short - 1 - i if (r & 1) else i
-    k = i - n_short
-    return n_short + (rem - 1 - k if (r & 1) else k)
-
-
 def iter_blobs(pk: dict):
-    """Yield (slice_index, bin, blob_bytes); slice j (heaviest first) lives in round j // n_bins."""
+    """Yield (blob_index, bin, blob_bytes) in image order: blob q is the (q % n_bins)-th blob of round q // n_bins and
+    belongs to bin first_bin + q % n_bins (the bins that own a blob in a round are a contiguous range)."""
     nb = pk["n_bins"]
-    for j in range(pk["n_slices"]):
-        R = pk["rounds"][j // nb]
-        b = bin_of(pk["n_slices"], nb, j)
-        assert R["first_bin"] <= b < R["first_bin"] + R["count"]
-        off = R["base"] + (b - R["first_bin"]) * R["stride"]
-        yield j, b, pk["blob"][off:off + R["stride"]]
+    q = 0
+    for r, R in enumerate(pk["rounds"]):
+        for k in range(R["count"]):
+            off = R["base"] + k * R["stride"]
+            yield r * nb + k, R["first_bin"] + k, pk["blob"][off:off + R["stride"]]
+            q += 1
+    assert q == pk["n_slices"]
 
 
 def emulate_packed_llk(pk: dict, pc1, pc2, alpha: float, min_af=5e-5, max_af=0.99995) -> float:

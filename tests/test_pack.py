@@ -35,8 +35,8 @@ def test_pack_counts_and_layout():
 
 
 def test_rounds_are_balanced_and_aligned():
-    """Snake dealing: every SM sub-partition bin gets (nearly) the same number of word rows; every blob is
-    16-byte aligned (TMA bulk copy) and its size a multiple of 16."""
+    """Dealing by cost (costliest slice of a round to the least loaded bin): every SM sub-partition bin gets (nearly)
+    the same number of word rows; every blob is 16-byte aligned (TMA bulk copy) and its size a multiple of 16."""
     panel = panels.load_bundled("1000g.phase3.10k.b37")
     p = synth.make_sample(panel, n_pc=2, depth=30.0, alpha=0.02, seed=3).problem
     pk = vb.pack_host(p, max_ctas=8)                       # 32 bins, 313 slices -> 10 rounds
@@ -48,7 +48,7 @@ def test_rounds_are_balanced_and_aligned():
         work[b] += wr + wa
         assert (j // pk["n_bins"], b) not in seen           # one blob per (round, bin)
         seen.add((j // pk["n_bins"], b))
-    assert work.max() <= 1.08 * work.mean()
+    assert work.max() <= 1.06 * work.mean()
     for R in pk["rounds"]:
         assert R["base"] % 16 == 0 and R["stride"] % 16 == 0
         assert R["stride"] == pk["off_words"] + 128 * R["rows"]

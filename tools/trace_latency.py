@@ -27,3 +27,17 @@ with vb.LLKEngine(s.problem) as eng:
             c = cyc[:, k]
             print("   %-18s cycles since CTA entry: min %6d  median %6d  max %6d" % (nme, c.min(), np.median(c), c.max()))
     print("info", eng.info())
+    os.environ["VB2_LLK_TRACE_SESSION"] = "1"
+    llk, st = eng.trace([0.01, 0.01], [0.01, 0.01], 0.03)
+    st = st.astype(np.int64)
+    print("session kernel, cycles since the CTA started polling for its LAST evaluation (idle wait included in the first two):")
+    for k, nme in [(1, "doorbell seen"), (2, "params published"), (3, "warp 0 slices done"), (15, "last warp slices done"), (6, "published")]:
+        c = st[:, k] - st[:, 0]
+        print("   %-22s min %7d  median %7d  max %7d" % (nme, c.min(), np.median(c), c.max()))
+    c = st[:, 6] - st[:, 2]
+    print("   params published -> partial published: min %d median %d max %d cycles" % (c.min(), np.median(c), c.max()))
+    c = st[:, 15] - st[:, 2]
+    print("   params published -> last warp done:    min %d median %d max %d cycles" % (c.min(), np.median(c), c.max()))
+    order = np.argsort(-c)
+    print("   slowest CTAs:", [(int(i), int(c[i])) for i in order[:12]])
+    print("   mean over CTAs 0..107: %d   108..147: %d" % (c[:108].mean(), c[108:].mean()))

@@ -308,6 +308,15 @@ void ContaminationEstimator::CreateEngines() {
     if (vb2_llk_get_info(c, &info) == VB2_OK) { markers += info.markers_used; reads += info.reads_used; }
   notice("GPU likelihood engine: %d device(s), %llu markers / %llu reads resident in HBM", numGPU,
          (unsigned long long)markers, (unsigned long long)reads);
+  // The simplex search evaluates this one sample several hundred times, each evaluation waiting for the last:
+  // keep a resident kernel with the sample in shared memory for the duration (include/vb2_llk.h, evaluation
+  // session).  Samples that do not fit on chip simply keep one launch per evaluation; a cohort evaluates all its
+  // samples in one launch per step instead.
+  if (!cohort && !getenv("VB2_NO_SESSION")) {
+    int n_session = 0;
+    for (vb2_llk_ctx *c : engines) n_session += vb2_llk_session_begin(c) == VB2_OK;
+    if (n_session) notice("evaluation session: resident kernel on %d device(s)", n_session);
+  }
 }
 
 void ContaminationEstimator::DestroyEngines() {

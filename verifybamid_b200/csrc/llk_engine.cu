@@ -222,22 +222,24 @@ __device__ __forceinline__ void eat_word_tail(uint32_t w, uint32_t n, const doub
     acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(Q.C2[p], t, fma(Q.C1[p], s, Q.C0[p])) * fma(lin[kNumPairs + p], e2, lin[p]);
 }
 
-// Rows that may carry 0xFF filler bytes (the last words of a lane whose run is shorter than its slice's),
-// read by read: acc *= F_p(e) = c0_p + c1_p e.
+// Rows that may carry 0xFF filler bytes (the last words of a lane whose run is shorter than its slice's).
+// Branch-free: every byte gives a factor F_p(e) = c0_p + c1_p e, replaced by 1 where the byte is a filler, so
+// the lanes of a warp never diverge (the slices with such rows are few but sit together in a handful of bins,
+// whose CTAs would otherwise finish a quarter later than the rest).
 template <bool ALT>
 __device__ __forceinline__ void eat_checked(const uint32_t *col, uint32_t n_rows, const double *lin,
                                             double (&acc)[kNumPairs]) {
 #pragma unroll 1
   for (uint32_t t = 0; t < n_rows; ++t) {
-    uint32_t w = col[t * 32];
-#pragma unroll 1
-    for (uint32_t b = 0; b < 4; ++b, w >>= 8) {
-      const uint32_t q = w & 0xFFu;
-      if (q != 0xFFu) {
-        const double e = s_e[q];
+    const uint32_t w = col[t * 32];
+    const uint32_t q0 = w & 0xFFu, q1 = (w >> 8) & 0xFFu, q2 = (w >> 16) & 0xFFu, q3 = w >> 24;
+    const double e0 = s_e[q0], e1 = s_e[q1], e2 = s_e[q2], e3 = s_e[q3];
 #pragma unroll
-        for (int p = 0; p < kNumPairs; ++p) acc[ALT ? (kNumPairs - 1 - p) : p] *= fma(lin[kNumPairs + p], e, lin[p]);
-      }
+    for (int p = 0; p < kNumPairs; ++p) {
+      const double c0 = lin[p], c1 = lin[kNumPairs + p];
+      const double f0 = q0 != 0xFFu ? fma(c1, e0, c0) : 1.0, f1 = q1 != 0xFFu ? fma(c1, e1, c0) : 1.0;
+      const double f2 = q2 != 0xFFu ? fma(c1, e2, c0) : 1.0, f3 = q3 != 0xFFu ? fma(c1, e3, c0) : 1.0;
+      acc[ALT ? (kNumPairs - 1 - p) : p] *= (f0 * f1) * (f2 * f3);
     }
   }
 }
@@ -959,8 +961,10 @@ __global__ void __launch_bounds__(32, 1) llk_reduce_kernel(const __grid_constant
 // SM, the geometry of llk_kernel, but every warp keeps ALL its blobs in shared memory (a 100k x 30x sample is
 // ~50 KB per SM) and the CTA then serves evaluations until told to stop:
 //   doorbell   host-mapped chunks {payload, seq}: the host writes the evaluation's coefficients and PCs and
-//              stamps every 16-byte chunk with the sequence number; warp 0 polls all chunks with one coalesced
-//              load (one PCIe round trip) until every chunk carries the number it waits for;
+//              stamps every 16-byte chunk with the sequence number; warp 0 of CTA 0 polls all chunks with one
+//              coalesced load (one PCIe round trip) until every chunk carries the number it waits for and
+//              forwards them to a copy in HBM, which the other CTAs poll in L2 (148 CTAs polling host memory
+//              would saturate the PCIe read path: measured 276 us per evaluation);
 //   compute    slice_begin / eat_runs / the marginals' meeting exactly as in llk_kernel (same bits), with no
 //              HBM or L2 traffic at all;
 //   answer     {CTA partial, seq} into the host mailbox; the host adds the partials in llk_kernel's order.
@@ -977,10 +981,13 @@ struct __align__(16) BellChunk {
 
 struct SessionArgs {
   SampleDev sample;
-  const BellChunk *bell;  // device view of the host-mapped doorbell
+  const BellChunk *bell;  // device view of the host-mapped doorbell (polled by CTA 0 only: PCIe reads)
+  BellChunk *relay;       // the same chunks in HBM: CTA 0 forwards the doorbell, the other CTAs poll this copy in L2
   Slot *mbox;             // device view of the host mailbox: slot [cta]
   unsigned long long first_seq, idle_cycles;
-  uint32_t kc, n_items, n_chunks, pad_;
+  uint32_t kc, n_items, n_chunks;
+  unsigned long long *trace;  // diagnostics: [grid_x][kTraceSlots] SM clock of thread 0 at the stages of the LAST evaluation
+  uint32_t null_eval;  // diagnostics (VB2_LLK_SESSION_NULL): answer without reading a single read -> the doorbell + mailbox round trip
   double phred[kPhredArgs];
   vb2::Round rounds[kMaxArgRounds];
 };
@@ -1040,13 +1047,19 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
   while (n_items < (uint32_t)kMaxSessionItems && s_item_r[warp][n_items] != 0xFFFFFFFFu) ++n_items;
   if (n_items) mbar_wait(&s_bar[warp], 0u);  // resident from here on
 
+  auto stamp = [&](int k) {
+    if (A.trace && threadIdx.x == 0) A.trace[blockIdx.x * kTraceSlots + k] = (unsigned long long)clock64();
+  };
   unsigned long long expected = A.first_seq;
 #pragma unroll 1
   for (;;) {
+    stamp(0);
     // ---- doorbell ----------------------------------------------------------------------------------
     if (warp == 0) {
       const unsigned long long t_idle = (unsigned long long)clock64();
       const uint32_t n_chunks = A.n_chunks;
+      const bool head = blockIdx.x == 0;  // the one CTA that talks to the host
+      const BellChunk *src = head ? A.bell : A.relay;
       uint32_t stop = 0;
       for (;;) {
         bool ok = true, bye = false;
@@ -1055,7 +1068,7 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
           const uint32_t i = base + (uint32_t)lane;
           if (i < n_chunks) {
             unsigned long long pay, seq;
-            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(pay), "=l"(seq) : "l"(A.bell + i) : "memory");
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(pay), "=l"(seq) : "l"(src + i) : "memory");
             bye = bye || seq == kBellExit;
             ok = ok && seq == expected;
             if (seq == expected) {
@@ -1069,13 +1082,28 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
         if (__all_sync(0xFFFFFFFFu, ok)) break;
         if ((unsigned long long)clock64() - t_idle > A.idle_cycles) { stop = 1; break; }
       }
+      if (head) {  // forward: the evaluation's chunks, or the order to leave
+#pragma unroll
+        for (uint32_t base = 0; base < (uint32_t)kMaxBellChunks; base += 32) {
+          const uint32_t i = base + (uint32_t)lane;
+          if (i < n_chunks) {
+            const uint32_t k = S.n_pc;
+            const uint32_t idx = i < 12u ? i : (i < 12u + k ? i : i - k + (uint32_t)VB2_MAX_PC);
+            const unsigned long long pay = (unsigned long long)__double_as_longlong(reinterpret_cast<const double *>(&s_job)[idx]);
+            const unsigned long long seq = stop ? kBellExit : expected;
+            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(A.relay + i), "l"(pay), "l"(seq) : "memory");
+          }
+        }
+      }
       if (lane == 0 && stop) s_stop = 1u;
+      stamp(1);
     }
     __syncthreads();  // parameters (or the stop flag) published
     if (s_stop) return;
+    stamp(2);
 
     // ---- the evaluation: every resident slice of this warp -------------------------------------------
-    if (n_items) {
+    if (n_items && !A.null_eval) {
       const double *lin = s_job.c0;
       Quad Q;
 #pragma unroll
@@ -1097,6 +1125,8 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
         s_L[(s_item_r[warp][j] * 4u + (uint32_t)(warp & 3)) * 32u + lane] = ((uint32_t)lane < H.n_valid && L > 0) ? L : 1.0;
       }
     }
+    stamp(3);
+    if (A.trace && lane == 0) atomicMax(A.trace + blockIdx.x * kTraceSlots + 15, (unsigned long long)clock64());
     __syncthreads();  // every marginal of the CTA's four bins is in shared memory
     if (warp < 4) {
       double vsum = 0.0, prod = 1.0;
@@ -1119,6 +1149,7 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
         const double cta = ((s_red[0] + s_red[1]) + s_red[2]) + s_red[3];
         *reinterpret_cast<ulonglong2 *>(A.mbox + blockIdx.x) =
             make_ulonglong2((unsigned long long)__double_as_longlong(cta), expected);
+        stamp(6);
       }
     }
     ++expected;
@@ -1194,6 +1225,7 @@ struct vb2_llk_ctx {
   bool trace_on = false;
   // evaluation session (llk_session_kernel resident on the device)
   BellChunk *h_bell = nullptr, *d_bell = nullptr;  // host-mapped doorbell
+  BellChunk *d_relay = nullptr;                    // its copy in HBM
   bool session_active = false;
   uint32_t session_relaunches = 0;
   double clock_khz = 0.0, session_idle_ms = 200.0;
@@ -1230,6 +1262,7 @@ int set_err(vb2_llk_ctx *ctx, int code, const std::string &msg) {
 
 int session_launch(vb2_llk_ctx *ctx, unsigned long long first_seq);
 void session_stop(vb2_llk_ctx *ctx);
+uint32_t env_kc(const char *name, uint32_t dflt);
 void fill_phred(LaunchArgs *A);
 
 template <typename T>
@@ -1350,7 +1383,7 @@ SessionGeometry session_geometry(const vb2_llk_ctx *ctx) {
   SessionGeometry g{1, 1, 0, false};
   const SampleDev &S = ctx->S;
   if (S.grid_x == 0 || ctx->chunked || ctx->rounds.size() > (size_t)kMaxArgRounds) return g;
-  g.kc = std::max(1u, std::min((uint32_t)kMaxConcRounds, S.n_rounds));
+  g.kc = std::max(1u, std::min(env_kc("VB2_LLK_SESSION_KC", (uint32_t)kMaxConcRounds), S.n_rounds));
   g.n_items = (S.n_rounds + g.kc - 1) / g.kc;
   g.smem = 4u * g.kc * g.n_items * S.buf_bytes + S.n_rounds * 1024u;
   g.ok = g.n_items <= (uint32_t)kMaxSessionItems && g.smem <= 200u * 1024u;
@@ -1364,12 +1397,16 @@ int session_launch(vb2_llk_ctx *ctx, unsigned long long first_seq) {
   memset(&A, 0, sizeof(A));
   A.sample = ctx->S;
   A.bell = ctx->d_bell;
+  A.relay = ctx->d_relay;
+  VB2_CUDA(ctx, cudaMemsetAsync(ctx->d_relay, 0, sizeof(BellChunk) * kMaxBellChunks, ctx->stream));
   A.mbox = ctx->d_mbox;
   A.first_seq = first_seq;
   A.idle_cycles = (unsigned long long)(ctx->session_idle_ms * ctx->clock_khz);
   A.kc = g.kc;
   A.n_items = g.n_items;
   A.n_chunks = 12u + 2u * ctx->S.n_pc;
+  A.null_eval = getenv("VB2_LLK_SESSION_NULL") ? 1u : 0u;
+  A.trace = ctx->trace_on ? ctx->d_trace : nullptr;
   LaunchArgs tmp;
   fill_phred(&tmp);
   memcpy(A.phred, tmp.phred, sizeof(A.phred));
@@ -1577,6 +1614,7 @@ void vb2_llk_destroy(vb2_llk_ctx *ctx) {
   if (ctx->d_queue) cudaFree(ctx->d_queue);
   if (ctx->d_trace) cudaFree(ctx->d_trace);
   if (ctx->h_bell) cudaFreeHost(ctx->h_bell);
+  if (ctx->d_relay) cudaFree(ctx->d_relay);
   if (ctx->d_many) cudaFree(ctx->d_many);
   if (ctx->d_slots) cudaFree(ctx->d_slots);
   if (ctx->h_mbox) cudaFreeHost(ctx->h_mbox);
@@ -2061,6 +2099,7 @@ int vb2_llk_session_begin(vb2_llk_ctx *ctx) {
     VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_bell, sizeof(BellChunk) * kMaxBellChunks, cudaHostAllocMapped));
     memset(ctx->h_bell, 0, sizeof(BellChunk) * kMaxBellChunks);
     VB2_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->d_bell, ctx->h_bell, 0));
+    VB2_CUDA(ctx, cudaMalloc(&ctx->d_relay, sizeof(BellChunk) * kMaxBellChunks));
   }
   int rc = session_launch(ctx, ctx->seq + 1);
   if (rc) return rc;
@@ -2092,7 +2131,14 @@ int vb2_llk_trace(vb2_llk_ctx *ctx, const double *pc_contam, const double *pc_in
   VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->trace_on = true;
   double llk = 0.0;
-  int rc = vb2_llk_eval(ctx, pc_contam, pc_intended, alpha, &llk);
+  int rc = VB2_OK;
+  if (getenv("VB2_LLK_TRACE_SESSION")) {  // stages of the 20th evaluation of a session (see llk_session_kernel)
+    rc = vb2_llk_session_begin(ctx);
+    for (int i = 0; i < 20 && rc == VB2_OK; ++i) rc = vb2_llk_eval(ctx, pc_contam, pc_intended, alpha, &llk);
+    if (rc == VB2_OK) rc = vb2_llk_session_end(ctx);
+  } else {
+    rc = vb2_llk_eval(ctx, pc_contam, pc_intended, alpha, &llk);
+  }
   ctx->trace_on = false;
   if (rc) return rc;
   if (llk_out) *llk_out = llk;

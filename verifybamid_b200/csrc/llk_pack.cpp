@@ -60,20 +60,6 @@ struct MarkerTmp {
 
 }  // namespace
 
-// Dealing rule.  Slices are sorted heaviest first; slice j goes to round j / n_bins.  If the last
-// round is partial (rem = n_slices % n_bins blobs) its blobs go to the LONG bins, the last rem bins.
-// To compensate, every full round gives its n_bins - rem heaviest slices to the short bins and its
-// rem lightest slices to the long bins; inside each group the direction alternates from round to
-// round (snake) so the group's bins stay level.
-uint32_t bin_of(uint32_t n_slices, uint32_t n_bins, uint32_t j) {
-  const uint32_t r = j / n_bins, i = j % n_bins;
-  const uint32_t rem = n_slices % n_bins, n_short = n_bins - rem;
-  if ((uint64_t)(r + 1) * n_bins > n_slices) return n_short + i;  // the partial last round
-  if (i < n_short) return (r & 1u) ? n_short - 1u - i : i;
-  const uint32_t k = i - n_short;
-  return n_short + ((r & 1u) ? rem - 1u - k : k);
-}
-
 int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phred, PackedSample *out,
                 std::string *err) {
   auto fail = [&](const char *m) { if (err) *err = m; return (int)VB2_ERR_INVALID; };
@@ -166,22 +152,36 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
   std::iota(order.begin(), order.end(), 0u);
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
   lap("2 sort markers");
-  // ---- 3. cut into 32-marker slices, heaviest first; slice s belongs to shard s % shard_count ----
+  // ---- 3. cut into 32-marker slices, costliest first; slice s belongs to shard s % shard_count ----
+  // Cost of a slice in quarter rows, as the kernel spends its time: a row of four real reads in every lane = 4,
+  // a uniform ragged tail = 2, a row that needs per-byte filler checks = 7, and 15 for the per-slice work
+  // (allele frequencies, priors, marginal, pipeline bookkeeping).
   const size_t total_slices = (order.size() + kSliceMarkers - 1) / kSliceMarkers;
-  struct SliceGeom { uint32_t wr, wa; size_t first; };
+  struct SliceGeom { uint32_t wr, wa, cost; size_t first; };
   std::vector<SliceGeom> all_geom(total_slices);
   for (size_t s = 0; s < total_slices; ++s) {
-    uint32_t wr = 0, wa = 0;
+    uint32_t wr = 0, wa = 0, fr = 0xFFFFFFFFu, fa = 0xFFFFFFFFu, nr0 = 0, na0 = 0;
+    bool same_r = true, same_a = true;
     for (size_t l = 0; l < (size_t)kSliceMarkers; ++l) {
       const size_t o = s * kSliceMarkers + l;
       if (o >= order.size()) break;
-      wr = std::max(wr, words_of(used[order[o]].n_ref));
-      wa = std::max(wa, words_of(used[order[o]].n_alt));
+      const MarkerTmp &m = used[order[o]];
+      wr = std::max(wr, words_of(m.n_ref));
+      wa = std::max(wa, words_of(m.n_alt));
+      fr = std::min(fr, m.n_ref / kReadsPerWord);
+      fa = std::min(fa, m.n_alt / kReadsPerWord);
+      if (l == 0) { nr0 = m.n_ref; na0 = m.n_alt; }
+      same_r = same_r && m.n_ref == nr0;
+      same_a = same_a && m.n_alt == na0;
     }
-    all_geom[s] = {wr, wa, s * kSliceMarkers};
+    const uint32_t rr = wr - fr, ra = wa - fa;
+    const bool tail_r = same_r && rr == 1, tail_a = same_a && ra == 1;
+    const uint32_t cost = 4u * (fr + fa) + (tail_r ? 2u : 7u * rr) + (tail_a ? 2u : 7u * ra) + 15u;
+    all_geom[s] = {wr, wa, cost, s * kSliceMarkers};
   }
-  std::stable_sort(all_geom.begin(), all_geom.end(),
-                   [](const SliceGeom &a, const SliceGeom &b) { return a.wr + a.wa > b.wr + b.wa; });
+  std::stable_sort(all_geom.begin(), all_geom.end(), [](const SliceGeom &a, const SliceGeom &b) {
+    return a.cost != b.cost ? a.cost > b.cost : a.wr + a.wa > b.wr + b.wa;
+  });
   std::vector<SliceGeom> geom;
   for (size_t s = d.shard_rank; s < total_slices; s += shard_count) geom.push_back(all_geom[s]);
   P.n_slices = (uint32_t)geom.size();
@@ -202,9 +202,46 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
   L.off_diag = off;  off += 3u * kSliceMarkers * 8u;
   L.off_words = off;
 
-  // ---- 5. deal the slices to SM sub-partition bins in rounds (snake order) -----------------------
+  // ---- 5. deal the slices to SM sub-partition bins in rounds ------------------------------------------
+  // Round r = the slices [r * n_bins, (r+1) * n_bins) of the cost order, one per bin.  Inside a round the
+  // costliest slice goes to the bin that has the least work so far (so the bins stay level whatever the cost
+  // profile is); a partial last round is dealt first, so the bins that own one blob more start with that handicap.  Bins are only labels, so they
+  // are renumbered at the end to put the bins that own a blob in the last round last: in every round the bins
+  // that own a blob are then a contiguous range and blob k of the round belongs to bin first_bin + k.
   P.grid_x = std::max(1u, std::min(cfg.max_ctas ? cfg.max_ctas : 1u, (P.n_slices + kBinsPerCta - 1) / kBinsPerCta));
   P.n_bins = P.grid_x * kBinsPerCta;
+  std::vector<uint32_t> slice_bin(P.n_slices, 0);  // provisional bin label of slice j
+  {
+    std::vector<uint64_t> load(P.n_bins, 0);
+    std::vector<uint32_t> by_load(P.n_bins);
+    std::iota(by_load.begin(), by_load.end(), 0u);
+    // the partial last round first: its slices are the handicap of the bins that will own six instead of five
+    const uint32_t n_full_rounds = P.n_slices / P.n_bins;
+    for (uint32_t j = n_full_rounds * P.n_bins, i = 0; j < P.n_slices; ++j, ++i) {
+      slice_bin[j] = i;
+      load[i] += geom[j].cost;
+    }
+    for (uint32_t r = 0; r < n_full_rounds; ++r) {
+      const uint32_t j0 = r * P.n_bins;
+      std::stable_sort(by_load.begin(), by_load.end(), [&](uint32_t a, uint32_t b) { return load[a] < load[b]; });
+      for (uint32_t i = 0; i < P.n_bins; ++i) {  // slice j0 + i is the (i+1)-th costliest of the round
+        slice_bin[j0 + i] = by_load[i];
+        load[by_load[i]] += geom[j0 + i].cost;
+      }
+    }
+    // renumber: bins without a blob in the (partial) last round first, in their old order
+    const uint32_t rem = P.n_slices % P.n_bins;
+    if (rem) {
+      std::vector<uint8_t> in_last(P.n_bins, 0);
+      for (uint32_t j = P.n_slices - rem; j < P.n_slices; ++j) in_last[slice_bin[j]] = 1;
+      std::vector<uint32_t> relabel(P.n_bins);
+      uint32_t next_short = 0, next_long = P.n_bins - rem;
+      for (uint32_t b = 0; b < P.n_bins; ++b) relabel[b] = in_last[b] ? next_long++ : next_short++;
+      for (uint32_t &b : slice_bin) b = relabel[b];
+    }
+  }
+  // blob_of[r * n_bins + (bin - first_bin of round r)] = the slice stored there
+  std::vector<uint32_t> blob_slice(P.n_slices, 0);
   uint64_t total_bytes = 0;
   for (uint32_t j0 = 0, r = 0; j0 < P.n_slices; j0 += P.n_bins, ++r) {
     const uint32_t cnt = std::min(P.n_bins, P.n_slices - j0);
@@ -212,8 +249,8 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
     for (uint32_t j = j0; j < j0 + cnt; ++j) wmax = std::max(wmax, geom[j].wr + geom[j].wa);
     const uint64_t stride64 = (uint64_t)L.off_words + (uint64_t)wmax * 128u;  // off_words % 16 == 0
     if (stride64 > 0x7FFFFFF0ull) return fail("marker too deep: one blob would exceed 2 GiB");
-    // a partial last round goes to the LONG bins, the last `cnt` ones (see bin_of below)
     Round R{total_bytes, (uint32_t)stride64, P.n_bins - cnt, cnt, wmax};
+    for (uint32_t j = j0; j < j0 + cnt; ++j) blob_slice[j0 + (slice_bin[j] - R.first_bin)] = j;
     P.rounds.push_back(R);
     P.max_stride = std::max(P.max_stride, R.stride);
     total_bytes += (uint64_t)R.stride * cnt;
@@ -226,12 +263,12 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
   // ---- 6. fill ------------------------------------------------------------------------------------
   struct SliceTotals { long double other = 0.0L; uint64_t used = 0, streamed = 0, folded = 0; uint32_t markers = 0; };
   std::vector<SliceTotals> totals(P.n_slices);
-  parallel_chunks(P.n_slices, n_threads, [&](size_t j0, size_t j1, unsigned) {
-  for (uint32_t j = (uint32_t)j0; j < (uint32_t)j1; ++j) {
-    SliceTotals &T = totals[j];
-    const Round &R = P.rounds[j / P.n_bins];
-    const uint32_t bin = bin_of(P.n_slices, P.n_bins, j);
-    uint8_t *blob = P.blob.data() + R.base + (uint64_t)(bin - R.first_bin) * R.stride;
+  parallel_chunks(P.n_slices, n_threads, [&](size_t q0, size_t q1, unsigned) {
+  for (uint32_t q = (uint32_t)q0; q < (uint32_t)q1; ++q) {  // q = blob position: round q / n_bins, k-th blob of it
+    SliceTotals &T = totals[q];
+    const Round &R = P.rounds[q / P.n_bins];
+    const uint32_t j = blob_slice[q];
+    uint8_t *blob = P.blob.data() + R.base + (uint64_t)(q % P.n_bins) * R.stride;
     const uint32_t wr = geom[j].wr, wa = geom[j].wa;
     uint32_t n_valid = 0, full_ref = wr, full_alt = wa;  // leading rows with four real reads in EVERY lane
     uint32_t nref0 = 0xFFFFFFFFu, nalt0 = 0xFFFFFFFFu;   // read counts if identical in every valid lane
@@ -260,7 +297,7 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
       if (nref0 == 0xFFFFFFFFu) { nref0 = m.n_ref; nalt0 = m.n_alt; }
       same_ref = same_ref && m.n_ref == nref0;
       same_alt = same_alt && m.n_alt == nalt0;
-      P.marker_index[(size_t)j * kSliceMarkers + l] = m.panel_row;
+      P.marker_index[(size_t)q * kSliceMarkers + l] = m.panel_row;
       if (P.known_af) {
         reinterpret_cast<double *>(blob + L.off_kaf)[l] = d.known_af[m.panel_row];
       } else {

@@ -12,10 +12,11 @@
 //     depend on alpha or the PCs -> three per-marker constants diag[g]
 //
 // Layout ("blobs in rounds", DESIGN.md "Data layout in HBM"):
-//   markers are sorted by (total words, alt words) so the 32 lanes of a warp run equal trip
+//   markers are sorted by (alt reads, ref reads) so the 32 lanes of a warp run equal trip
 //   counts, cut into 32-marker SLICES, and the slices are dealt to BINS -- one bin per SM
-//   sub-partition of the launch (4 per CTA, one CTA per SM) -- in ROUNDS, heaviest first, in
-//   snake order, so every sub-partition's FP64 pipe gets the same amount of work.  Everything a
+//   sub-partition of the launch (4 per CTA, one CTA per SM) -- in ROUNDS, costliest first, the
+//   costliest slice of a round to the least loaded bin, so every sub-partition gets the same
+//   amount of work (cost = what the kernel spends: rows, ragged rows, per-slice set-up).  Everything a
 //   warp needs for one slice -- header, UD columns, mu, diag, the packed quality bytes -- is ONE
 //   contiguous BLOB, and all blobs of a round have the same stride, so a warp finds its blob
 //   with arithmetic only (no descriptor load) and fetches it with one TMA bulk copy.
@@ -81,12 +82,9 @@ struct PackedSample {
   // u32 full_ref | full_alt << 16 (leading ref / alt rows in which every valid lane has four real reads:
   // the kernel streams those -- and uniform tails -- without looking for filler bytes).
   std::vector<uint8_t> blob;          // the whole image
-  std::vector<uint32_t> marker_index; // [n_slices*32] panel row per (slice, lane); slice j (heaviest
-                                      // first) is the blob of round j / n_bins, bin bin_of(j)
+  std::vector<uint32_t> marker_index; // [n_slices*32] panel row per (blob, lane) in image order: blob q is the
+                                      // (q % n_bins)-th blob of round q / n_bins, i.e. of bin first_bin + q % n_bins
 };
-
-// Bin of slice j (slices heaviest first); see llk_pack.cpp for the dealing rule.
-uint32_t bin_of(uint32_t n_slices, uint32_t n_bins, uint32_t j);
 
 // Returns VB2_OK or VB2_ERR_INVALID (message in *err).  phred[q] = 10^(-q/10), q = 0..93.
 int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phred, PackedSample *out,
