@@ -215,7 +215,8 @@ def run_ours(args):
     p = sample.problem
     k = p.n_pc
     # enough resident copies of this rank's shard to exceed L2 -> every step streams from HBM
-    probe = vb.LLKEngine(p, device=local, shard_rank=rank, shard_count=world, stream=stream.cuda_stream)
+    # (N > 1: every rank only ever evaluates its shard in batches -> the batched layout, include/vb2_llk.h)
+    probe = vb.LLKEngine(p, device=local, shard_rank=rank, shard_count=world, stream=stream.cuda_stream, batched=world > 1)
     info = probe.info()
     copies = max(2, int(np.ceil(2.0 * L2_BYTES / max(1, info["device_bytes"]))))
     copies = min(copies, 256)
@@ -223,7 +224,7 @@ def run_ours(args):
         c = torch.tensor([copies], dtype=torch.int64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.MAX)
         copies = int(c.item())
-    engines = [probe] + [vb.LLKEngine(p, device=local, shard_rank=rank, shard_count=world, stream=stream.cuda_stream)
+    engines = [probe] + [vb.LLKEngine(p, device=local, shard_rank=rank, shard_count=world, stream=stream.cuda_stream, batched=world > 1)
                          for _ in range(copies - 1)]
     reads_total = p.used_counts()[1]           # whole sample, all shards
     markers_total = p.used_counts()[0]
@@ -272,15 +273,28 @@ def run_ours(args):
         else:
             # `copies` steps per launch on every rank (its marker shard of each resident copy), then ONE
             # NCCL allreduce of the `copies` partial sums
-            d_many = torch.zeros(copies, dtype=torch.float64, device=dev)
+            # (two result buffers: the allreduce of one launch's partial sums runs on NCCL's stream while the next
+            # launch's kernel runs on ours)
+            d_many = [torch.zeros(copies, dtype=torch.float64, device=dev) for _ in range(2)]
+            works = [None, None]
             pcs = np.tile(start_pc, (copies, 1)); als = np.full(copies, 0.03)
+            turn = [0]
 
             def launch_steps(n: int):
-                vb.eval_many_device(engines[:n], pcs[:n], pcs[:n], als[:n], d_many.data_ptr())
-                allreduce_partials(d_many[:n])
+                b = turn[0] = turn[0] ^ 1
+                if works[b] is not None:
+                    works[b].wait()          # (stream-level: our stream waits for that buffer's previous allreduce)
+                vb.eval_many_device(engines[:n], pcs[:n], pcs[:n], als[:n], d_many[b].data_ptr())
+                works[b] = dist.all_reduce(d_many[b][:n], op=dist.ReduceOp.SUM, async_op=True)
+
+            def drain():
+                for w in works:
+                    if w is not None:
+                        w.wait()
             full, rem = divmod(args.steps, copies)
             for _ in range(max(1, args.warmup // copies)):
                 launch_steps(copies)
+            drain()
             barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(stream)
@@ -288,6 +302,7 @@ def run_ours(args):
                 launch_steps(copies)
             if rem:
                 launch_steps(rem)
+            drain()
             ev1.record(stream)
             barrier()
             dev_ms = ev0.elapsed_time(ev1)

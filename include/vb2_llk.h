@@ -52,8 +52,12 @@ enum vb2_panel_dtype {
 };
 
 enum vb2_flags {
-  VB2_FLAG_NO_SPIN = 1u << 0 /* wait with cudaStreamSynchronize instead of polling the
-                                host-mapped result mailbox                                   */
+  VB2_FLAG_NO_SPIN = 1u << 0, /* wait with cudaStreamSynchronize instead of polling the
+                                 host-mapped result mailbox                                  */
+  VB2_FLAG_BATCHED = 1u << 1  /* the context serves batched evaluation (vb2_llk_eval_batch / _many, e.g. a marker
+                                 shard of a multi-GPU run or a cohort member): lay a small sample out over fewer,
+                                 deeper bins (>= 5 slices each) so that a task of the many-evaluations kernel
+                                 amortises its set-up; one evaluation per launch then uses fewer SMs             */
 };
 
 typedef struct vb2_llk_ctx vb2_llk_ctx;

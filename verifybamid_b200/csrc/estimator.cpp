@@ -289,6 +289,7 @@ void ContaminationEstimator::CreateEngines() {
   d.avg_depth = viewer.avgDepth;
   d.sd_depth = viewer.sdDepth;
   d.panel_dtype = panelFp64 ? VB2_PANEL_FP64 : VB2_PANEL_FP32;
+  if (cohort) d.flags |= VB2_FLAG_BATCHED;  // a cohort member is only ever evaluated in the cohort's batched launches
   d.shard_count = (uint32_t)numGPU;
   for (int g = 0; g < numGPU; ++g) {
     d.shard_rank = (uint32_t)g;

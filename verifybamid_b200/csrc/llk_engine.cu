@@ -1217,8 +1217,13 @@ struct vb2_llk_ctx {
   std::vector<vb2::Round> rounds;  // host copy (kernel arguments)
   Slot *h_mbox = nullptr, *d_mbox = nullptr;
   uint32_t mbox_slots = 0;
-  JobParams *h_jobs = nullptr;  // pinned staging [VB2_MAX_BATCH]
-  JobParams *d_jobs = nullptr;
+  // Staging of parameter sets that do not fit in the kernel arguments: TWO sets used alternately, each guarded by
+  // an event recorded behind the launch that reads it, so staging launch i+1 never waits for launch i.
+  JobParams *h_jobs2 = nullptr, *d_jobs2 = nullptr;  // [2][VB2_MAX_BATCH] pinned / device
+  JobParams *h_jobs = nullptr, *d_jobs = nullptr;    // the set in use
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  bool stage_used[2] = {false, false};
+  int stage_idx = 0;
   double *d_out = nullptr;      // [VB2_MAX_BATCH]
   unsigned int *d_queue = nullptr;  // llk_stream_kernel task queue
   unsigned long long *d_trace = nullptr;  // vb2_llk_trace: [grid_x][kTraceSlots]
@@ -1230,8 +1235,8 @@ struct vb2_llk_ctx {
   uint32_t session_relaunches = 0;
   double clock_khz = 0.0, session_idle_ms = 200.0;
   // eval_many staging (owned by the leading context)
-  SampleDev *h_many = nullptr, *d_many = nullptr;
-  uint32_t *h_slots = nullptr, *d_slots = nullptr;
+  SampleDev *h_many2 = nullptr, *d_many2 = nullptr, *h_many = nullptr, *d_many = nullptr;  // [2][VB2_MAX_BATCH] / in use
+  uint32_t *h_slots2 = nullptr, *d_slots2 = nullptr, *h_slots = nullptr, *d_slots = nullptr;
   uint32_t many_n = 0, many_grid_x = 0, many_kc = 1, many_buf_bytes = 0;  // last staged eval_many launch
   int many_spec = 0;
   bool many_chunked = false;
@@ -1300,10 +1305,32 @@ void fill_job(JobParams *J, uint32_t n_pc, const double *pc1, const double *pc2,
 
 // Pinned + device staging for parameter sets that do not fit in the kernel arguments (allocated on first use).
 int ensure_job_staging(vb2_llk_ctx *ctx) {
-  if (ctx->h_jobs) return VB2_OK;
-  VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_jobs, sizeof(JobParams) * VB2_MAX_BATCH, cudaHostAllocDefault));
-  VB2_CUDA(ctx, cudaMalloc(&ctx->d_jobs, sizeof(JobParams) * VB2_MAX_BATCH));
+  if (ctx->h_jobs2) return VB2_OK;
+  VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_jobs2, sizeof(JobParams) * 2 * VB2_MAX_BATCH, cudaHostAllocDefault));
+  VB2_CUDA(ctx, cudaMalloc(&ctx->d_jobs2, sizeof(JobParams) * 2 * VB2_MAX_BATCH));
+  VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_many2, sizeof(SampleDev) * 2 * VB2_MAX_BATCH, cudaHostAllocDefault));
+  VB2_CUDA(ctx, cudaMalloc(&ctx->d_many2, sizeof(SampleDev) * 2 * VB2_MAX_BATCH));
+  VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_slots2, sizeof(uint32_t) * 2 * VB2_MAX_BATCH, cudaHostAllocDefault));
+  VB2_CUDA(ctx, cudaMalloc(&ctx->d_slots2, sizeof(uint32_t) * 2 * VB2_MAX_BATCH));
+  for (int i = 0; i < 2; ++i) VB2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
   return VB2_OK;
+}
+// Take the other staging set (waiting, if ever needed, for the launch that read it two stagings ago).
+int acquire_staging(vb2_llk_ctx *ctx) {
+  int rc = ensure_job_staging(ctx);
+  if (rc) return rc;
+  const int i = ctx->stage_idx ^= 1;
+  if (ctx->stage_used[i]) VB2_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[i]));
+  ctx->stage_used[i] = true;
+  const size_t o = (size_t)i * VB2_MAX_BATCH;
+  ctx->h_jobs = ctx->h_jobs2 + o; ctx->d_jobs = ctx->d_jobs2 + o;
+  ctx->h_many = ctx->h_many2 + o; ctx->d_many = ctx->d_many2 + o;
+  ctx->h_slots = ctx->h_slots2 + o; ctx->d_slots = ctx->d_slots2 + o;
+  return VB2_OK;
+}
+// Behind every launch that reads the staging set in use.
+void release_staging(vb2_llk_ctx *ctx) {
+  if (ctx->stage_ev[ctx->stage_idx]) cudaEventRecord(ctx->stage_ev[ctx->stage_idx], ctx->stream);
 }
 
 // Device-side reduction scratch: one row of n_bins = 4*grid_x partials + one ticket per concurrent job.
@@ -1525,10 +1552,8 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
     memcpy(A.rounds, ctx->rounds.data(), ctx->rounds.size() * sizeof(vb2::Round));
     for (int j = 0; j < n; ++j) fill_job(&A.jobs[j], k, pc1 + (size_t)j * k, pc2 + (size_t)j * k, alphas[j]);
   } else {
-    // the pinned staging buffer may still be read by the previous batch's copy
-    int rcs = ensure_job_staging(ctx);
+    int rcs = acquire_staging(ctx);
     if (rcs) return rcs;
-    VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int j = 0; j < n; ++j) fill_job(&ctx->h_jobs[j], k, pc1 + (size_t)j * k, pc2 + (size_t)j * k, alphas[j]);
     VB2_CUDA(ctx, cudaMemcpyAsync(ctx->d_jobs, ctx->h_jobs, (size_t)n * sizeof(JobParams), cudaMemcpyHostToDevice,
                                   ctx->stream));
@@ -1543,6 +1568,7 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
     const dim3 sgrid(stream_grid(ctx->sm_count, (uint32_t)n * A.n_bins_max), 1, 1);
     if (args) launch_stream<true>(sgrid, 8u * A.stage_bytes, ctx->stream, A, ctx->spec, ctx->chunked);
     else launch_stream<false>(sgrid, 8u * A.stage_bytes, ctx->stream, A, ctx->spec, ctx->chunked);
+    if (!args) release_staging(ctx);
     VB2_CUDA(ctx, cudaGetLastError());
     return VB2_OK;
   }
@@ -1550,6 +1576,7 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
   if (mode == Reduce::kHost) launch_llk<true, true>(grid, block, g.smem, ctx->stream, A, ctx->spec, ctx->chunked);
   else if (args) launch_llk<true, false>(grid, block, g.smem, ctx->stream, A, ctx->spec, ctx->chunked);
   else launch_llk<false, false>(grid, block, g.smem, ctx->stream, A, ctx->spec, ctx->chunked);
+  if (!args) release_staging(ctx);
   VB2_CUDA(ctx, cudaGetLastError());
   return VB2_OK;
 }
@@ -1609,18 +1636,20 @@ void vb2_llk_destroy(vb2_llk_ctx *ctx) {
   if (ctx->S.partials) cudaFree(ctx->S.partials);
   if (ctx->S.tickets) cudaFree(ctx->S.tickets);
   if (ctx->d_sample) cudaFree(ctx->d_sample);
-  if (ctx->d_jobs) cudaFree(ctx->d_jobs);
+  if (ctx->d_jobs2) cudaFree(ctx->d_jobs2);
   if (ctx->d_out) cudaFree(ctx->d_out);
   if (ctx->d_queue) cudaFree(ctx->d_queue);
   if (ctx->d_trace) cudaFree(ctx->d_trace);
   if (ctx->h_bell) cudaFreeHost(ctx->h_bell);
   if (ctx->d_relay) cudaFree(ctx->d_relay);
-  if (ctx->d_many) cudaFree(ctx->d_many);
-  if (ctx->d_slots) cudaFree(ctx->d_slots);
+  if (ctx->d_many2) cudaFree(ctx->d_many2);
+  if (ctx->d_slots2) cudaFree(ctx->d_slots2);
   if (ctx->h_mbox) cudaFreeHost(ctx->h_mbox);
-  if (ctx->h_jobs) cudaFreeHost(ctx->h_jobs);
-  if (ctx->h_many) cudaFreeHost(ctx->h_many);
-  if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
+  if (ctx->h_jobs2) cudaFreeHost(ctx->h_jobs2);
+  if (ctx->h_many2) cudaFreeHost(ctx->h_many2);
+  if (ctx->h_slots2) cudaFreeHost(ctx->h_slots2);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1664,6 +1693,7 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   vb2::PackConfig cfg;
   cfg.max_ctas = (uint32_t)ctx->sm_count;  // one persistent CTA per SM
   cfg.panel_fp64 = desc->panel_dtype == VB2_PANEL_FP64;
+  if (desc->flags & VB2_FLAG_BATCHED) cfg.min_rounds = 5;
   if (const char *t = getenv("VB2_LLK_MAX_CTAS")) cfg.max_ctas = (uint32_t)std::max(1, atoi(t));
   vb2::PackedSample &P = ctx->meta;
   std::string perr;
@@ -1870,17 +1900,10 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
   if (n > VB2_MAX_BATCH) return set_err(lead, VB2_ERR_INVALID, "batch size out of range");
   if (!pc_contam || !pc_intended || !alphas) return set_err(lead, VB2_ERR_INVALID, "null argument");
   VB2_CUDA(lead, cudaSetDevice(lead->device));
-  if (!lead->h_many) {
-    VB2_CUDA(lead, cudaHostAlloc((void **)&lead->h_many, sizeof(SampleDev) * VB2_MAX_BATCH, cudaHostAllocDefault));
-    VB2_CUDA(lead, cudaMalloc(&lead->d_many, sizeof(SampleDev) * VB2_MAX_BATCH));
-    VB2_CUDA(lead, cudaHostAlloc((void **)&lead->h_slots, sizeof(uint32_t) * VB2_MAX_BATCH, cudaHostAllocDefault));
-    VB2_CUDA(lead, cudaMalloc(&lead->d_slots, sizeof(uint32_t) * VB2_MAX_BATCH));
-  }
   {
-    int rcs = ensure_job_staging(lead);
+    int rcs = acquire_staging(lead);
     if (rcs) return rcs;
   }
-  VB2_CUDA(lead, cudaStreamSynchronize(lead->stream));  // staging buffers are free again
   const uint32_t k = lead->S.n_pc;
   // slot of job j inside its sample = number of earlier jobs on the same context
   for (int j = 0; j < n; ++j) {
@@ -1953,6 +1976,7 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
   A.queue = lead->d_queue;
   const dim3 grid(stream_grid(lead->sm_count, lead->many_n * A.n_bins_max), 1, 1);
   launch_stream<false>(grid, 8u * A.stage_bytes, lead->stream, A, lead->many_spec, lead->many_chunked);
+  release_staging(lead);
   VB2_CUDA(lead, cudaGetLastError());
   return VB2_OK;
 }

@@ -209,6 +209,7 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
   // are renumbered at the end to put the bins that own a blob in the last round last: in every round the bins
   // that own a blob are then a contiguous range and blob k of the round belongs to bin first_bin + k.
   P.grid_x = std::max(1u, std::min(cfg.max_ctas ? cfg.max_ctas : 1u, (P.n_slices + kBinsPerCta - 1) / kBinsPerCta));
+  if (cfg.min_rounds > 1) P.grid_x = std::max(1u, std::min(P.grid_x, P.n_slices / (kBinsPerCta * cfg.min_rounds)));
   P.n_bins = P.grid_x * kBinsPerCta;
   std::vector<uint32_t> slice_bin(P.n_slices, 0);  // provisional bin label of slice j
   {

@@ -43,6 +43,7 @@ constexpr uint32_t kMaxConcRounds = 6;  // rounds a CTA runs concurrently (4*6 =
 struct PackConfig {
   uint32_t max_ctas = 148;   // CTAs of one launch = SMs of the device (one persistent CTA per SM)
   bool panel_fp64 = false;   // UD / mu element type inside the blobs
+  uint32_t min_rounds = 1;   // use fewer CTAs' worth of bins if needed to give every bin about this many slices
 };
 
 // Byte offsets inside a blob (identical for every blob of a sample).

@@ -25,6 +25,7 @@ VB2_OK = 0
 VB2_PANEL_FP32 = 0
 VB2_PANEL_FP64 = 1
 VB2_FLAG_NO_SPIN = 1
+VB2_FLAG_BATCHED = 2
 VB2_MAX_PC = 16
 VB2_MAX_BATCH = 4096
 
@@ -167,7 +168,7 @@ def _f64(a, shape=None) -> np.ndarray:
 
 def make_desc(problem: PileupProblem, device: int = 0, panel_dtype: int = VB2_PANEL_FP32, shard_rank: int = 0,
               shard_count: int = 1, stream: Optional[int] = None, spin: bool = True, min_af: float = 0.0,
-              max_af: float = 0.0) -> _Desc:
+              max_af: float = 0.0, batched: bool = False) -> _Desc:
     """vb2_llk_desc over the numpy arrays of `problem` (which must stay alive during the call)."""
     d = _Desc()
     d.struct_size = ctypes.sizeof(_Desc)
@@ -188,7 +189,7 @@ def make_desc(problem: PileupProblem, device: int = 0, panel_dtype: int = VB2_PA
     d.sd_depth = float(problem.sd_depth)
     d.min_af, d.max_af = float(min_af), float(max_af)
     d.panel_dtype = int(panel_dtype)
-    d.flags = 0 if spin else VB2_FLAG_NO_SPIN
+    d.flags = (0 if spin else VB2_FLAG_NO_SPIN) | (VB2_FLAG_BATCHED if batched else 0)
     d.shard_rank, d.shard_count = int(shard_rank), int(shard_count)
     d.stream = stream
     return d
@@ -227,11 +228,11 @@ class LLKEngine:
 
     def __init__(self, problem: PileupProblem, device: int = 0, panel_dtype: int = VB2_PANEL_FP32,
                  shard_rank: int = 0, shard_count: int = 1, stream: Optional[int] = None, spin: bool = True,
-                 min_af: float = 0.0, max_af: float = 0.0):
+                 min_af: float = 0.0, max_af: float = 0.0, batched: bool = False):
         self._lib = load_library()
         self._ctx = ctypes.c_void_p()
         self.problem = problem
-        d = make_desc(problem, device, panel_dtype, shard_rank, shard_count, stream, spin, min_af, max_af)
+        d = make_desc(problem, device, panel_dtype, shard_rank, shard_count, stream, spin, min_af, max_af, batched)
         rc = self._lib.vb2_llk_create(ctypes.byref(d), ctypes.byref(self._ctx))
         if rc != VB2_OK:
             raise VB2Error(rc, self._lib.vb2_last_error(None).decode())
