@@ -182,16 +182,23 @@ __device__ __forceinline__ void eat4(double e0, double e1, double e2, double e3,
 // word and the four table look-ups of row t+1 are issued before the arithmetic of row t -- also after the last
 // row: the loop reads one row past the run (the next run, or the 128-byte pad every stage buffer ends with) and
 // drops what it read, which keeps the loop free of a peeled copy.
+// Phred error of byte b (0..3) of word w: one byte-extract and one multiply-add form the shared-memory address.
+template <int B>
+__device__ __forceinline__ double phred_of(uint32_t w) {
+  const uint32_t q = __byte_perm(w, 0u, 0x4440u + B);  // (0, 0, 0, byte B)
+  return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_e) + q * 8u);
+}
+
 template <bool ALT>
 __device__ __forceinline__ void eat_full_rows(const uint32_t *col, uint32_t n, const Quad &Q,
                                               double (&acc)[kNumPairs]) {
   if (n == 0) return;
   uint32_t w = col[0];
-  double e0 = s_e[w & 0xFFu], e1 = s_e[(w >> 8) & 0xFFu], e2 = s_e[(w >> 16) & 0xFFu], e3 = s_e[w >> 24];
+  double e0 = phred_of<0>(w), e1 = phred_of<1>(w), e2 = phred_of<2>(w), e3 = phred_of<3>(w);
 #pragma unroll 1
   for (uint32_t t = 1; t <= n; ++t) {
     w = col[t * 32];
-    const double n0 = s_e[w & 0xFFu], n1 = s_e[(w >> 8) & 0xFFu], n2 = s_e[(w >> 16) & 0xFFu], n3 = s_e[w >> 24];
+    const double n0 = phred_of<0>(w), n1 = phred_of<1>(w), n2 = phred_of<2>(w), n3 = phred_of<3>(w);
     eat4<ALT>(e0, e1, e2, e3, Q, acc);
     e0 = n0; e1 = n1; e2 = n2; e3 = n3;
   }
@@ -695,15 +702,14 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
 struct WarpCtl {
   const uint8_t *blob;     // the issue cursor's task: sample image, round table, sizes
   const vb2::Round *tab;
-  uint32_t next_task, job, bin, n_rounds, chunk_rows, off_words;
-  uint32_t first;          // no stage of the cursor's task has been issued yet
-  uint32_t rbase, mask;    // item table: entry i = round rbase + i; mask = entries not yet issued
-  uint32_t off16, rows, c, nch;  // the blob being issued (CHUNKED: chunk c of nch)
+  uint32_t next_task, task, bin, n_rounds, chunk_rows, off_words;
+  uint32_t rbase;          // item table: entry i = round rbase + i
+  uint32_t off16, rows, c, nch;  // CHUNKED: the blob being issued, chunk c of nch
   uint32_t done;           // queue exhausted
   uint32_t it_off16[32], it_rows[32];
-  struct StageDesc {
-    uint32_t job, bin, first, c, n_ch, chunk_rows;
-  } st[2];                 // what sits (or is landing) in each of the warp's two buffers
+  // what sits (or is landing) in each of the warp's two buffers: 0x80000000 | task for the first stage of a task,
+  // else 0; CHUNKED: also which chunk of how many
+  uint32_t st_task[2], st_c[2], st_nch[2], st_chunk_rows[2];
 };
 
 #ifndef VB2_STREAM_CTAS_PER_SM
@@ -738,10 +744,11 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
   };
   if (lane == 0) {
     W.next_task = blockIdx.x * 4u + (uint32_t)warp;
-    W.n_rounds = 0; W.first = 0; W.rbase = 0; W.mask = 0; W.c = 0; W.nch = 0; W.done = 0;
+    W.n_rounds = 0; W.rbase = 0; W.c = 0; W.nch = 0; W.done = 0;
   }
   fetch();
   __syncwarp();
+  const uint32_t n_bins_max = A.n_bins_max, n_tasks = A.n_jobs * n_bins_max;
 
   // v = this lane's share of task (job, bin): xor-shuffle tree over the lanes -> partials[job][bin]
   auto store_partial = [&](uint32_t job, uint32_t bin, double v) {
@@ -755,110 +762,112 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
   };
 
   // ---- issue side: put the next stage (blob, or chunk of a blob) of this warp's task sequence into buffer b.
-  // Every lane runs it with the same values (the state is read from and written back to shared memory); returns
-  // false when the queue is exhausted.
-  auto produce = [&](uint32_t b) -> bool {
-    if (W.done) return false;
-    uint32_t c = W.c, nch = W.nch, mask = W.mask, rbase = W.rbase, n_rounds = W.n_rounds, bin = W.bin;
-    uint32_t first = W.first, off16 = W.off16, rows = W.rows;
-    const uint32_t n_bins_max = A.n_bins_max, n_tasks = A.n_jobs * n_bins_max;
-    if (CHUNKED && c + 1 < nch) {
-      ++c;
-    } else {
-      while (mask == 0) {
-        rbase += 32;
-        if (rbase >= n_rounds) {  // the task's table is exhausted: take the next task
-          if (first) store_partial(W.job, bin, 0.0);  // (it had no blob at all: an empty bin still reports in)
-          first = 0;
-          n_rounds = 0;
-          const uint32_t t = W.next_task;
-          if (t >= n_tasks) {
-            __syncwarp();
-            if (lane == 0) W.done = 1;
-            __syncwarp();
-            return false;
-          }
-          const uint32_t nt = __shfl_sync(0xFFFFFFFFu, fetched, 0);
-          fetch();
-          const uint32_t job = t / n_bins_max;
-          bin = t - job * n_bins_max;
-          const SampleDev &S = (ARGS || !A.samples) ? A.sample : A.samples[job];
-          const bool active = bin < 4u * S.grid_x;  // eval_many: a sample may have fewer bins than the launch
+  // The two values every slice needs -- which items of the table are still to issue, and whether the task has
+  // issued anything yet -- live in registers; the rest of the cursor lives in shared memory (WarpCtl) and is
+  // touched when a task or a table runs out.  Returns false when the queue is exhausted.
+  uint32_t mask = 0, first = 0;
+  auto next_table = [&]() -> bool {  // mask == 0: the next 32 rounds of the task, or the next task; false = no more work
+    for (;;) {
+      uint32_t rbase = W.rbase + 32u, n_rounds = W.n_rounds, bin = W.bin;
+      if (rbase >= n_rounds) {  // the task's table is exhausted: take the next task
+        if (first) store_partial(W.task / n_bins_max, bin, 0.0);  // (no blob at all: an empty bin still reports in)
+        first = 0;
+        const uint32_t t = W.next_task;
+        if (t >= n_tasks) {
           __syncwarp();
-          if (lane == 0) {
-            W.next_task = nt;
-            W.job = job;
-            W.bin = bin;
-            if (active) {
-              W.blob = S.blob;
-              W.tab = ARGS ? A.rounds : S.rounds;
-              W.chunk_rows = S.chunk_rows;
-              W.off_words = S.off_words;
-            }
-          }
+          if (lane == 0) W.done = 1;
           __syncwarp();
-          if (!active) continue;
-          n_rounds = S.n_rounds;
-          first = 1;
-          rbase = 0;
+          return false;
         }
-        // item table of rounds [rbase, rbase + 32): lane i looks at round rbase + i
-        const uint32_t r = rbase + (uint32_t)lane;
-        bool mine = false;
-        if (r < n_rounds) {
-          const vb2::Round R = W.tab[r];
-          if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
-            mine = true;
-            W.it_off16[lane] = (uint32_t)((R.base + (uint64_t)(bin - R.first_bin) * R.stride) >> 4);
-            W.it_rows[lane] = R.rows;
+        const uint32_t nt = __shfl_sync(0xFFFFFFFFu, fetched, 0);
+        fetch();
+        const uint32_t job = t / n_bins_max;
+        bin = t - job * n_bins_max;
+        const SampleDev &S = (ARGS || !A.samples) ? A.sample : A.samples[job];
+        const bool active = bin < 4u * S.grid_x;  // eval_many: a sample may have fewer bins than the launch
+        n_rounds = active ? S.n_rounds : 0u;
+        __syncwarp();
+        if (lane == 0) {
+          W.next_task = nt;
+          W.task = t;
+          W.bin = bin;
+          W.n_rounds = n_rounds;
+          W.rbase = 0u - 32u;
+          if (active) {
+            W.blob = S.blob;
+            W.tab = ARGS ? A.rounds : S.rounds;
+            W.chunk_rows = S.chunk_rows;
+            W.off_words = S.off_words;
           }
         }
-        mask = __ballot_sync(0xFFFFFFFFu, mine);
+        __syncwarp();
+        if (!active) continue;
+        first = 1;
+        rbase = 0;
       }
-      const int i = __ffs((int)mask) - 1;
-      mask &= mask - 1u;
-      off16 = W.it_off16[i];
-      rows = W.it_rows[i];
-      c = 0;
-      const uint32_t chunk_rows = W.chunk_rows;
-      nch = (!CHUNKED || rows <= chunk_rows) ? 1u : (rows + chunk_rows - 1) / chunk_rows;
+      // item table of rounds [rbase, rbase + 32): lane i looks at round rbase + i
+      const uint32_t r = rbase + (uint32_t)lane;
+      bool mine = false;
+      if (r < n_rounds) {
+        const vb2::Round R = W.tab[r];
+        if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
+          mine = true;
+          W.it_off16[lane] = (uint32_t)((R.base + (uint64_t)(bin - R.first_bin) * R.stride) >> 4);
+          W.it_rows[lane] = R.rows;
+        }
+      }
+      if (lane == 0) W.rbase = rbase;
+      mask = __ballot_sync(0xFFFFFFFFu, mine);
+      if (mask) return true;
     }
+  };
+  auto produce = [&](uint32_t b) -> bool {
+    if (CHUNKED && W.c + 1 < W.nch) {  // the next chunk of the blob being issued
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t c = W.c + 1, chunk_rows = W.chunk_rows, rows = W.rows;
+        const uint32_t off = W.off_words + c * chunk_rows * 128u, n = rows - c * chunk_rows;
+        const uint32_t bytes = (n < chunk_rows ? n : chunk_rows) * 128u;
+        mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
+        bulk_g2s(mybuf + (size_t)b * stage_bytes, W.blob + ((uint64_t)W.off16 << 4) + off, bytes, &s_bar[warp][b]);
+        W.c = c;
+        W.st_task[b] = 0u; W.st_c[b] = c; W.st_nch[b] = W.nch; W.st_chunk_rows[b] = chunk_rows;
+      }
+      __syncwarp();
+      return true;
+    }
+    if (mask == 0) {
+      if (W.done || !next_table()) return false;
+    }
+    const int i = __ffs((int)mask) - 1;
+    mask &= mask - 1u;
     __syncwarp();
     if (lane == 0) {
-      // chunk 0 = header + panel + diag + the first chunk_rows word rows; chunk c >= 1 = the next rows
-      const uint32_t chunk_rows = W.chunk_rows;
+      const uint32_t off16 = W.it_off16[i], rows = W.it_rows[i];
       uint32_t off_words = W.off_words;
       if constexpr (Layout::kFixed) off_words = Layout::off_words;
-      uint32_t off = 0, bytes;
-      if (!CHUNKED) {
-        bytes = off_words + rows * 128u;
-      } else if (c == 0) {
-        bytes = off_words + (rows < chunk_rows ? rows : chunk_rows) * 128u;
-      } else {
-        off = off_words + c * chunk_rows * 128u;
-        const uint32_t n = rows - c * chunk_rows;
-        bytes = (n < chunk_rows ? n : chunk_rows) * 128u;
+      uint32_t bytes = off_words + rows * 128u;  // chunk 0 = header + panel + diag + the first chunk_rows word rows
+      if (CHUNKED) {
+        const uint32_t chunk_rows = W.chunk_rows;
+        const uint32_t nch = rows <= chunk_rows ? 1u : (rows + chunk_rows - 1) / chunk_rows;
+        if (nch > 1) bytes = off_words + chunk_rows * 128u;
+        W.off16 = off16; W.rows = rows; W.c = 0; W.nch = nch;
+        W.st_c[b] = 0; W.st_nch[b] = nch; W.st_chunk_rows[b] = chunk_rows;
       }
       mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
-      bulk_g2s(mybuf + (size_t)b * stage_bytes, W.blob + ((uint64_t)off16 << 4) + off, bytes, &s_bar[warp][b]);
-      WarpCtl::StageDesc &D = W.st[b];
-      D.job = W.job; D.bin = bin; D.first = (first && c == 0) ? 1u : 0u; D.c = c; D.n_ch = nch; D.chunk_rows = chunk_rows;
-      W.c = c; W.nch = nch; W.mask = mask; W.rbase = rbase; W.n_rounds = n_rounds; W.first = 0;
-      W.off16 = off16; W.rows = rows;
+      bulk_g2s(mybuf + (size_t)b * stage_bytes, W.blob + ((uint64_t)off16 << 4), bytes, &s_bar[warp][b]);
+      W.st_task[b] = first ? (0x80000000u | W.task) : 0u;
     }
+    first = 0;
     __syncwarp();
     return true;
   };
 
   // ---- consume ------------------------------------------------------------------------------------
-  uint32_t in_flight = 0, ib = 0, cb = 0, parity = 0;
+  uint32_t in_flight = 0, cb = 0, parity = 0;
   if (produce(0)) {
     in_flight = 1;
-    ib = 1;
-    if (produce(1)) {
-      in_flight = 2;
-      ib = 0;
-    }
+    if (produce(1)) in_flight = 2;
   }
   double vsum = 0.0, prod = 1.0;  // the running task: sum of log(marginal) = log(prod * 2^esum) + vsum
   int esum = 0;
@@ -879,12 +888,13 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
   double acc[kNumPairs], ldiag = 0.;
   SliceHeader H{0, 0, 0, 0, 0, 0};
   while (in_flight) {
-    const WarpCtl::StageDesc D = W.st[cb];
-    if (D.first) {  // a new task: close the previous one, load this evaluation's parameters
+    const uint32_t d_task = W.st_task[cb];
+    if (d_task) {  // a new task: close the previous one, load this evaluation's parameters
       if (have_task) store_partial(c_job, c_bin, task_value());
       have_task = true;
-      c_job = D.job;
-      c_bin = D.bin;
+      const uint32_t t = d_task & 0x7FFFFFFFu;
+      c_job = t / n_bins_max;
+      c_bin = t - c_job * n_bins_max;
       vsum = 0.0; prod = 1.0; esum = 0;
       const double *src = reinterpret_cast<const double *>(ARGS ? &A.jobs[c_job] : &A.jobs_dev[c_job]);
       double *dst = reinterpret_cast<double *>(&s_job[warp]);
@@ -903,22 +913,24 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
     mbar_wait(&s_bar[warp][cb], (parity >> cb) & 1u);
     parity ^= 1u << cb;
     const uint8_t *buf = mybuf + (size_t)cb * stage_bytes;
-    if (!CHUNKED || D.c == 0) slice_begin(buf, Y, J, lane, H, acc, ldiag);
     bool last = true;
     if (!CHUNKED) {
+      slice_begin(buf, Y, J, lane, H, acc, ldiag);
       eat_runs<false>(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, H.fr, H.wr - H.fr, H.tails & 0xFu,
                       H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, lin, Q, acc);
     } else {
-      const uint32_t t_lo = D.c * D.chunk_rows;
-      slice_rows<false>(reinterpret_cast<const uint32_t *>(buf + (D.c == 0 ? Y.off_words : 0u)) + lane, t_lo,
-                 t_lo + D.chunk_rows, H, lin, Q, acc);
-      last = D.c + 1 == D.n_ch;
+      const uint32_t d_c = W.st_c[cb], d_chunk_rows = W.st_chunk_rows[cb];
+      if (d_c == 0) slice_begin(buf, Y, J, lane, H, acc, ldiag);
+      const uint32_t t_lo = d_c * d_chunk_rows;
+      slice_rows<false>(reinterpret_cast<const uint32_t *>(buf + (d_c == 0 ? Y.off_words : 0u)) + lane, t_lo,
+                        t_lo + d_chunk_rows, H, lin, Q, acc);
+      last = d_c + 1 == W.st_nch[cb];
     }
     if (last) {  // h:307-311, as in llk_kernel
       const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));
       combine(((uint32_t)lane < H.n_valid && L > 0) ? L : 1.0);
     }
-    // the buffer just read is free: refill it (every lane passed the __syncwarp inside produce() only after
+    // the buffer just read is free: refill it (every lane passes the __syncwarp inside produce() only after
     // its last read of the buffer)
     --in_flight;
     if (produce(cb)) ++in_flight;
