@@ -243,25 +243,25 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # A launch makes ROTATIONS passes over the resident copies (a context may appear several times in a launch):
+    # the ramp and the tail of the persistent kernel are shared by more steps.
+    ROTATIONS = 8
+    per_launch = min(copies * ROTATIONS, 2048)
+    launch_list = (engines * ROTATIONS)[:per_launch]
+
     start_pc = np.full(k, 0.01)
 
     def keep_busy(seconds: float):
         # rank-local launches only (a time-based loop must not contain collectives)
         t_end = time.perf_counter() + seconds
         while time.perf_counter() < t_end:
-            vb.time_device_many(engines, 0, 20, start_pc, start_pc, 0.03)
+            vb.time_device_many(launch_list, 0, 3, start_pc, start_pc, 0.03)
 
     # ---- value: device-timed, EXACTLY K steps ---------------------------------------------------
     # N=1: steps are issued from C, `copies` steps per launch (vb2_llk_eval_many's kernel: step i
     # evaluates resident copy i % copies, so every step streams its sample from HBM and the launch
     # cost is shared by the steps of a launch).  N>1: each step is kernel + NCCL allreduce of the
     # scalar, one launch per step, issued from Python.
-    # A launch makes ROTATIONS passes over the resident copies (a context may appear several times in a launch):
-    # the ramp and the tail of the persistent kernel are shared by more steps.
-    ROTATIONS = 8
-    per_launch = copies * ROTATIONS
-    launch_list = engines * ROTATIONS
-
     def timed_steps(n_steps: int, warm: int) -> float:
         full, rem = divmod(n_steps, per_launch)
         ms = 0.0
@@ -277,35 +277,35 @@ def run_ours(args):
             dev_ms = timed_steps(args.steps, args.warmup)
             launches = 2 * (args.steps // per_launch + (1 if args.steps % per_launch else 0))  # stream kernel + reduce kernel
         else:
-            # `copies` steps per launch on every rank (its marker shard of each resident copy), then ONE
-            # NCCL allreduce of the `copies` partial sums
+            # `per_launch` steps per launch on every rank (its marker shard of each resident copy), then ONE
+            # NCCL allreduce of their partial sums
             # (two result buffers: the allreduce of one launch's partial sums runs on NCCL's stream while the next
             # launch's kernel runs on ours)
-            d_many = [torch.zeros(copies, dtype=torch.float64, device=dev) for _ in range(2)]
+            d_many = [torch.zeros(per_launch, dtype=torch.float64, device=dev) for _ in range(2)]
             works = [None, None]
-            pcs = np.tile(start_pc, (copies, 1)); als = np.full(copies, 0.03)
+            pcs = np.tile(start_pc, (per_launch, 1)); als = np.full(per_launch, 0.03)
             turn = [0]
 
             def launch_steps(n: int):
                 b = turn[0] = turn[0] ^ 1
                 if works[b] is not None:
                     works[b].wait()          # (stream-level: our stream waits for that buffer's previous allreduce)
-                vb.eval_many_device(engines[:n], pcs[:n], pcs[:n], als[:n], d_many[b].data_ptr())
+                vb.eval_many_device(launch_list[:n], pcs[:n], pcs[:n], als[:n], d_many[b].data_ptr())
                 works[b] = dist.all_reduce(d_many[b][:n], op=dist.ReduceOp.SUM, async_op=True)
 
             def drain():
                 for w in works:
                     if w is not None:
                         w.wait()
-            full, rem = divmod(args.steps, copies)
-            for _ in range(max(1, args.warmup // copies)):
-                launch_steps(copies)
+            full, rem = divmod(args.steps, per_launch)
+            for _ in range(max(1, args.warmup // per_launch)):
+                launch_steps(per_launch)
             drain()
             barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(stream)
             for _ in range(full):
-                launch_steps(copies)
+                launch_steps(per_launch)
             if rem:
                 launch_steps(rem)
             drain()
@@ -333,7 +333,7 @@ def run_ours(args):
     achieved = alg_bytes / (kern_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel": "llk_stream_kernel",
-                "evaluations_per_launch": per_launch if world == 1 else copies,
+                "evaluations_per_launch": per_launch,
                 "us_per_evaluation": kern_us, "us_per_evaluation_one_launch_each": one_ms * 1e3,
                 "algorithmic_bytes_per_evaluation": alg_bytes, "device_bytes_per_evaluation": info["device_bytes"],
                 "note": "co-bound by the FP64 pipe: 10 fp64 instructions per streamed read + ~40 per marker -> >= 2.2 us per "
@@ -345,9 +345,12 @@ def run_ours(args):
         # (a) the call as the simplex search makes it: several hundred dependent evaluations of ONE sample inside an
         #     evaluation session (vb2_llk_session_begin: resident kernel, the sample in shared memory, host-mapped
         #     doorbell in, host mailbox out).  Every step still moves its 2k+1 doubles in and its scalar out.
-        engines[0].session_begin()
-        e2e_s, last = vb.time_host(engines[:1], args.warmup, args.steps, start_pc, start_pc, 0.03)
-        engines[0].session_end()
+        if args.no_session:   # (profiler runs: ncu serialises launches, a resident kernel would wait for a doorbell
+            e2e_s, last = vb.time_host(engines, args.warmup, args.steps, start_pc, start_pc, 0.03)  # that cannot ring)
+        else:
+            engines[0].session_begin()
+            e2e_s, last = vb.time_host(engines[:1], args.warmup, args.steps, start_pc, start_pc, 0.03)
+            engines[0].session_end()
         # (b) one launch per evaluation (no session), rotating through the resident copies (HBM-cold every step)
         cold_s, last_cold = vb.time_host(engines, args.warmup, args.steps, start_pc, start_pc, 0.03)
         # the same call through the Python binding (interpreter + ctypes overhead included)
@@ -390,7 +393,8 @@ def run_ours(args):
     e2e_s = float(t.item())
     e2e = {"value": reads_total / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": (2 * k + 1) * 8 if world == 1 else 508,
            "d2h_bytes_per_step": 8, "us_per_step": e2e_s / args.steps * 1e6, "last_llk": last,
-           "caller": ("C loop over vb2_llk_eval (host buffers) inside an evaluation session: resident kernel, sample in "
+           "caller": ("C loop over vb2_llk_eval (host buffers), one launch per evaluation (--no-session)" if args.no_session else
+                      "C loop over vb2_llk_eval (host buffers) inside an evaluation session: resident kernel, sample in "
                       "shared memory, host-mapped doorbell/mailbox") if world == 1 else
                      "python: vb2_llk_eval_many_device over %d host parameter sets per call (marker shard) + NCCL allreduce + "
                      "D2H of the results" % copies,
@@ -418,7 +422,7 @@ def run_ours(args):
                            "n_pc": k, "parallelism": "marker shards x%d + 1 scalar allreduce/step" % world if world > 1
                            else "single GPU", "l2": "steps rotate through %d resident copies of the sample "
                            "(%.0f MB > 126 MB L2): every step streams from HBM" % (copies, copies * info["device_bytes"] / 1e6),
-                           "steps_per_launch": per_launch if world == 1 else copies,
+                           "steps_per_launch": per_launch,
                            "panel_dtype": "fp32 UD/mu in HBM, fp64 arithmetic"},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu}
@@ -434,6 +438,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-session", action="store_true", help="e2e with one launch per evaluation (for runs under ncu)")
     args = ap.parse_args()
     if args.steps is None:            # defaults that finish within minutes on either arm
         args.steps = 2000 if args.impl == "ours" else 200

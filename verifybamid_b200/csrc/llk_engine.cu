@@ -1186,22 +1186,6 @@ void launch_stream(dim3 grid, uint32_t smem, cudaStream_t stream, const LaunchAr
   else llk_stream_kernel<ARGS, 0, false><<<grid, block, smem, stream>>>(A);
   llk_reduce_kernel<<<dim3(A.n_jobs, 1, 1), dim3(32, 1, 1), 0, stream>>>(A);
 }
-template <bool ARGS>
-cudaError_t set_stream_smem_limit(int bytes) {
-  cudaError_t e = cudaFuncSetAttribute(llk_stream_kernel<ARGS, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<ARGS, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<ARGS, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<ARGS, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  return e;
-}
-template <bool ARGS, bool HOST_REDUCE>
-cudaError_t set_smem_limit(int bytes) {
-  cudaError_t e = cudaFuncSetAttribute(llk_kernel<ARGS, HOST_REDUCE, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_kernel<ARGS, HOST_REDUCE, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_kernel<ARGS, HOST_REDUCE, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_kernel<ARGS, HOST_REDUCE, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  return e;
-}
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -1410,10 +1394,6 @@ int wait_mailbox(vb2_llk_ctx *ctx, uint32_t n_slots, unsigned long long seq) {
 }
 
 // ---- evaluation session (llk_session_kernel) ---------------------------------------------------------------
-template <int NPC>
-cudaError_t session_smem_limit(int bytes) {
-  return cudaFuncSetAttribute(llk_session_kernel<NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-}
 struct SessionGeometry {
   uint32_t kc, n_items, smem;
   bool ok;
@@ -1594,16 +1574,29 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
 }
 
 // Phred table + kernel attributes of the CURRENT device (idempotent; the stream may be the default one).
-int init_device_tables(vb2_llk_ctx *ctx, cudaStream_t stream) {
+// Raise the dynamic shared-memory limit of the kernel instantiations a (layout, chunked) combination launches --
+// only those: with lazy module loading every instantiation touched here is loaded, and there are 23 of them.
+template <int NPC, bool CHUNKED>
+cudaError_t raise_smem_limits(int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(llk_kernel<true, true, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_kernel<true, false, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_kernel<false, false, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<true, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<false, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if constexpr (!CHUNKED)
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_session_kernel<NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return e;
+}
+int init_device_tables(vb2_llk_ctx *ctx, int device, int spec, bool chunked) {
+  static bool done[64][4] = {};  // [device][0: runtime layout, 1: NumPC 2, 2: NumPC 4, 3: chunked]
+  const int which = chunked ? 3 : (spec == 2 ? 1 : spec == 4 ? 2 : 0);
+  if (device >= 0 && device < 64 && done[device][which]) return VB2_OK;
   const int smem_max = 200 * 1024;
-  VB2_CUDA(ctx, (set_smem_limit<true, true>(smem_max)));
-  VB2_CUDA(ctx, (set_smem_limit<true, false>(smem_max)));
-  VB2_CUDA(ctx, (set_smem_limit<false, false>(smem_max)));
-  VB2_CUDA(ctx, (set_stream_smem_limit<true>(smem_max)));
-  VB2_CUDA(ctx, (set_stream_smem_limit<false>(smem_max)));
-  VB2_CUDA(ctx, (session_smem_limit<0>(smem_max)));
-  VB2_CUDA(ctx, (session_smem_limit<2>(smem_max)));
-  VB2_CUDA(ctx, (session_smem_limit<4>(smem_max)));
+  if (chunked) VB2_CUDA(ctx, (raise_smem_limits<0, true>(smem_max)));
+  else if (spec == 2) VB2_CUDA(ctx, (raise_smem_limits<2, false>(smem_max)));
+  else if (spec == 4) VB2_CUDA(ctx, (raise_smem_limits<4, false>(smem_max)));
+  else VB2_CUDA(ctx, (raise_smem_limits<0, false>(smem_max)));
+  if (device >= 0 && device < 64) done[device][which] = true;
   return VB2_OK;
 }
 
@@ -1634,7 +1627,7 @@ int vb2_llk_warmup(int device) {
   if (device < 0 || device >= ndev) return set_err(nullptr, VB2_ERR_NO_DEVICE, "device out of range");
   VB2_CUDA(nullptr, cudaSetDevice(device));
   VB2_CUDA(nullptr, cudaFree(0));  // context creation
-  return init_device_tables(nullptr, cudaStreamPerThread);  // module load
+  return init_device_tables(nullptr, device, 2, false);  // module load of the common instantiations
 }
 
 const char *vb2_last_error(const vb2_llk_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
@@ -1694,8 +1687,7 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   }
   ctx->spin = !(desc->flags & VB2_FLAG_NO_SPIN);
   if (const char *t = getenv("VB2_LLK_SPIN_TIMEOUT_MS")) ctx->spin_timeout_ms = atof(t);
-  int rc = init_device_tables(ctx, ctx->stream);
-  if (rc) return rc;
+  int rc = VB2_OK;
 
   // ---- flatten on the host ----------------------------------------------------------------------
   double phred[vb2::kNumQual];
@@ -1745,6 +1737,7 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   const bool default_clamps = S.min_af == 0.00005 && S.max_af == 0.99995;
   ctx->spec = (!cfg.panel_fp64 && !P.known_af && default_clamps && (P.n_pc == 2 || P.n_pc == 4)) ? (int)P.n_pc : 0;
   if (getenv("VB2_LLK_NO_SPEC")) ctx->spec = 0;  // (tests: force the runtime-layout kernel)
+  if ((rc = init_device_tables(ctx, ctx->device, ctx->spec, ctx->chunked))) return rc;
   S.n_buf = 2u;
   {
     const Geometry g = geometry(ctx, false);  // the one-evaluation launch (the larger CTA of the two geometries)
@@ -1986,6 +1979,10 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
   A.n_bins_max = vb2::kBinsPerCta * lead->many_grid_x;
   A.stage_bytes = lead->many_buf_bytes;
   A.queue = lead->d_queue;
+  {
+    int rca = init_device_tables(lead, lead->device, lead->many_spec, lead->many_chunked);
+    if (rca) return rca;
+  }
   const dim3 grid(stream_grid(lead->sm_count, lead->many_n * A.n_bins_max), 1, 1);
   launch_stream<false>(grid, 8u * A.stage_bytes, lead->stream, A, lead->many_spec, lead->many_chunked);
   release_staging(lead);
