@@ -285,12 +285,13 @@ def run_ours(args):
             works = [None, None]
             pcs = np.tile(start_pc, (per_launch, 1)); als = np.full(per_launch, 0.03)
             turn = [0]
+            ctx_arr = vb.context_array(launch_list)
 
             def launch_steps(n: int):
                 b = turn[0] = turn[0] ^ 1
                 if works[b] is not None:
                     works[b].wait()          # (stream-level: our stream waits for that buffer's previous allreduce)
-                vb.eval_many_device(launch_list[:n], pcs[:n], pcs[:n], als[:n], d_many[b].data_ptr())
+                vb.eval_many_device(launch_list[:n], pcs[:n], pcs[:n], als[:n], d_many[b].data_ptr(), ctx_arr)
                 works[b] = dist.all_reduce(d_many[b][:n], op=dist.ReduceOp.SUM, async_op=True)
 
             def drain():
@@ -331,8 +332,13 @@ def run_ours(args):
     alg_bytes = info["algorithmic_bytes"]       # this rank's shard, one evaluation
     kern_us = (dev_ms / args.steps) * 1e3       # per evaluation (N>1: includes the allreduce share)
     achieved = alg_bytes / (kern_us * 1e-6) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of this kernel (296 evaluations in the
+    # launch: 2,145,602,000 + 5,224,192 bytes; profiles/r01_llk_stream_kernel_ncu_details.txt), per evaluation:
+    traffic_per_eval = 7266305 if world == 1 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "llk_stream_kernel",
+                "traffic": traffic_per_eval * per_launch if traffic_per_eval else None,
+                "traffic_note": "bytes per launch of %d evaluations, from the committed ncu capture (7.27 MB per evaluation = "
+                                "the stored image, no re-reads; algorithmic 7.57 MB)" % per_launch, "peak_source": peak_src, "kernel": "llk_stream_kernel",
                 "evaluations_per_launch": per_launch,
                 "us_per_evaluation": kern_us, "us_per_evaluation_one_launch_each": one_ms * 1e3,
                 "algorithmic_bytes_per_evaluation": alg_bytes, "device_bytes_per_evaluation": info["device_bytes"],

@@ -26,6 +26,7 @@
 #include <new>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 
 #include "llk_pack.h"
@@ -1911,14 +1912,14 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
   }
   const uint32_t k = lead->S.n_pc;
   // slot of job j inside its sample = number of earlier jobs on the same context
+  std::unordered_map<const vb2_llk_ctx *, uint32_t> seen;
   for (int j = 0; j < n; ++j) {
     vb2_llk_ctx *c = ctxs[j];
     if (!c) return set_err(lead, VB2_ERR_INVALID, "null context in list");
     session_stop(c);
     if (c->device != lead->device) return set_err(lead, VB2_ERR_INVALID, "contexts live on different devices");
     if (c->S.n_pc != k) return set_err(lead, VB2_ERR_INVALID, "contexts differ in n_pc");
-    uint32_t slot = 0;
-    for (int i = 0; i < j; ++i) slot += (ctxs[i] == c);
+    const uint32_t slot = seen[c]++;  // (number of earlier jobs on the same context)
     int rc = ensure_slots(c, slot + 1);
     if (rc) return set_err(lead, rc, c->err);
     lead->h_slots[j] = slot;

@@ -342,13 +342,19 @@ def eval_many(engines: List[LLKEngine], pc_contam, pc_intended, alphas) -> np.nd
     return out
 
 
-def eval_many_device(engines: List[LLKEngine], pc_contam, pc_intended, alphas, d_out_ptr: int) -> None:
-    """Asynchronous eval_many: results stay in device memory at `d_out_ptr` (len(engines) doubles)."""
+def context_array(engines: List[LLKEngine]):
+    """The ctypes array of context handles the *_many calls take (build it once for a list that is used again)."""
+    return (ctypes.c_void_p * len(engines))(*[e._ctx for e in engines])
+
+
+def eval_many_device(engines: List[LLKEngine], pc_contam, pc_intended, alphas, d_out_ptr: int, ctx_array=None) -> None:
+    """Asynchronous eval_many: results stay in device memory at `d_out_ptr` (len(engines) doubles).  `ctx_array`:
+    context_array(engines) built beforehand (only its first len(engines) entries are used)."""
     n = len(engines)
     k = engines[0].n_pc
     al = _f64(alphas).ravel()
     a, b = _f64(pc_contam, (n, k)), _f64(pc_intended, (n, k))
-    arr = (ctypes.c_void_p * n)(*[e._ctx for e in engines])
+    arr = ctx_array if ctx_array is not None else context_array(engines)
     lib = load_library()
     rc = lib.vb2_llk_eval_many_device(arr, n, a.ctypes.data, b.ctypes.data, al.ctypes.data, ctypes.c_void_p(d_out_ptr))
     if rc != VB2_OK:
