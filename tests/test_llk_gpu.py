@@ -185,6 +185,31 @@ def test_eval_many_samples_one_launch():
             e.close()
 
 
+def test_batched_layout_and_many_jobs_per_launch(sample10k):
+    """VB2_FLAG_BATCHED shards (fewer, deeper bins) sum to the whole sample; a launch may carry hundreds of jobs that
+    reuse a few contexts (every job gets its own partial-sum slot)."""
+    p = sample10k.problem
+    ora = to_oracle(p)
+    parts = [vb.LLKEngine(p, shard_rank=r, shard_count=4, batched=True) for r in range(4)]
+    try:
+        assert all(e.info()["grid_x"] < 40 for e in parts)             # 78 slices -> 3 CTAs' worth of bins, not 20
+        n = 300
+        rng = np.random.default_rng(5)
+        pc1 = rng.normal(0, 0.02, (n, 2)); pc2 = rng.normal(0, 0.02, (n, 2)); al = rng.uniform(0.0, 0.5, n)
+        total = np.zeros(n)
+        for e in parts:
+            total += vb.eval_many([e] * n, pc1, pc2, al)
+        for j in (0, 1, 150, 299):
+            assert rel(total[j], ora.compute_mix_llks(pc1[j], pc2[j], al[j])) <= REL_FP32
+        mixed = vb.eval_many([parts[j % 4] for j in range(n)], pc1, pc2, al)   # contexts interleaved in one launch
+        again = vb.eval_many([parts[j % 4] for j in range(n)], pc1, pc2, al)
+        assert mixed.tolist() == again.tolist()
+        assert mixed[5] == vb.eval_many([parts[1]], pc1[5:6], pc2[5:6], al[5:6])[0]
+    finally:
+        for e in parts:
+            e.close()
+
+
 def test_deep_coverage_multi_stage(monkeypatch):
     """200x depth with a tiny shared-memory stage: every slice needs several double-buffered TMA stages."""
     panel = panels.load_bundled("1000g.phase3.10k.b37")

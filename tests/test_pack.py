@@ -40,7 +40,7 @@ def test_rounds_are_balanced_and_aligned():
     panel = panels.load_bundled("1000g.phase3.10k.b37")
     p = synth.make_sample(panel, n_pc=2, depth=30.0, alpha=0.02, seed=3).problem
     pk = vb.pack_host(p, max_ctas=8)                       # 32 bins, 313 slices -> 10 rounds
-    assert pk["n_bins"] == 32 and pk["n_rounds"] == -(-pk["n_slices"] // 32) and pk["conc_rounds"] == 6
+    assert pk["n_bins"] == 32 and pk["n_rounds"] == -(-pk["n_slices"] // 32) and pk["conc_rounds"] == 4
     work = np.zeros(pk["n_bins"])
     seen = set()
     for j, b, blob in iter_blobs(pk):
@@ -55,6 +55,27 @@ def test_rounds_are_balanced_and_aligned():
         assert R["first_bin"] + R["count"] == pk["n_bins"] or R["first_bin"] == 0
     strides = [R["stride"] for R in pk["rounds"]]
     assert strides == sorted(strides, reverse=True)         # heaviest slices first
+
+
+def test_deal_is_level_by_cost_and_batched_layout_is_deeper():
+    """The deal is by what the kernel spends (4 per full row, 2 per uniform tail, 7 per checked row, 15 per slice, in
+    quarter rows); VB2_FLAG_BATCHED lays a small shard out over fewer bins with >= 5 slices each -- same likelihood."""
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    s = synth.make_sample(panel, n_pc=2, depth=30.0, alpha=0.02, seed=3)
+    pk = vb.pack_host(s.problem, max_ctas=8)
+    cost = np.zeros(pk["n_bins"])
+    for _, b, blob in iter_blobs(pk):
+        wr, wa, z, w = (int(x) for x in blob[:16].view(np.uint32))
+        fr, fa, tr, ta = w & 0xFFFF, w >> 16, (z >> 8) & 0xF, (z >> 12) & 0xF
+        rr, ra = wr - fr, wa - fa
+        cost[b] += 4 * (fr + fa) + (2 if (tr and rr == 1) else 7 * rr) + (2 if (ta and ra == 1) else 7 * ra) + 15
+    assert cost.max() <= 1.03 * cost.mean()
+    wide = vb.pack_host(s.problem, shard_rank=1, shard_count=8)          # 1/8 of 313 slices over 148 SMs' bins
+    deep = vb.pack_host(s.problem, shard_rank=1, shard_count=8, batched=True)
+    assert wide["n_rounds"] == 1 and deep["n_rounds"] >= 5 and deep["n_bins"] < wide["n_bins"]
+    pt = ([0.02, -0.01], [-0.01, 0.027], 0.05)
+    a, b = emulate_packed_llk(wide, *pt), emulate_packed_llk(deep, *pt)
+    assert abs(a - b) <= 1e-12 * abs(a)
 
 
 @pytest.fixture(scope="module")

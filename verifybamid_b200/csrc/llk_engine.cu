@@ -34,7 +34,7 @@
 
 namespace {
 
-constexpr int kMaxConcRounds = 4;            // rounds a CTA runs concurrently in the latency geometry
+constexpr int kMaxConcRounds = (int)vb2::kMaxConcRounds;  // rounds of a bin a one-evaluation CTA keeps in flight
 constexpr int kMaxWarps = 4 * kMaxConcRounds;  // 16 warps (4 per SM sub-partition): 128 registers per thread
 constexpr int kMaxThreads = kMaxWarps * 32;
 constexpr int kMaxArgJobs = 4;    // evaluations whose parameters travel in the kernel arguments

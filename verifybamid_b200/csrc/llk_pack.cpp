@@ -367,6 +367,7 @@ extern "C" int vb2_llk_pack_host(const vb2_llk_desc *desc, uint32_t max_ctas, vb
   vb2::PackConfig cfg;
   cfg.max_ctas = max_ctas ? max_ctas : 148u;
   cfg.panel_fp64 = desc->panel_dtype == VB2_PANEL_FP64;
+  if (desc->flags & VB2_FLAG_BATCHED) cfg.min_rounds = 5;
   int rc = vb2::pack_sample(*desc, cfg, phred, P, &err);
   if (rc != VB2_OK) {
     delete P;

@@ -38,7 +38,7 @@ constexpr int kNumQual = 94;            // Phred 0..93 (h:60-74)
 constexpr uint32_t kBlobHeaderBytes = 16;
 
 constexpr uint32_t kBinsPerCta = 4;     // SM sub-partitions: warp w of a CTA issues on SMSP w % 4
-constexpr uint32_t kMaxConcRounds = 6;  // rounds a CTA runs concurrently (4*6 = 24 warps)
+constexpr uint32_t kMaxConcRounds = 4;  // rounds of a bin a one-evaluation CTA keeps in flight (4*4 = 16 warps)
 
 struct PackConfig {
   uint32_t max_ctas = 148;   // CTAs of one launch = SMs of the device (one persistent CTA per SM)

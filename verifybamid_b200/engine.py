@@ -196,13 +196,13 @@ def make_desc(problem: PileupProblem, device: int = 0, panel_dtype: int = VB2_PA
 
 
 def pack_host(problem: PileupProblem, shard_rank: int = 0, shard_count: int = 1, max_ctas: int = 148,
-              panel_dtype: int = VB2_PANEL_FP64) -> dict:
+              panel_dtype: int = VB2_PANEL_FP64, batched: bool = False) -> dict:
     """Host-only: the flattened image vb2_llk_create would upload, as numpy copies (no CUDA call).
 
     Returns the scalars of vb2_packed_view plus `blob` (uint8), `rounds` (list of dicts with base, stride,
     first_bin, count, rows) and `marker_index`."""
     lib = load_library()
-    d = make_desc(problem, shard_rank=shard_rank, shard_count=shard_count, panel_dtype=panel_dtype)
+    d = make_desc(problem, shard_rank=shard_rank, shard_count=shard_count, panel_dtype=panel_dtype, batched=batched)
     v = _PackedView()
     v.struct_size = ctypes.sizeof(_PackedView)
     rc = lib.vb2_llk_pack_host(ctypes.byref(d), int(max_ctas), ctypes.byref(v))
