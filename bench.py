@@ -246,7 +246,7 @@ def run_ours(args):
     # A launch makes ROTATIONS passes over the resident copies (a context may appear several times in a launch):
     # the ramp and the tail of the persistent kernel are shared by more steps.
     ROTATIONS = 8
-    per_launch = min(copies * ROTATIONS, 2048)
+    per_launch = min(copies * ROTATIONS, 2048, max(copies, args.steps // 4))  # (at least four launches to pipeline)
     launch_list = (engines * ROTATIONS)[:per_launch]
 
     start_pc = np.full(k, 0.01)
