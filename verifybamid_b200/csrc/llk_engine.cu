@@ -1,17 +1,23 @@
-// llk_engine.cu -- the sm_100a contamination-likelihood kernel and the C ABI around it
+// llk_engine.cu -- the sm_100a contamination-likelihood kernels and the C ABI around them
 // (include/vb2_llk.h).  Replaces, for one sample resident in HBM,
 //     FullLLKFunc::ComputeMixLLKs            reference ContaminationEstimator.h:194-314
-// One evaluation = one launch of llk_kernel, one persistent CTA per SM:
+// What every kernel computes for a 32-marker slice (one warp, one marker per lane):
 //   (i)   AF = (UD.PC + mu)/2 per marker (h:251-267) and Hardy-Weinberg priors (h:186-192);
 //   (ii)  per read, the six alpha-dependent genotype-pair emissions of the 3x3 mixture
 //         (h:213-229, in the closed form of SURVEY.md Appendix A: each is LINEAR in the Phred
-//         error e, F_p(e) = c0_p + c1_p*e, so one DFMA forms it and one DMUL accumulates it);
+//         error e, F_p(e) = c0_p + c1_p*e; two reads are eaten at once through the symmetric
+//         functions of their errors: 10 fp64 instructions per read for all six pairs);
 //         everything a warp needs for 32 markers is one contiguous blob fetched by ONE TMA
 //         bulk copy (cp.async.bulk + mbarrier) whose address is pure arithmetic;
-//   (iii) log of the marginal per marker (h:307-311), fixed-order warp-shuffle / CTA reduction
-//         in fp64 (h:232-236 is an OpenMP reduction); the per-CTA partials are either written
-//         straight into a host-mapped mailbox and added by the host in CTA order, or added by
-//         the last CTA on the device (results that stay in HBM for an NCCL allreduce).
+//   (iii) the marginal per marker (h:307-311); the marginals of a bin are multiplied up and one log
+//         per lane is taken; fixed-order lane / bin / CTA reduction in fp64 (h:232-236 is an OpenMP
+//         reduction), on the device or by the host over a host-mapped mailbox.
+// Three launch shapes of the same arithmetic (identical bits):
+//   llk_kernel          one evaluation per launch, one CTA per SM;
+//   llk_stream_kernel   many evaluations per launch: persistent grid, warps pull (evaluation, bin) tasks
+//                       from a queue; llk_reduce_kernel adds the per-bin partial sums;
+//   llk_session_kernel  resident: the sample stays in shared memory, evaluations arrive through a
+//                       host-mapped doorbell (vb2_llk_session_begin / _end).
 // Everything that is evaluation-invariant was folded at create time by llk_pack.cpp.
 //
 // There is NO CPU fallback in this file: without a CUDA device every entry point fails.
@@ -1496,14 +1502,15 @@ uint32_t stream_grid(int sm_count, uint32_t n_tasks) {
 }
 
 void fill_phred(LaunchArgs *A) {
-  static double table[kPhredArgs];
-  static bool ready = false;
-  if (!ready) {
-    vb2::build_phred_table(table);
-    for (int q = vb2::kNumQual; q < kPhredArgs; ++q) table[q] = 1.0;
-    ready = true;
-  }
-  memcpy(A->phred, table, sizeof(table));
+  struct Table {
+    double v[kPhredArgs];
+    Table() {
+      vb2::build_phred_table(v);
+      for (int q = vb2::kNumQual; q < kPhredArgs; ++q) v[q] = 1.0;
+    }
+  };
+  static const Table table;  // (thread-safe initialisation)
+  memcpy(A->phred, table.v, sizeof(table.v));
 }
 
 // Launch n evaluations of ONE sample.
