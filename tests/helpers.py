@@ -65,8 +65,13 @@ def iter_blobs(pk: dict):
     assert q == pk["n_slices"]
 
 
-def emulate_packed_llk(pk: dict, pc1, pc2, alpha: float, min_af=5e-5, max_af=0.99995) -> float:
-    """numpy restatement of llk_kernel over the packed image (CPU check of the flatten + the maths)."""
+def emulate_packed_llk(pk: dict, pc1, pc2, alpha: float, min_af=5e-5, max_af=0.99995, kernel_form: bool = False) -> float:
+    """numpy restatement of llk_kernel over the packed image (CPU check of the flatten + the maths).
+
+    kernel_form=False: one factor F_p(e) = c0_p + c1_p e per read, one log per marker.
+    kernel_form=True : the arithmetic the kernels actually run -- full rows two reads at a time through their symmetric
+    functions, F_p(ea) F_p(eb) = C0_p + C1_p (ea + eb) + C2_p ea eb, the marginals of a bin multiplied up per lane
+    with the exponent split off after every factor, one log per lane and bin (llk_engine.cu: eat4, combine)."""
     phred = np.power(10.0, np.arange(94) / -10.0)
     pairs, c0, c1 = job_coefficients(alpha)
     pdt = np.float64 if pk["panel_elem"] == 8 else np.float32
@@ -75,7 +80,9 @@ def emulate_packed_llk(pk: dict, pc1, pc2, alpha: float, min_af=5e-5, max_af=0.9
     def gf(af):
         af = np.clip(af, min_af, max_af)
         return np.stack([(1 - af) * (1 - af), 2 * af * (1 - af), af * af])
-    for _, _, blob in iter_blobs(pk):
+    C0, C1, C2 = c0 * c0, c0 * c1, c1 * c1
+    bin_prod, bin_exp, bin_extra = {}, {}, {}      # kernel_form: per bin, per lane running product / exponent / rare logs
+    for _, bin_id, blob in iter_blobs(pk):
         wr, wa, nv_tails, full = blob[:16].view(np.uint32)
         n_valid, tail_ref, tail_alt = int(nv_tails) & 0xFF, (int(nv_tails) >> 8) & 0xF, (int(nv_tails) >> 12) & 0xF
         if pk["known_af"]:
@@ -98,16 +105,41 @@ def emulate_packed_llk(pk: dict, pc1, pc2, alpha: float, min_af=5e-5, max_af=0.9
                 assert 1 <= tail <= 3 and row == (wr - 1 if row == fr else wr + wa - 1)
                 assert not (byts[row, :n_valid, :tail] == 0xFF).any() and (byts[row, :n_valid, tail:] == 0xFF).all()
         acc = np.ones((6, 32))
-        for sect, lo, hi in (("ref", 0, wr), ("alt", wr, wr + wa)):
+        for sect, lo, hi, n_full in (("ref", 0, wr, fr), ("alt", wr, wr + wa, fa)):
             q = byts[lo:hi].transpose(1, 0, 2).reshape(32, -1)      # [lane, reads]
             pad = q == 0xFF
             e = phred[np.where(pad, 0, q)]
             for p in range(6):
-                f = np.where(pad, 1.0, c1[p] * e + c0[p])
-                acc[p if sect == "ref" else 5 - p] *= f.prod(axis=1)
-        L = sum(diag[g] * g1v[g] * g2v[g] for g in range(3))
-        for p, (a, b) in enumerate(pairs):
-            L = L + acc[p] * g1v[a] * g2v[b]
+                tgt = p if sect == "ref" else 5 - p
+                if kernel_form:                                      # full rows: two reads at a time
+                    ef = e[:, :4 * n_full].reshape(32, -1, 2)
+                    g = C0[p] + C1[p] * (ef[:, :, 0] + ef[:, :, 1]) + C2[p] * (ef[:, :, 0] * ef[:, :, 1])
+                    acc[tgt] *= g.prod(axis=1)
+                    rest, rpad = e[:, 4 * n_full:], pad[:, 4 * n_full:]
+                    acc[tgt] *= np.where(rpad, 1.0, c1[p] * rest + c0[p]).prod(axis=1)
+                else:
+                    acc[tgt] *= np.where(pad, 1.0, c1[p] * e + c0[p]).prod(axis=1)
+        if kernel_form:                                              # running products start at their weights
+            L = sum(diag[g] * g1v[g] * g2v[g] for g in range(3)) + sum(acc[p] * g1v[a] * g2v[b] for p, (a, b) in enumerate(pairs))
+        else:
+            L = sum(diag[g] * g1v[g] * g2v[g] for g in range(3))
+            for p, (a, b) in enumerate(pairs):
+                L = L + acc[p] * g1v[a] * g2v[b]
         valid = (np.arange(32) < n_valid) & (L > 0)
-        total += float(np.log(L[valid]).sum())
+        if not kernel_form:
+            total += float(np.log(L[valid]).sum())
+            continue
+        Lv = np.where(valid, L, 1.0)
+        prod = bin_prod.setdefault(bin_id, np.ones(32))
+        esum = bin_exp.setdefault(bin_id, np.zeros(32, dtype=np.int64))
+        extra = bin_extra.setdefault(bin_id, np.zeros(32))
+        big = Lv > 1e-280
+        prod *= np.where(big, Lv, 1.0)
+        extra += np.where(big, 0.0, np.log(np.where(big, 1.0, Lv)))
+        m, ex = np.frexp(prod)                                       # prod = m * 2^ex, m in [0.5, 1)
+        prod[:] = m * 2.0
+        esum += ex - 1
+    if kernel_form:
+        for b in sorted(bin_prod):
+            total += float((bin_extra[b] + (np.log(bin_prod[b]) + bin_exp[b] * np.log(2.0))).sum())
     return total + pk["log_other_const"]

@@ -57,6 +57,21 @@ def test_rounds_are_balanced_and_aligned():
     assert strides == sorted(strides, reverse=True)         # heaviest slices first
 
 
+@pytest.mark.parametrize("q_lo,q_hi", [(20, 40), (0, 12)])
+def test_kernel_arithmetic_form_matches_oracle(q_lo, q_hi):
+    """The form the kernels run (pairs of reads through symmetric functions, log of the product of a bin's marginals)
+    against the oracle, including Phred 0..12 where the pair products cancel the most -- on the CPU, in numpy."""
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    s = synth.make_sample(panel, n_pc=2, depth=25.0, alpha=0.05, seed=21, n_markers=3000, q_lo=q_lo, q_hi=q_hi)
+    ora = to_oracle(s.problem)
+    pk = vb.pack_host(s.problem, max_ctas=8)
+    for pc1, pc2, a in [([0.01, 0.01], [0.01, 0.01], 0.03), ([0.02, -0.01], [-0.01, 0.027], 0.05),
+                        ([0.0, 0.0], [0.0, 0.0], 0.5), ([0.01, 0.01], [0.01, 0.01], 1e-6), ([0.05, -0.02], [0.01, 0.01], 0.999)]:
+        want = ora.compute_mix_llks(pc1, pc2, a)
+        assert abs(emulate_packed_llk(pk, pc1, pc2, a, kernel_form=True) - want) <= 1e-11 * abs(want)
+        assert abs(emulate_packed_llk(pk, pc1, pc2, a) - want) <= 1e-11 * abs(want)
+
+
 def test_deal_is_level_by_cost_and_batched_layout_is_deeper():
     """The deal is by what the kernel spends (4 per full row, 2 per uniform tail, 7 per checked row, 15 per slice, in
     quarter rows); VB2_FLAG_BATCHED lays a small shard out over fewer bins with >= 5 slices each -- same likelihood."""
