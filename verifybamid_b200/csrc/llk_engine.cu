@@ -128,9 +128,6 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -950,263 +947,6 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
   if (lane == 0 && fetched == 0xFFFFFFFFu) __threadfence();  // (retires the atomic still in flight)
 }
 
-// ---------------------------------------------------------------------------------------------
-// the many-evaluations kernel, warp-specialised (VB2_LLK_PAIRS)
-// ---------------------------------------------------------------------------------------------
-// llk_stream_kernel keeps four warps per SM sub-partition, each spending two thirds of a slice OUTSIDE the
-// 40-fp64-per-row read loop (set-up chain, pipeline bookkeeping), which leaves the FP64 pipe 41 % idle.  Here a
-// task sequence is served by a PAIR of warps on the same sub-partition:
-//   P (prep)  pulls tasks from the queue, issues the TMA bulk copies into a ring of kPairStages buffers and, for
-//             every landed slice, computes what does not need the reads -- allele frequencies, priors, the six
-//             starting weights and the diagonal term -- into the slice's hand-off slot;
-//   L (loop)  waits for a prepared slice, runs the read loops on it and folds the marginal into the task's product.
-// Three mbarriers per stage order them: full (TMA landed -> P), ready (P -> L), free (L -> P).  CTAs are 8 warps
-// (4 pairs), two per SM at 128 registers: two L warps per sub-partition that never leave fp64-dense code.
-// Same arithmetic, same per-(evaluation, bin) partial sums, same bits as llk_stream_kernel; not for chunked blobs.
-constexpr int kPairStages = 4;
-struct __align__(16) PairSlot {  // hand-off of one prepared slice (shared memory)
-  double acc0[kNumPairs][32];    // the running products' starting weights GF[g1]*GF2[g2]
-  double ldiag[32];              // the diagonal pairs' term
-  uint32_t task_flag;            // 0x80000000 | task: first slice of a task; 0: next slice; 0xFFFFFFFF: no more work
-  uint32_t pad_[3];
-};
-
-template <bool ARGS, int NPC>
-__global__ void __launch_bounds__(256, 2)
-llk_pair_kernel(const __grid_constant__ LaunchArgs A) {
-  using Layout = typename std::conditional<NPC != 0, FixedLayout<NPC>, RuntimeLayout>::type;
-  extern __shared__ __align__(128) uint8_t s_buf[];  // [pair][stage][stage_bytes], then PairSlot[pair][stage]
-  __shared__ __align__(16) JobParams s_job_p[4], s_job_l[4];  // the evaluation P / L of each pair is working on
-  __shared__ __align__(8) uint64_t s_full[4][kPairStages], s_ready[4][kPairStages], s_free[4][kPairStages];
-  __shared__ __align__(16) WarpCtl s_ctl[4];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = warp & 3;
-  const bool is_prep = warp >= 4;
-  const uint32_t stage_bytes = A.stage_bytes;
-  uint8_t *mybuf = s_buf + (size_t)pair * kPairStages * stage_bytes;
-  PairSlot *slots = reinterpret_cast<PairSlot *>(s_buf + (size_t)4 * kPairStages * stage_bytes) + pair * kPairStages;
-  if (is_prep && lane == 0) {
-    for (int s = 0; s < kPairStages; ++s) {
-      mbar_init(&s_full[pair][s], 1);
-      mbar_init(&s_ready[pair][s], 1);
-      mbar_init(&s_free[pair][s], 1);
-    }
-    mbar_fence_init();
-  }
-  for (int i = threadIdx.x; i < 256; i += 256) s_e[i] = i < kPhredArgs ? A.phred[i] : 1.0;
-  __syncthreads();  // the only CTA-wide barrier
-  const uint32_t n_bins_max = A.n_bins_max, n_tasks = A.n_jobs * n_bins_max;
-
-  // v = this lane's share of task (job, bin): xor-shuffle tree over the lanes -> partials[job][bin]
-  auto store_partial = [&](uint32_t job, uint32_t bin, double v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    if (lane == 0) {
-      const SampleDev &S = (ARGS || !A.samples) ? A.sample : A.samples[job];
-      const uint32_t pslot = A.slots ? A.slots[job] : job;
-      S.partials[(size_t)pslot * (4u * S.grid_x) + bin] = v;
-    }
-  };
-
-  if (is_prep) {
-    // =============================== P: queue, TMA, per-slice set-up ===============================
-    WarpCtl &W = s_ctl[pair];
-    uint32_t fetched = 0;  // (lane 0) the task after W.next_task; the atomic is in flight while a task runs
-    auto fetch = [&]() {
-      if (lane == 0) fetched = atomicAdd(A.queue, 1u) + gridDim.x * 4u;
-    };
-    if (lane == 0) {
-      W.next_task = blockIdx.x * 4u + (uint32_t)pair;
-      W.n_rounds = 0; W.rbase = 0; W.done = 0;
-    }
-    fetch();
-    __syncwarp();
-    uint32_t mask = 0, first = 0;
-    auto next_table = [&]() -> bool {  // mask == 0: the next 32 rounds of the task, or the next task; false = no more work
-      for (;;) {
-        uint32_t rbase = W.rbase + 32u, n_rounds = W.n_rounds, bin = W.bin;
-        if (rbase >= n_rounds) {  // the task's table is exhausted: take the next task
-          if (first) store_partial(W.task / n_bins_max, bin, 0.0);  // (no blob at all: an empty bin still reports in)
-          first = 0;
-          const uint32_t t = W.next_task;
-          if (t >= n_tasks) {
-            __syncwarp();
-            if (lane == 0) W.done = 1;
-            __syncwarp();
-            return false;
-          }
-          const uint32_t nt = __shfl_sync(0xFFFFFFFFu, fetched, 0);
-          fetch();
-          const uint32_t job = t / n_bins_max;
-          bin = t - job * n_bins_max;
-          const SampleDev &S = (ARGS || !A.samples) ? A.sample : A.samples[job];
-          const bool active = bin < 4u * S.grid_x;  // eval_many: a sample may have fewer bins than the launch
-          n_rounds = active ? S.n_rounds : 0u;
-          __syncwarp();
-          if (lane == 0) {
-            W.next_task = nt;
-            W.task = t;
-            W.bin = bin;
-            W.n_rounds = n_rounds;
-            W.rbase = 0u - 32u;
-            if (active) {
-              W.blob = S.blob;
-              W.tab = ARGS ? A.rounds : S.rounds;
-              W.off_words = S.off_words;
-            }
-          }
-          __syncwarp();
-          if (!active) continue;
-          first = 1;
-          rbase = 0;
-        }
-        const uint32_t r = rbase + (uint32_t)lane;  // item table of rounds [rbase, rbase + 32)
-        bool mine = false;
-        if (r < n_rounds) {
-          const vb2::Round R = W.tab[r];
-          if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
-            mine = true;
-            W.it_off16[lane] = (uint32_t)((R.base + (uint64_t)(bin - R.first_bin) * R.stride) >> 4);
-            W.it_rows[lane] = R.rows;
-          }
-        }
-        if (lane == 0) W.rbase = rbase;
-        mask = __ballot_sync(0xFFFFFFFFu, mine);
-        if (mask) return true;
-      }
-    };
-    uint32_t k_issue = 0, k_prep = 0;   // stages issued / prepared so far (stage k lives in slot k % kPairStages)
-    uint32_t full_par = 0, free_par = (1u << kPairStages) - 1u;  // a fresh barrier passes a wait on parity 1
-    bool more = true;
-    uint32_t p_task = 0;                // the task whose parameters sit in s_job_p
-    bool p_have = false;
-    Layout Y(A.sample);
-    const JobParams &J = s_job_p[pair];
-    for (;;) {
-      if (more && k_issue < k_prep + (uint32_t)(kPairStages - 1)) {
-        // ---- issue stage k_issue (its slot must have been freed by L) ----
-        const uint32_t s = k_issue % kPairStages;
-        mbar_wait(&s_free[pair][s], (free_par >> s) & 1u);
-        free_par ^= 1u << s;
-        if (mask == 0 && (W.done || !next_table())) {
-          more = false;  // no more work: tell L through this slot
-          if (lane == 0) slots[s].task_flag = 0xFFFFFFFFu;
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_ready[pair][s]);
-          continue;
-        }
-        const int i = __ffs((int)mask) - 1;
-        mask &= mask - 1u;
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t off16 = W.it_off16[i], rows = W.it_rows[i];
-          uint32_t off_words = W.off_words;
-          if constexpr (Layout::kFixed) off_words = Layout::off_words;
-          const uint32_t bytes = off_words + rows * 128u;
-          mbar_arrive_expect_tx(&s_full[pair][s], bytes);
-          bulk_g2s(mybuf + (size_t)s * stage_bytes, W.blob + ((uint64_t)off16 << 4), bytes, &s_full[pair][s]);
-          slots[s].task_flag = first ? (0x80000000u | W.task) : 0u;
-        }
-        first = 0;
-        __syncwarp();
-        ++k_issue;
-      } else if (k_prep < k_issue) {
-        // ---- prepare stage k_prep: everything of the slice that does not need its reads ----
-        const uint32_t s = k_prep % kPairStages;
-        const uint32_t flag = slots[s].task_flag;
-        if (flag & 0x80000000u) {  // first slice of a task: this evaluation's PCs
-          p_task = flag & 0x7FFFFFFFu;
-          const uint32_t job = p_task / n_bins_max;
-          const double *src = reinterpret_cast<const double *>(ARGS ? &A.jobs[job] : &A.jobs_dev[job]);
-          double *dst = reinterpret_cast<double *>(&s_job_p[pair]);
-          __syncwarp();
-          for (int i = lane; i < (int)(sizeof(JobParams) / sizeof(double)); i += 32) dst[i] = src[i];
-          __syncwarp();
-          if (!Layout::kFixed) Y = Layout((ARGS || !A.samples) ? A.sample : A.samples[job]);
-          p_have = true;
-        }
-        mbar_wait(&s_full[pair][s], (full_par >> s) & 1u);
-        full_par ^= 1u << s;
-        const uint8_t *buf = mybuf + (size_t)s * stage_bytes;
-        SliceHeader H{0, 0, 0, 0, 0, 0};
-        double acc[kNumPairs], ldiag = 0.;
-        slice_begin(buf, Y, J, lane, H, acc, ldiag);
-#pragma unroll
-        for (int p = 0; p < kNumPairs; ++p) slots[s].acc0[p][lane] = acc[p];
-        slots[s].ldiag[lane] = ldiag;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_ready[pair][s]);
-        ++k_prep;
-      } else if (!more) {
-        break;
-      }
-    }
-    (void)p_have;
-    if (lane == 0 && fetched == 0xFFFFFFFFu) __threadfence();  // (retires the atomic still in flight)
-  } else {
-    // =============================== L: the read loops ==============================================
-    double vsum = 0.0, prod = 1.0;  // the running task: sum of log(marginal) = log(prod * 2^esum) + vsum
-    int esum = 0;
-    auto combine = [&](double Lv) {
-      if (Lv > 1e-280) prod *= Lv;
-      else vsum += cold_log(Lv);
-      const int hi = __double2hiint(prod);
-      esum += (hi >> 20) - 1023;
-      prod = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(prod));
-    };
-    auto task_value = [&]() { return vsum + fma((double)esum, kLn2, log(prod)); };
-    bool have_task = false;
-    uint32_t c_job = 0, c_bin = 0, ready_par = 0;
-    const JobParams &J = s_job_l[pair];
-    const double *lin = J.c0;  // c0[6] then c1[6] (contiguous in JobParams)
-    uint32_t off_words = Layout::kFixed ? FixedLayout<NPC == 0 ? 2 : NPC>::off_words : 0u;
-    Quad Q;
-    for (uint32_t k = 0;; ++k) {
-      const uint32_t s = k % kPairStages;
-      mbar_wait(&s_ready[pair][s], (ready_par >> s) & 1u);
-      ready_par ^= 1u << s;
-      const uint32_t flag = slots[s].task_flag;
-      if (flag == 0xFFFFFFFFu) break;
-      if (flag & 0x80000000u) {  // a new task: close the previous one, load this evaluation's coefficients
-        if (have_task) store_partial(c_job, c_bin, task_value());
-        have_task = true;
-        const uint32_t t = flag & 0x7FFFFFFFu;
-        c_job = t / n_bins_max;
-        c_bin = t - c_job * n_bins_max;
-        vsum = 0.0; prod = 1.0; esum = 0;
-        const double *src = reinterpret_cast<const double *>(ARGS ? &A.jobs[c_job] : &A.jobs_dev[c_job]);
-        double *dst = reinterpret_cast<double *>(&s_job_l[pair]);
-        __syncwarp();
-        for (int i = lane; i < 2 * kNumPairs; i += 32) dst[i] = src[i];  // (c0[6], c1[6]: all L needs)
-        __syncwarp();
-#pragma unroll
-        for (int p = 0; p < kNumPairs; ++p) {
-          const double c0 = J.c0[p], c1 = J.c1[p];
-          Q.C0[p] = c0 * c0;
-          Q.C1[p] = c0 * c1;
-          Q.C2[p] = c1 * c1;
-        }
-        if (!Layout::kFixed) off_words = ((ARGS || !A.samples) ? A.sample : A.samples[c_job]).off_words;
-      }
-      const uint8_t *buf = mybuf + (size_t)s * stage_bytes;
-      const uint4 hdr = *reinterpret_cast<const uint4 *>(buf);
-      const uint32_t wr = hdr.x, wa = hdr.y, n_valid = hdr.z & 0xFFu, tails = hdr.z >> 8, fr = hdr.w & 0xFFFFu, fa = hdr.w >> 16;
-      double acc[kNumPairs];
-#pragma unroll
-      for (int p = 0; p < kNumPairs; ++p) acc[p] = slots[s].acc0[p][lane];
-      const double ldiag = slots[s].ldiag[lane];
-      eat_runs<false>(reinterpret_cast<const uint32_t *>(buf + off_words) + lane, fr, wr - fr, tails & 0xFu, fa, wa - fa,
-                      (tails >> 4) & 0xFu, lin, Q, acc);
-      const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));  // h:307-311
-      combine(((uint32_t)lane < n_valid && L > 0) ? L : 1.0);
-      __syncwarp();  // every lane is done with the slice's buffer and hand-off slot
-      if (lane == 0) mbar_arrive(&s_free[pair][s]);
-    }
-    if (have_task) store_partial(c_job, c_bin, task_value());
-  }
-}
-
 // Behind llk_stream_kernel on the same stream: evaluation j's partials -> d_out[j] / mailbox slot j, in the fixed
 // order of llk_kernel (the four bins of a CTA, those lane-strided over the CTAs, then a tree); rewinds the queue.
 __global__ void __launch_bounds__(32, 1) llk_reduce_kernel(const __grid_constant__ LaunchArgs A) {
@@ -1446,17 +1186,6 @@ void launch_llk(dim3 grid, dim3 block, uint32_t smem, cudaStream_t stream, const
 }
 template <bool ARGS>
 void launch_stream(dim3 grid, uint32_t smem, cudaStream_t stream, const LaunchArgs &A, int spec, bool chunked) {
-  static const bool pairs = getenv("VB2_LLK_PAIRS") != nullptr;  // warp-specialised variant (llk_pair_kernel)
-  if (pairs && !chunked) {
-    const uint32_t n_tasks = A.n_jobs * A.n_bins_max;
-    const dim3 pgrid(std::max(1u, std::min((grid.x + 1u) / 2u, (n_tasks + 3u) / 4u)), 1, 1), pblock(256, 1, 1);
-    const uint32_t psmem = 4u * kPairStages * (A.stage_bytes + (uint32_t)sizeof(PairSlot));
-    if (spec == 2) llk_pair_kernel<ARGS, 2><<<pgrid, pblock, psmem, stream>>>(A);
-    else if (spec == 4) llk_pair_kernel<ARGS, 4><<<pgrid, pblock, psmem, stream>>>(A);
-    else llk_pair_kernel<ARGS, 0><<<pgrid, pblock, psmem, stream>>>(A);
-    llk_reduce_kernel<<<dim3(A.n_jobs, 1, 1), dim3(32, 1, 1), 0, stream>>>(A);
-    return;
-  }
   const dim3 block(128, 1, 1);
   if (chunked) llk_stream_kernel<ARGS, 0, true><<<grid, block, smem, stream>>>(A);
   else if (spec == 2) llk_stream_kernel<ARGS, 2, false><<<grid, block, smem, stream>>>(A);
@@ -1862,13 +1591,8 @@ cudaError_t raise_smem_limits(int bytes) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_kernel<false, false, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<true, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<false, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if constexpr (!CHUNKED) {
+  if constexpr (!CHUNKED)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_session_kernel<NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (getenv("VB2_LLK_PAIRS")) {
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_pair_kernel<true, NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_pair_kernel<false, NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    }
-  }
   return e;
 }
 int init_device_tables(vb2_llk_ctx *ctx, int device, int spec, bool chunked) {
