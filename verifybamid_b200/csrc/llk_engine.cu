@@ -1419,6 +1419,7 @@ SessionGeometry session_geometry(const vb2_llk_ctx *ctx) {
 int session_launch(vb2_llk_ctx *ctx, unsigned long long first_seq) {
   const SessionGeometry g = session_geometry(ctx);
   if (!g.ok) return set_err(ctx, VB2_ERR_INVALID, "this sample cannot be held resident in shared memory");
+  VB2_CUDA(ctx, cudaSetDevice(ctx->device));  // (a re-launch from the wait loop may find another device current)
   SessionArgs A;
   memset(&A, 0, sizeof(A));
   A.sample = ctx->S;
