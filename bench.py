@@ -1,25 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- marker-reads/sec per LLK evaluation on BASELINE.json configs[1]
-(synthetic pileup, 1000g.phase3.100k.b37 panel, 100k markers x 30x, NumPC=2, alpha=0.02).
+"""bench.py -- marker-reads/sec per LLK evaluation (BASELINE.json `metric`).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one evaluation of the contamination log-likelihood (one call of the reference's
-ComputeMixLLKs) over the whole sample.  With N GPUs the markers are sharded across ranks
-(32-marker slices, round-robin) and a step is: every rank evaluates its shard, then ONE NCCL
-allreduce of the scalar partial -- strong scaling of a fixed sample.
+Headline workload (`--config 100k30x`, the default): BASELINE.json configs[1] -- synthetic pileup on the
+1000g.phase3.100k.b37 panel, 100k markers x 30x, NumPC=2, alpha=0.02.  Extra, non-headline lines:
+`--config k4` (configs[2]: NumPC=4), `--config hgdp200` (configs[4]: hgdp.100k x 200x, NumPC=4, the chunked deep-
+coverage path), `--config batch64` (configs[3]: 64 samples, spread over the GPUs, no collective).
+
+A STEP is one launch of the many-evaluations kernel over EVALS_PER_STEP (2,048) independent evaluations of the
+contamination log-likelihood (2,048 calls of the reference's ComputeMixLLKs, ContaminationEstimator.h:194-314); the
+same at every N, so `--steps 20` times about 0.1 s of device work.  With N GPUs the markers are sharded across the
+ranks (32-marker slices, round-robin), every rank evaluates its shard for the step's 2,048 parameter sets and ONE
+all-reduce adds the 2,048 partial sums (overlapped with the next step's kernel) -- strong scaling of a fixed sample.
 
 Keys of the JSON line (rank 0):
-  value     marker-reads/s with everything resident in HBM, device-timed (CUDA events on the launching
-            stream) over K back-to-back steps that rotate through enough resident copies of the sample
-            to exceed L2, so every step streams from HBM;
-  e2e       the same metric through the public call (vb2_llk_eval) with HOST parameter buffers, every step moving
-            its inputs (2k+1 doubles) to the device and its scalar result back, inside an evaluation session
-            (resident kernel, sample in shared memory) -- the way the simplex search calls it; the figure for one
-            launch per evaluation is reported beside it;
-  roofline  algorithmic bytes (2*R + 4*(k+2)*M') / measured kernel time vs measured HBM peak;
-  cpu_baseline  the reference's own CPU implementation (oracle/_ref, else the C port) on this host.
+  value     marker-reads/s = reads per evaluation x EVALS_PER_STEP / step time, everything resident in HBM, device-timed
+            (CUDA events on the launching stream) over exactly K steps; a step rotates through enough resident copies
+            of the sample to exceed L2, so every evaluation streams its sample from HBM;
+  e2e       the same metric through the public C-ABI call with HOST buffers, host<->device traffic of every evaluation
+            inside the timed region.  N=1: the call the simplex search makes -- EVALS_PER_STEP DEPENDENT evaluations
+            per step (vb2_llk_eval one after the other inside an evaluation session; the next one starts when the
+            last one's scalar is back on the host).  N>1: the batched public call (host parameter arrays in, all-
+            reduced results back in pinned host memory);
+  roofline  algorithmic bytes of one launch (2*R + 4*(k+2)*M' per evaluation x evaluations per launch)
+            / the launch's measured duration, against the measured HBM peak;
+  parity    the step's results and the e2e result checked against the CPU oracle inside this run (relative error);
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref, else the C port) on this host at 1, 4 and all threads.
 """
 from __future__ import annotations
 
@@ -39,16 +47,45 @@ if ROOT not in sys.path:
 
 METRIC = "marker-reads/sec per LLK eval"
 UNIT = "marker-reads/s"
-PANEL = "1000g.phase3.100k.b37"
-N_PC, DEPTH, ALPHA, SEED = 2, 30.0, 0.02, 1
-WORKLOAD = "synthetic pileup, %s panel, 100k markers x 30x, NumPC=2, alpha=0.02, sanity filter on (seed 1)" % PANEL
+EVALS_PER_STEP = 2048          # evaluations per step (= per launch of the many-evaluations kernel), at every N
+REF_EVALS_PER_STEP = 16        # reference arm: bounded sample of a step's evaluations
+ALPHA, SEED = 0.02, 1
 L2_BYTES = 126 * 1024 * 1024
+PARITY_TOL = 1e-8
+
+CONFIGS = {
+    # name: (panel, n_pc, depth, samples, BASELINE.json configs[] index, description)
+    "100k30x": ("1000g.phase3.100k.b37", 2, 30.0, 1, 1,
+                "synthetic pileup, 1000g.phase3.100k.b37 panel, 100k markers x 30x, NumPC=2, alpha=0.02, sanity filter on (seed 1)"),
+    "k4": ("1000g.phase3.100k.b37", 4, 30.0, 1, 2,
+           "synthetic pileup, 1000g.phase3.100k.b37 panel, 100k markers x 30x, NumPC=4, alpha=0.02, sanity filter on (seed 1)"),
+    "hgdp200": ("hgdp.100k.b37", 4, 200.0, 1, 4,
+                "synthetic pileup, hgdp.100k.b37 panel, 100k markers x 200x, NumPC=4, alpha=0.02, sanity filter on (seed 1)"),
+    "batch64": ("1000g.phase3.100k.b37", 2, 30.0, 64, 3,
+                "batch of 64 synthetic samples (seeds 1..64), 1000g.phase3.100k.b37 panel, 100k markers x 30x each, NumPC=2, "
+                "alpha=0.02, sanity filter on; samples spread over the GPUs, no collective"),
+}
 
 
-def make_workload():
+def make_workload(name: str, seed: int = SEED):
     from verifybamid_b200 import panels, synth
-    panel = panels.load_bundled(PANEL)
-    return synth.make_sample(panel, n_pc=N_PC, depth=DEPTH, alpha=ALPHA, seed=SEED, sanity_check=True)
+    panel_name, n_pc, depth, _, _, _ = CONFIGS[name]
+    panel = panels.load_bundled(panel_name)
+    return synth.make_sample(panel, n_pc=n_pc, depth=depth, alpha=ALPHA, seed=seed, sanity_check=True)
+
+
+def config_dict(name: str, sample, n_gpus: int) -> dict:
+    """The `config` object: identical in both arms (--impl ours / reference) for the same --config and --gpus."""
+    panel_name, n_pc, depth, n_samples, idx, text = CONFIGS[name]
+    markers, reads = sample.problem.used_counts()
+    if n_samples > 1:
+        par = "%d samples over %d GPU(s), one launch per step evaluates every sample of a GPU once, no collective" % (n_samples, n_gpus)
+    elif n_gpus > 1:
+        par = "marker shards x%d + 1 all-reduce of the step's %d partial sums" % (n_gpus, EVALS_PER_STEP)
+    else:
+        par = "single GPU"
+    return {"workload": text, "baseline_config_index": idx, "name": name, "reads_per_eval": reads, "markers_used": markers,
+            "n_pc": n_pc, "evals_per_step": EVALS_PER_STEP if n_samples == 1 else n_samples, "parallelism": par}
 
 
 def measured_peak_gbs():
@@ -109,35 +146,50 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own CPU implementation on this host's cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(sample, evals: int, warmup: int, threads: int, converge: bool = False):
-    """Time `evals` evaluations of the whole workload on the CPU.  Returns (seconds, kind, reads_used, conv)
-    where conv (when asked for) compares the wall-clock to converged alpha of the C++ GPU CLI and of the
-    reference binary on the same panel + pileup text files."""
-    from oracle import vb2_oracle as vo  # checker / baseline only -- never on the product path
-    p = sample.problem
-    conv = None
-    if vo.ref_available():
-        from verifybamid_b200 import panels
-        with tempfile.TemporaryDirectory() as td:
-            prefix = panels.write_text_panel(sample.panel, os.path.join(td, "panel"))
-            pile = sample.write_pileup(os.path.join(td, "sample.pileup"))
-            recs = vo.run_ref(["--SVDPrefix", prefix, "--PileupFile", pile, "--NumPC", str(N_PC), "--NumThread",
-                               str(threads), "--BenchEvals", str(evals), "--BenchWarmup", str(warmup),
-                               "--Output", os.path.join(td, "o")] + ([] if converge else ["--NoOptimize"]))
-            if converge:
-                conv = {"reference": converge_reference(recs, threads), "ours": converge_ours(prefix, pile, td)}
-                conv["abs_diff_alpha"] = abs(conv["ours"]["alpha"] - conv["reference"]["alpha"])
-                conv["abs_diff_pc_max"] = max(abs(a - b) for a, b in zip(conv["ours"]["pcs"], conv["reference"]["pcs"]))
-        b = [r for r in recs if r["phase"] == "bench"][0]
-        return float(b["seconds"]), "reference", int(b["reads_used"]), conv
-    ora = vo.Problem(p.ud, p.means, p.base_info_index, p.alt_base, p.info_offset, p.bases, p.quals, None,
-                     p.sanity_disabled, p.avg_depth, p.sd_depth, threads)
-    for _ in range(warmup):
-        ora.compute_mix_llks([0.01] * N_PC, [0.01] * N_PC, 0.03)
-    t0 = time.perf_counter()
-    for i in range(evals):
-        ora.compute_mix_llks([0.01 + 1e-6 * i] + [0.01] * (N_PC - 1), [0.01] * N_PC, 0.03)
-    return time.perf_counter() - t0, "port", ora.used_counts()[1], conv
+class CpuReference:
+    """The reference's CPU path on one workload: oracle/_ref/vb2_ref (the reference's own sources, built by
+    oracle/Makefile) when present, else the C port of the oracle.  Test/bench infrastructure only."""
+
+    def __init__(self, sample):
+        from oracle import vb2_oracle as vo  # checker / baseline only -- never on the product path
+        self.vo, self.sample, self.p = vo, sample, sample.problem
+        self.kind = "reference" if vo.ref_available() else "port"
+        self.td = None
+        self.n_pc = self.p.n_pc
+
+    def __enter__(self):
+        if self.kind == "reference":
+            from verifybamid_b200 import panels
+            self.td = tempfile.TemporaryDirectory()
+            self.prefix = panels.write_text_panel(self.sample.panel, os.path.join(self.td.name, "panel"))
+            self.pile = self.sample.write_pileup(os.path.join(self.td.name, "sample.pileup"))
+        return self
+
+    def __exit__(self, *exc):
+        if self.td:
+            self.td.cleanup()
+
+    def oracle_problem(self, threads: int):
+        p = self.p
+        return self.vo.Problem(p.ud, p.means, p.base_info_index, p.alt_base, p.info_offset, p.bases, p.quals, None,
+                               p.sanity_disabled, p.avg_depth, p.sd_depth, threads)
+
+    def time_evals(self, evals: int, warmup: int, threads: int, converge: bool = False):
+        """(seconds for `evals` full evaluations, records of the reference run or None)."""
+        if self.kind == "reference":
+            recs = self.vo.run_ref(["--SVDPrefix", self.prefix, "--PileupFile", self.pile, "--NumPC", str(self.n_pc),
+                                    "--NumThread", str(threads), "--BenchEvals", str(evals), "--BenchWarmup", str(warmup),
+                                    "--Output", os.path.join(self.td.name, "o")] + ([] if converge else ["--NoOptimize"]))
+            b = [r for r in recs if r["phase"] == "bench"][0]
+            return float(b["seconds"]), recs
+        ora = self.oracle_problem(threads)
+        k = self.n_pc
+        for _ in range(warmup):
+            ora.compute_mix_llks([0.01] * k, [0.01] * k, 0.03)
+        t0 = time.perf_counter()
+        for i in range(evals):
+            ora.compute_mix_llks([0.01 + 1e-6 * i] + [0.01] * (k - 1), [0.01] * k, 0.03)
+        return time.perf_counter() - t0, None
 
 
 def converge_reference(recs, threads):
@@ -147,14 +199,14 @@ def converge_reference(recs, threads):
             "pcs": o["pc_contam"] + o["pc_intended"], "read_panel_s": load["panel_s"], "read_pileup_s": load["pileup_s"]}
 
 
-def converge_ours(prefix, pile, td):
+def converge_ours(prefix, pile, td, n_pc):
     """Wall-clock to converged alpha through the product CLI (C++ host + GPU engine)."""
     import re
     from verifybamid_b200 import host
     out = os.path.join(td, "gpu")
     t0 = time.perf_counter()
     cp = subprocess.run([host.CLI_PATH, "--SVDPrefix", prefix, "--PileupFile", pile, "--Reference", "x", "--NumPC",
-                         str(N_PC), "--Output", out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, check=True)
+                         str(n_pc), "--Output", out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, check=True)
     wall = time.perf_counter() - t0
     phase = dict(re.findall(r"Finished phase: (.*?)  \[([0-9.]+) seconds\]", cp.stderr))
     m = re.search(r"Likelihood evaluations: (\d+), ([0-9.]+) ms inside the GPU engine", cp.stderr)
@@ -171,17 +223,24 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = make_workload()
+    sample = make_workload(args.config)
+    cfg = config_dict(args.config, sample, args.gpus)
     threads = os.cpu_count() or 1
-    secs, kind, reads, _ = cpu_reference_run(sample, args.steps, args.warmup, threads)
-    ms = secs / args.steps * 1e3
-    value = reads / (secs / args.steps)
+    reads = cfg["reads_per_eval"]
+    s_ref = min(REF_EVALS_PER_STEP, cfg["evals_per_step"])
+    with CpuReference(sample) as ref:
+        secs, _ = ref.time_evals(args.steps * s_ref, args.warmup * s_ref, threads)
+        kind = ref.kind
+    step_s = secs / args.steps
+    value = reads * s_ref / step_s
     cpu = {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-           "sample": "%d full evaluations of the workload (all %d reads each), %d threads" % (args.steps, reads, threads)}
+           "sample": "every step evaluates a bounded sample of %d of the step's %d evaluations (all %d reads each), "
+                     "%d OpenMP threads; %.3f ms per evaluation" % (s_ref, cfg["evals_per_step"], reads, threads,
+                                                                    step_s / s_ref * 1e3)}
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
                       "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": WORKLOAD, "reads_per_step": reads},
+                      "config": cfg, "evals_timed_per_step": s_ref,
                       "cpu_baseline": cpu,
                       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -189,12 +248,36 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def cpu_baseline_leg(sample, n_pc: int, want_converge: bool):
+    """The reference CPU path at 1, 4 (the CLI's default --NumThread) and all threads; about 10-20 s of CPU work."""
+    all_threads = os.cpu_count() or 1
+    by_threads, conv = {}, None
+    reads = sample.problem.used_counts()[1]
+    with CpuReference(sample) as ref:
+        for threads, n_eval in ((1, 12), (4, 40), (all_threads, 100)):
+            if str(threads) in by_threads:
+                continue
+            converge = want_converge and threads == all_threads and ref.kind == "reference"
+            secs, recs = ref.time_evals(n_eval, 3, threads, converge=converge)
+            by_threads[str(threads)] = {"value": reads / (secs / n_eval), "ms_per_eval": secs / n_eval * 1e3, "evals": n_eval}
+            if converge:
+                conv = {"reference": converge_reference(recs, threads),
+                        "ours": converge_ours(ref.prefix, ref.pile, ref.td.name, n_pc)}
+                conv["abs_diff_alpha"] = abs(conv["ours"]["alpha"] - conv["reference"]["alpha"])
+                conv["abs_diff_pc_max"] = max(abs(a - b) for a, b in zip(conv["ours"]["pcs"], conv["reference"]["pcs"]))
+        kind = ref.kind
+    top = by_threads[str(all_threads)]
+    return {"value": top["value"], "unit": UNIT, "cores": all_threads, "kind": kind,
+            "sample": "%d full evaluations of the same workload (%d reads each) on all %d threads (%.2f ms per evaluation); "
+                      "12 at 1 thread, 40 at 4 threads (the reference CLI's default)" % (top["evals"], reads, all_threads, top["ms_per_eval"]),
+            "by_threads": by_threads, "wall_clock_to_converged_alpha": conv}
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     import verifybamid_b200 as vb
-    from verifybamid_b200.distributed import allreduce_partials
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,31 +294,13 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
-    sample = make_workload()
+    panel_name, k, depth, n_samples, _, _ = CONFIGS[args.config]
+    cohort = n_samples > 1
+    sample = make_workload(args.config)
+    cfg = config_dict(args.config, sample, world)
     p = sample.problem
-    k = p.n_pc
-    # enough resident copies of this rank's shard to exceed L2 -> every step streams from HBM
-    # (N > 1: every rank only ever evaluates its shard in batches -> the batched layout, include/vb2_llk.h)
-    probe = vb.LLKEngine(p, device=local, shard_rank=rank, shard_count=world, stream=stream.cuda_stream, batched=world > 1)
-    info = probe.info()
-    copies = max(2, int(np.ceil(2.0 * L2_BYTES / max(1, info["device_bytes"]))))
-    copies = min(copies, 256)
-    if world > 1:                               # shards differ slightly in size: every rank must agree
-        c = torch.tensor([copies], dtype=torch.int64, device=dev)
-        dist.all_reduce(c, op=dist.ReduceOp.MAX)
-        copies = int(c.item())
-    engines = [probe] + [vb.LLKEngine(p, device=local, shard_rank=rank, shard_count=world, stream=stream.cuda_stream, batched=world > 1)
-                         for _ in range(copies - 1)]
-    reads_total = p.used_counts()[1]           # whole sample, all shards
-    markers_total = p.used_counts()[0]
-    d_out = torch.zeros(1, dtype=torch.float64, device=dev)
-    pc_a = np.full((1, k), 0.01); pc_b = np.full((1, k), 0.01); al = np.array([0.03])
-
-    def step(i: int):
-        # rank-local kernel on this rank's marker shard, then ONE allreduce of the scalar partial
-        pc_a[0, 0] = 0.01 + 1e-7 * (i % 1000)
-        engines[i % copies].eval_batch_device(pc_a, pc_b, al, d_out.data_ptr())
-        allreduce_partials(d_out)
+    reads_per_eval, markers_used = cfg["reads_per_eval"], cfg["markers_used"]
+    per_step = cfg["evals_per_step"]
 
     def barrier():
         torch.cuda.synchronize()
@@ -243,77 +308,89 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # A launch makes ROTATIONS passes over the resident copies (a context may appear several times in a launch):
-    # the ramp and the tail of the persistent kernel are shared by more steps.
-    ROTATIONS = 8
-    per_launch = min(copies * ROTATIONS, 2048, max(copies, args.steps // 4))  # (at least four launches to pipeline)
-    launch_list = (engines * ROTATIONS)[:per_launch]
+    # ---- resident samples ----------------------------------------------------------------------------------
+    if cohort:
+        # configs[3]: sample s lives on GPU s % world; a step evaluates every sample once, no collective
+        mine = [s for s in range(n_samples) if s % world == rank]
+        probs = [p if s == 0 else make_workload(args.config, seed=SEED + s).problem for s in mine]
+        engines = [vb.LLKEngine(q, device=local, stream=stream.cuda_stream, batched=True) for q in probs]
+        reads_step_total = None   # summed over ranks below
+        launch_list = engines
+        info = engines[0].info()
+        copies = len(engines)
+        reads_mine = float(sum(q.used_counts()[1] for q in probs))
+        t = torch.tensor([reads_mine], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+        reads_step_total = float(t.item())
+    else:
+        # enough resident copies of this rank's shard to exceed L2 -> every evaluation streams from HBM
+        # (N > 1: a rank only ever evaluates its shard in batches -> the batched layout, include/vb2_llk.h)
+        mk = lambda: vb.LLKEngine(p, device=local, shard_rank=rank, shard_count=world, stream=stream.cuda_stream, batched=world > 1)
+        probe = mk()
+        info = probe.info()
+        copies = min(256, max(2, int(np.ceil(2.0 * L2_BYTES / max(1, info["device_bytes"])))))
+        if world > 1:                               # shards differ slightly in size: every rank must agree
+            c = torch.tensor([copies], dtype=torch.int64, device=dev)
+            dist.all_reduce(c, op=dist.ReduceOp.MAX)
+            copies = int(c.item())
+        engines = [probe] + [mk() for _ in range(copies - 1)]
+        launch_list = (engines * (per_step // copies + 1))[:per_step]   # evaluation i of a step runs on copy i % copies
+        reads_step_total = float(reads_per_eval) * per_step
 
+    n_jobs = len(launch_list)
     start_pc = np.full(k, 0.01)
+    pcs = np.tile(start_pc, (n_jobs, 1)); als = np.full(n_jobs, 0.03)
+    ctx_arr = vb.context_array(launch_list)
+    d_step = [torch.zeros(n_jobs, dtype=torch.float64, device=dev) for _ in range(2)]
+    collective = world > 1 and not cohort
 
     def keep_busy(seconds: float):
         # rank-local launches only (a time-based loop must not contain collectives)
         t_end = time.perf_counter() + seconds
         while time.perf_counter() < t_end:
-            vb.time_device_many(launch_list, 0, 3, start_pc, start_pc, 0.03)
+            vb.time_device_many(launch_list, 0, 2, start_pc, start_pc, 0.03)
 
-    # ---- value: device-timed, EXACTLY K steps ---------------------------------------------------
-    # N=1: steps are issued from C, `copies` steps per launch (vb2_llk_eval_many's kernel: step i
-    # evaluates resident copy i % copies, so every step streams its sample from HBM and the launch
-    # cost is shared by the steps of a launch).  N>1: each step is kernel + NCCL allreduce of the
-    # scalar, one launch per step, issued from Python.
-    def timed_steps(n_steps: int, warm: int) -> float:
-        full, rem = divmod(n_steps, per_launch)
-        ms = 0.0
-        if full:
-            ms += vb.time_device_many(launch_list, max(1, warm // per_launch), full, start_pc, start_pc, 0.03)
-        if rem:
-            ms += vb.time_device_many(launch_list[:rem], 1, 1, start_pc, start_pc, 0.03)
-        return ms
+    # ---- value: device-timed, EXACTLY K steps; a step = one launch over the step's evaluations -----------------------
     with ClockSampler(local) as clocks:
         keep_busy(0.3)                      # let nvidia-smi attach before the timed region
         barrier()
-        if world == 1:
-            dev_ms = timed_steps(args.steps, args.warmup)
-            launches = 2 * (args.steps // per_launch + (1 if args.steps % per_launch else 0))  # stream kernel + reduce kernel
+        if not collective:
+            # steps are issued back to back from C (vb2_llk_time_device_many: `warmup` untimed launches, then K timed
+            # ones bracketed by CUDA events on the launching stream)
+            barrier()
+            dev_ms = vb.time_device_many(launch_list, args.warmup, args.steps, start_pc, start_pc, 0.03)
         else:
-            # `per_launch` steps per launch on every rank (its marker shard of each resident copy), then ONE
-            # NCCL allreduce of their partial sums
-            # (two result buffers: the allreduce of one launch's partial sums runs on NCCL's stream while the next
-            # launch's kernel runs on ours)
-            d_many = [torch.zeros(per_launch, dtype=torch.float64, device=dev) for _ in range(2)]
+            # every step: this rank's marker shard for the step's parameter sets, then ONE NCCL all-reduce of the partial
+            # sums (two result buffers: the all-reduce of one step runs on NCCL's stream while the next step's kernel
+            # runs on ours)
             works = [None, None]
-            pcs = np.tile(start_pc, (per_launch, 1)); als = np.full(per_launch, 0.03)
             turn = [0]
-            ctx_arr = vb.context_array(launch_list)
 
-            def launch_steps(n: int):
+            def one_step():
                 b = turn[0] = turn[0] ^ 1
                 if works[b] is not None:
-                    works[b].wait()          # (stream-level: our stream waits for that buffer's previous allreduce)
-                vb.eval_many_device(launch_list[:n], pcs[:n], pcs[:n], als[:n], d_many[b].data_ptr(), ctx_arr)
-                works[b] = dist.all_reduce(d_many[b][:n], op=dist.ReduceOp.SUM, async_op=True)
+                    works[b].wait()          # (stream-level: our stream waits for that buffer's previous all-reduce)
+                vb.eval_many_device(launch_list, pcs, pcs, als, d_step[b].data_ptr(), ctx_arr)
+                works[b] = dist.all_reduce(d_step[b], op=dist.ReduceOp.SUM, async_op=True)
 
             def drain():
                 for w in works:
                     if w is not None:
                         w.wait()
-            full, rem = divmod(args.steps, per_launch)
-            for _ in range(max(1, args.warmup // per_launch)):
-                launch_steps(per_launch)
+            for _ in range(args.warmup):
+                one_step()
             drain()
             barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(stream)
-            for _ in range(full):
-                launch_steps(per_launch)
-            if rem:
-                launch_steps(rem)
+            for _ in range(args.steps):
+                one_step()
             drain()
             ev1.record(stream)
             barrier()
             dev_ms = ev0.elapsed_time(ev1)
-            launches = 2 * (full + (1 if rem else 0))  # stream kernel + reduce kernel per launch_steps()
+        launches = 2 * args.steps           # llk_stream_kernel + llk_reduce_kernel per step
         keep_busy(0.5)                      # clocks under the same load, for the sampler
         barrier()
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -321,116 +398,164 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     ms_per_step = dev_ms / args.steps
-    value = reads_total / (ms_per_step * 1e-3)
+    value = reads_step_total / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant (only) kernel -------------------------------------------------
-    # N=1: the kernel of the timed region above (algorithmic bytes of one launch / its duration).
-    # Also reported: the same kernel launched once per step (latency geometry), which on this part
-    # cannot go below the ~4 us cost of any launch that contains a block-wide barrier.
-    one_ms = vb.time_device(engines, args.warmup, min(args.steps, 2000), start_pc, start_pc, 0.03) / min(args.steps, 2000)
+    # ---- parity inside the run: one step's results (after the all-reduce) against the CPU oracle -------------------
+    par_pcs = np.tile(np.asarray(sample.pc_contam, dtype=np.float64)[:k], (n_jobs, 1))
+    par_pc2 = np.tile(np.asarray(sample.pc_intended, dtype=np.float64)[:k], (n_jobs, 1))
+    par_al = np.full(n_jobs, ALPHA)
+    par_pcs[:, 0] += 1e-3 * (np.arange(n_jobs) % 7)          # seven different points over the step
+    vb.eval_many_device(launch_list, par_pcs, par_pc2, par_al, d_step[0].data_ptr(), ctx_arr)
+    if collective:
+        dist.all_reduce(d_step[0], op=dist.ReduceOp.SUM)
+    got = d_step[0].cpu().numpy()
+    parity = None
+    if rank == 0:
+        from oracle import vb2_oracle as vo  # the checker, never the thing measured
+        probs0 = [p] if not cohort else probs[:2]
+        worst = 0.0
+        for si, q in enumerate(probs0):
+            ora = vo.Problem(q.ud, q.means, q.base_info_index, q.alt_base, q.info_offset, q.bases, q.quals, None,
+                             q.sanity_disabled, q.avg_depth, q.sd_depth, min(16, os.cpu_count() or 1))
+            if cohort:
+                want = ora.compute_mix_llks(list(par_pcs[si]), list(par_pc2[si]), float(par_al[si]))
+                worst = max(worst, abs(got[si] - want) / abs(want))
+            else:   # every evaluation of the step against the oracle's value for its parameter set
+                wants = [ora.compute_mix_llks(list(par_pcs[j]), list(par_pc2[j]), float(par_al[j])) for j in range(7)]
+                for j in range(n_jobs):
+                    worst = max(worst, abs(got[j] - wants[j % 7]) / abs(wants[j % 7]))
+        parity = {"batched_rel": worst, "tolerance": PARITY_TOL,
+                  "checked": "all %d evaluations of one step (7 distinct parameter sets) vs the CPU oracle" % n_jobs
+                             if not cohort else "first %d samples of the step vs the CPU oracle" % len(probs0)}
+        if not worst <= PARITY_TOL:
+            raise SystemExit("bench.py: parity check failed: %r" % parity)
+
+    # ---- roofline of the dominant kernel: the launch timed above ----------------------------------------------
     peak, peak_src = measured_peak_gbs()
-    alg_bytes = info["algorithmic_bytes"]       # this rank's shard, one evaluation
-    kern_us = (dev_ms / args.steps) * 1e3       # per evaluation (N>1: includes the allreduce share)
-    achieved = alg_bytes / (kern_us * 1e-6) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of this kernel (296 evaluations in the
-    # launch: 2,145,602,000 + 5,224,192 bytes; profiles/r01_llk_stream_kernel_ncu_details.txt), per evaluation:
-    traffic_per_eval = 7266305 if world == 1 else None
+    if cohort:
+        alg_launch = float(sum(e.info()["algorithmic_bytes"] for e in engines))
+        dev_launch = float(sum(e.info()["device_bytes"] for e in engines))
+    else:
+        alg_launch = float(info["algorithmic_bytes"]) * n_jobs   # this rank's shard x the launch's evaluations
+        dev_launch = float(info["device_bytes"]) * n_jobs
+    launch_us = ms_per_step * 1e3
+    achieved = alg_launch / (launch_us * 1e-6) / 1e9
+    one_ms = None
+    if not cohort and world == 1:
+        n1 = 500
+        one_ms = vb.time_device(engines, 20, n1, start_pc, start_pc, 0.03) / n1
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of this kernel (profiles/): 7.266 MB per
+    # evaluation of the headline workload at N=1 = the stored image, no re-reads (algorithmic: 7.573 MB)
+    traffic = 7266305.0 * n_jobs if (args.config == "100k30x" and world == 1) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic_per_eval * per_launch if traffic_per_eval else None,
-                "traffic_note": "bytes per launch of %d evaluations, from the committed ncu capture (7.27 MB per evaluation = "
-                                "the stored image, no re-reads; algorithmic 7.57 MB)" % per_launch, "peak_source": peak_src, "kernel": "llk_stream_kernel",
-                "evaluations_per_launch": per_launch,
-                "us_per_evaluation": kern_us, "us_per_evaluation_one_launch_each": one_ms * 1e3,
-                "algorithmic_bytes_per_evaluation": alg_bytes, "device_bytes_per_evaluation": info["device_bytes"],
-                "note": "co-bound by the FP64 pipe: 10 fp64 instructions per streamed read + ~40 per marker -> >= 2.2 us per "
-                        "evaluation at 64 lanes/clk/SM (DESIGN.md section 4)"}
+                "traffic": traffic,
+                "traffic_note": "bytes per launch of %d evaluations, from the committed ncu capture of this kernel (7.27 MB per "
+                                "evaluation = the stored image, no re-reads)" % n_jobs if traffic else None,
+                "peak_source": peak_src, "kernel": "llk_stream_kernel", "evaluations_per_launch": n_jobs,
+                "launch_us": launch_us, "us_per_evaluation": launch_us / n_jobs * (1 if not cohort else 1),
+                "us_per_evaluation_one_launch_each": one_ms * 1e3 if one_ms else None,
+                "algorithmic_bytes_per_launch": alg_launch, "device_bytes_per_launch": dev_launch,
+                "includes_allreduce": collective,
+                "note": "co-bound by the FP64 pipe: 10 fp64 instructions per streamed read + ~40 per marker -> >= 1.9 us per "
+                        "evaluation of the headline workload at 64 fp64 lanes/clk/SM (DESIGN.md section 4)"}
 
-    # ---- e2e: the public C-ABI call with HOST buffers; every step moves the step's inputs (2k+1 doubles)
-    # to the device and the scalar result back to the host ------------------------------------------------
-    if world == 1:
-        # (a) the call as the simplex search makes it: several hundred dependent evaluations of ONE sample inside an
-        #     evaluation session (vb2_llk_session_begin: resident kernel, the sample in shared memory, host-mapped
-        #     doorbell in, host mailbox out).  Every step still moves its 2k+1 doubles in and its scalar out.
+    # ---- e2e: the public C-ABI call with HOST buffers, host<->device traffic inside the timed region ----------------
+    e2e_extra = {}
+    if not cohort and world == 1:
+        # the call as the simplex search makes it: per step EVALS_PER_STEP DEPENDENT evaluations of ONE sample, each one
+        # moving its 2k+1 doubles in and its scalar out before the next starts, inside an evaluation session
+        n_dep = args.steps * per_step
+        n_warm = args.warmup * per_step // 8 + 16
         if args.no_session:   # (profiler runs: ncu serialises launches, a resident kernel would wait for a doorbell
-            e2e_s, last = vb.time_host(engines, args.warmup, args.steps, start_pc, start_pc, 0.03)  # that cannot ring)
+            e2e_s, last = vb.time_host(engines, n_warm, n_dep, start_pc, start_pc, 0.03)  # that cannot ring)
         else:
             engines[0].session_begin()
-            e2e_s, last = vb.time_host(engines[:1], args.warmup, args.steps, start_pc, start_pc, 0.03)
+            e2e_s, last = vb.time_host(engines[:1], n_warm, n_dep, start_pc, start_pc, 0.03)
             engines[0].session_end()
-        # (b) one launch per evaluation (no session), rotating through the resident copies (HBM-cold every step)
-        cold_s, last_cold = vb.time_host(engines, args.warmup, args.steps, start_pc, start_pc, 0.03)
-        # the same call through the Python binding (interpreter + ctypes overhead included)
+        last_pc = start_pc.copy(); last_pc[0] = 0.01 + 1e-7 * ((n_dep - 1 + n_warm) % 1000)
+        e2e_point = (last_pc, start_pc, 0.03)
+        # one launch per evaluation (no session), rotating through the resident copies (HBM-cold every evaluation)
+        n_cold = min(n_dep, 4000)
+        cold_s, _ = vb.time_host(engines, 50, n_cold, start_pc, start_pc, 0.03)
+        # the batched public call: one vb2_llk_eval_many per step with host arrays in and out
+        t0 = time.perf_counter()
+        nb = max(2, min(args.steps, 10))
+        for _ in range(nb):
+            vb.eval_many(launch_list, pcs, pcs, als)
+        batched_s = (time.perf_counter() - t0) / nb
         t0 = time.perf_counter()
         for i in range(200):
             engines[i % copies].compute_mix_llks(start_pc, start_pc, 0.03)
-        py_us = (time.perf_counter() - t0) / 200 * 1e6
+        e2e_extra = {"us_per_evaluation_one_launch_per_evaluation": cold_s / n_cold * 1e6,
+                     "us_per_evaluation_batched_public_call": batched_s / n_jobs * 1e6,
+                     "python_binding_us_per_evaluation": (time.perf_counter() - t0) / 200 * 1e6}
+        h2d, d2h = (2 * k + 1) * 8 * per_step, 8 * per_step
+        caller = ("C loop over vb2_llk_eval (host buffers), one launch per evaluation (--no-session)" if args.no_session else
+                  "C loop over vb2_llk_eval (host buffers): %d dependent evaluations per step inside an evaluation session "
+                  "(resident kernel, sample in shared memory, host-mapped doorbell/mailbox)" % per_step)
     else:
-        # Marker shards cannot shorten ONE dependent evaluation (a ~3 us kernel against a ~30 us collective), so the
-        # sharded public call is the batched one: every call takes `copies` parameter sets from HOST arrays
-        # (vb2_llk_eval_many_device stages them: 508 bytes per evaluation), evaluates this rank's shard of each,
-        # all-reduces the partial sums and copies the `copies` results back to pinned host memory.
-        host_out = torch.zeros(copies, dtype=torch.float64).pin_memory()
-        d_e2e = torch.zeros(copies, dtype=torch.float64, device=dev)
-        host_pcs = np.tile(start_pc, (copies, 1)); host_als = np.full(copies, 0.03)
+        # marker shards (or a cohort) go through the batched public call: per step, host parameter arrays in
+        # (vb2_llk_eval_many_device stages them), this rank's launch, all-reduce (shards only), results back to pinned
+        # host memory
+        host_out = torch.zeros(n_jobs, dtype=torch.float64).pin_memory()
+        host_pcs = pcs.copy()
 
-        def e2e_batch(i: int, n: int) -> float:
+        def e2e_step(i: int) -> float:
             host_pcs[:, 0] = 0.01 + 1e-7 * (i % 1000)
-            vb.eval_many_device(engines[:n], host_pcs[:n], host_pcs[:n], host_als[:n], d_e2e.data_ptr())
-            allreduce_partials(d_e2e[:n])
-            host_out[:n].copy_(d_e2e[:n], non_blocking=False)
-            return float(host_out[n - 1])
-        for i in range(max(1, args.warmup // copies)):
-            e2e_batch(i, copies)
+            vb.eval_many_device(launch_list, host_pcs, pcs, als, d_step[0].data_ptr(), ctx_arr)
+            if collective:
+                dist.all_reduce(d_step[0], op=dist.ReduceOp.SUM)
+            host_out.copy_(d_step[0], non_blocking=False)
+            return float(host_out[n_jobs - 1])
+        for i in range(args.warmup):
+            e2e_step(i)
         barrier()
         t0 = time.perf_counter()
         last = 0.0
-        full, rem = divmod(args.steps, copies)
-        for i in range(full):
-            last = e2e_batch(i, copies)
-        if rem:
-            last = e2e_batch(full, rem)
+        for i in range(args.steps):
+            last = e2e_step(i)
         barrier()
         e2e_s = time.perf_counter() - t0
-        py_us = None
-        cold_s = None
+        last_pc = start_pc.copy(); last_pc[0] = 0.01 + 1e-7 * ((args.steps - 1) % 1000)
+        e2e_point = (last_pc, start_pc, 0.03)
+        h2d, d2h = n_jobs * (2 * k + 1) * 8, n_jobs * 8
+        caller = "python: vb2_llk_eval_many_device over %d host parameter sets per step%s + D2H of the results" % (
+            n_jobs, " (marker shard) + NCCL all-reduce" if collective else " (this GPU's samples)")
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    e2e = {"value": reads_total / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": (2 * k + 1) * 8 if world == 1 else 508,
-           "d2h_bytes_per_step": 8, "us_per_step": e2e_s / args.steps * 1e6, "last_llk": last,
-           "caller": ("C loop over vb2_llk_eval (host buffers), one launch per evaluation (--no-session)" if args.no_session else
-                      "C loop over vb2_llk_eval (host buffers) inside an evaluation session: resident kernel, sample in "
-                      "shared memory, host-mapped doorbell/mailbox") if world == 1 else
-                     "python: vb2_llk_eval_many_device over %d host parameter sets per call (marker shard) + NCCL allreduce + "
-                     "D2H of the results" % copies,
-           "us_per_step_one_launch_per_evaluation": (cold_s / args.steps * 1e6) if cold_s else None,
-           "python_binding_us_per_step": py_us}
+    e2e = {"value": reads_step_total / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "us_per_evaluation": e2e_s / args.steps / n_jobs * 1e6 * (1 if not cohort else 1), "ms_per_step": e2e_s / args.steps * 1e3,
+           "last_llk": last, "caller": caller}
+    e2e.update(e2e_extra)
+    if rank == 0:   # the e2e result against the oracle too (cohort: the last sample of rank 0)
+        from oracle import vb2_oracle as vo
+        q = p if not cohort else probs[-1]
+        ora = vo.Problem(q.ud, q.means, q.base_info_index, q.alt_base, q.info_offset, q.bases, q.quals, None,
+                         q.sanity_disabled, q.avg_depth, q.sd_depth, min(16, os.cpu_count() or 1))
+        want = ora.compute_mix_llks(list(e2e_point[0]), list(e2e_point[1]), e2e_point[2])
+        parity["e2e_rel"] = abs(last - want) / abs(want)
+        if not parity["e2e_rel"] <= PARITY_TOL:
+            raise SystemExit("bench.py: e2e parity check failed: got %.17g want %.17g" % (last, want))
 
     # ---- cpu baseline beside it (rank 0, N=1 only) --------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        n_eval = 100
-        secs, kind, reads, conv = cpu_reference_run(sample, n_eval, 3, threads, converge=True)
-        cpu = {"value": reads / (secs / n_eval), "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": "%d full evaluations of the same workload (%d reads each), %d OpenMP threads; %.2f ms/eval"
-                         % (n_eval, reads, threads, secs / n_eval * 1e3),
-               "wall_clock_to_converged_alpha": conv}
+        cpu = cpu_baseline_leg(sample, k, want_converge=(args.config != "batch64"))
 
     for e in engines:
         e.close()
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "reads_per_step": reads_total, "markers_used": markers_total,
-                           "n_pc": k, "parallelism": "marker shards x%d + 1 scalar allreduce/step" % world if world > 1
-                           else "single GPU", "l2": "steps rotate through %d resident copies of the sample "
-                           "(%.0f MB > 126 MB L2): every step streams from HBM" % (copies, copies * info["device_bytes"] / 1e6),
-                           "steps_per_launch": per_launch,
-                           "panel_dtype": "fp32 UD/mu in HBM, fp64 arithmetic"},
-                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "us_per_evaluation": ms_per_step * 1e3 / n_jobs if not cohort else None,
+                "cache": "a step rotates through %d resident copies of the sample (%.0f MB > 126 MB L2): every evaluation streams "
+                         "from HBM" % (copies, copies * info["device_bytes"] / 1e6) if not cohort else
+                         "%d resident samples on this GPU (%.0f MB > 126 MB L2)" % (copies, dev_launch / 1e6),
+                "precision": "fp32 UD/mu in HBM, fp64 arithmetic",
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "parity": parity,
                 "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
@@ -441,17 +566,18 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="100k30x", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-session", action="store_true", help="e2e with one launch per evaluation (for runs under ncu)")
     args = ap.parse_args()
     if args.steps is None:            # defaults that finish within minutes on either arm
-        args.steps = 2000 if args.impl == "ours" else 200
+        args.steps = 20
+    args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
-        args.warmup = max(args.warmup, 3)
         run_ours(args)
 
 

@@ -185,6 +185,28 @@ def test_eval_many_samples_one_launch():
             e.close()
 
 
+def test_eval_many_with_a_sample_that_has_no_usable_marker():
+    """One empty (or fully filtered) pileup in a cohort answers 0.0 -- the reference's empty sum (h:231,:313) -- and
+    does not disturb the other samples of the launch."""
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    s = synth.make_sample(panel, n_pc=2, depth=20.0, alpha=0.02, seed=5, n_markers=2500)
+    p = s.problem
+    none = vb.PileupProblem(p.ud, p.means, np.full(p.n_marker, -1, np.int32), p.alt_base, np.zeros(1, np.int64),
+                            np.zeros(0, np.uint8), np.zeros(0, np.uint8))
+    engines = [vb.LLKEngine(p, batched=True), vb.LLKEngine(none, batched=True), vb.LLKEngine(p, batched=True)]
+    try:
+        pcs = np.array([[0.01, 0.01], [0.0, 0.0], [0.02, -0.01]])
+        al = np.array([0.03, 0.5, 0.1])
+        got = vb.eval_many(engines, pcs, pcs, al)
+        assert got[1] == 0.0
+        assert got[0] == engines[0].compute_mix_llks(pcs[0], pcs[0], al[0])
+        assert got[2] == engines[2].compute_mix_llks(pcs[2], pcs[2], al[2])
+        assert vb.eval_many([engines[1]], pcs[1:2], pcs[1:2], al[1:2]).tolist() == [0.0]   # nothing to launch at all
+    finally:
+        for e in engines:
+            e.close()
+
+
 def test_batched_layout_and_many_jobs_per_launch(sample10k):
     """VB2_FLAG_BATCHED shards (fewer, deeper bins) sum to the whole sample; a launch may carry hundreds of jobs that
     reuse a few contexts (every job gets its own partial-sum slot)."""

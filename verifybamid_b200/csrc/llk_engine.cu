@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -738,6 +739,19 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 256; i += 128) s_e[i] = i < kPhredArgs ? A.phred[i] : 1.0;
+#ifdef VB2_PHASE_CLOCK
+  // diagnostics build (tools/gpu_phase.sh): cycles every warp spends in each phase of a slice, summed into A.trace
+  __shared__ unsigned long long s_ph[4][kTraceSlots];
+  if (lane < kTraceSlots) s_ph[warp][lane] = 0ull;
+  unsigned long long ph_t = 0;
+#define VB2_PH_START() do { if (lane == 0) ph_t = (unsigned long long)clock64(); } while (0)
+#define VB2_PH(k) do { if (lane == 0) { const unsigned long long n_ = (unsigned long long)clock64(); s_ph[warp][k] += n_ - ph_t; ph_t = n_; } } while (0)
+#define VB2_PH_COUNT(k) do { if (lane == 0) s_ph[warp][k] += 1ull; } while (0)
+#else
+#define VB2_PH_START() do { } while (0)
+#define VB2_PH(k) do { } while (0)
+#define VB2_PH_COUNT(k) do { } while (0)
+#endif
   __syncthreads();  // the only CTA-wide barrier
 
   const uint32_t stage_bytes = A.stage_bytes;
@@ -894,9 +908,11 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
   Quad Q;
   double acc[kNumPairs], ldiag = 0.;
   SliceHeader H{0, 0, 0, 0, 0, 0};
+  VB2_PH_START();
   while (in_flight) {
     const uint32_t d_task = W.st_task[cb];
     if (d_task) {  // a new task: close the previous one, load this evaluation's parameters
+      VB2_PH_COUNT(9);
       if (have_task) store_partial(c_job, c_bin, task_value());
       have_task = true;
       const uint32_t t = d_task & 0x7FFFFFFFu;
@@ -916,15 +932,33 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
         Q.C2[p] = c1 * c1;
       }
       if (!Layout::kFixed) Y = Layout((ARGS || !A.samples) ? A.sample : A.samples[c_job]);
+      VB2_PH(1);
     }
+    VB2_PH(0);
     mbar_wait(&s_bar[warp][cb], (parity >> cb) & 1u);
     parity ^= 1u << cb;
+    VB2_PH(2);
+    VB2_PH_COUNT(8);
     const uint8_t *buf = mybuf + (size_t)cb * stage_bytes;
     bool last = true;
     if (!CHUNKED) {
       slice_begin(buf, Y, J, lane, H, acc, ldiag);
+#ifdef VB2_PHASE_CLOCK
+      if (__double2hiint(acc[0] + ldiag) == 0x7FF12345) H.wr = 0;  // (keeps the set-up ahead of the stamp)
+      VB2_PH(3);
+      {
+        const uint32_t *col = reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane;
+        eat_rows<false>(col, H.fr, H.wr - H.fr, H.tails & 0xFu, lin, Q, acc);
+        if (__double2hiint(acc[0]) == 0x7FF12345) H.wa = 0;
+        VB2_PH(4);
+        eat_rows<true>(col + (size_t)H.wr * 32, H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, lin, Q, acc);
+        if (__double2hiint(acc[5]) == 0x7FF12345) H.n_valid = 0;
+        VB2_PH(5);
+      }
+#else
       eat_runs<false>(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, H.fr, H.wr - H.fr, H.tails & 0xFu,
                       H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, lin, Q, acc);
+#endif
     } else {
       const uint32_t d_c = W.st_c[cb], d_chunk_rows = W.st_chunk_rows[cb];
       if (d_c == 0) slice_begin(buf, Y, J, lane, H, acc, ldiag);
@@ -939,12 +973,18 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
     }
     // the buffer just read is free: refill it (every lane passes the __syncwarp inside produce() only after
     // its last read of the buffer)
+    VB2_PH(6);
     --in_flight;
     if (produce(cb)) ++in_flight;
     cb ^= 1u;
+    VB2_PH(7);
   }
   if (have_task) store_partial(c_job, c_bin, task_value());
   if (lane == 0 && fetched == 0xFFFFFFFFu) __threadfence();  // (retires the atomic still in flight)
+#ifdef VB2_PHASE_CLOCK
+  __syncwarp();
+  if (A.trace && lane < kTraceSlots) atomicAdd(A.trace + lane, s_ph[warp][lane]);
+#endif
 }
 
 // Behind llk_stream_kernel on the same stream: evaluation j's partials -> d_out[j] / mailbox slot j, in the fixed
@@ -1597,15 +1637,17 @@ cudaError_t raise_smem_limits(int bytes) {
   return e;
 }
 int init_device_tables(vb2_llk_ctx *ctx, int device, int spec, bool chunked) {
-  static bool done[64][4] = {};  // [device][0: runtime layout, 1: NumPC 2, 2: NumPC 4, 3: chunked]
+  static std::atomic<bool> done[64][4];  // [device][0: runtime layout, 1: NumPC 2, 2: NumPC 4, 3: chunked]
   const int which = chunked ? 3 : (spec == 2 ? 1 : spec == 4 ? 2 : 0);
-  if (device >= 0 && device < 64 && done[device][which]) return VB2_OK;
+  // (concurrent first calls -- the CLI's warm-up threads, one create per cohort worker -- may both set the
+  // attributes: the calls are idempotent, the flag only saves the repeat)
+  if (device >= 0 && device < 64 && done[device][which].load(std::memory_order_acquire)) return VB2_OK;
   const int smem_max = 200 * 1024;
   if (chunked) VB2_CUDA(ctx, (raise_smem_limits<0, true>(smem_max)));
   else if (spec == 2) VB2_CUDA(ctx, (raise_smem_limits<2, false>(smem_max)));
   else if (spec == 4) VB2_CUDA(ctx, (raise_smem_limits<4, false>(smem_max)));
   else VB2_CUDA(ctx, (raise_smem_limits<0, false>(smem_max)));
-  if (device >= 0 && device < 64) done[device][which] = true;
+  if (device >= 0 && device < 64) done[device][which].store(true, std::memory_order_release);
   return VB2_OK;
 }
 
@@ -1951,9 +1993,7 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
   *nothing_to_do = !any;
   lead->many_n = 0;
   if (!any) return VB2_OK;
-  for (int j = 0; j < n; ++j)
-    if (ctxs[j]->S.grid_x == 0)
-      return set_err(lead, VB2_ERR_INVALID, "vb2_llk_eval_many: a sample has no usable marker");
+  // (a sample without a usable marker has no active bin: llk_reduce_kernel returns the reference's empty sum, 0.0)
   VB2_CUDA(lead, cudaMemcpyAsync(lead->d_many, lead->h_many, sizeof(SampleDev) * n, cudaMemcpyHostToDevice, lead->stream));
   VB2_CUDA(lead, cudaMemcpyAsync(lead->d_slots, lead->h_slots, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, lead->stream));
   VB2_CUDA(lead, cudaMemcpyAsync(lead->d_jobs, lead->h_jobs, sizeof(JobParams) * n, cudaMemcpyHostToDevice, lead->stream));
@@ -1972,6 +2012,13 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
   LaunchArgs A;
   memset(&A, 0, sizeof(A));
   A.trace = nullptr;
+#ifdef VB2_PHASE_CLOCK
+  if (!lead->d_trace) {
+    VB2_CUDA(lead, cudaMalloc(&lead->d_trace, sizeof(unsigned long long) * kTraceSlots * 1024));
+    VB2_CUDA(lead, cudaMemset(lead->d_trace, 0, sizeof(unsigned long long) * kTraceSlots * 1024));
+  }
+  A.trace = lead->d_trace;
+#endif
   fill_phred(&A);
   A.samples = lead->d_many;
   A.slots = lead->d_slots;
@@ -2059,6 +2106,19 @@ int vb2_llk_time_device_many(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup_lau
   if (rc == VB2_OK) cudaEventElapsedTime(elapsed_ms, e0, e1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+#ifdef VB2_PHASE_CLOCK
+  if (rc == VB2_OK && lead->d_trace) {
+    unsigned long long ph[kTraceSlots];
+    cudaMemcpy(ph, lead->d_trace, sizeof(ph), cudaMemcpyDeviceToHost);
+    static const char *name[kTraceSlots] = {"loop head", "task switch", "mbar wait", "slice_begin", "ref run", "alt run",
+                                            "finish", "produce", "#slices", "#tasks", "", "", "", "", "", ""};
+    const double n_slices = (double)std::max(1ull, ph[8]);
+    fprintf(stderr, "phase clock (cycles per slice per warp; %.0f slices, %.0f tasks):", n_slices, (double)ph[9]);
+    for (int k = 0; k < 8; ++k) fprintf(stderr, " %s %.0f;", name[k], (double)ph[k] / n_slices);
+    fprintf(stderr, "\n");
+    cudaMemset(lead->d_trace, 0, sizeof(ph));
+  }
+#endif
   return rc;
 }
 
