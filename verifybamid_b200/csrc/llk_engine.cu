@@ -87,11 +87,25 @@ struct __align__(16) Slot {
   unsigned long long seq;
 };
 
+// One job of a many-evaluations launch, as llk_stream_kernel prefetches it: everything a warp needs to know to run
+// a task of this job sits in ONE 16-byte aligned record that a single TMA bulk copy brings into shared memory a
+// whole task ahead of its use -- no dependent chain of global loads (sample table -> round table -> parameters)
+// at a task switch.  Round tables longer than kMaxArgRounds continue in HBM (S.rounds).
+constexpr int kRecRounds = 16;
+struct __align__(16) TaskRec {
+  SampleDev S;                      // the job's sample
+  uint32_t pslot, pad_;             // its partial-sum slot inside the sample
+  vb2::Round rounds[kRecRounds];    // S.rounds[0 .. min(n_rounds, kRecRounds))
+  JobParams J;                      // the job's parameters
+};
+static_assert(sizeof(TaskRec) % 16 == 0, "TaskRec is copied with cp.async.bulk");
+
 struct LaunchArgs {
   SampleDev sample;           // ARGS kernels: the sample itself
-  const SampleDev *samples;   // generic kernel: job j evaluates samples[j]
-  const uint32_t *slots;      // generic kernel: partial/ticket slot of job j inside its sample
-  const JobParams *jobs_dev;  // generic kernel: parameters in HBM
+  const SampleDev *samples;   // generic llk_kernel: job j evaluates samples[j]
+  const uint32_t *slots;      // generic llk_kernel: partial/ticket slot of job j inside its sample
+  const JobParams *jobs_dev;  // generic llk_kernel: parameters in HBM
+  const TaskRec *recs;        // llk_stream_kernel / llk_reduce_kernel: job j = recs[j]
   double *d_out;              // [n_jobs] device results (device-side reduction; may be nullptr)
   Slot *mbox;                 // device view of the host mailbox (may be nullptr)
   unsigned long long seq;
@@ -108,6 +122,7 @@ struct LaunchArgs {
   JobParams jobs[kMaxArgJobs];       // ARGS kernels: parameters of job blockIdx.y
 };
 static_assert(sizeof(LaunchArgs) <= 4000, "kernel arguments must stay below 4 KiB");
+static_assert(kRecRounds == kMaxArgRounds, "one round-table size");
 
 // 10^(-q/10), q = 0..93, travels in the kernel arguments (LaunchArgs::phred) exactly as the host computes it
 // (ContaminationEstimator.h:65-74); entries 94..255 of the shared-memory copy are 1.0 (a 0xFF filler byte indexes 255).
@@ -139,6 +154,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "bra LAB_WAIT;\n"
       "DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one non-blocking look at an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// expect-tx + bulk copy as ONE predicated pair (no branch: the caller's basic block stays whole)
+__device__ __forceinline__ void bulk_g2s_if(bool pred, void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "setp.ne.u32 P1, %4, 0;\n"
+      "@P1 mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n"
+      "@P1 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+      "}\n" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "r"((uint32_t)pred) : "memory");
 }
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -707,37 +743,64 @@ llk_kernel(const __grid_constant__ LaunchArgs A) {
 // llk_reduce_kernel, launched behind it, adds every evaluation's partials in the fixed order llk_kernel and
 // the host use.  Everything the pipeline's issue side knows lives in shared memory (WarpCtl), so the read
 // loops keep the registers.
+constexpr int kRecRing = 4;  // task records resident per warp: the issue cursor's, <= 2 with unconsumed stages, 1 landing
 struct WarpCtl {
-  const uint8_t *blob;     // the issue cursor's task: sample image, round table, sizes
-  const vb2::Round *tab;
-  uint32_t next_task, task, bin, n_rounds, chunk_rows, off_words;
+  uint32_t next_task, n_rounds;
   uint32_t rbase;          // item table: entry i = round rbase + i
   uint32_t off16, rows, c, nch;  // CHUNKED: the blob being issued, chunk c of nch
   uint32_t done;           // queue exhausted
+  uint32_t next_rec;       // ring slot of the next task's record (landing or landed)
+  uint32_t rec_parity;     // bit s: mbarrier phase to wait for on ring slot s
   uint32_t it_off16[32], it_rows[32];
-  // what sits (or is landing) in each of the warp's two buffers: 0x80000000 | task for the first stage of a task,
-  // else 0; CHUNKED: also which chunk of how many
-  uint32_t st_task[2], st_c[2], st_nch[2], st_chunk_rows[2];
+  uint32_t st_c[2], st_nch[2], st_chunk_rows[2];  // CHUNKED: which chunk of how many sits in each buffer
 };
+// What sits (or is landing) in one of a warp's two stage buffers -- a register, the same in every lane:
+//   bit 31 = first stage of its task, bits 28..29 = ring slot of the task's record, bits 0..27 = the task's bin.
+constexpr uint32_t kTagFirst = 0x80000000u;
+__device__ __forceinline__ uint32_t tag_rec(uint32_t tag) { return (tag >> 28) & 3u; }
+__device__ __forceinline__ uint32_t tag_bin(uint32_t tag) { return tag & 0x0FFFFFFFu; }
 
 #ifndef VB2_STREAM_CTAS_PER_SM
 #define VB2_STREAM_CTAS_PER_SM 4
 #endif
-template <bool ARGS, int NPC, bool CHUNKED>
+#ifndef VB2_STREAM_PIPELINED
+#define VB2_STREAM_PIPELINED 1   // 0: the plain consume loop for every shape (A/B builds)
+#endif
+template <int NPC, bool CHUNKED>
 __global__ void __launch_bounds__(128, VB2_STREAM_CTAS_PER_SM)
 llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
   using Layout = typename std::conditional<NPC != 0, FixedLayout<NPC>, RuntimeLayout>::type;
   extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][2][stage_bytes]
-  __shared__ __align__(16) JobParams s_job[4];       // the evaluation each warp is working on
-  __shared__ __align__(8) uint64_t s_bar[4][2];
+  __shared__ __align__(16) TaskRec s_rec[4][kRecRing];  // per warp: a ring of task records (TMA destinations)
+  __shared__ __align__(8) uint64_t s_bar[4][2], s_rbar[4][kRecRing];
   __shared__ __align__(16) WarpCtl s_ctl[4];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_bins_max = A.n_bins_max, n_tasks = A.n_jobs * n_bins_max;
+  WarpCtl &W = s_ctl[warp];
+  // the record of task t -> ring slot `slot` (lane 0)
+  auto prefetch = [&](uint32_t t, uint32_t slot) {
+    mbar_arrive_expect_tx(&s_rbar[warp][slot], (uint32_t)sizeof(TaskRec));
+    bulk_g2s(&s_rec[warp][slot], A.recs + t / n_bins_max, (uint32_t)sizeof(TaskRec), &s_rbar[warp][slot]);
+  };
+  // ---- task queue: the first task is the warp's own index, the rest come from an atomic counter whose next
+  // value is fetched one task ahead; the RECORD of the next task is fetched as soon as its number is known
+  uint32_t fetched = 0;  // (lane 0) the task after W.next_task; the atomic is in flight while a task runs
+  auto fetch = [&]() {
+    if (lane == 0) fetched = atomicAdd(A.queue, 1u) + gridDim.x * 4u;
+  };
   if (lane == 0) {
     mbar_init(&s_bar[warp][0], 1);
     mbar_init(&s_bar[warp][1], 1);
+    for (int i = 0; i < kRecRing; ++i) mbar_init(&s_rbar[warp][i], 1);
     mbar_fence_init();
+    const uint32_t t0 = blockIdx.x * 4u + (uint32_t)warp;
+    if (t0 < n_tasks) prefetch(t0, 0);
+    W.next_task = t0;
+    W.n_rounds = 0; W.rbase = 0; W.c = 0; W.nch = 0; W.done = 0;
+    W.next_rec = 0; W.rec_parity = 0;
   }
+  fetch();
   for (int i = threadIdx.x; i < 256; i += 128) s_e[i] = i < kPhredArgs ? A.phred[i] : 1.0;
 #ifdef VB2_PHASE_CLOCK
   // diagnostics build (tools/gpu_phase.sh): cycles every warp spends in each phase of a slice, summed into A.trace
@@ -756,42 +819,27 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
 
   const uint32_t stage_bytes = A.stage_bytes;
   uint8_t *mybuf = s_buf + (size_t)warp * 2u * stage_bytes;
-  WarpCtl &W = s_ctl[warp];
 
-  // ---- task queue ------------------------------------------------------------------------------
-  uint32_t fetched = 0;  // (lane 0) the task after W.next_task; the atomic is in flight while a task runs
-  auto fetch = [&]() {
-    if (lane == 0) fetched = atomicAdd(A.queue, 1u) + gridDim.x * 4u;
-  };
-  if (lane == 0) {
-    W.next_task = blockIdx.x * 4u + (uint32_t)warp;
-    W.n_rounds = 0; W.rbase = 0; W.c = 0; W.nch = 0; W.done = 0;
-  }
-  fetch();
-  __syncwarp();
-  const uint32_t n_bins_max = A.n_bins_max, n_tasks = A.n_jobs * n_bins_max;
-
-  // v = this lane's share of task (job, bin): xor-shuffle tree over the lanes -> partials[job][bin]
-  auto store_partial = [&](uint32_t job, uint32_t bin, double v) {
+  // v = this lane's share of a task (record R, bin): xor-shuffle tree over the lanes -> partials[pslot][bin]
+  auto store_partial = [&](const TaskRec &R, uint32_t bin, double v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    if (lane == 0) {
-      const SampleDev &S = (ARGS || !A.samples) ? A.sample : A.samples[job];
-      const uint32_t pslot = A.slots ? A.slots[job] : job;
-      S.partials[(size_t)pslot * (4u * S.grid_x) + bin] = v;
-    }
+    if (lane == 0) R.S.partials[(size_t)R.pslot * (4u * R.S.grid_x) + bin] = v;
   };
 
-  // ---- issue side: put the next stage (blob, or chunk of a blob) of this warp's task sequence into buffer b.
-  // The two values every slice needs -- which items of the table are still to issue, and whether the task has
-  // issued anything yet -- live in registers; the rest of the cursor lives in shared memory (WarpCtl) and is
-  // touched when a task or a table runs out.  Returns false when the queue is exhausted.
-  uint32_t mask = 0, first = 0;
-  auto next_table = [&]() -> bool {  // mask == 0: the next 32 rounds of the task, or the next task; false = no more work
+  // ---- issue side ----------------------------------------------------------------------------------
+  // Everything a stage needs lives in registers that hold the same value in every lane: the items of the current
+  // table still to issue (mask), the issue cursor's task (its bin and record slot, whether it has issued anything
+  // yet, the base of its sample's image) and the tags of the two stage buffers.  Shared memory (WarpCtl) holds the
+  // item table and what is touched only when a task or a table runs out.
+  uint32_t mask = 0, first = 0, i_bin = 0, i_rec = 0, tag0 = 0, tag1 = 0;
+  const uint8_t *i_blob = nullptr;
+  // mask == 0: the next 32 rounds of the task, or the next task; false = no more work
+  auto next_table = [&]() -> bool {
     for (;;) {
-      uint32_t rbase = W.rbase + 32u, n_rounds = W.n_rounds, bin = W.bin;
+      uint32_t rbase = W.rbase + 32u, n_rounds = W.n_rounds;
       if (rbase >= n_rounds) {  // the task's table is exhausted: take the next task
-        if (first) store_partial(W.task / n_bins_max, bin, 0.0);  // (no blob at all: an empty bin still reports in)
+        if (first) store_partial(s_rec[warp][i_rec], i_bin, 0.0);  // (no blob at all: an empty bin still reports in)
         first = 0;
         const uint32_t t = W.next_task;
         if (t >= n_tasks) {
@@ -800,26 +848,28 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
           __syncwarp();
           return false;
         }
+        // the record of task t was requested when the previous task was taken (or at kernel entry)
+        const uint32_t rec = W.next_rec, rpar = W.rec_parity;
+        mbar_wait(&s_rbar[warp][rec], (rpar >> rec) & 1u);
         const uint32_t nt = __shfl_sync(0xFFFFFFFFu, fetched, 0);
         fetch();
-        const uint32_t job = t / n_bins_max;
-        bin = t - job * n_bins_max;
-        const SampleDev &S = (ARGS || !A.samples) ? A.sample : A.samples[job];
-        const bool active = bin < 4u * S.grid_x;  // eval_many: a sample may have fewer bins than the launch
-        n_rounds = active ? S.n_rounds : 0u;
+        // the next record lands in a ring slot that is neither this task's nor that of a stage not yet consumed
+        const uint32_t busy = (1u << rec) | (1u << tag_rec(tag0)) | (1u << tag_rec(tag1));
+        const uint32_t nrec = (uint32_t)__ffs((int)(~busy & ((1u << kRecRing) - 1u))) - 1u;
+        const TaskRec &R = s_rec[warp][rec];
+        i_rec = rec;
+        i_bin = t % n_bins_max;
+        i_blob = R.S.blob;
+        const bool active = i_bin < 4u * R.S.grid_x;  // eval_many: a sample may have fewer bins than the launch
+        n_rounds = active ? R.S.n_rounds : 0u;
         __syncwarp();
         if (lane == 0) {
+          if (nt < n_tasks) prefetch(nt, nrec);
           W.next_task = nt;
-          W.task = t;
-          W.bin = bin;
           W.n_rounds = n_rounds;
           W.rbase = 0u - 32u;
-          if (active) {
-            W.blob = S.blob;
-            W.tab = ARGS ? A.rounds : S.rounds;
-            W.chunk_rows = S.chunk_rows;
-            W.off_words = S.off_words;
-          }
+          W.next_rec = nrec;
+          W.rec_parity = rpar ^ (1u << rec);
         }
         __syncwarp();
         if (!active) continue;
@@ -830,57 +880,79 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
       const uint32_t r = rbase + (uint32_t)lane;
       bool mine = false;
       if (r < n_rounds) {
-        const vb2::Round R = W.tab[r];
-        if (bin - R.first_bin < R.count) {  // unsigned: also false when bin < first_bin
+        const TaskRec &R = s_rec[warp][i_rec];
+        const vb2::Round Rd = r < (uint32_t)kRecRounds ? R.rounds[r] : R.S.rounds[r];
+        if (i_bin - Rd.first_bin < Rd.count) {  // unsigned: also false when bin < first_bin
           mine = true;
-          W.it_off16[lane] = (uint32_t)((R.base + (uint64_t)(bin - R.first_bin) * R.stride) >> 4);
-          W.it_rows[lane] = R.rows;
+          W.it_off16[lane] = (uint32_t)((Rd.base + (uint64_t)(i_bin - Rd.first_bin) * Rd.stride) >> 4);
+          W.it_rows[lane] = Rd.rows;
         }
       }
+      __syncwarp();
       if (lane == 0) W.rbase = rbase;
-      mask = __ballot_sync(0xFFFFFFFFu, mine);
+      mask = __ballot_sync(0xFFFFFFFFu, mine);  // (also orders the table's stores before every lane's reads)
       if (mask) return true;
     }
   };
-  auto produce = [&](uint32_t b) -> bool {
-    if (CHUNKED && W.c + 1 < W.nch) {  // the next chunk of the blob being issued
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t c = W.c + 1, chunk_rows = W.chunk_rows, rows = W.rows;
-        const uint32_t off = W.off_words + c * chunk_rows * 128u, n = rows - c * chunk_rows;
-        const uint32_t bytes = (n < chunk_rows ? n : chunk_rows) * 128u;
-        mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
-        bulk_g2s(mybuf + (size_t)b * stage_bytes, W.blob + ((uint64_t)W.off16 << 4) + off, bytes, &s_bar[warp][b]);
-        W.c = c;
-        W.st_task[b] = 0u; W.st_c[b] = c; W.st_nch[b] = W.nch; W.st_chunk_rows[b] = chunk_rows;
-      }
-      __syncwarp();
-      return true;
-    }
-    if (mask == 0) {
-      if (W.done || !next_table()) return false;
-    }
+  // make sure there is an item to issue; false when the queue is exhausted (the rare path, kept out of line)
+  auto prepare = [&]() -> bool {
+    if (mask != 0) return true;
+    return !W.done && next_table();
+  };
+  // Issue the next item (mask != 0) into buffer b; returns the buffer's tag.  Branch-free: every lane computes the
+  // address, lane 0's copy is predicated.  The caller has made sure that every lane is done reading buffer b.
+  auto issue_item = [&](uint32_t b) -> uint32_t {
     const int i = __ffs((int)mask) - 1;
     mask &= mask - 1u;
-    __syncwarp();
-    if (lane == 0) {
-      const uint32_t off16 = W.it_off16[i], rows = W.it_rows[i];
-      uint32_t off_words = W.off_words;
-      if constexpr (Layout::kFixed) off_words = Layout::off_words;
-      uint32_t bytes = off_words + rows * 128u;  // chunk 0 = header + panel + diag + the first chunk_rows word rows
-      if (CHUNKED) {
-        const uint32_t chunk_rows = W.chunk_rows;
-        const uint32_t nch = rows <= chunk_rows ? 1u : (rows + chunk_rows - 1) / chunk_rows;
-        if (nch > 1) bytes = off_words + chunk_rows * 128u;
+    const uint32_t off16 = W.it_off16[i], rows = W.it_rows[i];
+    uint32_t off_words;
+    if constexpr (Layout::kFixed) off_words = Layout::off_words;
+    else off_words = s_rec[warp][i_rec].S.off_words;
+    uint32_t bytes = off_words + rows * 128u;  // chunk 0 = header + panel + diag + the first chunk_rows word rows
+    if (CHUNKED) {
+      const uint32_t chunk_rows = s_rec[warp][i_rec].S.chunk_rows;
+      const uint32_t nch = rows <= chunk_rows ? 1u : (rows + chunk_rows - 1) / chunk_rows;
+      if (nch > 1) bytes = off_words + chunk_rows * 128u;
+      __syncwarp();
+      if (lane == 0) {
         W.off16 = off16; W.rows = rows; W.c = 0; W.nch = nch;
         W.st_c[b] = 0; W.st_nch[b] = nch; W.st_chunk_rows[b] = chunk_rows;
       }
-      mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
-      bulk_g2s(mybuf + (size_t)b * stage_bytes, W.blob + ((uint64_t)off16 << 4), bytes, &s_bar[warp][b]);
-      W.st_task[b] = first ? (0x80000000u | W.task) : 0u;
+      __syncwarp();
     }
+    bulk_g2s_if(lane == 0, mybuf + (size_t)b * stage_bytes, i_blob + ((uint64_t)off16 << 4), bytes, &s_bar[warp][b]);
+    const uint32_t tag = (first ? kTagFirst : 0u) | (i_rec << 28) | i_bin;
     first = 0;
+    return tag;
+  };
+  // CHUNKED: the next chunk of the blob being issued, if any
+  auto issue_chunk = [&](uint32_t b, uint32_t &tag) -> bool {
+    if (!(W.c + 1 < W.nch)) return false;
     __syncwarp();
+    if (lane == 0) {
+      const SampleDev &S = s_rec[warp][i_rec].S;
+      const uint32_t c = W.c + 1, chunk_rows = S.chunk_rows, rows = W.rows;
+      const uint32_t off = S.off_words + c * chunk_rows * 128u, n = rows - c * chunk_rows;
+      const uint32_t bytes = (n < chunk_rows ? n : chunk_rows) * 128u;
+      mbar_arrive_expect_tx(&s_bar[warp][b], bytes);
+      bulk_g2s(mybuf + (size_t)b * stage_bytes, i_blob + ((uint64_t)W.off16 << 4) + off, bytes, &s_bar[warp][b]);
+      W.c = c;
+      W.st_c[b] = c; W.st_nch[b] = W.nch; W.st_chunk_rows[b] = chunk_rows;
+    }
+    __syncwarp();
+    tag = (i_rec << 28) | i_bin;
+    return true;
+  };
+  // the next stage of this warp's task sequence into buffer b (all lanes are done with it); false: nothing left
+  auto produce = [&](uint32_t b) -> bool {
+    uint32_t tag = 0;
+    if (!(CHUNKED && issue_chunk(b, tag))) {
+      if (!prepare()) return false;
+      __syncwarp();
+      tag = issue_item(b);
+    }
+    if (b) tag1 = tag;
+    else tag0 = tag;
     return true;
   };
 
@@ -900,86 +972,136 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
     prod = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(prod));
   };
   auto task_value = [&]() { return vsum + fma((double)esum, kLn2, log(prod)); };
-  bool have_task = false;
-  uint32_t c_job = 0, c_bin = 0;
-  const JobParams &J = s_job[warp];
-  const double *lin = J.c0;  // c0[6] then c1[6] (contiguous in JobParams)
-  Layout Y(A.sample);
+  uint32_t c_bin = 0;
+  const TaskRec *c_rec = &s_rec[warp][0];  // the record of the task being consumed
   Quad Q;
+  auto load_quad = [&]() {
+#pragma unroll
+    for (int p = 0; p < kNumPairs; ++p) {
+      const double c0 = c_rec->J.c0[p], c1 = c_rec->J.c1[p];
+      Q.C0[p] = c0 * c0;
+      Q.C1[p] = c0 * c1;
+      Q.C2[p] = c1 * c1;
+    }
+  };
   double acc[kNumPairs], ldiag = 0.;
   SliceHeader H{0, 0, 0, 0, 0, 0};
   VB2_PH_START();
-  while (in_flight) {
-    const uint32_t d_task = W.st_task[cb];
-    if (d_task) {  // a new task: close the previous one, load this evaluation's parameters
+
+  if constexpr (Layout::kFixed && !CHUNKED && VB2_STREAM_PIPELINED != 0) {
+    // ---- the common shape, software-pipelined: while the warp still holds the products of slice n it (a) takes
+    // the marginal of slice n, (b) sets up slice n+1 (header, allele frequencies, priors, starting weights) from
+    // the other buffer and (c) issues slice n+2 into the buffer slice n has just left -- three independent
+    // dependency chains in ONE basic block, so they overlap instead of queueing behind each other.
+    const Layout Y(A.sample);
+    if (in_flight) {
+      mbar_wait(&s_bar[warp][0], 0u);
+      parity = 1u;
+      c_rec = &s_rec[warp][tag_rec(tag0)];
+      c_bin = tag_bin(tag0);
+      load_quad();
+      slice_begin(mybuf, Y, c_rec->J, lane, H, acc, ldiag);
       VB2_PH_COUNT(9);
-      if (have_task) store_partial(c_job, c_bin, task_value());
-      have_task = true;
-      const uint32_t t = d_task & 0x7FFFFFFFu;
-      c_job = t / n_bins_max;
-      c_bin = t - c_job * n_bins_max;
-      vsum = 0.0; prod = 1.0; esum = 0;
-      const double *src = reinterpret_cast<const double *>(ARGS ? &A.jobs[c_job] : &A.jobs_dev[c_job]);
-      double *dst = reinterpret_cast<double *>(&s_job[warp]);
-      __syncwarp();
-      for (int i = lane; i < (int)(sizeof(JobParams) / sizeof(double)); i += 32) dst[i] = src[i];
-      __syncwarp();
-#pragma unroll
-      for (int p = 0; p < kNumPairs; ++p) {
-        const double c0 = J.c0[p], c1 = J.c1[p];
-        Q.C0[p] = c0 * c0;
-        Q.C1[p] = c0 * c1;
-        Q.C2[p] = c1 * c1;
-      }
-      if (!Layout::kFixed) Y = Layout((ARGS || !A.samples) ? A.sample : A.samples[c_job]);
-      VB2_PH(1);
-    }
-    VB2_PH(0);
-    mbar_wait(&s_bar[warp][cb], (parity >> cb) & 1u);
-    parity ^= 1u << cb;
-    VB2_PH(2);
-    VB2_PH_COUNT(8);
-    const uint8_t *buf = mybuf + (size_t)cb * stage_bytes;
-    bool last = true;
-    if (!CHUNKED) {
-      slice_begin(buf, Y, J, lane, H, acc, ldiag);
-#ifdef VB2_PHASE_CLOCK
-      if (__double2hiint(acc[0] + ldiag) == 0x7FF12345) H.wr = 0;  // (keeps the set-up ahead of the stamp)
-      VB2_PH(3);
-      {
-        const uint32_t *col = reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane;
-        eat_rows<false>(col, H.fr, H.wr - H.fr, H.tails & 0xFu, lin, Q, acc);
-        if (__double2hiint(acc[0]) == 0x7FF12345) H.wa = 0;
+      for (;;) {
+        VB2_PH(0);
+        VB2_PH_COUNT(8);
+        const uint8_t *buf = mybuf + (size_t)cb * stage_bytes;
+        eat_runs<false>(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, H.fr, H.wr - H.fr, H.tails & 0xFu,
+                        H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, c_rec->J.c0, Q, acc);
+        __syncwarp();  // every lane is done with buffer cb
         VB2_PH(4);
-        eat_rows<true>(col + (size_t)H.wr * 32, H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, lin, Q, acc);
-        if (__double2hiint(acc[5]) == 0x7FF12345) H.n_valid = 0;
-        VB2_PH(5);
+        const bool more = in_flight > 1;  // slice n+1 is in (or on its way into) the other buffer
+        const bool can = prepare();       // there is a slice n+2 to issue
+        const uint32_t ob = cb ^ 1u, tagN = cb ? tag0 : tag1;
+        if (more && !mbar_test(&s_bar[warp][ob], (parity >> ob) & 1u)) mbar_wait(&s_bar[warp][ob], (parity >> ob) & 1u);
+        VB2_PH(2);
+        // h:307-311, as in llk_kernel
+        const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));
+        const double Lv = ((uint32_t)lane < H.n_valid && L > 0) ? L : 1.0;
+        const TaskRec *recN = (tagN & kTagFirst) ? &s_rec[warp][tag_rec(tagN)] : c_rec;
+        if (more && can) {  // steady state
+          slice_begin(mybuf + (size_t)ob * stage_bytes, Y, recN->J, lane, H, acc, ldiag);
+          const uint32_t t = issue_item(cb);
+          if (cb) tag1 = t;
+          else tag0 = t;
+          combine(Lv);
+        } else {            // the warp's last slices
+          combine(Lv);
+          if (more) slice_begin(mybuf + (size_t)ob * stage_bytes, Y, recN->J, lane, H, acc, ldiag);
+          if (can) {
+            const uint32_t t = issue_item(cb);
+            if (cb) tag1 = t;
+            else tag0 = t;
+          }
+        }
+        VB2_PH(3);
+        in_flight += (can ? 1u : 0u) - 1u;
+        if (!more) break;  // (then nothing was issued either: the queue ran dry before the pipeline did)
+        parity ^= 1u << ob;
+        if (tagN & kTagFirst) {  // slice n+1 opens a new task: close this one, switch to the new parameters
+          VB2_PH_COUNT(9);
+          store_partial(*c_rec, c_bin, task_value());
+          c_rec = recN;
+          c_bin = tag_bin(tagN);
+          vsum = 0.0; prod = 1.0; esum = 0;
+          load_quad();
+          VB2_PH(1);
+        }
+        cb = ob;
       }
-#else
-      eat_runs<false>(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, H.fr, H.wr - H.fr, H.tails & 0xFu,
-                      H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, lin, Q, acc);
-#endif
-    } else {
-      const uint32_t d_c = W.st_c[cb], d_chunk_rows = W.st_chunk_rows[cb];
-      if (d_c == 0) slice_begin(buf, Y, J, lane, H, acc, ldiag);
-      const uint32_t t_lo = d_c * d_chunk_rows;
-      slice_rows<false>(reinterpret_cast<const uint32_t *>(buf + (d_c == 0 ? Y.off_words : 0u)) + lane, t_lo,
-                        t_lo + d_chunk_rows, H, lin, Q, acc);
-      last = d_c + 1 == W.st_nch[cb];
+      store_partial(*c_rec, c_bin, task_value());
     }
-    if (last) {  // h:307-311, as in llk_kernel
-      const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));
-      combine(((uint32_t)lane < H.n_valid && L > 0) ? L : 1.0);
+  } else {
+    Layout Y(A.sample);
+    bool have_task = false;
+    while (in_flight) {
+      const uint32_t tag = cb ? tag1 : tag0;
+      if (tag & kTagFirst) {  // a new task: close the previous one, switch to this evaluation's parameters (on chip)
+        VB2_PH_COUNT(9);
+        if (have_task) store_partial(*c_rec, c_bin, task_value());
+        have_task = true;
+        c_rec = &s_rec[warp][tag_rec(tag)];
+        c_bin = tag_bin(tag);
+        vsum = 0.0; prod = 1.0; esum = 0;
+        load_quad();
+        if (!Layout::kFixed) Y = Layout(c_rec->S);
+        VB2_PH(1);
+      }
+      const JobParams &J = c_rec->J;
+      const double *lin = J.c0;  // c0[6] then c1[6] (contiguous in JobParams)
+      VB2_PH(0);
+      mbar_wait(&s_bar[warp][cb], (parity >> cb) & 1u);
+      parity ^= 1u << cb;
+      VB2_PH(2);
+      VB2_PH_COUNT(8);
+      const uint8_t *buf = mybuf + (size_t)cb * stage_bytes;
+      bool last = true;
+      if (!CHUNKED) {
+        slice_begin(buf, Y, J, lane, H, acc, ldiag);
+        eat_runs<false>(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, H.fr, H.wr - H.fr, H.tails & 0xFu,
+                        H.fa, H.wa - H.fa, (H.tails >> 4) & 0xFu, lin, Q, acc);
+      } else {
+        const uint32_t d_c = W.st_c[cb], d_chunk_rows = W.st_chunk_rows[cb];
+        if (d_c == 0) slice_begin(buf, Y, J, lane, H, acc, ldiag);
+        const uint32_t t_lo = d_c * d_chunk_rows;
+        slice_rows<false>(reinterpret_cast<const uint32_t *>(buf + (d_c == 0 ? Y.off_words : 0u)) + lane, t_lo,
+                          t_lo + d_chunk_rows, H, lin, Q, acc);
+        last = d_c + 1 == W.st_nch[cb];
+      }
+      if (last) {  // h:307-311, as in llk_kernel
+        const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));
+        combine(((uint32_t)lane < H.n_valid && L > 0) ? L : 1.0);
+      }
+      // the buffer just read is free: refill it
+      VB2_PH(6);
+      __syncwarp();  // every lane is done with buffer cb
+      --in_flight;
+      if (produce(cb)) ++in_flight;
+      cb ^= 1u;
+      VB2_PH(7);
     }
-    // the buffer just read is free: refill it (every lane passes the __syncwarp inside produce() only after
-    // its last read of the buffer)
-    VB2_PH(6);
-    --in_flight;
-    if (produce(cb)) ++in_flight;
-    cb ^= 1u;
-    VB2_PH(7);
+    if (have_task) store_partial(*c_rec, c_bin, task_value());
   }
-  if (have_task) store_partial(c_job, c_bin, task_value());
   if (lane == 0 && fetched == 0xFFFFFFFFu) __threadfence();  // (retires the atomic still in flight)
 #ifdef VB2_PHASE_CLOCK
   __syncwarp();
@@ -991,8 +1113,8 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
 // order of llk_kernel (the four bins of a CTA, those lane-strided over the CTAs, then a tree); rewinds the queue.
 __global__ void __launch_bounds__(32, 1) llk_reduce_kernel(const __grid_constant__ LaunchArgs A) {
   const uint32_t job = blockIdx.x, lane = threadIdx.x;
-  const SampleDev &S = !A.samples ? A.sample : A.samples[job];
-  const uint32_t pslot = A.slots ? A.slots[job] : job;
+  const SampleDev &S = A.recs[job].S;
+  const uint32_t pslot = A.recs[job].pslot;
   const uint32_t grid_x = S.grid_x;
   const double *part = S.partials + (size_t)pslot * (4u * grid_x);
   double s = 0.0;
@@ -1224,13 +1346,28 @@ void launch_llk(dim3 grid, dim3 block, uint32_t smem, cudaStream_t stream, const
   else if (spec == 4) llk_kernel<ARGS, HOST_REDUCE, 4, false><<<grid, block, smem, stream>>>(A);
   else llk_kernel<ARGS, HOST_REDUCE, 0, false><<<grid, block, smem, stream>>>(A);
 }
-template <bool ARGS>
-void launch_stream(dim3 grid, uint32_t smem, cudaStream_t stream, const LaunchArgs &A, int spec, bool chunked) {
-  const dim3 block(128, 1, 1);
-  if (chunked) llk_stream_kernel<ARGS, 0, true><<<grid, block, smem, stream>>>(A);
-  else if (spec == 2) llk_stream_kernel<ARGS, 2, false><<<grid, block, smem, stream>>>(A);
-  else if (spec == 4) llk_stream_kernel<ARGS, 4, false><<<grid, block, smem, stream>>>(A);
-  else llk_stream_kernel<ARGS, 0, false><<<grid, block, smem, stream>>>(A);
+// CTAs of an llk_stream_kernel launch: as many as are co-resident (occupancy x SMs), never more than the tasks need.
+template <int NPC, bool CHUNKED>
+void launch_stream_as(uint32_t smem, cudaStream_t stream, const LaunchArgs &A, int sm_count) {
+  static thread_local uint32_t cached_smem = ~0u, cached_per_sm = 0;  // (per instantiation and host thread)
+  if (cached_smem != smem) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, llk_stream_kernel<NPC, CHUNKED>, 128, smem) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 1;
+    }
+    cached_per_sm = (uint32_t)per_sm;
+    cached_smem = smem;
+  }
+  const uint32_t n_tasks = A.n_jobs * A.n_bins_max;
+  const uint32_t grid = std::max(1u, std::min(cached_per_sm * (uint32_t)std::max(1, sm_count), (n_tasks + 3u) / 4u));
+  llk_stream_kernel<NPC, CHUNKED><<<dim3(grid, 1, 1), dim3(128, 1, 1), smem, stream>>>(A);
+}
+void launch_stream(uint32_t smem, cudaStream_t stream, const LaunchArgs &A, int spec, bool chunked, int sm_count) {
+  if (chunked) launch_stream_as<0, true>(smem, stream, A, sm_count);
+  else if (spec == 2) launch_stream_as<2, false>(smem, stream, A, sm_count);
+  else if (spec == 4) launch_stream_as<4, false>(smem, stream, A, sm_count);
+  else launch_stream_as<0, false>(smem, stream, A, sm_count);
   llk_reduce_kernel<<<dim3(A.n_jobs, 1, 1), dim3(32, 1, 1), 0, stream>>>(A);
 }
 
@@ -1278,8 +1415,7 @@ struct vb2_llk_ctx {
   uint32_t session_relaunches = 0;
   double clock_khz = 0.0, session_idle_ms = 200.0;
   // eval_many staging (owned by the leading context)
-  SampleDev *h_many2 = nullptr, *d_many2 = nullptr, *h_many = nullptr, *d_many = nullptr;  // [2][VB2_MAX_BATCH] / in use
-  uint32_t *h_slots2 = nullptr, *d_slots2 = nullptr, *h_slots = nullptr, *d_slots = nullptr;
+  TaskRec *h_recs2 = nullptr, *d_recs2 = nullptr, *h_recs = nullptr, *d_recs = nullptr;  // [2][VB2_MAX_BATCH] / in use
   uint32_t many_n = 0, many_grid_x = 0, many_kc = 1, many_buf_bytes = 0;  // last staged eval_many launch
   int many_spec = 0;
   bool many_chunked = false;
@@ -1351,10 +1487,8 @@ int ensure_job_staging(vb2_llk_ctx *ctx) {
   if (ctx->h_jobs2) return VB2_OK;
   VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_jobs2, sizeof(JobParams) * 2 * VB2_MAX_BATCH, cudaHostAllocDefault));
   VB2_CUDA(ctx, cudaMalloc(&ctx->d_jobs2, sizeof(JobParams) * 2 * VB2_MAX_BATCH));
-  VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_many2, sizeof(SampleDev) * 2 * VB2_MAX_BATCH, cudaHostAllocDefault));
-  VB2_CUDA(ctx, cudaMalloc(&ctx->d_many2, sizeof(SampleDev) * 2 * VB2_MAX_BATCH));
-  VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_slots2, sizeof(uint32_t) * 2 * VB2_MAX_BATCH, cudaHostAllocDefault));
-  VB2_CUDA(ctx, cudaMalloc(&ctx->d_slots2, sizeof(uint32_t) * 2 * VB2_MAX_BATCH));
+  VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_recs2, sizeof(TaskRec) * 2 * VB2_MAX_BATCH, cudaHostAllocDefault));
+  VB2_CUDA(ctx, cudaMalloc(&ctx->d_recs2, sizeof(TaskRec) * 2 * VB2_MAX_BATCH));
   for (int i = 0; i < 2; ++i) VB2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
   return VB2_OK;
 }
@@ -1367,8 +1501,7 @@ int acquire_staging(vb2_llk_ctx *ctx) {
   ctx->stage_used[i] = true;
   const size_t o = (size_t)i * VB2_MAX_BATCH;
   ctx->h_jobs = ctx->h_jobs2 + o; ctx->d_jobs = ctx->d_jobs2 + o;
-  ctx->h_many = ctx->h_many2 + o; ctx->d_many = ctx->d_many2 + o;
-  ctx->h_slots = ctx->h_slots2 + o; ctx->d_slots = ctx->d_slots2 + o;
+  ctx->h_recs = ctx->h_recs2 + o; ctx->d_recs = ctx->d_recs2 + o;
   return VB2_OK;
 }
 // Behind every launch that reads the staging set in use.
@@ -1537,11 +1670,6 @@ Geometry geometry(const vb2_llk_ctx *ctx, bool throughput) {
   return g;
 }
 
-// CTAs of an llk_stream_kernel launch: four per SM (128 threads x 128 registers), never more than the tasks need.
-uint32_t stream_grid(int sm_count, uint32_t n_tasks) {
-  return std::max(1u, std::min((uint32_t)VB2_STREAM_CTAS_PER_SM * (uint32_t)std::max(1, sm_count), (n_tasks + 3u) / 4u));
-}
-
 void fill_phred(LaunchArgs *A) {
   struct Table {
     double v[kPhredArgs];
@@ -1552,6 +1680,17 @@ void fill_phred(LaunchArgs *A) {
   };
   static const Table table;  // (thread-safe initialisation)
   memcpy(A->phred, table.v, sizeof(table.v));
+}
+
+// Job record of the many-evaluations kernel: sample, partial-sum slot, the head of the round table, parameters.
+void fill_rec(TaskRec *R, const vb2_llk_ctx *c, uint32_t pslot, const double *pc1, const double *pc2, double alpha) {
+  R->S = c->S;
+  R->pslot = pslot;
+  R->pad_ = 0;
+  const size_t nr = std::min<size_t>(c->rounds.size(), (size_t)kRecRounds);
+  memcpy(R->rounds, c->rounds.data(), nr * sizeof(vb2::Round));
+  if (nr < (size_t)kRecRounds) memset(R->rounds + nr, 0, ((size_t)kRecRounds - nr) * sizeof(vb2::Round));
+  fill_job(&R->J, c->S.n_pc, pc1, pc2, alpha);
 }
 
 // Launch n evaluations of ONE sample.
@@ -1566,8 +1705,8 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
   VB2_CUDA(ctx, cudaSetDevice(ctx->device));
   session_stop(ctx);  // (any other launch on this context ends its evaluation session)
   const uint32_t k = ctx->S.n_pc;
-  const bool args = n <= kMaxArgJobs && ctx->rounds.size() <= (size_t)kMaxArgRounds;
-  if (mode == Reduce::kHost && (!args || n != 1))
+  const bool args = n == 1 && ctx->rounds.size() <= (size_t)kMaxArgRounds;  // everything travels in the kernel arguments
+  if (mode == Reduce::kHost && !args)
     return set_err(ctx, VB2_ERR_INVALID, "internal: host reduction is for one evaluation with ARGS");
   if (mode == Reduce::kDevice) {
     int rc = ensure_slots(ctx, (uint32_t)n);
@@ -1575,7 +1714,7 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
   }
   LaunchArgs A;
   A.sample = ctx->S;
-  A.samples = nullptr; A.slots = nullptr; A.jobs_dev = nullptr;
+  A.samples = nullptr; A.slots = nullptr; A.jobs_dev = nullptr; A.recs = nullptr;
   A.d_out = d_out;
   A.mbox = nullptr;
   A.seq = 0;
@@ -1591,14 +1730,21 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
   A.n_buf = g.n_buf;
   if (args) {
     memcpy(A.rounds, ctx->rounds.data(), ctx->rounds.size() * sizeof(vb2::Round));
-    for (int j = 0; j < n; ++j) fill_job(&A.jobs[j], k, pc1 + (size_t)j * k, pc2 + (size_t)j * k, alphas[j]);
+    fill_job(&A.jobs[0], k, pc1, pc2, alphas[0]);
   } else {
     int rcs = acquire_staging(ctx);
     if (rcs) return rcs;
-    for (int j = 0; j < n; ++j) fill_job(&ctx->h_jobs[j], k, pc1 + (size_t)j * k, pc2 + (size_t)j * k, alphas[j]);
-    VB2_CUDA(ctx, cudaMemcpyAsync(ctx->d_jobs, ctx->h_jobs, (size_t)n * sizeof(JobParams), cudaMemcpyHostToDevice,
-                                  ctx->stream));
-    A.jobs_dev = ctx->d_jobs;
+    if (n == 1) {  // one evaluation whose round table does not fit in the arguments: parameters through HBM
+      fill_job(&ctx->h_jobs[0], k, pc1, pc2, alphas[0]);
+      VB2_CUDA(ctx, cudaMemcpyAsync(ctx->d_jobs, ctx->h_jobs, sizeof(JobParams), cudaMemcpyHostToDevice, ctx->stream));
+      A.jobs_dev = ctx->d_jobs;
+    } else {       // the many-evaluations kernel: one record per job
+      for (int j = 0; j < n; ++j)
+        fill_rec(&ctx->h_recs[j], ctx, (uint32_t)j, pc1 + (size_t)j * k, pc2 + (size_t)j * k, alphas[j]);
+      VB2_CUDA(ctx, cudaMemcpyAsync(ctx->d_recs, ctx->h_recs, (size_t)n * sizeof(TaskRec), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+      A.recs = ctx->d_recs;
+    }
   }
   if (to_mailbox || mode == Reduce::kHost) {
     A.mbox = ctx->d_mbox;
@@ -1606,10 +1752,8 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
     if (seq_out) *seq_out = A.seq;
   }
   if (n > 1) {  // several evaluations: the persistent task-queue kernel
-    const dim3 sgrid(stream_grid(ctx->sm_count, (uint32_t)n * A.n_bins_max), 1, 1);
-    if (args) launch_stream<true>(sgrid, 8u * A.stage_bytes, ctx->stream, A, ctx->spec, ctx->chunked);
-    else launch_stream<false>(sgrid, 8u * A.stage_bytes, ctx->stream, A, ctx->spec, ctx->chunked);
-    if (!args) release_staging(ctx);
+    launch_stream(8u * A.stage_bytes, ctx->stream, A, ctx->spec, ctx->chunked, ctx->sm_count);
+    release_staging(ctx);
     VB2_CUDA(ctx, cudaGetLastError());
     return VB2_OK;
   }
@@ -1630,8 +1774,8 @@ cudaError_t raise_smem_limits(int bytes) {
   cudaError_t e = cudaFuncSetAttribute(llk_kernel<true, true, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_kernel<true, false, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_kernel<false, false, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<true, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<false, NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<NPC, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<NPC, CHUNKED>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if constexpr (!CHUNKED)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_session_kernel<NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   return e;
@@ -1698,12 +1842,10 @@ void vb2_llk_destroy(vb2_llk_ctx *ctx) {
   if (ctx->d_trace) cudaFree(ctx->d_trace);
   if (ctx->h_bell) cudaFreeHost(ctx->h_bell);
   if (ctx->d_relay) cudaFree(ctx->d_relay);
-  if (ctx->d_many2) cudaFree(ctx->d_many2);
-  if (ctx->d_slots2) cudaFree(ctx->d_slots2);
+  if (ctx->d_recs2) cudaFree(ctx->d_recs2);
   if (ctx->h_mbox) cudaFreeHost(ctx->h_mbox);
   if (ctx->h_jobs2) cudaFreeHost(ctx->h_jobs2);
-  if (ctx->h_many2) cudaFreeHost(ctx->h_many2);
-  if (ctx->h_slots2) cudaFreeHost(ctx->h_slots2);
+  if (ctx->h_recs2) cudaFreeHost(ctx->h_recs2);
   for (int i = 0; i < 2; ++i)
     if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1963,23 +2105,24 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
   const uint32_t k = lead->S.n_pc;
   // slot of job j inside its sample = number of earlier jobs on the same context
   std::unordered_map<const vb2_llk_ctx *, uint32_t> seen;
+  std::vector<uint32_t> slot_of((size_t)n);
   for (int j = 0; j < n; ++j) {
     vb2_llk_ctx *c = ctxs[j];
     if (!c) return set_err(lead, VB2_ERR_INVALID, "null context in list");
     session_stop(c);
     if (c->device != lead->device) return set_err(lead, VB2_ERR_INVALID, "contexts live on different devices");
     if (c->S.n_pc != k) return set_err(lead, VB2_ERR_INVALID, "contexts differ in n_pc");
-    const uint32_t slot = seen[c]++;  // (number of earlier jobs on the same context)
-    int rc = ensure_slots(c, slot + 1);
-    if (rc) return set_err(lead, rc, c->err);
-    lead->h_slots[j] = slot;
+    slot_of[j] = seen[c]++;  // (number of earlier jobs on the same context)
+  }
+  for (auto &kv : seen) {  // (before the records are filled: growing the slots moves S.partials)
+    int rc = ensure_slots(const_cast<vb2_llk_ctx *>(kv.first), kv.second);
+    if (rc) return set_err(lead, rc, kv.first->err);
   }
   bool any = false, chunked = false;
   int spec = ctxs[0]->spec;
   uint32_t grid_x = 0, kc = 1, buf_bytes = 0;
   for (int j = 0; j < n; ++j) {
     vb2_llk_ctx *c = ctxs[j];
-    lead->h_many[j] = c->S;
     chunked = chunked || c->chunked;
     if (c->spec != spec) spec = 0;
     // the launch uses the largest geometry; every sample indexes shared memory with its own buf_bytes
@@ -1988,15 +2131,13 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
     kc = std::max(kc, g.kc);
     buf_bytes = std::max(buf_bytes, c->S.buf_bytes);
     any |= c->S.grid_x > 0;
-    fill_job(&lead->h_jobs[j], k, pc_contam + (size_t)j * k, pc_intended + (size_t)j * k, alphas[j]);
+    fill_rec(&lead->h_recs[j], c, slot_of[j], pc_contam + (size_t)j * k, pc_intended + (size_t)j * k, alphas[j]);
   }
   *nothing_to_do = !any;
   lead->many_n = 0;
   if (!any) return VB2_OK;
   // (a sample without a usable marker has no active bin: llk_reduce_kernel returns the reference's empty sum, 0.0)
-  VB2_CUDA(lead, cudaMemcpyAsync(lead->d_many, lead->h_many, sizeof(SampleDev) * n, cudaMemcpyHostToDevice, lead->stream));
-  VB2_CUDA(lead, cudaMemcpyAsync(lead->d_slots, lead->h_slots, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, lead->stream));
-  VB2_CUDA(lead, cudaMemcpyAsync(lead->d_jobs, lead->h_jobs, sizeof(JobParams) * n, cudaMemcpyHostToDevice, lead->stream));
+  VB2_CUDA(lead, cudaMemcpyAsync(lead->d_recs, lead->h_recs, sizeof(TaskRec) * n, cudaMemcpyHostToDevice, lead->stream));
   lead->many_n = (uint32_t)n;
   lead->many_grid_x = grid_x;
   lead->many_kc = kc;
@@ -2006,7 +2147,7 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
   return VB2_OK;
 }
 
-// eval_many, step 2: one launch over whatever stage_many staged last (generic kernel, device reduction).
+// eval_many, step 2: one launch over whatever stage_many staged last (device reduction).
 static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq_out, double *d_out = nullptr) {
   if (!lead->many_n) return set_err(lead, VB2_ERR_INVALID, "internal: nothing staged");
   LaunchArgs A;
@@ -2020,9 +2161,7 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
   A.trace = lead->d_trace;
 #endif
   fill_phred(&A);
-  A.samples = lead->d_many;
-  A.slots = lead->d_slots;
-  A.jobs_dev = lead->d_jobs;
+  A.recs = lead->d_recs;
   A.n_jobs = lead->many_n;
   A.d_out = d_out ? d_out : lead->d_out;
   A.kc = lead->many_kc;
@@ -2039,8 +2178,7 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
     int rca = init_device_tables(lead, lead->device, lead->many_spec, lead->many_chunked);
     if (rca) return rca;
   }
-  const dim3 grid(stream_grid(lead->sm_count, lead->many_n * A.n_bins_max), 1, 1);
-  launch_stream<false>(grid, 8u * A.stage_bytes, lead->stream, A, lead->many_spec, lead->many_chunked);
+  launch_stream(8u * A.stage_bytes, lead->stream, A, lead->many_spec, lead->many_chunked, lead->sm_count);
   release_staging(lead);
   VB2_CUDA(lead, cudaGetLastError());
   return VB2_OK;
@@ -2115,6 +2253,7 @@ int vb2_llk_time_device_many(vb2_llk_ctx *const *ctxs, int n_ctx, int warmup_lau
     const double n_slices = (double)std::max(1ull, ph[8]);
     fprintf(stderr, "phase clock (cycles per slice per warp; %.0f slices, %.0f tasks):", n_slices, (double)ph[9]);
     for (int k = 0; k < 8; ++k) fprintf(stderr, " %s %.0f;", name[k], (double)ph[k] / n_slices);
+
     fprintf(stderr, "\n");
     cudaMemset(lead->d_trace, 0, sizeof(ph));
   }
