@@ -460,16 +460,36 @@ def run_ours(args):
                         "evaluation of the headline workload at 64 fp64 lanes/clk/SM (DESIGN.md section 4)"}
 
     # ---- e2e: the public C-ABI call with HOST buffers, host<->device traffic inside the timed region ----------------
-    e2e_extra = {}
+    e2e_extra, r_last = {}, None
     if not cohort and world == 1:
-        # the call as the simplex search makes it: per step EVALS_PER_STEP DEPENDENT evaluations of ONE sample, each one
-        # moving its 2k+1 doubles in and its scalar out before the next starts, inside an evaluation session
+        # the call as the estimator makes it: DEPENDENT evaluations of ONE sample -- a step is a run of simplex searches
+        # (vb2_llk_minimize: host start point + model in, AmoebaMinimizer::Minimize on the device inside an evaluation
+        # session, result out) that adds up to at least EVALS_PER_STEP evaluations; the metric counts the evaluations
+        # the engine reports
         n_dep = args.steps * per_step
         n_warm = args.warmup * per_step // 8 + 16
+        nm_start = list(start_pc) + list(start_pc) + [float(np.log(0.03 / 0.97))]
+        nm_model = (list(range(k)), list(range(k, 2 * k)), 2 * k)
+        searches_per_step, dev_evals, min_bytes, r_last = None, 0, (0, 0), None
+        if not args.no_session and 2 * k + 1 <= vb.VB2_MIN_MAX_DIM:
+            engines[0].session_begin()
+            r0 = engines[0].minimize(nm_start, *nm_model, ftol=1e-8)           # (also the warm-up)
+            searches_per_step = max(1, -(-per_step // max(1, r0["evals"])))
+            for _ in range(max(0, args.warmup - 1)):
+                engines[0].minimize(nm_start, *nm_model, ftol=1e-8)
+            t0 = time.perf_counter()
+            for i in range(args.steps * searches_per_step):
+                nm_start[0] = 0.01 + 1e-7 * (i % 1000)                         # a different starting point every search
+                r_last = engines[0].minimize(nm_start, *nm_model, ftol=1e-8)
+                dev_evals += r_last["evals"]
+            min_s = time.perf_counter() - t0
+            min_bytes = (searches_per_step * (280 + 16 * (13 + 2 * k)), searches_per_step * 208)
+        # the same dependent evaluations driven from the host, one vb2_llk_eval per evaluation (doorbell in, mailbox out)
         if args.no_session:   # (profiler runs: ncu serialises launches, a resident kernel would wait for a doorbell
             e2e_s, last = vb.time_host(engines, n_warm, n_dep, start_pc, start_pc, 0.03)  # that cannot ring)
         else:
-            engines[0].session_begin()
+            if searches_per_step is None:
+                engines[0].session_begin()
             e2e_s, last = vb.time_host(engines[:1], n_warm, n_dep, start_pc, start_pc, 0.03)
             engines[0].session_end()
         last_pc = start_pc.copy(); last_pc[0] = 0.01 + 1e-7 * ((n_dep - 1 + n_warm) % 1000)
@@ -486,13 +506,23 @@ def run_ours(args):
         t0 = time.perf_counter()
         for i in range(200):
             engines[i % copies].compute_mix_llks(start_pc, start_pc, 0.03)
-        e2e_extra = {"us_per_evaluation_one_launch_per_evaluation": cold_s / n_cold * 1e6,
+        e2e_extra = {"us_per_evaluation_host_driven_session": e2e_s / n_dep * 1e6,
+                     "us_per_evaluation_one_launch_per_evaluation": cold_s / n_cold * 1e6,
                      "us_per_evaluation_batched_public_call": batched_s / n_jobs * 1e6,
                      "python_binding_us_per_evaluation": (time.perf_counter() - t0) / 200 * 1e6}
         h2d, d2h = (2 * k + 1) * 8 * per_step, 8 * per_step
         caller = ("C loop over vb2_llk_eval (host buffers), one launch per evaluation (--no-session)" if args.no_session else
                   "C loop over vb2_llk_eval (host buffers): %d dependent evaluations per step inside an evaluation session "
                   "(resident kernel, sample in shared memory, host-mapped doorbell/mailbox)" % per_step)
+        e2e_evals_per_step = per_step
+        if searches_per_step is not None:   # the headline: the searches on the device
+            e2e_s = min_s
+            e2e_evals_per_step = dev_evals / args.steps
+            h2d, d2h = min_bytes
+            caller = ("python: %d x vb2_llk_minimize per step (host start point + model in, Nelder-Mead next to the kernel inside "
+                      "an evaluation session, result out): %.0f dependent evaluations per step" % (searches_per_step, e2e_evals_per_step))
+            e2e_extra["searches_per_step"] = searches_per_step
+            e2e_extra["evaluations_per_search"] = r0["evals"]
     else:
         # marker shards (or a cohort) go through the batched public call: per step, host parameter arrays in
         # (vb2_llk_eval_many_device stages them), this rank's launch, all-reduce (shards only), results back to pinned
@@ -525,9 +555,11 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    e2e = {"value": reads_step_total / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "us_per_evaluation": e2e_s / args.steps / n_jobs * 1e6 * (1 if not cohort else 1), "ms_per_step": e2e_s / args.steps * 1e3,
-           "last_llk": last, "caller": caller}
+    e2e_reads_step = reads_step_total if (cohort or world > 1) else float(reads_per_eval) * e2e_evals_per_step
+    e2e_n = n_jobs if (cohort or world > 1) else e2e_evals_per_step
+    e2e = {"value": e2e_reads_step / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "us_per_evaluation": e2e_s / args.steps / e2e_n * 1e6, "ms_per_step": e2e_s / args.steps * 1e3,
+           "evaluations_per_step": e2e_n, "last_llk": last, "caller": caller}
     e2e.update(e2e_extra)
     if rank == 0:   # the e2e result against the oracle too (cohort: the last sample of rank 0)
         from oracle import vb2_oracle as vo
@@ -538,6 +570,14 @@ def run_ours(args):
         parity["e2e_rel"] = abs(last - want) / abs(want)
         if not parity["e2e_rel"] <= PARITY_TOL:
             raise SystemExit("bench.py: e2e parity check failed: got %.17g want %.17g" % (last, want))
+        if not cohort and world == 1 and r_last is not None:   # the last search on the device: its minimum at its best point
+            v = r_last["point"]
+            a = float(np.exp(v[2 * k])); a = a / (1.0 + a)
+            want = -ora.compute_mix_llks(list(v[:k]), list(v[k:2 * k]), a)
+            parity["search_fmin_rel"] = abs(r_last["fmin"] - want) / abs(want)
+            parity["search_alpha"] = a
+            if not (parity["search_fmin_rel"] <= PARITY_TOL and r_last["converged"]):
+                raise SystemExit("bench.py: device search parity check failed: %r" % (r_last,))
 
     # ---- cpu baseline beside it (rank 0, N=1 only) --------------------------------------------
     cpu = None

@@ -187,6 +187,53 @@ int vb2_llk_eval_many_device(vb2_llk_ctx *const *ctxs, int n, const double *pc_c
 int vb2_llk_session_begin(vb2_llk_ctx *ctx);
 int vb2_llk_session_end(vb2_llk_ctx *ctx);
 
+/* ---- the simplex search next to the kernel ------------------------------------------------------------------
+ * vb2_llk_minimize runs AmoebaMinimizer::Minimize (MathGenMin.cpp:326-423: Nelder-Mead, the reference's exact control
+ * flow and operation order) ON THE DEVICE, inside the resident kernel of an evaluation session: the first warp of the
+ * first CTA proposes the next point, every CTA evaluates its share of the markers from shared memory, the partial sums
+ * meet in L2 -- no host round trip per evaluation; the host rings ONE doorbell and reads ONE result.
+ *
+ * The model says how a simplex vector v maps to ComputeMixLLKs' arguments -- the six branches of
+ * FullLLKFunc::Evaluate (ContaminationEstimator.h:339-442) as a table:
+ *   pc_contam[k]   = pc1_from[k] >= 0 ? v[pc1_from[k]] : pc1_fixed[k]
+ *   pc_intended[k] = pc2_from[k] >= 0 ? v[pc2_from[k]] : pc2_fixed[k]
+ *   alpha          = alpha_from  >= 0 ? InvLogit(v[alpha_from]) : alpha_fixed          (h:119-122)
+ * and the objective is f(v) = -ComputeMixLLKs(pc_contam, pc_intended, alpha) (h:344).  Like Evaluate, the search keeps
+ * the best point over ALL its evaluations: llk1 (in: the best value so far, out: the new one), and -- when it
+ * improved -- the free components of the best point (best_pc_contam / best_pc_intended / best_alpha).
+ * Limits: dim <= VB2_MIN_MAX_DIM, n_pc <= 4, an evaluation session must be open on the context (vb2_llk_session_begin);
+ * otherwise VB2_ERR_INVALID -- the caller then drives the simplex itself with vb2_llk_eval, as the reference does.  */
+#define VB2_MIN_MAX_DIM 9
+typedef struct vb2_llk_model {
+  uint32_t struct_size;
+  uint32_t dim;                    /* length of the simplex vector                                          */
+  int32_t pc1_from[VB2_MAX_PC];    /* index into v, or -1: fixed                                             */
+  int32_t pc2_from[VB2_MAX_PC];
+  int32_t alpha_from;
+  int32_t pad_;
+  double pc1_fixed[VB2_MAX_PC];
+  double pc2_fixed[VB2_MAX_PC];
+  double alpha_fixed;
+} vb2_llk_model;
+
+typedef struct vb2_llk_min_result {
+  uint32_t struct_size;
+  int32_t converged;               /* 0: cycleMax exceeded (Minimize returned numeric_limits<double>::max()) */
+  double fmin;                     /* value at the best vertex                                               */
+  double point[VB2_MIN_MAX_DIM];   /* the best vertex (AmoebaMinimizer::point on return)                     */
+  int64_t evals;                   /* likelihood evaluations made                                            */
+  int64_t cycle_count;             /* AmoebaMinimizer::cycleCount on return                                  */
+  double llk1;                     /* best objective value over all evaluations, starting from llk1_in       */
+  int32_t improved;                /* 1: some evaluation beat llk1_in; then the best_* fields are valid      */
+  int32_t pad_;
+  double best_pc_contam[4], best_pc_intended[4], best_alpha;
+} vb2_llk_min_result;
+
+/* start[dim]: the starting point; the initial simplex is start + scale * e_i (GeneralMinimizer::Reset, MathGenMin.cpp:17-25);
+ * ftol, cycle_max: AmoebaMinimizer::Minimize's tolerance and cycleMax (50000 in the reference).                */
+int vb2_llk_minimize(vb2_llk_ctx *ctx, const vb2_llk_model *model, const double *start, double scale, double ftol,
+                     int64_t cycle_max, double llk1_in, vb2_llk_min_result *result);
+
 /* Block until everything queued on the context's stream has finished. */
 int vb2_llk_sync(vb2_llk_ctx *ctx);
 

@@ -176,3 +176,42 @@ def test_cohort_mode_equals_one_sample_at_a_time(tmp_path):
                 str(tmp_path))
         for ext in (".Ancestry", ".selfSM"):
             assert open(out + ext).read() == open(str(tmp_path / ("cohort%d" % i)) + ext).read(), (i, ext)
+
+
+def _evals(stderr: str):
+    import re
+    m = re.search(r"Likelihood evaluations: (\d+)", stderr)
+    d = re.search(r"Simplex search on the device: (\d+)", stderr)
+    return int(m.group(1)), int(d.group(1)) if d else 0
+
+
+@pytest.mark.parametrize("golden,pileup,flags", MODES)
+def test_device_simplex_follows_the_host_simplex(tmp_path, golden, pileup, flags):
+    """vb2_llk_minimize (AmoebaMinimizer::Minimize on the device, MathGenMin.cpp:326-423) against the same search driven
+    evaluation by evaluation from the host (VB2_HOST_SIMPLEX=1): same number of evaluations, same files, all six models."""
+    args = ["--DisableSanityCheck", "--PileupFile", pileup, "--SVDPrefix", HAPMAP, "--Reference", "x", "--NumPC", "2", *flags]
+    dev = run_cli([*args, "--Output", str(tmp_path / "dev")], str(tmp_path))
+    env = dict(os.environ, VB2_HOST_SIMPLEX="1")
+    hostrun = subprocess.run([host.CLI_PATH, *args, "--Output", str(tmp_path / "host")], cwd=str(tmp_path), env=env,
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert hostrun.returncode == 0, hostrun.stderr[-2000:]
+    n_dev, on_dev = _evals(dev.stderr)
+    n_host, on_dev_host = _evals(hostrun.stderr)
+    assert on_dev > 0 and on_dev_host == 0          # the search really ran where it should
+    assert n_dev == n_host, (n_dev, n_host)
+    for ext in (".Ancestry", ".selfSM"):
+        assert open(str(tmp_path / "dev") + ext).read() == open(str(tmp_path / "host") + ext).read(), ext
+    assert dev.stdout == hostrun.stdout
+
+
+def test_device_simplex_on_synthetic_10k(synthetic10k):
+    s, prefix, pile, td = synthetic10k
+    outs = {}
+    for name, env in (("dev", os.environ), ("host", dict(os.environ, VB2_HOST_SIMPLEX="1"))):
+        out = str(td / ("simplex_" + name))
+        cp = subprocess.run([host.CLI_PATH, "--PileupFile", pile, "--SVDPrefix", prefix, "--Reference", "x", "--NumPC", "2",
+                             "--Output", out], cwd=str(td), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                            timeout=600)
+        assert cp.returncode == 0, cp.stderr[-2000:]
+        outs[name] = (_evals(cp.stderr)[0], open(out + ".Ancestry").read(), open(out + ".selfSM").read())
+    assert outs["dev"] == outs["host"]

@@ -388,3 +388,93 @@ def test_runtime_layout_kernel_equals_specialised_kernel(sample10k, monkeypatch)
         assert [eng.compute_mix_llks(*pt) for pt in POINTS] == fast
         assert eng.eval_batch(np.array([p[0] for p in POINTS]), np.array([p[1] for p in POINTS]),
                               np.array([p[2] for p in POINTS])).tolist() == fast_batch == fast
+
+
+def test_minimize_on_the_device_matches_a_host_nelder_mead(sample10k):
+    """vb2_llk_minimize against a plain Python transcription of AmoebaMinimizer::Minimize (MathGenMin.cpp:326-443) that
+    calls the same engine one evaluation at a time: same evaluations, same best point, same bookkeeping."""
+    import math
+    p = sample10k.problem
+    k = p.n_pc
+    calls = []
+    with vb.LLKEngine(p) as eng:
+        def f(v):
+            a = math.exp(v[2 * k]); a = a / (1.0 + a)
+            val = 0.0 - eng.compute_mix_llks(v[:k], v[k:2 * k], a)
+            calls.append((val, list(v[:k]), list(v[k:2 * k]), a))
+            return val
+
+        def amoeba(start, ftol, cycle_max=50000):
+            dim = len(start); nv = dim + 1
+            simplex = [[start[j] + (1.0 if j == i else 0.0) for j in range(dim)] for i in range(dim)] + [list(start)]
+            y = [f(simplex[i]) for i in range(nv)]
+            psum = list(simplex[0])
+            for m in range(1, nv):
+                for j in range(dim):
+                    psum[j] += simplex[m][j]
+            cycles = nv
+
+            def trial(ihi, factor):
+                fac = (1.0 - factor) / dim
+                pt = [fac * psum[j] + (factor - fac) * simplex[ihi][j] for j in range(dim)]
+                yt = f(pt)
+                if yt < y[ihi]:
+                    y[ihi] = yt
+                    for j in range(dim):
+                        psum[j] = psum[j] - simplex[ihi][j] + pt[j]
+                    simplex[ihi] = pt
+                return yt
+            while True:
+                if y[0] > y[1]:
+                    ilo = inhi = 1; ihi = 0
+                else:
+                    ilo = inhi = 0; ihi = 1
+                for i in range(2, nv):
+                    if y[i] <= y[ilo]:
+                        ilo = i
+                    elif y[i] > y[ihi]:
+                        inhi = ihi; ihi = i
+                    elif y[i] > y[inhi]:
+                        inhi = i
+                rtol = 2 * abs(y[ihi] - y[ilo]) / (abs(y[ihi]) + abs(y[ilo]) + 3.0e-10)
+                if rtol < ftol:
+                    return simplex[ilo], y[ilo], cycles
+                assert cycles <= cycle_max
+                cycles += 2
+                yt = trial(ihi, -1.0)
+                if yt <= y[ilo]:
+                    trial(ihi, 2.0)
+                elif yt >= y[inhi]:
+                    ysave = y[ihi]
+                    yt = trial(ihi, 0.5)
+                    if yt >= ysave:
+                        for i in range(nv):
+                            if i != ilo:
+                                simplex[i] = [(simplex[i][j] + simplex[ilo][j]) * 0.5 for j in range(dim)]
+                                y[i] = f(simplex[i])
+                        cycles += dim
+                        psum = list(simplex[0])
+                        for m in range(1, nv):
+                            for j in range(dim):
+                                psum[j] += simplex[m][j]
+                else:
+                    cycles -= 1
+
+        start = [0.01] * (2 * k) + [math.log(0.03 / 0.97)]
+        eng.session_begin()
+        want_pt, want_f, want_cycles = amoeba(start, 1e-8)
+        got = eng.minimize(start, list(range(k)), list(range(k, 2 * k)), 2 * k, ftol=1e-8)
+        # a second search in the same session, a model with fixed parts: alpha fixed, one set of PCs for both samples
+        got2 = eng.minimize([0.01] * k, list(range(k)), list(range(k)), -1, alpha_fixed=0.05, ftol=1e-8, llk1=got["llk1"])
+        one = eng.compute_mix_llks(got2["point"], got2["point"], 0.05)       # evaluations still work after a search
+        eng.session_end()
+    assert got["converged"] and got["evals"] == len(calls), (got["evals"], len(calls))
+    assert got["cycle_count"] == want_cycles
+    assert got["point"] == want_pt                                        # the same trajectory, bit for bit
+    # (alpha = InvLogit(v) goes through exp(): the device's and the host's may differ in the last bit)
+    assert rel(got["fmin"], want_f) <= 1e-13
+    best = min(calls, key=lambda c: c[0])
+    assert got["improved"] and rel(got["llk1"], best[0]) <= 1e-13
+    assert got["best_pc_contam"] == best[1] and got["best_pc_intended"] == best[2] and rel(got["best_alpha"], best[3]) <= 1e-15
+    assert got2["converged"] and got2["fmin"] == 0.0 - one
+    assert got2["fmin"] >= got["fmin"] - 1e-9 * abs(got["fmin"])          # a constrained model cannot beat the free one

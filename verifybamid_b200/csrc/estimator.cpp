@@ -411,7 +411,78 @@ int ContaminationEstimator::OptimizeLLK(const std::string &OutputPrefix) {
   if (!fout) error("Errors detected when writing to file %s !", fileName.c_str());
   notice("Likelihood evaluations: %ld, %.3f ms inside the GPU engine (%.1f us per evaluation)", fn.evalCount,
          engineSeconds * 1e3, fn.evalCount ? engineSeconds * 1e6 / fn.evalCount : 0.0);
+  if (deviceSimplexEvals) notice("Simplex search on the device: %ld of the evaluations", deviceSimplexEvals);
   return 0;
+}
+
+// The simplex search of every Optimize* (ContaminationEstimator.cpp:192-332: Reset, point = start, Minimize(epsilon)).
+// With one resident engine it runs next to the kernel (vb2_llk_minimize: AmoebaMinimizer::Minimize on the device,
+// Evaluate's unpacking as a table); otherwise -- marker shards on several GPUs, a cohort, --Verbose, a sample that
+// does not fit on chip, more than four PCs -- the host drives it evaluation by evaluation, as the reference does.
+double ContaminationEstimator::RunMinimizer(AmoebaMinimizer &myMinimizer, const std::vector<double> &startingPoint) {
+  const int dim = (int)startingPoint.size();
+  myMinimizer.func = &fn;
+  myMinimizer.Reset(dim);
+  myMinimizer.point = startingPoint;
+  if (engines.size() == 1 && !cohort && !verbose && dim <= VB2_MIN_MAX_DIM && numPC <= 4 && !getenv("VB2_HOST_SIMPLEX")) {
+    vb2_llk_model M;
+    memset(&M, 0, sizeof(M));
+    M.struct_size = sizeof(M);
+    M.dim = (uint32_t)dim;
+    // FullLLKFunc::Evaluate's six branches (h:339-442): which entries of v feed which argument
+    const bool pcFree = !isPCFixed, alphaFree = !isAlphaFixed || isPCFixed;  // (isPCFixed is tested first)
+    for (int k = 0; k < VB2_MAX_PC; ++k) M.pc1_from[k] = M.pc2_from[k] = -1;
+    M.alpha_from = -1;
+    M.alpha_fixed = fn.fixAlpha;
+    for (int k = 0; k < numPC; ++k) {
+      M.pc1_fixed[k] = fn.fixPC[k];
+      M.pc2_fixed[k] = fn.fixPC2[k];
+    }
+    if (!isHeter) {
+      if (isPCFixed) M.alpha_from = 0;                                    // v = (logit alpha); PCs fixed
+      else {
+        for (int k = 0; k < numPC; ++k) M.pc1_from[k] = M.pc2_from[k] = k;  // one set of PCs for both samples
+        if (alphaFree) M.alpha_from = numPC;
+      }
+    } else {
+      if (isPCFixed) {                                                    // intended PCs fixed, contaminant's free
+        for (int k = 0; k < numPC; ++k) M.pc1_from[k] = k;
+        M.alpha_from = numPC;
+      } else {
+        for (int k = 0; k < numPC; ++k) { M.pc1_from[k] = k; M.pc2_from[k] = numPC + k; }
+        if (alphaFree) M.alpha_from = 2 * numPC;
+      }
+    }
+    (void)pcFree;
+    vb2_llk_min_result R;
+    memset(&R, 0, sizeof(R));
+    R.struct_size = sizeof(R);
+    auto t0 = std::chrono::steady_clock::now();
+    const int rc = vb2_llk_minimize(engines[0], &M, startingPoint.data(), 1.0, epsilon, myMinimizer.cycleMax, fn.llk1, &R);
+    if (rc == VB2_OK) {
+      engineSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      fn.evalCount += (long)R.evals;
+      deviceSimplexEvals += (long)R.evals;
+      if (R.improved) {  // Evaluate's best-so-far bookkeeping, for the components this model leaves free
+        fn.llk1 = R.llk1;
+        for (int k = 0; k < numPC; ++k) {
+          if (M.pc1_from[k] >= 0) fn.globalPC[k] = R.best_pc_contam[k];
+          if (M.pc2_from[k] >= 0) fn.globalPC2[k] = R.best_pc_intended[k];
+        }
+        if (M.alpha_from >= 0) fn.globalAlpha = R.best_alpha;
+      }
+      myMinimizer.point.assign(R.point, R.point + dim);
+      myMinimizer.cycleCount = (long)R.cycle_count;
+      if (!R.converged) {
+        fprintf(stderr, "WARNING - Amoeba.Minimize - Couldn't converge in %ld cycles\n", myMinimizer.cycleMax);
+        return std::numeric_limits<double>::max();
+      }
+      return myMinimizer.fmin = R.fmin;
+    }
+    if (rc != VB2_ERR_INVALID) error("GPU engine: %s", vb2_last_error(engines[0]));
+    // (no session on this sample, or a shape the device search does not take: the host drives the simplex)
+  }
+  return myMinimizer.Minimize(epsilon);
 }
 
 bool ContaminationEstimator::OptimizeHeter(AmoebaMinimizer &myMinimizer) {
@@ -423,10 +494,7 @@ bool ContaminationEstimator::OptimizeHeter(AmoebaMinimizer &myMinimizer) {
     for (int i = 0; i < numPC * 2; ++i) std::cerr << startingPoint[i] << "\t";
     std::cerr << "and alpha:\t" << alpha << std::endl;
   }
-  myMinimizer.func = &fn;
-  myMinimizer.Reset(numPC * 2 + 1);
-  myMinimizer.point = startingPoint;
-  double ret = myMinimizer.Minimize(epsilon);
+  double ret = RunMinimizer(myMinimizer, startingPoint);
   alpha = FullLLKFunc::InvLogit(myMinimizer.point[numPC * 2]);
   for (int i = 0; i < numPC; ++i) PC[0][i] = myMinimizer.point[i];
   for (int i = numPC; i < numPC * 2; ++i) PC[1][i - numPC] = myMinimizer.point[i];
@@ -440,10 +508,7 @@ bool ContaminationEstimator::OptimizeHeterFixedAlpha(AmoebaMinimizer &myMinimize
     std::cerr << "Start point:";
     for (int i = 0; i < numPC * 2; ++i) std::cerr << startingPoint[i] << "\t";
   }
-  myMinimizer.func = &fn;
-  myMinimizer.Reset(numPC * 2);
-  myMinimizer.point = startingPoint;
-  myMinimizer.Minimize(epsilon);
+  RunMinimizer(myMinimizer, startingPoint);
   for (int i = 0; i < numPC; ++i) PC[0][i] = myMinimizer.point[i];
   for (int i = numPC; i < numPC * 2; ++i) PC[1][i - numPC] = myMinimizer.point[i];
   return true;  // fixAlpha usually converges well
@@ -460,10 +525,7 @@ bool ContaminationEstimator::OptimizeHomo(AmoebaMinimizer &myMinimizer) {
     for (int i = 0; i < numPC; ++i) std::cerr << startingPoint[i] << "\t";
     std::cerr << "and alpha:\t" << alpha << std::endl;
   }
-  myMinimizer.func = &fn;
-  myMinimizer.Reset(numPC + 1);
-  myMinimizer.point = startingPoint;
-  double ret = myMinimizer.Minimize(epsilon);
+  double ret = RunMinimizer(myMinimizer, startingPoint);
   alpha = FullLLKFunc::InvLogit(myMinimizer.point[numPC]);
   for (int i = 0; i < numPC; ++i) PC[0][i] = myMinimizer.point[i];
   return ret != std::numeric_limits<double>::max();
@@ -476,10 +538,7 @@ bool ContaminationEstimator::OptimizeHomoFixedAlpha(AmoebaMinimizer &myMinimizer
     std::cerr << "Start point:";
     for (int i = 0; i < numPC; ++i) std::cerr << startingPoint[i] << "\t";
   }
-  myMinimizer.func = &fn;
-  myMinimizer.Reset(numPC);
-  myMinimizer.point = startingPoint;
-  myMinimizer.Minimize(epsilon);
+  RunMinimizer(myMinimizer, startingPoint);
   for (int i = 0; i < numPC; ++i) PC[0][i] = myMinimizer.point[i];
   return true;  // fixAlpha usually converges well
 }
@@ -491,10 +550,7 @@ bool ContaminationEstimator::OptimizeHomoFixedPC(AmoebaMinimizer &myMinimizer) {
     std::cerr << "Start point";
     std::cerr << "alpha:\t" << alpha << std::endl;
   }
-  myMinimizer.func = &fn;
-  myMinimizer.Reset(1);
-  myMinimizer.point = startingPoint;
-  double ret = myMinimizer.Minimize(epsilon);
+  double ret = RunMinimizer(myMinimizer, startingPoint);
   alpha = FullLLKFunc::InvLogit(myMinimizer.point[0]);
   return ret != std::numeric_limits<double>::max();
 }

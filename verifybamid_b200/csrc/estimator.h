@@ -89,6 +89,7 @@ class ContaminationEstimator {
   bool IsSanityCheckOK();                      // cpp:543-587
   void BuildResolvedMarkers();                 // cpp:67-86
   int OptimizeLLK(const std::string &OutputPrefix);  // cpp:88-190
+  double RunMinimizer(AmoebaMinimizer &m, const std::vector<double> &startingPoint);  // Reset + Minimize(epsilon)
   bool OptimizeHomoFixedPC(AmoebaMinimizer &m);      // cpp:315-332
   bool OptimizeHomoFixedAlpha(AmoebaMinimizer &m);   // cpp:291-313
   bool OptimizeHomo(AmoebaMinimizer &m);             // cpp:265-289
@@ -101,6 +102,7 @@ class ContaminationEstimator {
   void DestroyEngines();
   std::vector<vb2_llk_ctx *> engines;
   double engineSeconds = 0;  // wall time spent inside ComputeMixLLKs
+  long deviceSimplexEvals = 0;  // evaluations made by searches that ran on the device
 };
 
 }  // namespace vb2

@@ -1151,22 +1151,216 @@ __global__ void __launch_bounds__(32, 1) llk_reduce_kernel(const __grid_constant
 //   answer     {CTA partial, seq} into the host mailbox; the host adds the partials in llk_kernel's order.
 // The kernel leaves on the exit doorbell, or by itself after idle_cycles without a doorbell (so a host that
 // went away cannot leave the GPU spinning); the host notices and relaunches.
-constexpr int kMaxBellChunks = 12 + 2 * VB2_MAX_PC;  // c0[6], c1[6], pc_contam[k], pc_intended[k]
+constexpr int kMaxBellChunks = 12 + 2 * VB2_MAX_PC + 1;  // c0[6], c1[6], pc_contam[k], pc_intended[k], control
 constexpr int kMaxSessionItems = 4;                  // blobs a warp may hold resident
 constexpr unsigned long long kBellExit = ~0ull;
+// A doorbell whose control chunk carries this flag (next to the sequence number in every other chunk) starts a
+// simplex search on the device instead of one evaluation (vb2_llk_minimize).
+constexpr unsigned long long kCtlMinimize = 1ull << 62;
+constexpr unsigned long long kCtlDeviceMailbox = 1ull;  // relay only: this evaluation's partials go to the L2 mailbox
 
 struct __align__(16) BellChunk {
   double payload;
   unsigned long long seq;
 };
 
+// ---- the simplex search on the device (vb2_llk_minimize) ---------------------------------------------------------
+// Request and result live in host-mapped memory; the state lives in the shared memory of the first CTA.
+constexpr int kMinDim = VB2_MIN_MAX_DIM;
+constexpr int kMinPc = 4;
+struct MinRequest {   // host -> device
+  int32_t dim, n_pc, alpha_from, pad_;
+  int32_t pc1_from[kMinPc], pc2_from[kMinPc];
+  double pc1_fixed[kMinPc], pc2_fixed[kMinPc], alpha_fixed;
+  double start[kMinDim], scale, ftol, llk1;
+  long long cycle_max;
+};
+struct MinResult {    // device -> host; `done` is written last and carries the sequence number of the last evaluation
+  double fmin, point[kMinDim], llk1, best_pc1[kMinPc], best_pc2[kMinPc], best_alpha;
+  long long evals, cycle_count;
+  int32_t converged, improved;
+  unsigned long long done;
+};
+enum NmPhase : int { kNmIdle = 0, kNmInit, kNmReflect, kNmExpand, kNmContract, kNmShrink };
+struct NmState {
+  MinRequest rq;
+  int phase, i, ilo, ihi, inhi, improved;
+  long long cycle_count, evals;
+  double fmin, ysave, llk1, best_alpha;
+  double simplex[kMinDim + 1][kMinDim], y[kMinDim + 1], psum[kMinDim], ptry[kMinDim];
+  double best_pc1[kMinPc], best_pc2[kMinPc];
+  double cur_pc1[kMinPc], cur_pc2[kMinPc], cur_alpha;  // ComputeMixLLKs' arguments of the evaluation in flight
+  const double *req;  // the point being evaluated (a simplex row, or ptry)
+};
+
+// AmoebaMinimizer (MathGenMin.cpp:326-443) as a resumable machine: nm_resume() takes the value of the point it asked
+// for last and either asks for the next one (true: N.req) or finishes (false).  One thread; every operation is the
+// reference's, rounded where the reference rounds (no contraction: __dadd_rn / __dmul_rn / __ddiv_rn), so that the
+// simplex visits the reference's points when it is fed the reference's values.
+__device__ __forceinline__ void nm_psum(NmState &N) {  // MathGenMin.cpp:347-349, :412-415
+  const int dim = N.rq.dim;
+  for (int j = 0; j < dim; ++j) N.psum[j] = N.simplex[0][j];
+  for (int m = 1; m <= dim; ++m)
+    for (int j = 0; j < dim; ++j) N.psum[j] = __dadd_rn(N.psum[j], N.simplex[m][j]);
+}
+__device__ __forceinline__ void nm_try(NmState &N, double factor) {  // MathGenMin.cpp:425-433: the trial point
+  const int dim = N.rq.dim;
+  const double fac = __ddiv_rn(__dsub_rn(1.0, factor), (double)dim), fac2 = __dsub_rn(factor, fac);
+  for (int j = 0; j < dim; ++j) N.ptry[j] = __dadd_rn(__dmul_rn(fac, N.psum[j]), __dmul_rn(fac2, N.simplex[N.ihi][j]));
+  N.req = N.ptry;
+}
+__device__ __forceinline__ void nm_accept(NmState &N, double ytry) {  // MathGenMin.cpp:434-442
+  if (ytry < N.y[N.ihi]) {
+    const int dim = N.rq.dim;
+    N.y[N.ihi] = ytry;
+    for (int j = 0; j < dim; ++j) {
+      N.psum[j] = __dadd_rn(__dsub_rn(N.psum[j], N.simplex[N.ihi][j]), N.ptry[j]);
+      N.simplex[N.ihi][j] = N.ptry[j];
+    }
+  }
+}
+__device__ __noinline__ bool nm_resume(NmState &N, double f, int *converged) {
+  const int dim = N.rq.dim, nvertex = dim + 1;
+  switch (N.phase) {
+    case kNmIdle:  // start: the initial simplex, vertex by vertex (MathGenMin.cpp:335-345)
+      N.fmin = 1.0e+100;
+      N.i = 0;
+      N.phase = kNmInit;
+      for (int j = 0; j < dim; ++j) N.simplex[0][j] = __dadd_rn(N.rq.start[j], j == 0 ? N.rq.scale : 0.0);
+      N.req = N.simplex[0];
+      return true;
+    case kNmInit:
+      N.y[N.i] = f;
+      if (f < N.fmin) N.fmin = f;
+      if (++N.i < nvertex) {
+        const int i = N.i;
+        for (int j = 0; j < dim; ++j) N.simplex[i][j] = i < dim ? __dadd_rn(N.rq.start[j], j == i ? N.rq.scale : 0.0) : N.rq.start[j];
+        N.req = N.simplex[i];
+        return true;
+      }
+      N.cycle_count = nvertex;
+      nm_psum(N);
+      break;
+    case kNmReflect: {
+      nm_accept(N, f);
+      if (f <= N.y[N.ilo]) {  // MathGenMin.cpp:392-394: expand
+        nm_try(N, 2.0);
+        N.phase = kNmExpand;
+        return true;
+      }
+      if (f >= N.y[N.inhi]) {  // :395-399: contract
+        N.ysave = N.y[N.ihi];
+        nm_try(N, 0.5);
+        N.phase = kNmContract;
+        return true;
+      }
+      --N.cycle_count;  // :419
+      break;
+    }
+    case kNmExpand:
+      nm_accept(N, f);
+      break;
+    case kNmContract:
+      nm_accept(N, f);
+      if (f >= N.ysave) {  // :402-416: shrink everything towards the best vertex, re-evaluating vertex by vertex
+        N.phase = kNmShrink;
+        N.i = -1;
+        f = 0.0;
+        goto shrink_next;
+      }
+      break;
+    case kNmShrink:
+      N.y[N.i] = f;
+    shrink_next:
+      for (++N.i; N.i < nvertex; ++N.i)
+        if (N.i != N.ilo) {
+          const int i = N.i;
+          for (int j = 0; j < dim; ++j) N.simplex[i][j] = __dmul_rn(__dadd_rn(N.simplex[i][j], N.simplex[N.ilo][j]), 0.5);
+          N.req = N.simplex[i];
+          return true;
+        }
+      N.cycle_count += dim;
+      nm_psum(N);
+      break;
+  }
+  // the top of the loop (MathGenMin.cpp:357-390): order the vertices, test for convergence, reflect
+  int ilo, ihi, inhi;
+  if (N.y[0] > N.y[1]) { ilo = inhi = 1; ihi = 0; } else { ilo = inhi = 0; ihi = 1; }
+  for (int i = 2; i < nvertex; ++i) {
+    if (N.y[i] <= N.y[ilo]) ilo = i;
+    else if (N.y[i] > N.y[ihi]) { inhi = ihi; ihi = i; }
+    else if (N.y[i] > N.y[inhi]) inhi = i;
+  }
+  N.ilo = ilo; N.ihi = ihi; N.inhi = inhi;
+  const double rtol = __ddiv_rn(2 * fabs(__dsub_rn(N.y[ihi], N.y[ilo])),
+                                __dadd_rn(__dadd_rn(fabs(N.y[ihi]), fabs(N.y[ilo])), 3.0e-10));  // ZEPS
+  if (rtol < N.rq.ftol) {
+    N.fmin = N.y[ilo];
+    *converged = 1;
+    N.phase = kNmIdle;
+    return false;
+  }
+  if (N.cycle_count > N.rq.cycle_max) {
+    *converged = 0;
+    N.phase = kNmIdle;
+    return false;
+  }
+  N.cycle_count += 2;
+  nm_try(N, -1.0);
+  N.phase = kNmReflect;
+  return true;
+}
+// FullLLKFunc::Evaluate's unpacking of v (h:339-442) and fill_job's coefficients, rounded as the host rounds them
+__device__ __forceinline__ void nm_job(NmState &N, JobParams &J) {
+  const MinRequest &R = N.rq;
+  const double *v = N.req;
+  for (int k = 0; k < kMinPc; ++k) {
+    N.cur_pc1[k] = k < R.n_pc ? (R.pc1_from[k] >= 0 ? v[R.pc1_from[k]] : R.pc1_fixed[k]) : 0.0;
+    N.cur_pc2[k] = k < R.n_pc ? (R.pc2_from[k] >= 0 ? v[R.pc2_from[k]] : R.pc2_fixed[k]) : 0.0;
+    J.pc1[k] = N.cur_pc1[k];
+    J.pc2[k] = N.cur_pc2[k];
+  }
+  double alpha = R.alpha_fixed;
+  if (R.alpha_from >= 0) {  // InvLogit, h:119-122
+    const double e = exp(v[R.alpha_from]);
+    alpha = __ddiv_rn(e, __dadd_rn(1., e));
+  }
+  N.cur_alpha = alpha;
+  const double E[3] = {0.0, 1.0 / 6.0, 1.0 / 3.0}, Nn[3] = {1.0, 0.5, 0.0};
+  const double oma = __dsub_rn(1.0, alpha);
+#pragma unroll
+  for (int p = 0; p < kNumPairs; ++p) {
+    const int g1 = pair_g1(p), g2 = pair_g2(p);
+    const double e_mix = __dadd_rn(__dmul_rn(alpha, E[g1]), __dmul_rn(oma, E[g2]));
+    const double n_mix = __dadd_rn(__dmul_rn(alpha, Nn[g1]), __dmul_rn(oma, Nn[g2]));
+    J.c0[p] = n_mix;
+    J.c1[p] = __dsub_rn(e_mix, n_mix);
+  }
+}
+// Evaluate's best-so-far bookkeeping (h:344-440): the free components of the best point over all evaluations
+__device__ __forceinline__ void nm_track_best(NmState &N, double f) {
+  if (f < N.llk1) {
+    const MinRequest &R = N.rq;
+    N.llk1 = f;
+    N.improved = 1;
+    for (int k = 0; k < kMinPc; ++k) {
+      if (R.pc1_from[k] >= 0) N.best_pc1[k] = N.cur_pc1[k];
+      if (R.pc2_from[k] >= 0) N.best_pc2[k] = N.cur_pc2[k];
+    }
+    if (R.alpha_from >= 0) N.best_alpha = N.cur_alpha;
+  }
+}
+
 struct SessionArgs {
   SampleDev sample;
   const BellChunk *bell;  // device view of the host-mapped doorbell (polled by CTA 0 only: PCIe reads)
   BellChunk *relay;       // the same chunks in HBM: CTA 0 forwards the doorbell, the other CTAs poll this copy in L2
   Slot *mbox;             // device view of the host mailbox: slot [cta]
+  Slot *dmbox;            // the mailbox in HBM/L2: slot [cta] (evaluations of a search on the device)
+  const MinRequest *min_req;  // device views of the host-mapped request / result of vb2_llk_minimize
+  MinResult *min_res;
   unsigned long long first_seq, idle_cycles;
-  uint32_t kc, n_items, n_chunks;
+  uint32_t kc, n_items, n_chunks;  // n_chunks = 12 + 2 n_pc parameter chunks; the control chunk follows them
   unsigned long long *trace;  // diagnostics: [grid_x][kTraceSlots] SM clock of thread 0 at the stages of the LAST evaluation
   uint32_t null_eval;  // diagnostics (VB2_LLK_SESSION_NULL): answer without reading a single read -> the doorbell + mailbox round trip
   double phred[kPhredArgs];
@@ -1182,7 +1376,8 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
   __shared__ double s_red[4];
   __shared__ __align__(8) uint64_t s_bar[kMaxWarps];
   __shared__ uint32_t s_item_r[kMaxWarps][kMaxSessionItems];
-  __shared__ uint32_t s_stop;
+  __shared__ uint32_t s_stop, s_mode;
+  __shared__ NmState s_nm;  // (used by the first CTA only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SampleDev &S = A.sample;
@@ -1220,7 +1415,11 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
   }
   if (threadIdx.x < 256) s_e[threadIdx.x] = threadIdx.x < (uint32_t)kPhredArgs ? A.phred[threadIdx.x] : 1.0;
   if (blockDim.x < 256 && threadIdx.x < 128) s_e[threadIdx.x + 128] = 1.0;
-  if (threadIdx.x == 0) s_stop = 0u;
+  if (threadIdx.x == 0) {
+    s_stop = 0u;
+    s_mode = 0u;
+    s_nm.phase = kNmIdle;
+  }
 #pragma unroll 1
   for (uint32_t i = threadIdx.x; i < n_rounds * 128u; i += blockDim.x) s_L[i] = 1.0;  // neutral marginals
   __syncwarp();
@@ -1231,56 +1430,109 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
   auto stamp = [&](int k) {
     if (A.trace && threadIdx.x == 0) A.trace[blockIdx.x * kTraceSlots + k] = (unsigned long long)clock64();
   };
+  // chunk i of the doorbell <-> JobParams: c0[6], c1[6], pc1[k] (at 12), pc2[k] (at 12 + VB2_MAX_PC)
+  const uint32_t n_chunks = A.n_chunks, n_pc_chunks = S.n_pc;
+  auto chunk_slot = [&](uint32_t i) { return i < 12u ? i : (i < 12u + n_pc_chunks ? i : i - n_pc_chunks + (uint32_t)VB2_MAX_PC); };
+  const bool head = blockIdx.x == 0;  // the one CTA that talks to the host (and runs the simplex)
   unsigned long long expected = A.first_seq;
+  bool searching = false;  // (head CTA, warp 0) a simplex search is running: the next point comes from s_nm
 #pragma unroll 1
   for (;;) {
     stamp(0);
-    // ---- doorbell ----------------------------------------------------------------------------------
+    // ---- the next evaluation's parameters ----------------------------------------------------------------
     if (warp == 0) {
-      const unsigned long long t_idle = (unsigned long long)clock64();
-      const uint32_t n_chunks = A.n_chunks;
-      const bool head = blockIdx.x == 0;  // the one CTA that talks to the host
-      const BellChunk *src = head ? A.bell : A.relay;
-      uint32_t stop = 0;
-      for (;;) {
-        bool ok = true, bye = false;
+      uint32_t stop = 0, mode = 0;
+      if (head && searching) {
+        // the search proposes the point itself: Evaluate's unpacking + fill_job, then straight to the relay
+        if (lane == 0) nm_job(s_nm, s_job);
+        __syncwarp();
+        mode = (uint32_t)kCtlDeviceMailbox;
+      } else {
+        const unsigned long long t_idle = (unsigned long long)clock64();
+        // Only the head CTA decides that the session has been idle for too long (and says so through the relay);
+        // the others would only give up, much later, on a head that has gone away.
+        const unsigned long long patience = head ? A.idle_cycles : A.idle_cycles * 64ull;
+        const BellChunk *src = head ? A.bell : A.relay;
+        for (;;) {
+          bool ok = true, bye = false;
+          unsigned long long xsum = 0ull, ctl = 0ull;
 #pragma unroll
-        for (uint32_t base = 0; base < (uint32_t)kMaxBellChunks; base += 32) {
-          const uint32_t i = base + (uint32_t)lane;
-          if (i < n_chunks) {
-            unsigned long long pay, seq;
-            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(pay), "=l"(seq) : "l"(src + i) : "memory");
-            bye = bye || seq == kBellExit;
-            ok = ok && seq == expected;
-            if (seq == expected) {
-              const uint32_t k = S.n_pc;  // chunk -> JobParams: c0[6], c1[6], pc1[k] (at 12), pc2[k] (at 12 + VB2_MAX_PC)
-              const uint32_t idx = i < 12u ? i : (i < 12u + k ? i : i - k + (uint32_t)VB2_MAX_PC);
-              reinterpret_cast<double *>(&s_job)[idx] = __longlong_as_double((long long)pay);
+          for (uint32_t base = 0; base < (uint32_t)kMaxBellChunks; base += 32) {
+            const uint32_t i = base + (uint32_t)lane;
+            if (i <= n_chunks) {
+              // ONE 16-byte load per chunk: payload and stamp arrive together (a naturally aligned 16-byte access is
+              // a single transaction on this part; the host's control chunk also carries a checksum of the
+              // payloads, so a torn read could not pass for a doorbell)
+              unsigned long long pay, seq;
+              asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(pay), "=l"(seq) : "l"(src + i) : "memory");
+              bye = bye || seq == kBellExit;
+              if (i < n_chunks) {
+                ok = ok && seq == expected;
+                xsum ^= pay;
+                if (seq == expected) reinterpret_cast<double *>(&s_job)[chunk_slot(i)] = __longlong_as_double((long long)pay);
+              } else {  // the control chunk
+                ok = ok && (seq & ~kCtlMinimize) == expected;
+                ctl = (seq & kCtlMinimize) | (pay & 0xFFull);
+                if (head) xsum ^= pay & ~0xFFull;
+              }
             }
           }
+          if (__any_sync(0xFFFFFFFFu, bye)) { stop = 1; break; }
+          if (__all_sync(0xFFFFFFFFu, ok)) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+              xsum ^= __shfl_xor_sync(0xFFFFFFFFu, xsum, o);
+              ctl |= __shfl_xor_sync(0xFFFFFFFFu, ctl, o);
+            }
+            if (!head || (xsum & ~0xFFull) == 0ull) {  // (host doorbell: the payloads' checksum, bits 8..63, must match)
+              mode = (uint32_t)(ctl & 0xFFull);
+              if (head && (ctl & kCtlMinimize)) {  // start a search: the request sits in host-mapped memory
+                if (lane == 0) {
+                  __threadfence_system();
+                  const volatile MinRequest *rq = A.min_req;
+                  MinRequest &dst = s_nm.rq;
+                  for (uint32_t w = 0; w < sizeof(MinRequest) / 8u; ++w)
+                    reinterpret_cast<unsigned long long *>(&dst)[w] = reinterpret_cast<const volatile unsigned long long *>(rq)[w];
+                  s_nm.phase = kNmIdle;
+                  s_nm.evals = 0;
+                  s_nm.improved = 0;
+                  s_nm.llk1 = dst.llk1;
+                  int conv = 0;
+                  nm_resume(s_nm, 0.0, &conv);  // (asks for the first vertex)
+                  nm_job(s_nm, s_job);
+                }
+                __syncwarp();
+                searching = true;
+                mode = (uint32_t)kCtlDeviceMailbox;
+              }
+              break;
+            }
+          }
+          if ((unsigned long long)clock64() - t_idle > patience) { stop = 1; break; }
         }
-        if (__any_sync(0xFFFFFFFFu, bye)) { stop = 1; break; }
-        if (__all_sync(0xFFFFFFFFu, ok)) break;
-        if ((unsigned long long)clock64() - t_idle > A.idle_cycles) { stop = 1; break; }
       }
       if (head) {  // forward: the evaluation's chunks, or the order to leave
 #pragma unroll
         for (uint32_t base = 0; base < (uint32_t)kMaxBellChunks; base += 32) {
           const uint32_t i = base + (uint32_t)lane;
-          if (i < n_chunks) {
-            const uint32_t k = S.n_pc;
-            const uint32_t idx = i < 12u ? i : (i < 12u + k ? i : i - k + (uint32_t)VB2_MAX_PC);
-            const unsigned long long pay = (unsigned long long)__double_as_longlong(reinterpret_cast<const double *>(&s_job)[idx]);
+          if (i <= n_chunks) {
+            const unsigned long long pay = i < n_chunks
+                ? (unsigned long long)__double_as_longlong(reinterpret_cast<const double *>(&s_job)[chunk_slot(i)])
+                : (unsigned long long)mode;
             const unsigned long long seq = stop ? kBellExit : expected;
             asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(A.relay + i), "l"(pay), "l"(seq) : "memory");
           }
         }
       }
-      if (lane == 0 && stop) s_stop = 1u;
+      if (lane == 0) {
+        if (stop) s_stop = 1u;
+        s_mode = mode;
+      }
       stamp(1);
     }
     __syncthreads();  // parameters (or the stop flag) published
     if (s_stop) return;
+    const uint32_t mode = s_mode;
     stamp(2);
 
     // ---- the evaluation: every resident slice of this warp -------------------------------------------
@@ -1326,11 +1578,55 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
       for (int o = 16; o; o >>= 1) vsum += __shfl_xor_sync(0xFFFFFFFFu, vsum, o);
       if (lane == 0) s_red[warp] = vsum;
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 0 && lane == 0) {
-        const double cta = ((s_red[0] + s_red[1]) + s_red[2]) + s_red[3];
-        *reinterpret_cast<ulonglong2 *>(A.mbox + blockIdx.x) =
-            make_ulonglong2((unsigned long long)__double_as_longlong(cta), expected);
-        stamp(6);
+      if (warp == 0) {
+        if (lane == 0) {
+          const double cta = ((s_red[0] + s_red[1]) + s_red[2]) + s_red[3];
+          Slot *slot = (mode & (uint32_t)kCtlDeviceMailbox) ? A.dmbox + blockIdx.x : A.mbox + blockIdx.x;
+          asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"((unsigned long long)__double_as_longlong(cta)),
+                       "l"(expected) : "memory");
+          stamp(6);
+        }
+        if (head && searching) {
+          // ---- the search takes the sum itself: every CTA's partial from the L2 mailbox, added in the order the
+          // host (and llk_kernel's last CTA) use: lane-strided sums, then a butterfly
+          const uint32_t gx = S.grid_x;
+          double sum = 0.0;
+          for (uint32_t c = lane; c < gx; c += 32) {
+            unsigned long long val, seq;
+            do {
+              asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(val), "=l"(seq) : "l"(A.dmbox + c) : "memory");
+            } while (seq != expected);
+            sum += __longlong_as_double((long long)val);
+          }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+          uint32_t more = 1;
+          if (lane == 0) {
+            const double f = 0 - (sum + S.log_other_const);  // h:344
+            ++s_nm.evals;
+            nm_track_best(s_nm, f);
+            int conv = 0;
+            if (!nm_resume(s_nm, f, &conv)) {  // finished: the result, then its stamp
+              more = 0;
+              volatile MinResult *res = A.min_res;
+              res->fmin = s_nm.fmin;
+              // (without convergence AmoebaMinimizer::point is never assigned: it still is the starting point)
+              for (int j = 0; j < kMinDim; ++j)
+                res->point[j] = j < s_nm.rq.dim ? (conv ? s_nm.simplex[s_nm.ilo][j] : s_nm.rq.start[j]) : 0.0;
+              res->llk1 = s_nm.llk1;
+              for (int k = 0; k < kMinPc; ++k) { res->best_pc1[k] = s_nm.best_pc1[k]; res->best_pc2[k] = s_nm.best_pc2[k]; }
+              res->best_alpha = s_nm.best_alpha;
+              res->evals = s_nm.evals;
+              res->cycle_count = s_nm.cycle_count;
+              res->converged = conv;
+              res->improved = s_nm.improved;
+              __threadfence_system();
+              res->done = expected;
+            }
+          }
+          more = __shfl_sync(0xFFFFFFFFu, more, 0);
+          searching = more != 0;
+        }
       }
     }
     ++expected;
@@ -1411,6 +1707,9 @@ struct vb2_llk_ctx {
   // evaluation session (llk_session_kernel resident on the device)
   BellChunk *h_bell = nullptr, *d_bell = nullptr;  // host-mapped doorbell
   BellChunk *d_relay = nullptr;                    // its copy in HBM
+  Slot *d_dmbox = nullptr;                         // per-CTA partials of a search on the device (HBM/L2)
+  MinRequest *h_minreq = nullptr, *d_minreq = nullptr;  // host-mapped request / result of vb2_llk_minimize
+  MinResult *h_minres = nullptr, *d_minres = nullptr;
   bool session_active = false;
   uint32_t session_relaunches = 0;
   double clock_khz = 0.0, session_idle_ms = 200.0;
@@ -1600,6 +1899,10 @@ int session_launch(vb2_llk_ctx *ctx, unsigned long long first_seq) {
   A.relay = ctx->d_relay;
   VB2_CUDA(ctx, cudaMemsetAsync(ctx->d_relay, 0, sizeof(BellChunk) * kMaxBellChunks, ctx->stream));
   A.mbox = ctx->d_mbox;
+  A.dmbox = ctx->d_dmbox;
+  VB2_CUDA(ctx, cudaMemsetAsync(ctx->d_dmbox, 0, sizeof(Slot) * std::max(1u, ctx->S.grid_x), ctx->stream));
+  A.min_req = ctx->d_minreq;
+  A.min_res = ctx->d_minres;
   A.first_seq = first_seq;
   A.idle_cycles = (unsigned long long)(ctx->session_idle_ms * ctx->clock_khz);
   A.kc = g.kc;
@@ -1620,10 +1923,14 @@ int session_launch(vb2_llk_ctx *ctx, unsigned long long first_seq) {
 }
 // ring the doorbell for sequence number `seq`: every chunk's payload first, its stamp after it (x86 keeps the
 // order of the two stores; the device reads a chunk with one 16-byte load)
-void session_ring(vb2_llk_ctx *ctx, const JobParams &J, unsigned long long seq) {
+void session_ring(vb2_llk_ctx *ctx, const JobParams &J, unsigned long long seq, bool minimize = false) {
   const uint32_t k = ctx->S.n_pc;
   volatile BellChunk *bell = ctx->h_bell;
+  unsigned long long xsum = 0ull;
   auto put = [&](uint32_t i, double v) {
+    unsigned long long bits;
+    memcpy(&bits, &v, sizeof(bits));
+    xsum ^= bits;
     bell[i].payload = v;
     __atomic_store_n(&ctx->h_bell[i].seq, seq, __ATOMIC_RELEASE);
   };
@@ -1635,6 +1942,11 @@ void session_ring(vb2_llk_ctx *ctx, const JobParams &J, unsigned long long seq) 
     put(12u + j, J.pc1[j]);
     put(12u + k + j, J.pc2[j]);
   }
+  // the control chunk: bits 8..63 of the payloads' checksum (a doorbell read torn between a new stamp and an old
+  // payload cannot pass), the request type next to the sequence number
+  const unsigned long long ctl = xsum & ~0xFFull;
+  memcpy((void *)&ctx->h_bell[12u + 2u * k].payload, &ctl, sizeof(ctl));
+  __atomic_store_n(&ctx->h_bell[12u + 2u * k].seq, seq | (minimize ? kCtlMinimize : 0ull), __ATOMIC_RELEASE);
 }
 // stop the resident kernel (exit doorbell) and wait for it; no-op without a session
 void session_stop(vb2_llk_ctx *ctx) {
@@ -1842,6 +2154,9 @@ void vb2_llk_destroy(vb2_llk_ctx *ctx) {
   if (ctx->d_trace) cudaFree(ctx->d_trace);
   if (ctx->h_bell) cudaFreeHost(ctx->h_bell);
   if (ctx->d_relay) cudaFree(ctx->d_relay);
+  if (ctx->d_dmbox) cudaFree(ctx->d_dmbox);
+  if (ctx->h_minreq) cudaFreeHost(ctx->h_minreq);
+  if (ctx->h_minres) cudaFreeHost(ctx->h_minres);
   if (ctx->d_recs2) cudaFree(ctx->d_recs2);
   if (ctx->h_mbox) cudaFreeHost(ctx->h_mbox);
   if (ctx->h_jobs2) cudaFreeHost(ctx->h_jobs2);
@@ -2341,6 +2656,13 @@ int vb2_llk_session_begin(vb2_llk_ctx *ctx) {
     memset(ctx->h_bell, 0, sizeof(BellChunk) * kMaxBellChunks);
     VB2_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->d_bell, ctx->h_bell, 0));
     VB2_CUDA(ctx, cudaMalloc(&ctx->d_relay, sizeof(BellChunk) * kMaxBellChunks));
+    VB2_CUDA(ctx, cudaMalloc(&ctx->d_dmbox, sizeof(Slot) * std::max(1u, ctx->S.grid_x)));
+    VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_minreq, sizeof(MinRequest), cudaHostAllocMapped));
+    VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_minres, sizeof(MinResult), cudaHostAllocMapped));
+    memset(ctx->h_minreq, 0, sizeof(MinRequest));
+    memset(ctx->h_minres, 0, sizeof(MinResult));
+    VB2_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->d_minreq, ctx->h_minreq, 0));
+    VB2_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->d_minres, ctx->h_minres, 0));
   }
   int rc = session_launch(ctx, ctx->seq + 1);
   if (rc) return rc;
@@ -2355,6 +2677,78 @@ int vb2_llk_session_end(vb2_llk_ctx *ctx) {
   session_stop(ctx);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(ctx, VB2_ERR_CUDA, std::string("llk_session_kernel: ") + cudaGetErrorString(e));
+  return VB2_OK;
+}
+
+int vb2_llk_minimize(vb2_llk_ctx *ctx, const vb2_llk_model *model, const double *start, double scale, double ftol,
+                     int64_t cycle_max, double llk1_in, vb2_llk_min_result *result) {
+  if (!ctx) return set_err(nullptr, VB2_ERR_INVALID, "null context");
+  if (!model || !start || !result) return set_err(ctx, VB2_ERR_INVALID, "null argument");
+  if (model->struct_size != sizeof(vb2_llk_model) || result->struct_size != sizeof(vb2_llk_min_result))
+    return set_err(ctx, VB2_ERR_INVALID, "struct_size mismatch (ABI version skew)");
+  const uint32_t k = ctx->S.n_pc;
+  if (model->dim < 1 || model->dim > (uint32_t)kMinDim || k > (uint32_t)kMinPc)
+    return set_err(ctx, VB2_ERR_INVALID, "vb2_llk_minimize: dim must be in [1, VB2_MIN_MAX_DIM] and n_pc <= 4");
+  if (!ctx->session_active || ctx->S.grid_x == 0)
+    return set_err(ctx, VB2_ERR_INVALID, "vb2_llk_minimize needs an open evaluation session on a sample with usable markers");
+  if (ctx->pending_n) return set_err(ctx, VB2_ERR_INVALID, "an evaluation is pending on this context");
+  for (uint32_t j = 0; j < k; ++j)
+    if (model->pc1_from[j] >= (int32_t)model->dim || model->pc2_from[j] >= (int32_t)model->dim)
+      return set_err(ctx, VB2_ERR_INVALID, "vb2_llk_model: index beyond dim");
+  if (model->alpha_from >= (int32_t)model->dim) return set_err(ctx, VB2_ERR_INVALID, "vb2_llk_model: index beyond dim");
+  VB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  MinRequest rq;
+  memset(&rq, 0, sizeof(rq));
+  rq.dim = (int32_t)model->dim;
+  rq.n_pc = (int32_t)k;
+  rq.alpha_from = model->alpha_from < 0 ? -1 : model->alpha_from;
+  for (uint32_t j = 0; j < (uint32_t)kMinPc; ++j) {
+    rq.pc1_from[j] = j < k && model->pc1_from[j] >= 0 ? model->pc1_from[j] : -1;
+    rq.pc2_from[j] = j < k && model->pc2_from[j] >= 0 ? model->pc2_from[j] : -1;
+    rq.pc1_fixed[j] = j < k ? model->pc1_fixed[j] : 0.0;
+    rq.pc2_fixed[j] = j < k ? model->pc2_fixed[j] : 0.0;
+  }
+  rq.alpha_fixed = model->alpha_fixed;
+  for (uint32_t j = 0; j < model->dim; ++j) rq.start[j] = start[j];
+  rq.scale = scale;
+  rq.ftol = ftol;
+  rq.llk1 = llk1_in;
+  rq.cycle_max = (long long)cycle_max;
+  memcpy(ctx->h_minreq, &rq, sizeof(rq));
+  __atomic_store_n(&ctx->h_minres->done, 0ull, __ATOMIC_RELEASE);
+  const unsigned long long s0 = ctx->seq + 1;
+  JobParams none;
+  memset(&none, 0, sizeof(none));
+  session_ring(ctx, none, s0, true);
+  // wait for the result's stamp; a resident kernel that left on its idle watchdog is brought back (the bell still rings)
+  unsigned long spins = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  unsigned long long done = 0;
+  while ((done = __atomic_load_n(&ctx->h_minres->done, __ATOMIC_ACQUIRE)) == 0ull) {
+    if ((++spins & 0xFFFFu) == 0) {
+      cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady)
+        return set_err(ctx, VB2_ERR_CUDA, std::string("llk_session_kernel: ") + cudaGetErrorString(q));
+      if (q == cudaSuccess && __atomic_load_n(&ctx->h_minres->done, __ATOMIC_ACQUIRE) == 0ull) {
+        ++ctx->session_relaunches;
+        int rc = session_launch(ctx, s0);
+        if (rc) return rc;
+      }
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (ms > std::max(ctx->spin_timeout_ms, 120000.0)) return set_err(ctx, VB2_ERR_TIMEOUT, "timed out waiting for the device");
+    }
+  }
+  ctx->seq = done;  // the search used the sequence numbers s0 .. done
+  const MinResult &R = *ctx->h_minres;
+  result->converged = R.converged;
+  result->fmin = R.fmin;
+  for (int j = 0; j < kMinDim; ++j) result->point[j] = R.point[j];
+  result->evals = R.evals;
+  result->cycle_count = R.cycle_count;
+  result->llk1 = R.llk1;
+  result->improved = R.improved;
+  for (int j = 0; j < kMinPc; ++j) { result->best_pc_contam[j] = R.best_pc1[j]; result->best_pc_intended[j] = R.best_pc2[j]; }
+  result->best_alpha = R.best_alpha;
   return VB2_OK;
 }
 

@@ -28,6 +28,7 @@ VB2_FLAG_NO_SPIN = 1
 VB2_FLAG_BATCHED = 2
 VB2_MAX_PC = 16
 VB2_MAX_BATCH = 4096
+VB2_MIN_MAX_DIM = 9
 
 _STATUS = {1: "VB2_ERR_INVALID", 2: "VB2_ERR_NO_DEVICE", 3: "VB2_ERR_CUDA", 4: "VB2_ERR_NOMEM", 5: "VB2_ERR_TIMEOUT"}
 
@@ -36,7 +37,7 @@ ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_warmup", "vb2_llk
                "vb2_llk_eval", "vb2_llk_eval_begin", "vb2_llk_eval_end", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many", "vb2_llk_eval_many_device",
                "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free",
                "vb2_llk_time_device", "vb2_llk_time_device_many", "vb2_llk_time_host", "vb2_llk_trace",
-               "vb2_llk_session_begin", "vb2_llk_session_end")
+               "vb2_llk_session_begin", "vb2_llk_session_end", "vb2_llk_minimize")
 
 
 class VB2Error(RuntimeError):
@@ -79,6 +80,22 @@ class _PackedView(ctypes.Structure):
                 ("log_other_const", ctypes.c_double),
                 ("blob", ctypes.POINTER(ctypes.c_uint8)), ("rounds", ctypes.POINTER(ctypes.c_uint32)),
                 ("marker_index", ctypes.POINTER(ctypes.c_uint32)), ("owner", ctypes.c_void_p)]
+
+
+class _Model(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("dim", ctypes.c_uint32),
+                ("pc1_from", ctypes.c_int32 * VB2_MAX_PC), ("pc2_from", ctypes.c_int32 * VB2_MAX_PC),
+                ("alpha_from", ctypes.c_int32), ("pad_", ctypes.c_int32),
+                ("pc1_fixed", ctypes.c_double * VB2_MAX_PC), ("pc2_fixed", ctypes.c_double * VB2_MAX_PC),
+                ("alpha_fixed", ctypes.c_double)]
+
+
+class _MinResult(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("converged", ctypes.c_int32), ("fmin", ctypes.c_double),
+                ("point", ctypes.c_double * VB2_MIN_MAX_DIM), ("evals", ctypes.c_int64), ("cycle_count", ctypes.c_int64),
+                ("llk1", ctypes.c_double), ("improved", ctypes.c_int32), ("pad_", ctypes.c_int32),
+                ("best_pc_contam", ctypes.c_double * 4), ("best_pc_intended", ctypes.c_double * 4),
+                ("best_alpha", ctypes.c_double)]
 
 
 _lib = None
@@ -133,6 +150,9 @@ def load_library() -> ctypes.CDLL:
         if hasattr(lib, name):
             getattr(lib, name).restype = ctypes.c_int
             getattr(lib, name).argtypes = [ctypes.c_void_p]
+    lib.vb2_llk_minimize.restype = ctypes.c_int
+    lib.vb2_llk_minimize.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Model), ctypes.c_void_p, ctypes.c_double, ctypes.c_double,
+                                     ctypes.c_int64, ctypes.c_double, ctypes.POINTER(_MinResult)]
     lib.vb2_llk_sync.restype = ctypes.c_int
     lib.vb2_llk_sync.argtypes = [ctypes.c_void_p]
     lib.vb2_llk_time_device.restype = ctypes.c_int
@@ -308,6 +328,31 @@ class LLKEngine:
 
     def session_end(self) -> None:
         self._check(self._lib.vb2_llk_session_end(self._ctx))
+
+    def minimize(self, start, pc1_from, pc2_from, alpha_from: int, pc1_fixed=None, pc2_fixed=None, alpha_fixed: float = 0.0,
+                 scale: float = 1.0, ftol: float = 1e-8, cycle_max: int = 50000, llk1: float = 1e300) -> dict:
+        """AmoebaMinimizer::Minimize on the device (include/vb2_llk.h, vb2_llk_minimize); needs session_begin().
+        pc1_from / pc2_from: per PC the index into the simplex vector, or -1 = the fixed value; alpha_from likewise
+        (alpha = InvLogit(v[alpha_from])).  Returns the fields of vb2_llk_min_result."""
+        v = _f64(start).ravel()
+        m = _Model()
+        m.struct_size = ctypes.sizeof(_Model)
+        m.dim = v.size
+        for k in range(VB2_MAX_PC):
+            m.pc1_from[k] = int(pc1_from[k]) if k < len(pc1_from) else -1
+            m.pc2_from[k] = int(pc2_from[k]) if k < len(pc2_from) else -1
+            m.pc1_fixed[k] = float(pc1_fixed[k]) if pc1_fixed is not None and k < len(pc1_fixed) else 0.0
+            m.pc2_fixed[k] = float(pc2_fixed[k]) if pc2_fixed is not None and k < len(pc2_fixed) else 0.0
+        m.alpha_from = int(alpha_from)
+        m.alpha_fixed = float(alpha_fixed)
+        r = _MinResult()
+        r.struct_size = ctypes.sizeof(_MinResult)
+        self._check(self._lib.vb2_llk_minimize(self._ctx, ctypes.byref(m), v.ctypes.data, float(scale), float(ftol),
+                                               int(cycle_max), float(llk1), ctypes.byref(r)))
+        return {"converged": bool(r.converged), "fmin": r.fmin, "point": [r.point[i] for i in range(v.size)], "evals": int(r.evals),
+                "cycle_count": int(r.cycle_count), "llk1": r.llk1, "improved": bool(r.improved),
+                "best_pc_contam": [r.best_pc_contam[i] for i in range(self.n_pc)],
+                "best_pc_intended": [r.best_pc_intended[i] for i in range(self.n_pc)], "best_alpha": r.best_alpha}
 
     def trace(self, pc_contam, pc_intended, alpha: float):
         """One evaluation with the kernel's stage clock on: (llk, stamps[cta][VB2_TRACE_SLOTS]) (include/vb2_llk.h)."""
