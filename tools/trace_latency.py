@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import verifybamid_b200 as vb
 
-s = bench.make_workload()
+s = bench.make_workload("100k30x")
 with vb.LLKEngine(s.problem) as eng:
     for _ in range(20):
         eng.compute_mix_llks([0.01, 0.01], [0.01, 0.01], 0.03)
@@ -41,3 +41,12 @@ with vb.LLKEngine(s.problem) as eng:
     order = np.argsort(-c)
     print("   slowest CTAs:", [(int(i), int(c[i])) for i in order[:12]])
     print("   mean over CTAs 0..107: %d   108..147: %d" % (c[:108].mean(), c[108:].mean()))
+    os.environ["VB2_LLK_TRACE_SESSION"] = "search"
+    for rep in range(2):
+        llk, st = eng.trace([0.01, 0.01], [0.01, 0.01], 0.03)
+    st = st.astype(np.int64)
+    print("search on the device (vb2_llk_minimize), LAST evaluation, cycles since the top of the CTA's loop:")
+    for k, nme in [(1, "point + coefficients ready"), (2, "CTA barrier passed"), (3, "warp 0 slices done"), (15, "last warp slices done"),
+                   (6, "partial pushed to all"), (4, "all partials gathered"), (5, "simplex stepped")]:
+        c = st[:, k] - st[:, 0]
+        print("   %-28s min %7d  median %7d  max %7d" % (nme, c.min(), np.median(c), c.max()))

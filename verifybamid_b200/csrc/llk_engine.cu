@@ -1185,170 +1185,218 @@ enum NmPhase : int { kNmIdle = 0, kNmInit, kNmReflect, kNmExpand, kNmContract, k
 struct NmState {
   MinRequest rq;
   int phase, i, ilo, ihi, inhi, improved;
+  int req_row;  // the point being evaluated: simplex row, or -1 = ptry
+  int pad_;
   long long cycle_count, evals;
   double fmin, ysave, llk1, best_alpha;
   double simplex[kMinDim + 1][kMinDim], y[kMinDim + 1], psum[kMinDim], ptry[kMinDim];
   double best_pc1[kMinPc], best_pc2[kMinPc];
   double cur_pc1[kMinPc], cur_pc2[kMinPc], cur_alpha;  // ComputeMixLLKs' arguments of the evaluation in flight
-  const double *req;  // the point being evaluated (a simplex row, or ptry)
+  double fac[3], fac2[3];  // MathGenMin.cpp:427: (1 - factor) / dim and factor - that, for factor = -1, 2, 0.5
 };
 
-// AmoebaMinimizer (MathGenMin.cpp:326-443) as a resumable machine: nm_resume() takes the value of the point it asked
-// for last and either asks for the next one (true: N.req) or finishes (false).  One thread; every operation is the
-// reference's, rounded where the reference rounds (no contraction: __dadd_rn / __dmul_rn / __ddiv_rn), so that the
-// simplex visits the reference's points when it is fed the reference's values.
-__device__ __forceinline__ void nm_psum(NmState &N) {  // MathGenMin.cpp:347-349, :412-415
-  const int dim = N.rq.dim;
-  for (int j = 0; j < dim; ++j) N.psum[j] = N.simplex[0][j];
-  for (int m = 1; m <= dim; ++m)
-    for (int j = 0; j < dim; ++j) N.psum[j] = __dadd_rn(N.psum[j], N.simplex[m][j]);
-}
-__device__ __forceinline__ void nm_try(NmState &N, double factor) {  // MathGenMin.cpp:425-433: the trial point
-  const int dim = N.rq.dim;
-  const double fac = __ddiv_rn(__dsub_rn(1.0, factor), (double)dim), fac2 = __dsub_rn(factor, fac);
-  for (int j = 0; j < dim; ++j) N.ptry[j] = __dadd_rn(__dmul_rn(fac, N.psum[j]), __dmul_rn(fac2, N.simplex[N.ihi][j]));
-  N.req = N.ptry;
-}
-__device__ __forceinline__ void nm_accept(NmState &N, double ytry) {  // MathGenMin.cpp:434-442
-  if (ytry < N.y[N.ihi]) {
-    const int dim = N.rq.dim;
-    N.y[N.ihi] = ytry;
-    for (int j = 0; j < dim; ++j) {
-      N.psum[j] = __dadd_rn(__dsub_rn(N.psum[j], N.simplex[N.ihi][j]), N.ptry[j]);
-      N.simplex[N.ihi][j] = N.ptry[j];
-    }
-  }
-}
-__device__ __noinline__ bool nm_resume(NmState &N, double f, int *converged) {
+// AmoebaMinimizer (MathGenMin.cpp:326-443) as a resumable machine run by ONE WARP: nm_resume() takes the value of the
+// point it asked for last and either asks for the next one (true: N.req_row) or finishes (false).  Lane j owns
+// component j of every vector (the element-wise loops of statgen/MathVector.cpp:123-176 become one instruction per
+// lane); the scalars live in shared memory, written by lane 0 and read by every lane into registers at entry, so the
+// control flow is uniform and the decisions are taken on registers.  Every operation is the reference's, rounded
+// where the reference rounds (no contraction: __dadd_rn / __dmul_rn / __ddiv_rn), so the simplex visits the
+// reference's points when it is fed the reference's values.
+__device__ __forceinline__ bool nm_resume(NmState &N, double f, int lane, int *converged) {
   const int dim = N.rq.dim, nvertex = dim + 1;
-  switch (N.phase) {
+  const int phase = N.phase, i0 = N.i, ilo0 = N.ilo, ihi0 = N.ihi, inhi0 = N.inhi;
+  const double ysave0 = N.ysave, fmin0 = N.fmin, ftol = N.rq.ftol, scale = N.rq.scale;
+  long long cycles = N.cycle_count;
+  const long long cycle_max = N.rq.cycle_max;
+  double y[kMinDim + 1];  // every lane's copy of the vertex values
+#pragma unroll
+  for (int i = 0; i <= kMinDim; ++i) y[i] = N.y[i];
+  // this lane's column of the simplex (lanes >= dim idle along)
+  const bool mine = lane < dim;
+  const int col = mine ? lane : 0;
+  double psum = N.psum[col], ptry = N.ptry[col];
+  const double start = N.rq.start[col];
+  __syncwarp();  // every lane holds what it decides on; from here on the shared copies may be overwritten
+  auto y_at = [&](int i) {  // (register array with a runtime index: a short select chain, no local memory)
+    double v = y[0];
+#pragma unroll
+    for (int k = 1; k <= kMinDim; ++k) v = i == k ? y[k] : v;
+    return v;
+  };
+  auto y_set = [&](int i, double v) {
+#pragma unroll
+    for (int k = 0; k <= kMinDim; ++k) y[k] = i == k ? v : y[k];
+    if (lane == 0) N.y[i] = v;
+  };
+  auto compute_psum = [&]() {  // MathGenMin.cpp:347-349, :412-415
+    double s = N.simplex[0][col];
+    for (int m = 1; m <= dim; ++m) s = __dadd_rn(s, N.simplex[m][col]);
+    psum = s;
+  };
+  // MathGenMin.cpp:425-433: the trial point through the face opposite vertex ihi
+  auto make_try = [&](int ihi, int which) {  // which: 0 reflect (factor -1), 1 expand (2), 2 contract (0.5)
+    const double fac = N.fac[which], fac2 = N.fac2[which];
+    ptry = __dadd_rn(__dmul_rn(fac, psum), __dmul_rn(fac2, N.simplex[ihi][col]));
+    if (mine) N.ptry[col] = ptry;
+    if (lane == 0) N.req_row = -1;
+  };
+  // MathGenMin.cpp:434-442: the trial point replaces vertex ihi when it is better
+  auto accept = [&](int ihi, double ytry) {
+    if (ytry < y_at(ihi)) {
+      y_set(ihi, ytry);
+      psum = __dadd_rn(__dsub_rn(psum, N.simplex[ihi][col]), ptry);
+      if (mine) N.simplex[ihi][col] = ptry;
+    }
+  };
+  auto leave = [&](bool more) {  // write the lane-owned / lane-0 state back
+    if (mine) N.psum[col] = psum;
+    if (lane == 0) N.cycle_count = cycles;
+    __syncwarp();
+    return more;
+  };
+  auto ask_vertex = [&](int i, int next_phase) {
+    if (lane == 0) { N.i = i; N.req_row = i; N.phase = next_phase; }
+    return leave(true);
+  };
+  switch (phase) {
     case kNmIdle:  // start: the initial simplex, vertex by vertex (MathGenMin.cpp:335-345)
-      N.fmin = 1.0e+100;
-      N.i = 0;
-      N.phase = kNmInit;
-      for (int j = 0; j < dim; ++j) N.simplex[0][j] = __dadd_rn(N.rq.start[j], j == 0 ? N.rq.scale : 0.0);
-      N.req = N.simplex[0];
-      return true;
-    case kNmInit:
-      N.y[N.i] = f;
-      if (f < N.fmin) N.fmin = f;
-      if (++N.i < nvertex) {
-        const int i = N.i;
-        for (int j = 0; j < dim; ++j) N.simplex[i][j] = i < dim ? __dadd_rn(N.rq.start[j], j == i ? N.rq.scale : 0.0) : N.rq.start[j];
-        N.req = N.simplex[i];
-        return true;
+      if (lane < 3) {
+        const double factor = lane == 0 ? -1.0 : (lane == 1 ? 2.0 : 0.5);
+        const double fac = __ddiv_rn(__dsub_rn(1.0, factor), (double)dim);
+        N.fac[lane] = fac;
+        N.fac2[lane] = __dsub_rn(factor, fac);
       }
-      N.cycle_count = nvertex;
-      nm_psum(N);
+      if (mine) N.simplex[0][col] = __dadd_rn(start, col == 0 ? scale : 0.0);
+      if (lane == 0) { N.fmin = 1.0e+100; N.ilo = N.ihi = N.inhi = 0; }
+      return ask_vertex(0, kNmInit);
+    case kNmInit: {
+      y_set(i0, f);
+      if (lane == 0 && f < fmin0) N.fmin = f;
+      const int i = i0 + 1;
+      if (i < nvertex) {
+        if (mine) N.simplex[i][col] = i < dim ? __dadd_rn(start, col == i ? scale : 0.0) : start;
+        return ask_vertex(i, kNmInit);
+      }
+      cycles = nvertex;
+      compute_psum();
       break;
+    }
     case kNmReflect: {
-      nm_accept(N, f);
-      if (f <= N.y[N.ilo]) {  // MathGenMin.cpp:392-394: expand
-        nm_try(N, 2.0);
-        N.phase = kNmExpand;
-        return true;
+      const double y_ihi = y_at(ihi0);
+      accept(ihi0, f);
+      if (f <= y_at(ilo0)) {  // MathGenMin.cpp:392-394: expand
+        make_try(ihi0, 1);
+        if (lane == 0) N.phase = kNmExpand;
+        return leave(true);
       }
-      if (f >= N.y[N.inhi]) {  // :395-399: contract
-        N.ysave = N.y[N.ihi];
-        nm_try(N, 0.5);
-        N.phase = kNmContract;
-        return true;
+      if (f >= y_at(inhi0)) {  // :395-399: contract (ysave = y[ihi] after the reflection was, or was not, accepted)
+        make_try(ihi0, 2);
+        if (lane == 0) { N.ysave = f < y_ihi ? f : y_ihi; N.phase = kNmContract; }
+        return leave(true);
       }
-      --N.cycle_count;  // :419
+      --cycles;  // :419
       break;
     }
     case kNmExpand:
-      nm_accept(N, f);
+      accept(ihi0, f);
       break;
     case kNmContract:
-      nm_accept(N, f);
-      if (f >= N.ysave) {  // :402-416: shrink everything towards the best vertex, re-evaluating vertex by vertex
-        N.phase = kNmShrink;
-        N.i = -1;
-        f = 0.0;
-        goto shrink_next;
-      }
-      break;
-    case kNmShrink:
-      N.y[N.i] = f;
-    shrink_next:
-      for (++N.i; N.i < nvertex; ++N.i)
-        if (N.i != N.ilo) {
-          const int i = N.i;
-          for (int j = 0; j < dim; ++j) N.simplex[i][j] = __dmul_rn(__dadd_rn(N.simplex[i][j], N.simplex[N.ilo][j]), 0.5);
-          N.req = N.simplex[i];
-          return true;
+      accept(ihi0, f);
+      if (!(f >= ysave0)) break;
+      // :402-416: shrink everything towards the best vertex, re-evaluating vertex by vertex
+      for (int i = 0; i < nvertex; ++i)
+        if (i != ilo0) {
+          if (mine) N.simplex[i][col] = __dmul_rn(__dadd_rn(N.simplex[i][col], N.simplex[ilo0][col]), 0.5);
+          return ask_vertex(i, kNmShrink);
         }
-      N.cycle_count += dim;
-      nm_psum(N);
+      break;  // (dim == 0 cannot happen)
+    case kNmShrink:
+      y_set(i0, f);
+      for (int i = i0 + 1; i < nvertex; ++i)
+        if (i != ilo0) {
+          if (mine) N.simplex[i][col] = __dmul_rn(__dadd_rn(N.simplex[i][col], N.simplex[ilo0][col]), 0.5);
+          return ask_vertex(i, kNmShrink);
+        }
+      cycles += dim;
+      compute_psum();
       break;
   }
   // the top of the loop (MathGenMin.cpp:357-390): order the vertices, test for convergence, reflect
   int ilo, ihi, inhi;
-  if (N.y[0] > N.y[1]) { ilo = inhi = 1; ihi = 0; } else { ilo = inhi = 0; ihi = 1; }
-  for (int i = 2; i < nvertex; ++i) {
-    if (N.y[i] <= N.y[ilo]) ilo = i;
-    else if (N.y[i] > N.y[ihi]) { inhi = ihi; ihi = i; }
-    else if (N.y[i] > N.y[inhi]) inhi = i;
-  }
-  N.ilo = ilo; N.ihi = ihi; N.inhi = inhi;
-  const double rtol = __ddiv_rn(2 * fabs(__dsub_rn(N.y[ihi], N.y[ilo])),
-                                __dadd_rn(__dadd_rn(fabs(N.y[ihi]), fabs(N.y[ilo])), 3.0e-10));  // ZEPS
-  if (rtol < N.rq.ftol) {
-    N.fmin = N.y[ilo];
+  if (y[0] > y[1]) { ilo = inhi = 1; ihi = 0; } else { ilo = inhi = 0; ihi = 1; }
+  double v_lo = y_at(ilo), v_hi = y_at(ihi), v_nhi = y_at(inhi);
+#pragma unroll
+  for (int i = 2; i <= kMinDim; ++i)
+    if (i < nvertex) {
+      const double yi = y[i];
+      if (yi <= v_lo) { ilo = i; v_lo = yi; }
+      else if (yi > v_hi) { inhi = ihi; v_nhi = v_hi; ihi = i; v_hi = yi; }
+      else if (yi > v_nhi) { inhi = i; v_nhi = yi; }
+    }
+  const double rtol = __ddiv_rn(2 * fabs(__dsub_rn(v_hi, v_lo)), __dadd_rn(__dadd_rn(fabs(v_hi), fabs(v_lo)), 3.0e-10));  // ZEPS
+  if (lane == 0) { N.ilo = ilo; N.ihi = ihi; N.inhi = inhi; }
+  if (rtol < ftol) {
+    if (lane == 0) { N.fmin = v_lo; N.phase = kNmIdle; }
     *converged = 1;
-    N.phase = kNmIdle;
-    return false;
+    return leave(false);
   }
-  if (N.cycle_count > N.rq.cycle_max) {
+  if (cycles > cycle_max) {
+    if (lane == 0) N.phase = kNmIdle;
     *converged = 0;
-    N.phase = kNmIdle;
-    return false;
+    return leave(false);
   }
-  N.cycle_count += 2;
-  nm_try(N, -1.0);
-  N.phase = kNmReflect;
-  return true;
+  cycles += 2;
+  make_try(ihi, 0);
+  if (lane == 0) N.phase = kNmReflect;
+  return leave(true);
 }
-// FullLLKFunc::Evaluate's unpacking of v (h:339-442) and fill_job's coefficients, rounded as the host rounds them
-__device__ __forceinline__ void nm_job(NmState &N, JobParams &J) {
+// FullLLKFunc::Evaluate's unpacking of v (h:339-442) and fill_job's coefficients, rounded as the host rounds them:
+// lane k takes PC k, lane p the genotype pair p
+__device__ __forceinline__ void nm_job(NmState &N, JobParams &J, int lane) {
   const MinRequest &R = N.rq;
-  const double *v = N.req;
-  for (int k = 0; k < kMinPc; ++k) {
-    N.cur_pc1[k] = k < R.n_pc ? (R.pc1_from[k] >= 0 ? v[R.pc1_from[k]] : R.pc1_fixed[k]) : 0.0;
-    N.cur_pc2[k] = k < R.n_pc ? (R.pc2_from[k] >= 0 ? v[R.pc2_from[k]] : R.pc2_fixed[k]) : 0.0;
-    J.pc1[k] = N.cur_pc1[k];
-    J.pc2[k] = N.cur_pc2[k];
+  const double *v = N.req_row >= 0 ? N.simplex[N.req_row] : N.ptry;
+  if (lane < kMinPc) {
+    const double a = lane < R.n_pc ? (R.pc1_from[lane] >= 0 ? v[R.pc1_from[lane]] : R.pc1_fixed[lane]) : 0.0;
+    const double b = lane < R.n_pc ? (R.pc2_from[lane] >= 0 ? v[R.pc2_from[lane]] : R.pc2_fixed[lane]) : 0.0;
+    N.cur_pc1[lane] = a; N.cur_pc2[lane] = b;
+    J.pc1[lane] = a; J.pc2[lane] = b;
   }
   double alpha = R.alpha_fixed;
   if (R.alpha_from >= 0) {  // InvLogit, h:119-122
     const double e = exp(v[R.alpha_from]);
     alpha = __ddiv_rn(e, __dadd_rn(1., e));
   }
-  N.cur_alpha = alpha;
-  const double E[3] = {0.0, 1.0 / 6.0, 1.0 / 3.0}, Nn[3] = {1.0, 0.5, 0.0};
-  const double oma = __dsub_rn(1.0, alpha);
-#pragma unroll
-  for (int p = 0; p < kNumPairs; ++p) {
-    const int g1 = pair_g1(p), g2 = pair_g2(p);
-    const double e_mix = __dadd_rn(__dmul_rn(alpha, E[g1]), __dmul_rn(oma, E[g2]));
-    const double n_mix = __dadd_rn(__dmul_rn(alpha, Nn[g1]), __dmul_rn(oma, Nn[g2]));
-    J.c0[p] = n_mix;
-    J.c1[p] = __dsub_rn(e_mix, n_mix);
+  if (lane == 0) N.cur_alpha = alpha;
+  if (lane < kNumPairs) {
+    const int g1 = lane < 2 ? 0 : (lane < 4 ? 1 : 2);
+    const int g2 = lane == 0 ? 1 : lane == 1 ? 2 : lane == 2 ? 0 : lane == 3 ? 2 : lane == 4 ? 0 : 1;
+    const double Eg1 = g1 == 0 ? 0.0 : (g1 == 1 ? 1.0 / 6.0 : 1.0 / 3.0), Eg2 = g2 == 0 ? 0.0 : (g2 == 1 ? 1.0 / 6.0 : 1.0 / 3.0);
+    const double Ng1 = g1 == 0 ? 1.0 : (g1 == 1 ? 0.5 : 0.0), Ng2 = g2 == 0 ? 1.0 : (g2 == 1 ? 0.5 : 0.0);
+    const double oma = __dsub_rn(1.0, alpha);
+    const double e_mix = __dadd_rn(__dmul_rn(alpha, Eg1), __dmul_rn(oma, Eg2));
+    const double n_mix = __dadd_rn(__dmul_rn(alpha, Ng1), __dmul_rn(oma, Ng2));
+    J.c0[lane] = n_mix;
+    J.c1[lane] = __dsub_rn(e_mix, n_mix);
   }
+  __syncwarp();
 }
 // Evaluate's best-so-far bookkeeping (h:344-440): the free components of the best point over all evaluations
-__device__ __forceinline__ void nm_track_best(NmState &N, double f) {
-  if (f < N.llk1) {
+__device__ __forceinline__ void nm_track_best(NmState &N, double f, int lane) {
+  const bool better = f < N.llk1;
+  __syncwarp();
+  if (better) {
     const MinRequest &R = N.rq;
-    N.llk1 = f;
-    N.improved = 1;
-    for (int k = 0; k < kMinPc; ++k) {
-      if (R.pc1_from[k] >= 0) N.best_pc1[k] = N.cur_pc1[k];
-      if (R.pc2_from[k] >= 0) N.best_pc2[k] = N.cur_pc2[k];
+    if (lane < kMinPc) {
+      if (R.pc1_from[lane] >= 0) N.best_pc1[lane] = N.cur_pc1[lane];
+      if (R.pc2_from[lane] >= 0) N.best_pc2[lane] = N.cur_pc2[lane];
     }
-    if (R.alpha_from >= 0) N.best_alpha = N.cur_alpha;
+    if (lane == 0) {
+      N.llk1 = f;
+      N.improved = 1;
+      if (R.alpha_from >= 0) N.best_alpha = N.cur_alpha;
+    }
   }
+  __syncwarp();
 }
 
 struct SessionArgs {
@@ -1356,9 +1404,10 @@ struct SessionArgs {
   const BellChunk *bell;  // device view of the host-mapped doorbell (polled by CTA 0 only: PCIe reads)
   BellChunk *relay;       // the same chunks in HBM: CTA 0 forwards the doorbell, the other CTAs poll this copy in L2
   Slot *mbox;             // device view of the host mailbox: slot [cta]
-  Slot *dmbox;            // the mailbox in HBM/L2: slot [cta] (evaluations of a search on the device)
+  Slot *dmbox;            // the inboxes in HBM/L2: slot [seq & 1][destination CTA][source CTA] (a search on the device)
   const MinRequest *min_req;  // device views of the host-mapped request / result of vb2_llk_minimize
   MinResult *min_res;
+  MinRequest *min_req_dev;    // the request, forwarded into HBM by CTA 0 for the other CTAs
   unsigned long long first_seq, idle_cycles;
   uint32_t kc, n_items, n_chunks;  // n_chunks = 12 + 2 n_pc parameter chunks; the control chunk follows them
   unsigned long long *trace;  // diagnostics: [grid_x][kTraceSlots] SM clock of thread 0 at the stages of the LAST evaluation
@@ -1367,6 +1416,10 @@ struct SessionArgs {
   vb2::Round rounds[kMaxArgRounds];
 };
 
+// A search on the device (vb2_llk_minimize) runs in EVERY CTA at once: the simplex is a deterministic function of
+// the values it is fed, so instead of one CTA proposing points and broadcasting them, every CTA's first warp keeps
+// its own copy of the simplex, all-gathers the per-CTA partial sums of an evaluation through a two-bank mailbox in
+// L2, adds them in the one fixed order and steps its copy -- the same bits everywhere, and one L2 hop per evaluation.
 template <int NPC>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 llk_session_kernel(const __grid_constant__ SessionArgs A) {
@@ -1377,7 +1430,7 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
   __shared__ __align__(8) uint64_t s_bar[kMaxWarps];
   __shared__ uint32_t s_item_r[kMaxWarps][kMaxSessionItems];
   __shared__ uint32_t s_stop, s_mode;
-  __shared__ NmState s_nm;  // (used by the first CTA only)
+  __shared__ __align__(16) NmState s_nm;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SampleDev &S = A.sample;
@@ -1419,6 +1472,8 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
     s_stop = 0u;
     s_mode = 0u;
     s_nm.phase = kNmIdle;
+    s_nm.i = s_nm.ilo = s_nm.ihi = s_nm.inhi = 0;
+    s_nm.rq.dim = 1;
   }
 #pragma unroll 1
   for (uint32_t i = threadIdx.x; i < n_rounds * 128u; i += blockDim.x) s_L[i] = 1.0;  // neutral marginals
@@ -1433,19 +1488,18 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
   // chunk i of the doorbell <-> JobParams: c0[6], c1[6], pc1[k] (at 12), pc2[k] (at 12 + VB2_MAX_PC)
   const uint32_t n_chunks = A.n_chunks, n_pc_chunks = S.n_pc;
   auto chunk_slot = [&](uint32_t i) { return i < 12u ? i : (i < 12u + n_pc_chunks ? i : i - n_pc_chunks + (uint32_t)VB2_MAX_PC); };
-  const bool head = blockIdx.x == 0;  // the one CTA that talks to the host (and runs the simplex)
+  const bool head = blockIdx.x == 0;  // the one CTA that talks to the host
   unsigned long long expected = A.first_seq;
-  bool searching = false;  // (head CTA, warp 0) a simplex search is running: the next point comes from s_nm
+  bool searching = false;  // (warp 0) a simplex search is running: the next point comes from this CTA's s_nm
 #pragma unroll 1
   for (;;) {
     stamp(0);
     // ---- the next evaluation's parameters ----------------------------------------------------------------
     if (warp == 0) {
       uint32_t stop = 0, mode = 0;
-      if (head && searching) {
-        // the search proposes the point itself: Evaluate's unpacking + fill_job, then straight to the relay
-        if (lane == 0) nm_job(s_nm, s_job);
-        __syncwarp();
+      if (searching) {
+        // the search proposes the point itself: Evaluate's unpacking + fill_job (no doorbell, no relay)
+        nm_job(s_nm, s_job, lane);
         mode = (uint32_t)kCtlDeviceMailbox;
       } else {
         const unsigned long long t_idle = (unsigned long long)clock64();
@@ -1453,9 +1507,11 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
         // the others would only give up, much later, on a head that has gone away.
         const unsigned long long patience = head ? A.idle_cycles : A.idle_cycles * 64ull;
         const BellChunk *src = head ? A.bell : A.relay;
+        unsigned long long ctl = 0ull;
         for (;;) {
           bool ok = true, bye = false;
-          unsigned long long xsum = 0ull, ctl = 0ull;
+          unsigned long long xsum = 0ull;
+          ctl = 0ull;
 #pragma unroll
           for (uint32_t base = 0; base < (uint32_t)kMaxBellChunks; base += 32) {
             const uint32_t i = base + (uint32_t)lane;
@@ -1472,8 +1528,8 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
                 if (seq == expected) reinterpret_cast<double *>(&s_job)[chunk_slot(i)] = __longlong_as_double((long long)pay);
               } else {  // the control chunk
                 ok = ok && (seq & ~kCtlMinimize) == expected;
-                ctl = (seq & kCtlMinimize) | (pay & 0xFFull);
-                if (head) xsum ^= pay & ~0xFFull;
+                ctl = seq & kCtlMinimize;
+                if (head) xsum ^= pay;
               }
             }
           }
@@ -1484,44 +1540,60 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
               xsum ^= __shfl_xor_sync(0xFFFFFFFFu, xsum, o);
               ctl |= __shfl_xor_sync(0xFFFFFFFFu, ctl, o);
             }
-            if (!head || (xsum & ~0xFFull) == 0ull) {  // (host doorbell: the payloads' checksum, bits 8..63, must match)
-              mode = (uint32_t)(ctl & 0xFFull);
-              if (head && (ctl & kCtlMinimize)) {  // start a search: the request sits in host-mapped memory
-                if (lane == 0) {
-                  __threadfence_system();
-                  const volatile MinRequest *rq = A.min_req;
-                  MinRequest &dst = s_nm.rq;
-                  for (uint32_t w = 0; w < sizeof(MinRequest) / 8u; ++w)
-                    reinterpret_cast<unsigned long long *>(&dst)[w] = reinterpret_cast<const volatile unsigned long long *>(rq)[w];
-                  s_nm.phase = kNmIdle;
-                  s_nm.evals = 0;
-                  s_nm.improved = 0;
-                  s_nm.llk1 = dst.llk1;
-                  int conv = 0;
-                  nm_resume(s_nm, 0.0, &conv);  // (asks for the first vertex)
-                  nm_job(s_nm, s_job);
-                }
-                __syncwarp();
-                searching = true;
-                mode = (uint32_t)kCtlDeviceMailbox;
-              }
-              break;
-            }
+            if (!head || (xsum & ~0xFFull) == 0ull) break;  // (host doorbell: the payloads' checksum, bits 8..63, must match)
           }
           if ((unsigned long long)clock64() - t_idle > patience) { stop = 1; break; }
         }
-      }
-      if (head) {  // forward: the evaluation's chunks, or the order to leave
-#pragma unroll
-        for (uint32_t base = 0; base < (uint32_t)kMaxBellChunks; base += 32) {
-          const uint32_t i = base + (uint32_t)lane;
-          if (i <= n_chunks) {
-            const unsigned long long pay = i < n_chunks
-                ? (unsigned long long)__double_as_longlong(reinterpret_cast<const double *>(&s_job)[chunk_slot(i)])
-                : (unsigned long long)mode;
-            const unsigned long long seq = stop ? kBellExit : expected;
-            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(A.relay + i), "l"(pay), "l"(seq) : "memory");
+        if (!stop && (ctl & kCtlMinimize)) {
+          // start a search: the request travels host -> head CTA -> HBM -> every other CTA
+          constexpr uint32_t kWords = (uint32_t)(sizeof(MinRequest) / 8u);
+          unsigned long long *dst = reinterpret_cast<unsigned long long *>(&s_nm.rq);
+          if (head) {
+            __threadfence_system();
+            const volatile unsigned long long *rq = reinterpret_cast<const volatile unsigned long long *>(A.min_req);
+            unsigned long long *fwd = reinterpret_cast<unsigned long long *>(A.min_req_dev);
+            for (uint32_t w = lane; w < kWords; w += 32) {
+              const unsigned long long x = rq[w];
+              dst[w] = x;
+              asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(fwd + w), "l"(x) : "memory");
+            }
+            __threadfence();
+          } else {
+            __threadfence();
+            const unsigned long long *fwd = reinterpret_cast<const unsigned long long *>(A.min_req_dev);
+            for (uint32_t w = lane; w < kWords; w += 32) {
+              unsigned long long x;
+              asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(x) : "l"(fwd + w) : "memory");
+              dst[w] = x;
+            }
           }
+          if (lane == 0) {
+            s_nm.phase = kNmIdle;
+            s_nm.evals = 0;
+            s_nm.improved = 0;
+          }
+          __syncwarp();
+          if (lane == 0) s_nm.llk1 = s_nm.rq.llk1;
+          int conv = 0;
+          nm_resume(s_nm, 0.0, lane, &conv);  // (asks for the first vertex)
+          searching = true;
+        }
+        if (head) {  // forward: the evaluation's chunks (or the start of a search), or the order to leave
+          __syncwarp();
+#pragma unroll
+          for (uint32_t base = 0; base < (uint32_t)kMaxBellChunks; base += 32) {
+            const uint32_t i = base + (uint32_t)lane;
+            if (i <= n_chunks) {
+              const unsigned long long pay = i < n_chunks
+                  ? (unsigned long long)__double_as_longlong(reinterpret_cast<const double *>(&s_job)[chunk_slot(i)]) : 0ull;
+              const unsigned long long seq = stop ? kBellExit : (i < n_chunks ? expected : (expected | (ctl & kCtlMinimize)));
+              asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(A.relay + i), "l"(pay), "l"(seq) : "memory");
+            }
+          }
+        }
+        if (searching) {
+          nm_job(s_nm, s_job, lane);
+          mode = (uint32_t)kCtlDeviceMailbox;
         }
       }
       if (lane == 0) {
@@ -1579,35 +1651,61 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
       if (lane == 0) s_red[warp] = vsum;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 0) {
-        if (lane == 0) {
-          const double cta = ((s_red[0] + s_red[1]) + s_red[2]) + s_red[3];
-          Slot *slot = (mode & (uint32_t)kCtlDeviceMailbox) ? A.dmbox + blockIdx.x : A.mbox + blockIdx.x;
-          asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"((unsigned long long)__double_as_longlong(cta)),
-                       "l"(expected) : "memory");
+        const uint32_t gx = S.grid_x;
+        double cta = 0.0;
+        if (lane == 0) cta = ((s_red[0] + s_red[1]) + s_red[2]) + s_red[3];
+        if (!(mode & (uint32_t)kCtlDeviceMailbox)) {
+          if (lane == 0) {
+            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(A.mbox + blockIdx.x),
+                         "l"((unsigned long long)__double_as_longlong(cta)), "l"(expected) : "memory");
+            stamp(6);
+          }
+        } else {
+          // ---- all-gather, push style: this CTA's partial goes into EVERY CTA's inbox (148 posted 16-byte stores,
+          // spread over the L2 slices), and every CTA then polls only its own inbox -- all CTAs polling one shared
+          // mailbox would queue thousands of loads on the one L2 slice that holds it.  Two banks (by the parity of
+          // the sequence number): a fast CTA's next partial must not overwrite the one a slow CTA still waits for.
+          cta = __shfl_sync(0xFFFFFFFFu, cta, 0);
+          Slot *bank = A.dmbox + (size_t)(expected & 1ull) * gx * gx;
+          for (uint32_t dest = lane; dest < gx; dest += 32)
+            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(bank + (size_t)dest * gx + blockIdx.x),
+                         "l"((unsigned long long)__double_as_longlong(cta)), "l"(expected) : "memory");
           stamp(6);
-        }
-        if (head && searching) {
-          // ---- the search takes the sum itself: every CTA's partial from the L2 mailbox, added in the order the
-          // host (and llk_kernel's last CTA) use: lane-strided sums, then a butterfly
-          const uint32_t gx = S.grid_x;
+          // the partials are added in the order the host (and llk_kernel's last CTA) use -- lane-strided sums, then a
+          // butterfly -- so every CTA steps its simplex on the same bits
+          const Slot *inbox = bank + (size_t)blockIdx.x * gx;
           double sum = 0.0;
-          for (uint32_t c = lane; c < gx; c += 32) {
-            unsigned long long val, seq;
-            do {
-              asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(val), "=l"(seq) : "l"(A.dmbox + c) : "memory");
-            } while (seq != expected);
-            sum += __longlong_as_double((long long)val);
+          for (uint32_t c0 = 0; c0 < gx; c0 += 256) {  // up to eight slots per lane in flight at once
+            unsigned long long val[8], seq[8];
+            for (;;) {
+              bool all = true;
+#pragma unroll
+              for (uint32_t u = 0; u < 8; ++u) {
+                const uint32_t c = c0 + u * 32u + (uint32_t)lane;
+                val[u] = 0ull; seq[u] = expected;
+                if (c < gx)
+                  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(val[u]), "=l"(seq[u]) : "l"(inbox + c) : "memory");
+              }
+#pragma unroll
+              for (uint32_t u = 0; u < 8; ++u) all = all && seq[u] == expected;
+              if (all) break;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 8; ++u)   // (c ascending per lane: the host's order)
+              if (c0 + u * 32u + (uint32_t)lane < gx) sum += __longlong_as_double((long long)val[u]);
           }
 #pragma unroll
           for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-          uint32_t more = 1;
-          if (lane == 0) {
-            const double f = 0 - (sum + S.log_other_const);  // h:344
-            ++s_nm.evals;
-            nm_track_best(s_nm, f);
-            int conv = 0;
-            if (!nm_resume(s_nm, f, &conv)) {  // finished: the result, then its stamp
-              more = 0;
+          const double f = 0 - (sum + S.log_other_const);  // h:344
+          stamp(4);
+          if (lane == 0) ++s_nm.evals;
+          nm_track_best(s_nm, f, lane);
+          int conv = 0;
+          const bool more = nm_resume(s_nm, f, lane, &conv);
+          stamp(5);
+          if (!more) {  // finished everywhere; the head CTA reports: the result, then its stamp
+            searching = false;
+            if (head && lane == 0) {
               volatile MinResult *res = A.min_res;
               res->fmin = s_nm.fmin;
               // (without convergence AmoebaMinimizer::point is never assigned: it still is the starting point)
@@ -1624,8 +1722,6 @@ llk_session_kernel(const __grid_constant__ SessionArgs A) {
               res->done = expected;
             }
           }
-          more = __shfl_sync(0xFFFFFFFFu, more, 0);
-          searching = more != 0;
         }
       }
     }
@@ -1707,7 +1803,8 @@ struct vb2_llk_ctx {
   // evaluation session (llk_session_kernel resident on the device)
   BellChunk *h_bell = nullptr, *d_bell = nullptr;  // host-mapped doorbell
   BellChunk *d_relay = nullptr;                    // its copy in HBM
-  Slot *d_dmbox = nullptr;                         // per-CTA partials of a search on the device (HBM/L2)
+  Slot *d_dmbox = nullptr;                         // per-CTA partials of a search on the device (HBM/L2), two banks
+  MinRequest *d_minreq_fwd = nullptr;              // the request as the head CTA forwards it to the others
   MinRequest *h_minreq = nullptr, *d_minreq = nullptr;  // host-mapped request / result of vb2_llk_minimize
   MinResult *h_minres = nullptr, *d_minres = nullptr;
   bool session_active = false;
@@ -1900,7 +1997,8 @@ int session_launch(vb2_llk_ctx *ctx, unsigned long long first_seq) {
   VB2_CUDA(ctx, cudaMemsetAsync(ctx->d_relay, 0, sizeof(BellChunk) * kMaxBellChunks, ctx->stream));
   A.mbox = ctx->d_mbox;
   A.dmbox = ctx->d_dmbox;
-  VB2_CUDA(ctx, cudaMemsetAsync(ctx->d_dmbox, 0, sizeof(Slot) * std::max(1u, ctx->S.grid_x), ctx->stream));
+  VB2_CUDA(ctx, cudaMemsetAsync(ctx->d_dmbox, 0, sizeof(Slot) * 2 * (size_t)ctx->S.grid_x * ctx->S.grid_x, ctx->stream));
+  A.min_req_dev = ctx->d_minreq_fwd;
   A.min_req = ctx->d_minreq;
   A.min_res = ctx->d_minres;
   A.first_seq = first_seq;
@@ -2155,6 +2253,7 @@ void vb2_llk_destroy(vb2_llk_ctx *ctx) {
   if (ctx->h_bell) cudaFreeHost(ctx->h_bell);
   if (ctx->d_relay) cudaFree(ctx->d_relay);
   if (ctx->d_dmbox) cudaFree(ctx->d_dmbox);
+  if (ctx->d_minreq_fwd) cudaFree(ctx->d_minreq_fwd);
   if (ctx->h_minreq) cudaFreeHost(ctx->h_minreq);
   if (ctx->h_minres) cudaFreeHost(ctx->h_minres);
   if (ctx->d_recs2) cudaFree(ctx->d_recs2);
@@ -2656,7 +2755,8 @@ int vb2_llk_session_begin(vb2_llk_ctx *ctx) {
     memset(ctx->h_bell, 0, sizeof(BellChunk) * kMaxBellChunks);
     VB2_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->d_bell, ctx->h_bell, 0));
     VB2_CUDA(ctx, cudaMalloc(&ctx->d_relay, sizeof(BellChunk) * kMaxBellChunks));
-    VB2_CUDA(ctx, cudaMalloc(&ctx->d_dmbox, sizeof(Slot) * std::max(1u, ctx->S.grid_x)));
+    VB2_CUDA(ctx, cudaMalloc(&ctx->d_dmbox, sizeof(Slot) * 2 * (size_t)std::max(1u, ctx->S.grid_x) * std::max(1u, ctx->S.grid_x)));
+    VB2_CUDA(ctx, cudaMalloc(&ctx->d_minreq_fwd, sizeof(MinRequest)));
     VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_minreq, sizeof(MinRequest), cudaHostAllocMapped));
     VB2_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_minres, sizeof(MinResult), cudaHostAllocMapped));
     memset(ctx->h_minreq, 0, sizeof(MinRequest));
@@ -2767,7 +2867,31 @@ int vb2_llk_trace(vb2_llk_ctx *ctx, const double *pc_contam, const double *pc_in
   ctx->trace_on = true;
   double llk = 0.0;
   int rc = VB2_OK;
-  if (getenv("VB2_LLK_TRACE_SESSION")) {  // stages of the 20th evaluation of a session (see llk_session_kernel)
+  const char *trace_mode = getenv("VB2_LLK_TRACE_SESSION");
+  if (trace_mode && !strcmp(trace_mode, "search")) {  // stages of the last evaluation of a search on the device
+    rc = vb2_llk_session_begin(ctx);
+    if (rc == VB2_OK) {
+      const uint32_t k = ctx->S.n_pc;
+      vb2_llk_model M;
+      memset(&M, 0, sizeof(M));
+      M.struct_size = sizeof(M);
+      M.dim = 2 * k + 1;
+      for (uint32_t j = 0; j < VB2_MAX_PC; ++j) { M.pc1_from[j] = j < k ? (int32_t)j : -1; M.pc2_from[j] = j < k ? (int32_t)(k + j) : -1; }
+      M.alpha_from = (int32_t)(2 * k);
+      std::vector<double> start(M.dim, 0.01);
+      start[2 * k] = log(alpha / (1 - alpha));
+      vb2_llk_min_result R;
+      memset(&R, 0, sizeof(R));
+      R.struct_size = sizeof(R);
+      auto t0 = std::chrono::steady_clock::now();
+      rc = vb2_llk_minimize(ctx, &M, start.data(), 1.0, 1e-8, 50000, 1e300, &R);
+      const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+      fprintf(stderr, "vb2_llk_trace: search on the device: %lld evaluations in %.1f us = %.2f us each\n", (long long)R.evals, us,
+              R.evals ? us / (double)R.evals : 0.0);
+      llk = -R.fmin;
+    }
+    if (rc == VB2_OK) rc = vb2_llk_session_end(ctx);
+  } else if (trace_mode) {  // stages of the 20th evaluation of a session (see llk_session_kernel)
     rc = vb2_llk_session_begin(ctx);
     for (int i = 0; i < 20 && rc == VB2_OK; ++i) rc = vb2_llk_eval(ctx, pc_contam, pc_intended, alpha, &llk);
     if (rc == VB2_OK) rc = vb2_llk_session_end(ctx);
