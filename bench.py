@@ -471,8 +471,12 @@ def run_ours(args):
         nm_start = list(start_pc) + list(start_pc) + [float(np.log(0.03 / 0.97))]
         nm_model = (list(range(k)), list(range(k, 2 * k)), 2 * k)
         searches_per_step, dev_evals, min_bytes, r_last = None, 0, (0, 0), None
+        if not args.no_session:
+            try:
+                engines[0].session_begin()
+            except vb.VB2Error:            # the sample does not fit on chip (deep coverage): one launch per evaluation
+                args.no_session = True
         if not args.no_session and 2 * k + 1 <= vb.VB2_MIN_MAX_DIM:
-            engines[0].session_begin()
             r0 = engines[0].minimize(nm_start, *nm_model, ftol=1e-8)           # (also the warm-up)
             searches_per_step = max(1, -(-per_step // max(1, r0["evals"])))
             for _ in range(max(0, args.warmup - 1)):
@@ -488,8 +492,6 @@ def run_ours(args):
         if args.no_session:   # (profiler runs: ncu serialises launches, a resident kernel would wait for a doorbell
             e2e_s, last = vb.time_host(engines, n_warm, n_dep, start_pc, start_pc, 0.03)  # that cannot ring)
         else:
-            if searches_per_step is None:
-                engines[0].session_begin()
             e2e_s, last = vb.time_host(engines[:1], n_warm, n_dep, start_pc, start_pc, 0.03)
             engines[0].session_end()
         last_pc = start_pc.copy(); last_pc[0] = 0.01 + 1e-7 * ((n_dep - 1 + n_warm) % 1000)
