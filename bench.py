@@ -81,7 +81,7 @@ def config_dict(name: str, sample, n_gpus: int) -> dict:
     if n_samples > 1:
         par = "%d samples over %d GPU(s), one launch per step evaluates every sample of a GPU once, no collective" % (n_samples, n_gpus)
     elif n_gpus > 1:
-        par = "marker shards x%d + 1 all-reduce of the step's %d partial sums" % (n_gpus, EVALS_PER_STEP)
+        par = "marker shards x%d, the step's %d shard sums added across the GPUs once per step" % (n_gpus, EVALS_PER_STEP)
     else:
         par = "single GPU"
     return {"workload": text, "baseline_config_index": idx, "name": name, "reads_per_eval": reads, "markers_used": markers,
@@ -344,6 +344,23 @@ def run_ours(args):
     ctx_arr = vb.context_array(launch_list)
     d_step = [torch.zeros(n_jobs, dtype=torch.float64, device=dev) for _ in range(2)]
     collective = world > 1 and not cohort
+    peer = None
+    if collective and args.collective == "peer":
+        def exchange(handle: bytes):
+            mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+            every = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(every, mine)
+            torch.cuda.synchronize()
+            return [e.cpu().numpy().tobytes() for e in every]
+        peer = vb.PeerReduce(local, rank, world, exchange)
+
+    def shard_step(params_a, params_b, alphas, out):
+        """This rank's shard of one step + the sum over the shards, left in `out` (device)."""
+        if peer is not None:
+            peer.eval_many_device(launch_list, params_a, params_b, alphas, out.data_ptr(), ctx_arr)
+            return None
+        vb.eval_many_device(launch_list, params_a, params_b, alphas, out.data_ptr(), ctx_arr)
+        return dist.all_reduce(out, op=dist.ReduceOp.SUM, async_op=True)
 
     def keep_busy(seconds: float):
         # rank-local launches only (a time-based loop must not contain collectives)
@@ -371,8 +388,7 @@ def run_ours(args):
                 b = turn[0] = turn[0] ^ 1
                 if works[b] is not None:
                     works[b].wait()          # (stream-level: our stream waits for that buffer's previous all-reduce)
-                vb.eval_many_device(launch_list, pcs, pcs, als, d_step[b].data_ptr(), ctx_arr)
-                works[b] = dist.all_reduce(d_step[b], op=dist.ReduceOp.SUM, async_op=True)
+                works[b] = shard_step(pcs, pcs, als, d_step[b])
 
             def drain():
                 for w in works:
@@ -405,9 +421,12 @@ def run_ours(args):
     par_pc2 = np.tile(np.asarray(sample.pc_intended, dtype=np.float64)[:k], (n_jobs, 1))
     par_al = np.full(n_jobs, ALPHA)
     par_pcs[:, 0] += 1e-3 * (np.arange(n_jobs) % 7)          # seven different points over the step
-    vb.eval_many_device(launch_list, par_pcs, par_pc2, par_al, d_step[0].data_ptr(), ctx_arr)
     if collective:
-        dist.all_reduce(d_step[0], op=dist.ReduceOp.SUM)
+        w = shard_step(par_pcs, par_pc2, par_al, d_step[0])
+        if w is not None:
+            w.wait()
+    else:
+        vb.eval_many_device(launch_list, par_pcs, par_pc2, par_al, d_step[0].data_ptr(), ctx_arr)
     got = d_step[0].cpu().numpy()
     parity = None
     if rank == 0:
@@ -534,9 +553,12 @@ def run_ours(args):
 
         def e2e_step(i: int) -> float:
             host_pcs[:, 0] = 0.01 + 1e-7 * (i % 1000)
-            vb.eval_many_device(launch_list, host_pcs, pcs, als, d_step[0].data_ptr(), ctx_arr)
             if collective:
-                dist.all_reduce(d_step[0], op=dist.ReduceOp.SUM)
+                w = shard_step(host_pcs, pcs, als, d_step[0])
+                if w is not None:
+                    w.wait()
+            else:
+                vb.eval_many_device(launch_list, host_pcs, pcs, als, d_step[0].data_ptr(), ctx_arr)
             host_out.copy_(d_step[0], non_blocking=False)
             return float(host_out[n_jobs - 1])
         for i in range(args.warmup):
@@ -552,7 +574,8 @@ def run_ours(args):
         e2e_point = (last_pc, start_pc, 0.03)
         h2d, d2h = n_jobs * (2 * k + 1) * 8, n_jobs * 8
         caller = "python: vb2_llk_eval_many_device over %d host parameter sets per step%s + D2H of the results" % (
-            n_jobs, " (marker shard) + NCCL all-reduce" if collective else " (this GPU's samples)")
+            n_jobs, (" (marker shard) + " + ("peer stores over NVLink" if peer is not None else "NCCL all-reduce")) if collective
+            else " (this GPU's samples)")
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -586,6 +609,9 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_leg(sample, k, want_converge=(args.config != "batch64"))
 
+    if peer is not None:
+        barrier()
+        peer.close()
     for e in engines:
         e.close()
     if rank == 0:
@@ -597,6 +623,9 @@ def run_ours(args):
                          "from HBM" % (copies, copies * info["device_bytes"] / 1e6) if not cohort else
                          "%d resident samples on this GPU (%.0f MB > 126 MB L2)" % (copies, dev_launch / 1e6),
                 "precision": "fp32 UD/mu in HBM, fp64 arithmetic",
+                "collective": (None if not collective else "peer stores over NVLink from llk_reduce_kernel + llk_gather_kernel "
+                               "(%d bytes pushed per rank and step)" % (8 * n_jobs * world) if peer is not None else
+                               "NCCL all-reduce of %d doubles per step, overlapped with the next step's kernel" % n_jobs),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "parity": parity,
                 "cpu_baseline": cpu}
         print(json.dumps(line))
@@ -611,6 +640,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="100k30x", choices=sorted(CONFIGS))
+    ap.add_argument("--collective", default="nccl", choices=["nccl", "peer"],
+                    help="N>1: how the shard sums meet -- an NCCL all-reduce behind the kernel, or peer stores over NVLink from "
+                         "the reduce kernel itself (vb2_peer_*)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-session", action="store_true", help="e2e with one launch per evaluation (for runs under ncu)")
     args = ap.parse_args()

@@ -176,6 +176,20 @@ int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
 int vb2_llk_eval_many_device(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
                              const double *alphas, double *d_llk_out);
 
+/* ---- marker shards on several GPUs, one process per GPU: the collective fused into the kernels ------------------
+ * Instead of an NCCL all-reduce behind vb2_llk_eval_many_device, the reduce kernel PUSHES every evaluation's shard sum
+ * into every rank's buffer over NVLink (peer stores) and a small gather kernel on every rank adds the shards in rank
+ * order: vb2_llk_eval_many_device_peer leaves the SUMS OVER ALL SHARDS in d_llk_out, on ctxs[0]'s stream, identical
+ * bits on every rank.  Set-up: every rank creates its buffer (vb2_peer_create returns a 64-byte CUDA IPC handle), the
+ * ranks exchange the handles by whatever means they have (bench.py: one all_gather), then vb2_peer_connect maps the
+ * peers' buffers.  Every rank must issue the same sequence of calls (a launch waits for all ranks' sums).  world <= 8. */
+typedef struct vb2_peer vb2_peer;
+int vb2_peer_create(int device, uint32_t rank, uint32_t world, vb2_peer **out, void *ipc_handle_out /* 64 bytes */);
+int vb2_peer_connect(vb2_peer *peer, const void *ipc_handles /* [world][64] bytes, in rank order */);
+void vb2_peer_destroy(vb2_peer *peer);
+int vb2_llk_eval_many_device_peer(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
+                                  const double *alphas, vb2_peer *peer, double *d_llk_out);
+
 /* Evaluation session: for the several hundred DEPENDENT evaluations of one sample that a simplex search makes
  * (AmoebaMinimizer::Minimize, MathGenMin.cpp:326-423).  vb2_llk_session_begin launches one resident kernel that
  * keeps the whole sample in shared memory; until vb2_llk_session_end, vb2_llk_eval / _eval_begin / _eval_end on this

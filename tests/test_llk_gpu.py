@@ -478,3 +478,16 @@ def test_minimize_on_the_device_matches_a_host_nelder_mead(sample10k):
     assert got["best_pc_contam"] == best[1] and got["best_pc_intended"] == best[2] and rel(got["best_alpha"], best[3]) <= 1e-15
     assert got2["converged"] and got2["fmin"] == 0.0 - one
     assert got2["fmin"] >= got["fmin"] - 1e-9 * abs(got["fmin"])          # a constrained model cannot beat the free one
+
+
+@pytest.mark.skipif(vb.device_count() < 2, reason="needs two GPUs")
+def test_peer_stores_give_the_same_sums_as_nccl():
+    """vb2_peer_*: the shard sums pushed over NVLink by the reduce kernel + gather kernel, against an NCCL all-reduce of the
+    same shard sums, two processes (tools/collective_ab.py under torchrun)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cp = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                         "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "collective_ab.py")],
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert cp.returncode == 0, cp.stdout[-2000:]
+    assert "same sums: True" in cp.stdout, cp.stdout[-2000:]

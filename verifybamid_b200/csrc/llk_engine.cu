@@ -100,12 +100,26 @@ struct __align__(16) TaskRec {
 };
 static_assert(sizeof(TaskRec) % 16 == 0, "TaskRec is copied with cp.async.bulk");
 
+// Marker shards on several GPUs of one box (one process per GPU): instead of an NCCL all-reduce behind the kernel, the
+// reduce kernel itself PUSHES every job's shard sum into every rank's buffer over NVLink (peer stores), stamps a flag
+// when all of a launch's sums are out, and a small gather kernel on every rank adds the shards in rank order --
+// a one-shot all-gather + local sum, two banks deep.  Buffers are exchanged as CUDA IPC handles (vb2_peer_*).
+constexpr int kMaxPeers = 8;
+struct PeerDev {
+  double *vals[kMaxPeers];               // rank p's buffer: [2 banks][world][VB2_MAX_BATCH] shard sums ...
+  unsigned long long *flags[kMaxPeers];  // ... and [2 banks][world] launch stamps behind them
+  unsigned int *ticket;                  // (local) CTAs of the reduce kernel that have pushed their job
+  uint32_t world, rank;
+};
+
 struct LaunchArgs {
   SampleDev sample;           // ARGS kernels: the sample itself
   const SampleDev *samples;   // generic llk_kernel: job j evaluates samples[j]
   const uint32_t *slots;      // generic llk_kernel: partial/ticket slot of job j inside its sample
   const JobParams *jobs_dev;  // generic llk_kernel: parameters in HBM
   const TaskRec *recs;        // llk_stream_kernel / llk_reduce_kernel: job j = recs[j]
+  const PeerDev *peer;        // llk_reduce_kernel: push the shard sums to the peers (else nullptr)
+  unsigned long long peer_seq;  // the stamp of this launch on the peers' flags (its parity picks the bank)
   double *d_out;              // [n_jobs] device results (device-side reduction; may be nullptr)
   Slot *mbox;                 // device view of the host mailbox (may be nullptr)
   unsigned long long seq;
@@ -1130,6 +1144,53 @@ __global__ void __launch_bounds__(32, 1) llk_reduce_kernel(const __grid_constant
     if (A.mbox)
       *reinterpret_cast<ulonglong2 *>(A.mbox + job) = make_ulonglong2((unsigned long long)__double_as_longlong(out), A.seq);
     if (job == 0) A.queue[0] = 0u;
+  }
+  if (A.peer) {  // ---- fused with the collective: this shard's sum goes straight into every rank's buffer (NVLink stores)
+    const PeerDev &P = *A.peer;
+    const double out = __shfl_sync(0xFFFFFFFFu, s, 0) + S.log_other_const;
+    const size_t bank = (size_t)(A.peer_seq & 1ull);
+    if (lane < P.world)
+      asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(P.vals[lane] + (bank * P.world + P.rank) * VB2_MAX_BATCH + job), "d"(out) : "memory");
+    __threadfence_system();
+    unsigned int t = 0;
+    if (lane == 0) t = atomicAdd(P.ticket, 1u);
+    t = __shfl_sync(0xFFFFFFFFu, t, 0);
+    if (t == gridDim.x - 1) {  // the launch's last job is out: stamp every rank's flag for this shard
+      __threadfence_system();
+      if (lane == 0) *P.ticket = 0u;
+      if (lane < P.world)
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(P.flags[lane] + bank * P.world + P.rank), "l"(A.peer_seq) : "memory");
+    }
+  }
+}
+
+// Behind llk_reduce_kernel (peer mode): wait until every rank's shard sums of this launch have landed in THIS rank's
+// buffer, then add them in rank order (the same order on every rank: the same bits everywhere).
+__global__ void __launch_bounds__(256, 1) llk_gather_kernel(PeerDev P, unsigned long long seq, uint32_t n_jobs, double *d_out,
+                                                           unsigned long long patience) {
+  __shared__ int s_ok;
+  const size_t bank = (size_t)(seq & 1ull);
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if (threadIdx.x < P.world) {
+    const unsigned long long *flag = P.flags[P.rank] + bank * P.world + threadIdx.x;
+    const unsigned long long t0 = (unsigned long long)clock64();
+    unsigned long long v;
+    do {
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    } while (v != seq && (unsigned long long)clock64() - t0 < patience);
+    if (v != seq) s_ok = 0;  // a rank never arrived: poison the results instead of spinning for ever
+  }
+  __syncthreads();
+  const double *vals = P.vals[P.rank] + bank * P.world * VB2_MAX_BATCH;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_jobs; j += gridDim.x * blockDim.x) {
+    double sum = 0.0;
+    for (uint32_t r = 0; r < P.world; ++r) {
+      double v;
+      asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(vals + (size_t)r * VB2_MAX_BATCH + j) : "memory");
+      sum += v;
+    }
+    d_out[j] = s_ok ? sum : __longlong_as_double(0x7FF8000000000000ll);
   }
 }
 
@@ -2562,7 +2623,21 @@ static int stage_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
 }
 
 // eval_many, step 2: one launch over whatever stage_many staged last (device reduction).
-static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq_out, double *d_out = nullptr) {
+struct vb2_peer {
+  int device = 0;
+  uint32_t rank = 0, world = 1;
+  void *own = nullptr;                 // this rank's buffer (cudaMalloc, exported by IPC handle)
+  void *opened[kMaxPeers] = {};        // the peers' buffers as mapped into this process
+  PeerDev host{};                      // pointers into the buffers
+  PeerDev *d_dev = nullptr;            // the same in device memory (llk_reduce_kernel reads it)
+  unsigned long long seq = 0;          // launches so far (the same on every rank: they issue the same calls)
+  bool connected = false;
+  double clock_khz = 1.9e6;
+};
+static size_t peer_vals_bytes(uint32_t world) { return sizeof(double) * 2 * (size_t)world * VB2_MAX_BATCH; }
+
+static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq_out, double *d_out = nullptr,
+                     vb2_peer *peer = nullptr) {
   if (!lead->many_n) return set_err(lead, VB2_ERR_INVALID, "internal: nothing staged");
   LaunchArgs A;
   memset(&A, 0, sizeof(A));
@@ -2578,6 +2653,11 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
   A.recs = lead->d_recs;
   A.n_jobs = lead->many_n;
   A.d_out = d_out ? d_out : lead->d_out;
+  if (peer) {  // the shard sums go to the peers; the gather kernel behind writes d_out
+    A.d_out = nullptr;
+    A.peer = peer->d_dev;
+    A.peer_seq = ++peer->seq;
+  }
   A.kc = lead->many_kc;
   A.n_buf = 2;
   if (to_mailbox) {
@@ -2593,9 +2673,91 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
     if (rca) return rca;
   }
   launch_stream(8u * A.stage_bytes, lead->stream, A, lead->many_spec, lead->many_chunked, lead->sm_count);
+  if (peer) {
+    const unsigned long long patience = (unsigned long long)(20000.0 * peer->clock_khz);  // 20 s
+    llk_gather_kernel<<<dim3((lead->many_n + 255u) / 256u, 1, 1), dim3(256, 1, 1), 0, lead->stream>>>(
+        peer->host, A.peer_seq, lead->many_n, d_out ? d_out : lead->d_out, patience);
+  }
   release_staging(lead);
   VB2_CUDA(lead, cudaGetLastError());
   return VB2_OK;
+}
+
+// ---- peer buffers (marker shards, one process per GPU) ------------------------------------------------------------
+int vb2_peer_create(int device, uint32_t rank, uint32_t world, vb2_peer **out, void *ipc_handle_out) {
+  if (!out || !ipc_handle_out) return set_err(nullptr, VB2_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (world < 1 || world > (uint32_t)kMaxPeers || rank >= world) return set_err(nullptr, VB2_ERR_INVALID, "vb2_peer_create: bad rank / world (<= 8)");
+  VB2_CUDA(nullptr, cudaSetDevice(device));
+  vb2_peer *P = new (std::nothrow) vb2_peer();
+  if (!P) return set_err(nullptr, VB2_ERR_NOMEM, "out of host memory");
+  P->device = device; P->rank = rank; P->world = world;
+  const size_t bytes = peer_vals_bytes(world) + sizeof(unsigned long long) * 2 * world + 64;
+  cudaError_t e = cudaMalloc(&P->own, bytes);
+  if (e == cudaSuccess) e = cudaMemset(P->own, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, P->own);
+  if (e == cudaSuccess) e = cudaMalloc(&P->d_dev, sizeof(PeerDev));
+  if (e != cudaSuccess) {
+    if (P->own) cudaFree(P->own);
+    delete P;
+    return set_err(nullptr, VB2_ERR_CUDA, std::string("vb2_peer_create: ") + cudaGetErrorString(e));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles travel as 64 bytes");
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+  if (khz > 0) P->clock_khz = (double)khz;
+  *out = P;
+  return VB2_OK;
+}
+
+int vb2_peer_connect(vb2_peer *P, const void *ipc_handles) {
+  if (!P || !ipc_handles) return set_err(nullptr, VB2_ERR_INVALID, "null argument");
+  VB2_CUDA(nullptr, cudaSetDevice(P->device));
+  for (uint32_t r = 0; r < P->world; ++r) {
+    void *base = P->own;
+    if (r != P->rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, static_cast<const char *>(ipc_handles) + 64 * (size_t)r, sizeof(h));
+      cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return set_err(nullptr, VB2_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+      P->opened[r] = base;
+    }
+    P->host.vals[r] = static_cast<double *>(base);
+    P->host.flags[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(base) + peer_vals_bytes(P->world));
+  }
+  P->host.ticket = reinterpret_cast<unsigned int *>(static_cast<char *>(P->own) + peer_vals_bytes(P->world) +
+                                                     sizeof(unsigned long long) * 2 * P->world);
+  P->host.world = P->world;
+  P->host.rank = P->rank;
+  VB2_CUDA(nullptr, cudaMemcpy(P->d_dev, &P->host, sizeof(PeerDev), cudaMemcpyHostToDevice));
+  P->connected = true;
+  return VB2_OK;
+}
+
+void vb2_peer_destroy(vb2_peer *P) {
+  if (!P) return;
+  cudaSetDevice(P->device);
+  cudaDeviceSynchronize();
+  for (uint32_t r = 0; r < P->world; ++r)
+    if (P->opened[r]) cudaIpcCloseMemHandle(P->opened[r]);
+  if (P->own) cudaFree(P->own);
+  if (P->d_dev) cudaFree(P->d_dev);
+  delete P;
+}
+
+int vb2_llk_eval_many_device_peer(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
+                                  const double *alphas, vb2_peer *peer, double *d_llk_out) {
+  if (!d_llk_out || !peer) return set_err(ctxs && n > 0 ? ctxs[0] : nullptr, VB2_ERR_INVALID, "null argument");
+  if (!peer->connected) return set_err(ctxs && n > 0 ? ctxs[0] : nullptr, VB2_ERR_INVALID, "vb2_peer_connect has not been called");
+  bool nothing = false;
+  int rc = stage_many(ctxs, n, pc_contam, pc_intended, alphas, &nothing);
+  if (rc) return rc;
+  vb2_llk_ctx *lead = ctxs[0];
+  if (nothing)  // (every rank must still take part in the exchange: a shard without a usable marker is a shard of zeros)
+    return set_err(lead, VB2_ERR_INVALID, "vb2_llk_eval_many_device_peer: this rank's shard has no usable marker");
+  return fire_many(lead, false, nullptr, d_llk_out, peer);
 }
 
 int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,

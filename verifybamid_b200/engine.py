@@ -37,7 +37,8 @@ ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_warmup", "vb2_llk
                "vb2_llk_eval", "vb2_llk_eval_begin", "vb2_llk_eval_end", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many", "vb2_llk_eval_many_device",
                "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free",
                "vb2_llk_time_device", "vb2_llk_time_device_many", "vb2_llk_time_host", "vb2_llk_trace",
-               "vb2_llk_session_begin", "vb2_llk_session_end", "vb2_llk_minimize")
+               "vb2_llk_session_begin", "vb2_llk_session_end", "vb2_llk_minimize",
+               "vb2_peer_create", "vb2_peer_connect", "vb2_peer_destroy", "vb2_llk_eval_many_device_peer")
 
 
 class VB2Error(RuntimeError):
@@ -150,6 +151,15 @@ def load_library() -> ctypes.CDLL:
         if hasattr(lib, name):
             getattr(lib, name).restype = ctypes.c_int
             getattr(lib, name).argtypes = [ctypes.c_void_p]
+    lib.vb2_peer_create.restype = ctypes.c_int
+    lib.vb2_peer_create.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]
+    lib.vb2_peer_connect.restype = ctypes.c_int
+    lib.vb2_peer_connect.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.vb2_peer_destroy.restype = None
+    lib.vb2_peer_destroy.argtypes = [ctypes.c_void_p]
+    lib.vb2_llk_eval_many_device_peer.restype = ctypes.c_int
+    lib.vb2_llk_eval_many_device_peer.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.vb2_llk_minimize.restype = ctypes.c_int
     lib.vb2_llk_minimize.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Model), ctypes.c_void_p, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_int64, ctypes.c_double, ctypes.POINTER(_MinResult)]
@@ -404,6 +414,43 @@ def eval_many_device(engines: List[LLKEngine], pc_contam, pc_intended, alphas, d
     rc = lib.vb2_llk_eval_many_device(arr, n, a.ctypes.data, b.ctypes.data, al.ctypes.data, ctypes.c_void_p(d_out_ptr))
     if rc != VB2_OK:
         raise VB2Error(rc, lib.vb2_last_error(engines[0]._ctx).decode())
+
+
+class PeerReduce:
+    """The cross-GPU sum fused into the kernels (include/vb2_llk.h, vb2_peer_*): one process per GPU, buffers exchanged as
+    CUDA IPC handles through `exchange(handle_bytes) -> list of every rank's handle bytes, in rank order`."""
+
+    def __init__(self, device: int, rank: int, world: int, exchange):
+        self._lib = load_library()
+        self._peer = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        rc = self._lib.vb2_peer_create(int(device), int(rank), int(world), ctypes.byref(self._peer), handle)
+        if rc != VB2_OK:
+            raise VB2Error(rc, self._lib.vb2_last_error(None).decode())
+        handles = exchange(bytes(handle))
+        if len(handles) != world or any(len(h) != 64 for h in handles):
+            raise ValueError("exchange() must return one 64-byte handle per rank")
+        blob = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        rc = self._lib.vb2_peer_connect(self._peer, blob)
+        if rc != VB2_OK:
+            raise VB2Error(rc, self._lib.vb2_last_error(None).decode())
+
+    def eval_many_device(self, engines: List[LLKEngine], pc_contam, pc_intended, alphas, d_out_ptr: int, ctx_array=None) -> None:
+        """Every rank's shard of the same evaluations; the sums over all shards land in device memory at `d_out_ptr`."""
+        n = len(engines)
+        k = engines[0].n_pc
+        al = _f64(alphas).ravel()
+        a, b = _f64(pc_contam, (n, k)), _f64(pc_intended, (n, k))
+        arr = ctx_array if ctx_array is not None else context_array(engines)
+        rc = self._lib.vb2_llk_eval_many_device_peer(arr, n, a.ctypes.data, b.ctypes.data, al.ctypes.data, self._peer,
+                                                     ctypes.c_void_p(d_out_ptr))
+        if rc != VB2_OK:
+            raise VB2Error(rc, self._lib.vb2_last_error(engines[0]._ctx).decode())
+
+    def close(self) -> None:
+        if self._peer:
+            self._lib.vb2_peer_destroy(self._peer)
+            self._peer = ctypes.c_void_p()
 
 
 def time_device(engines: List[LLKEngine], warmup: int, steps: int, pc_contam, pc_intended, alpha: float) -> float:
