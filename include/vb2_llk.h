@@ -41,7 +41,8 @@ enum vb2_status {
   VB2_ERR_NO_DEVICE = 2, /* no CUDA device, or desc.device out of range           */
   VB2_ERR_CUDA = 3,      /* a CUDA runtime call or kernel failed                  */
   VB2_ERR_NOMEM = 4,     /* host or device allocation failed                      */
-  VB2_ERR_TIMEOUT = 5    /* the device did not answer (VB2_LLK_SPIN_TIMEOUT_MS)   */
+  VB2_ERR_TIMEOUT = 5,   /* the device did not answer (VB2_LLK_SPIN_TIMEOUT_MS)   */
+  VB2_ERR_UNSUPPORTED = 6 /* the device ingest does not take this input: use the host reader + vb2_llk_create */
 };
 
 enum vb2_panel_dtype {
@@ -175,6 +176,60 @@ int vb2_llk_eval_many(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, 
  * partial sums of n evaluations ready for ONE all-reduce.                                        */
 int vb2_llk_eval_many_device(vb2_llk_ctx *const *ctxs, int n, const double *pc_contam, const double *pc_intended,
                              const double *alphas, double *d_llk_out);
+
+/* ---- the stage in front of the kernels, on the device: pileup text -> image ------------------------------------
+ * For well-formed samtools-pileup text the device does what SimplePileupViewer::ReadPileup / ParsePileupSeqBasesOnly
+ * (SimplePileupViewer.cpp:711-833), ContaminationEstimator::BuildResolvedMarkers (ContaminationEstimator.cpp:67-86) and
+ * the host flatten of vb2_llk_create do, and leaves a context whose image is byte-identical to the one vb2_llk_create
+ * builds from the host reader's arrays.  Three calls, with the caller's marker sanity check (IsSanityCheckOK,
+ * cpp:543-587) between the last two:
+ *   vb2_panel_create   the panel on the device, once for any number of samples: UD, mu, per row the chromosome (an index
+ *                      into chrom_names), the 1-based position (PosVec) and the ALT base as resolved through ChooseBed;
+ *   vb2_ingest_parse   text -> lines -> fields -> kept bases; join with the panel.  info->row_depth[i] = number of kept
+ *                      bases on panel row i's pileup line, -1 when the pileup has no line for it; n_matched =
+ *                      effectiveNumSite and num_bases = numBases as ReadPileup leaves them (cpp:826-831);
+ *   vb2_ingest_flatten skip rules with the caller's avg_depth / sd_depth, class counts, marker order, slice geometry,
+ *                      the fill -- all on the device; only the deal of ~3k slices to bins runs on the host.
+ * Text that the reference parses with its stream-extraction quirks (short or empty lines, non-numeric position/depth,
+ * duplicated positions, '.' reference allele next to '.'/',' bases, an indel length without digits, > 65,535 reads on a
+ * site, >= 2 GiB of text) is answered with VB2_ERR_UNSUPPORTED: the caller then uses its host reader and vb2_llk_create,
+ * which reproduce those quirks.                                                                                  */
+typedef struct vb2_panel_desc {
+  uint32_t struct_size, n_marker, n_pc, ud_stride;
+  const double *ud, *means;
+  const uint16_t *chrom_id;  /* per row: index into chrom_names                                                 */
+  const int32_t *pos;        /* per row: 1-based position (column 3 of the .bed)                                */
+  const char *alt_base;      /* per row: ChooseBed[chr][pos].second                                             */
+  const char *chrom_names;   /* n_chrom NUL-terminated names, back to back                                      */
+  uint32_t n_chrom;
+  int32_t device;
+} vb2_panel_desc;
+typedef struct vb2_panel vb2_panel;
+typedef struct vb2_ingest vb2_ingest;
+typedef struct vb2_ingest_info {
+  uint32_t struct_size, n_lines;
+  uint32_t n_matched, pad_;
+  uint64_t num_bases;
+  const int32_t *row_depth;  /* [n_marker], owned by the ingest object                                          */
+} vb2_ingest_info;
+typedef struct vb2_flatten_desc {
+  uint32_t struct_size;
+  int32_t device;
+  void *stream;              /* the context's stream (NULL: its own)                                            */
+  uint32_t flags;            /* enum vb2_flags                                                                  */
+  int32_t panel_dtype;       /* enum vb2_panel_dtype                                                            */
+  double min_af, max_af;     /* 0, 0 = defaults                                                                 */
+  int32_t sanity_disabled;
+  uint32_t shard_rank, shard_count, pad_;  /* whole samples only: 0/0 or 0/1                                    */
+  double avg_depth, sd_depth;
+} vb2_flatten_desc;
+int vb2_panel_create(const vb2_panel_desc *desc, vb2_panel **out);
+void vb2_panel_destroy(vb2_panel *panel);
+int vb2_ingest_parse(const vb2_panel *panel, const char *text, uint64_t n_bytes, vb2_ingest **out, vb2_ingest_info *info);
+int vb2_ingest_flatten(vb2_ingest *ingest, const vb2_flatten_desc *desc, vb2_llk_ctx **out);
+void vb2_ingest_destroy(vb2_ingest *ingest);
+/* diagnostics: the first n_bytes of a context's image as it sits in device memory (tests compare it with the host flatten) */
+int vb2_llk_debug_image(vb2_llk_ctx *ctx, void *dst, uint64_t n_bytes);
 
 /* ---- marker shards on several GPUs, one process per GPU: the collective fused into the kernels ------------------
  * Instead of an NCCL all-reduce behind vb2_llk_eval_many_device, the reduce kernel PUSHES every evaluation's shard sum

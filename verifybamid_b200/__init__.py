@@ -9,5 +9,5 @@ Only what that one path needs lives here:
   synth.py     synthetic contaminated pileups (BASELINE.json configs)
 """
 from .problem import PileupProblem  # noqa: F401
-from .engine import (LLKEngine, PeerReduce, VB2Error, eval_many, eval_many_device, context_array, load_library, build_library, device_count,  # noqa: F401
+from .engine import (LLKEngine, DevicePanel, PeerReduce, VB2Error, VB2_ERR_UNSUPPORTED, eval_many, eval_many_device, context_array, load_library, build_library, device_count,  # noqa: F401
                      pack_host, time_device, time_device_many, time_host, VB2_PANEL_FP32, VB2_PANEL_FP64, VB2_MIN_MAX_DIM, ABI_SYMBOLS)

@@ -36,6 +36,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "llk_internal.h"
 #include "llk_pack.h"
 #include "vb2_llk.h"
 
@@ -2327,14 +2328,19 @@ void vb2_llk_destroy(vb2_llk_ctx *ctx) {
   delete ctx;
 }
 
-static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
+}  // extern "C"
+
+namespace vb2 {
+// ---- context construction, in two parts (shared by vb2_llk_create and the device ingest, llk_ingest.cu) --------------
+// part 1: the device, the stream, the wait mode
+int ctx_open(const CreateParams &cp, vb2_llk_ctx *ctx) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
     return set_err(ctx, VB2_ERR_NO_DEVICE, "no CUDA device available (this engine has no CPU fallback)");
   }
-  if (desc->device < 0 || desc->device >= ndev) return set_err(ctx, VB2_ERR_NO_DEVICE, "desc.device out of range");
-  ctx->device = desc->device;
+  if (cp.device < 0 || cp.device >= ndev) return set_err(ctx, VB2_ERR_NO_DEVICE, "desc.device out of range");
+  ctx->device = cp.device;
   VB2_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaDeviceProp prop;
   VB2_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
@@ -2347,49 +2353,56 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
     ctx->clock_khz = khz > 0 ? (double)khz : 1.9e6;
     if (const char *t = getenv("VB2_LLK_SESSION_IDLE_MS")) ctx->session_idle_ms = std::max(1.0, atof(t));
   }
-  if (desc->stream) {
-    ctx->stream = static_cast<cudaStream_t>(desc->stream);
+  if (cp.stream) {
+    ctx->stream = static_cast<cudaStream_t>(cp.stream);
   } else {
     VB2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
   }
-  ctx->spin = !(desc->flags & VB2_FLAG_NO_SPIN);
+  ctx->spin = !(cp.flags & VB2_FLAG_NO_SPIN);
   if (const char *t = getenv("VB2_LLK_SPIN_TIMEOUT_MS")) ctx->spin_timeout_ms = atof(t);
-  int rc = VB2_OK;
-
-  // ---- flatten on the host ----------------------------------------------------------------------
-  double phred[vb2::kNumQual];
-  vb2::build_phred_table(phred);
-  if (desc->panel_dtype != VB2_PANEL_FP64 && desc->panel_dtype != VB2_PANEL_FP32)
+  if (cp.panel_dtype != VB2_PANEL_FP64 && cp.panel_dtype != VB2_PANEL_FP32)
     return set_err(ctx, VB2_ERR_INVALID, "unknown panel_dtype");
-  vb2::PackConfig cfg;
+  return VB2_OK;
+}
+PackConfig ctx_pack_config(const vb2_llk_ctx *ctx, const CreateParams &cp) {
+  PackConfig cfg;
   cfg.max_ctas = (uint32_t)ctx->sm_count;  // one persistent CTA per SM
-  cfg.panel_fp64 = desc->panel_dtype == VB2_PANEL_FP64;
-  if (desc->flags & VB2_FLAG_BATCHED) cfg.min_rounds = 5;
+  cfg.panel_fp64 = cp.panel_dtype == VB2_PANEL_FP64;
+  if (cp.flags & VB2_FLAG_BATCHED) cfg.min_rounds = 5;
   if (const char *t = getenv("VB2_LLK_MAX_CTAS")) cfg.max_ctas = (uint32_t)std::max(1, atoi(t));
-  vb2::PackedSample &P = ctx->meta;
-  std::string perr;
-  rc = vb2::pack_sample(*desc, cfg, phred, &P, &perr);
-  if (rc) return set_err(ctx, rc, perr);
-  ctx->rounds = P.rounds;
+  return cfg;
+}
+cudaStream_t ctx_stream(const vb2_llk_ctx *ctx) { return ctx->stream; }
+int ctx_error(vb2_llk_ctx *ctx, int code, const std::string &msg) { return set_err(ctx, code, msg); }
 
-  // ---- upload ---------------------------------------------------------------------------------
+// part 2: adopt an image that already sits in device memory (d_blob belongs to the context from here on; P = its sizes,
+// layout and round table)
+int ctx_adopt_image(vb2_llk_ctx *ctx, const CreateParams &cp, const PackedSample &P, uint8_t *d_blob) {
+  int rc = VB2_OK;
+  ctx->meta = P;
+  ctx->meta.blob = {};
+  ctx->meta.marker_index = {};  // keep only the sizes
+  ctx->rounds = P.rounds;
+  if (d_blob) {
+    ctx->allocs.push_back(d_blob);
+    ctx->device_bytes += P.blob_bytes;
+  }
+  const bool panel_fp64 = cp.panel_dtype == VB2_PANEL_FP64;
   SampleDev &S = ctx->S;
-  const uint8_t *d_blob = nullptr;
   const vb2::Round *d_rounds = nullptr;
-  if ((rc = upload(ctx, P.blob, &d_blob))) return rc;
   if ((rc = upload(ctx, P.rounds, &d_rounds, false))) return rc;
   S.blob = d_blob;
   S.rounds = d_rounds;
   S.log_other_const = P.log_other_const;
-  S.min_af = desc->min_af != 0.0 ? desc->min_af : 0.00005;  // h:94
-  S.max_af = desc->max_af != 0.0 ? desc->max_af : 0.99995;  // h:95
+  S.min_af = cp.min_af != 0.0 ? cp.min_af : 0.00005;  // h:94
+  S.max_af = cp.max_af != 0.0 ? cp.max_af : 0.99995;  // h:95
   S.n_rounds = (uint32_t)P.rounds.size();
   S.n_bins = P.n_bins;
   S.grid_x = P.n_slices ? P.grid_x : 0u;
   S.conc_rounds = P.conc_rounds;
   S.n_pc = P.n_pc;
-  S.panel_fp64 = cfg.panel_fp64 ? 1u : 0u;
+  S.panel_fp64 = panel_fp64 ? 1u : 0u;
   S.known_af = P.known_af ? 1u : 0u;
   S.off_ud = P.layout.off_ud; S.off_mu = P.layout.off_mu; S.off_kaf = P.layout.off_kaf;
   S.off_diag = P.layout.off_diag; S.off_words = P.layout.off_words;
@@ -2403,7 +2416,7 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   S.buf_bytes = S.off_words + S.chunk_rows * 128u + 128u;  // (+ one row: the read loop looks one row ahead)
   ctx->chunked = max_rows > S.chunk_rows;
   const bool default_clamps = S.min_af == 0.00005 && S.max_af == 0.99995;
-  ctx->spec = (!cfg.panel_fp64 && !P.known_af && default_clamps && (P.n_pc == 2 || P.n_pc == 4)) ? (int)P.n_pc : 0;
+  ctx->spec = (!panel_fp64 && !P.known_af && default_clamps && (P.n_pc == 2 || P.n_pc == 4)) ? (int)P.n_pc : 0;
   if (getenv("VB2_LLK_NO_SPEC")) ctx->spec = 0;  // (tests: force the runtime-layout kernel)
   if ((rc = init_device_tables(ctx, ctx->device, ctx->spec, ctx->chunked))) return rc;
   S.n_buf = 2u;
@@ -2425,8 +2438,45 @@ static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
   VB2_CUDA(ctx, cudaMalloc(&ctx->d_sample, sizeof(SampleDev)));
   if ((rc = ensure_slots(ctx, 8))) return rc;
   VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  P.blob = {}; P.marker_index = {};  // keep only the sizes
   return VB2_OK;
+}
+vb2_llk_ctx *ctx_new() { return new (std::nothrow) vb2_llk_ctx(); }
+// diagnostics: the image as it sits in device memory (tests compare it with the host flatten's)
+int ctx_read_image(vb2_llk_ctx *ctx, uint8_t *dst, uint64_t n) {
+  if (n > ctx->meta.blob_bytes) return set_err(ctx, VB2_ERR_INVALID, "image is smaller than that");
+  VB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n) VB2_CUDA(ctx, cudaMemcpy(dst, ctx->S.blob, n, cudaMemcpyDeviceToHost));
+  return VB2_OK;
+}
+}  // namespace vb2
+
+extern "C" {
+
+static int create_impl(const vb2_llk_desc *desc, vb2_llk_ctx *ctx) {
+  const vb2::CreateParams cp{desc->device, desc->stream, desc->flags, desc->panel_dtype, desc->min_af, desc->max_af};
+  int rc = vb2::ctx_open(cp, ctx);
+  if (rc) return rc;
+  // ---- flatten on the host ----------------------------------------------------------------------
+  double phred[vb2::kNumQual];
+  vb2::build_phred_table(phred);
+  const vb2::PackConfig cfg = vb2::ctx_pack_config(ctx, cp);
+  vb2::PackedSample P;
+  std::string perr;
+  rc = vb2::pack_sample(*desc, cfg, phred, &P, &perr);
+  if (rc) return set_err(ctx, rc, perr);
+  // ---- upload ---------------------------------------------------------------------------------
+  uint8_t *d_blob = nullptr;
+  if (!P.blob.empty()) {
+    VB2_CUDA(ctx, cudaMalloc(&d_blob, P.blob.size()));
+    cudaError_t e = cudaMemcpyAsync(d_blob, P.blob.data(), P.blob.size(), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      cudaFree(d_blob);
+      return set_err(ctx, VB2_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(e));
+    }
+  }
+  return vb2::ctx_adopt_image(ctx, cp, P, d_blob);
 }
 
 int vb2_llk_create(const vb2_llk_desc *desc, vb2_llk_ctx **out) {

@@ -60,6 +60,132 @@ struct MarkerTmp {
 
 }  // namespace
 
+// Per-(class, q, g) single-read emission A_bc[g] = E[g]*e + N[g]*(1-e)  (COND_LK, ContaminationEstimator.h:164-177;
+// the same expression as h:223-224 with g1 == g2), and log(2e/3) of a class-2 read.
+void emission_tables(const double *phred, double (*a_ref)[3], double (*a_alt)[3], double *log_other) {
+  for (int q = 0; q < kNumQual; ++q) {
+    const double e = phred[q], ne = 1.0 - e;
+    a_ref[q][0] = 0.0 * e + 1.0 * ne;
+    a_ref[q][1] = (1.0 / 6.0) * e + 0.5 * ne;
+    a_ref[q][2] = (1.0 / 3.0) * e + 0.0 * ne;
+    a_alt[q][0] = (1.0 / 3.0) * e + 0.0 * ne;
+    a_alt[q][1] = (1.0 / 6.0) * e + 0.5 * ne;
+    a_alt[q][2] = 0.0 * e + 1.0 * ne;
+    log_other[q] = std::log((2.0 / 3.0) * e + 0.0 * ne);
+  }
+}
+// sum over the folded (class-2) reads of log(2e/3), from their histogram over the qualities
+double other_const(const uint64_t *hist, const double *log_other) {
+  long double sum = 0.0L;
+  for (int q = 0; q < kNumQual; ++q) sum += (long double)hist[q] * (long double)log_other[q];
+  return (double)sum;
+}
+
+// Cost of a slice in quarter rows, as the kernel spends its time: a row of four real reads in every lane = 4,
+// a uniform ragged tail = 2, a row that needs per-byte filler checks = 7, and 15 for the per-slice work
+// (allele frequencies, priors, marginal, pipeline bookkeeping).  fr / fa = leading rows that are full in every lane.
+uint32_t slice_cost(uint32_t wr, uint32_t wa, uint32_t fr, uint32_t fa, bool same_r, bool same_a) {
+  const uint32_t rr = wr - fr, ra = wa - fa;
+  const bool tail_r = same_r && rr == 1, tail_a = same_a && ra == 1;
+  return 4u * (fr + fa) + (tail_r ? 2u : 7u * rr) + (tail_a ? 2u : 7u * ra) + 15u;
+}
+
+// Steps 3b-5 of the flatten: order the slices by cost, keep this shard's, deal them to the SM sub-partition bins in
+// rounds, lay the rounds out.  Shared by the host flatten (pack_sample) and the device flatten (llk_ingest.cu), so both
+// produce the same image.
+int plan_layout(std::vector<SliceGeom> all_geom, uint32_t n_pc, bool known_af, uint32_t shard_rank, uint32_t shard_count,
+                const PackConfig &cfg, PackedSample *out, std::vector<SliceGeom> *geom_out, std::vector<uint32_t> *blob_slice_out,
+                std::string *err) {
+  PackedSample &P = *out;
+  // ---- 3b. costliest first; slice s of that order belongs to shard s % shard_count ----
+  std::stable_sort(all_geom.begin(), all_geom.end(), [](const SliceGeom &a, const SliceGeom &b) {
+    return a.cost != b.cost ? a.cost > b.cost : a.wr + a.wa > b.wr + b.wa;
+  });
+  std::vector<SliceGeom> &geom = *geom_out;
+  geom.clear();
+  for (size_t s = shard_rank; s < all_geom.size(); s += shard_count) geom.push_back(all_geom[s]);
+  P.n_slices = (uint32_t)geom.size();
+  // ---- 4. blob layout ------------------------------------------------------------------------------
+  BlobLayout &L = P.layout;
+  L = BlobLayout();
+  L.panel_elem = cfg.panel_fp64 ? 8u : 4u;
+  uint32_t off = kBlobHeaderBytes;
+  if (known_af) {
+    L.off_kaf = off; off += kSliceMarkers * 8u;
+  } else {
+    L.off_ud = off;  off += n_pc * kSliceMarkers * L.panel_elem;
+    L.off_mu = off;  off += kSliceMarkers * L.panel_elem;
+    off = (off + 7u) & ~7u;
+  }
+  L.off_diag = off;  off += 3u * kSliceMarkers * 8u;
+  L.off_words = off;
+
+  // ---- 5. deal the slices to SM sub-partition bins in rounds ------------------------------------------
+  // Round r = the slices [r * n_bins, (r+1) * n_bins) of the cost order, one per bin.  Inside a round the
+  // costliest slice goes to the bin that has the least work so far (so the bins stay level whatever the cost
+  // profile is); a partial last round is dealt first, so the bins that own one blob more start with that handicap.  Bins are only labels, so they
+  // are renumbered at the end to put the bins that own a blob in the last round last: in every round the bins
+  // that own a blob are then a contiguous range and blob k of the round belongs to bin first_bin + k.
+  P.grid_x = std::max(1u, std::min(cfg.max_ctas ? cfg.max_ctas : 1u, (P.n_slices + kBinsPerCta - 1) / kBinsPerCta));
+  if (cfg.min_rounds > 1) P.grid_x = std::max(1u, std::min(P.grid_x, P.n_slices / (kBinsPerCta * cfg.min_rounds)));
+  P.n_bins = P.grid_x * kBinsPerCta;
+  std::vector<uint32_t> slice_bin(P.n_slices, 0);  // provisional bin label of slice j
+  {
+    std::vector<uint64_t> load(P.n_bins, 0);
+    std::vector<uint32_t> by_load(P.n_bins);
+    std::iota(by_load.begin(), by_load.end(), 0u);
+    // the partial last round first: its slices are the handicap of the bins that will own six instead of five
+    const uint32_t n_full_rounds = P.n_slices / P.n_bins;
+    for (uint32_t j = n_full_rounds * P.n_bins, i = 0; j < P.n_slices; ++j, ++i) {
+      slice_bin[j] = i;
+      load[i] += geom[j].cost;
+    }
+    for (uint32_t r = 0; r < n_full_rounds; ++r) {
+      const uint32_t j0 = r * P.n_bins;
+      std::stable_sort(by_load.begin(), by_load.end(), [&](uint32_t a, uint32_t b) { return load[a] < load[b]; });
+      for (uint32_t i = 0; i < P.n_bins; ++i) {  // slice j0 + i is the (i+1)-th costliest of the round
+        slice_bin[j0 + i] = by_load[i];
+        load[by_load[i]] += geom[j0 + i].cost;
+      }
+    }
+    // renumber: bins without a blob in the (partial) last round first, in their old order
+    const uint32_t rem = P.n_slices % P.n_bins;
+    if (rem) {
+      std::vector<uint8_t> in_last(P.n_bins, 0);
+      for (uint32_t j = P.n_slices - rem; j < P.n_slices; ++j) in_last[slice_bin[j]] = 1;
+      std::vector<uint32_t> relabel(P.n_bins);
+      uint32_t next_short = 0, next_long = P.n_bins - rem;
+      for (uint32_t b = 0; b < P.n_bins; ++b) relabel[b] = in_last[b] ? next_long++ : next_short++;
+      for (uint32_t &b : slice_bin) b = relabel[b];
+    }
+  }
+  // blob_slice[r * n_bins + (bin - first_bin of round r)] = the slice stored there
+  std::vector<uint32_t> &blob_slice = *blob_slice_out;
+  blob_slice.assign(P.n_slices, 0);
+  P.rounds.clear();
+  P.max_stride = 0;
+  uint64_t total_bytes = 0;
+  for (uint32_t j0 = 0, r = 0; j0 < P.n_slices; j0 += P.n_bins, ++r) {
+    const uint32_t cnt = std::min(P.n_bins, P.n_slices - j0);
+    uint32_t wmax = 0;
+    for (uint32_t j = j0; j < j0 + cnt; ++j) wmax = std::max(wmax, geom[j].wr + geom[j].wa);
+    const uint64_t stride64 = (uint64_t)L.off_words + (uint64_t)wmax * 128u;  // off_words % 16 == 0
+    if (stride64 > 0x7FFFFFF0ull) {
+      if (err) *err = "marker too deep: one blob would exceed 2 GiB";
+      return VB2_ERR_INVALID;
+    }
+    Round R{total_bytes, (uint32_t)stride64, P.n_bins - cnt, cnt, wmax};
+    for (uint32_t j = j0; j < j0 + cnt; ++j) blob_slice[j0 + (slice_bin[j] - R.first_bin)] = j;
+    P.rounds.push_back(R);
+    P.max_stride = std::max(P.max_stride, R.stride);
+    total_bytes += (uint64_t)R.stride * cnt;
+    total_bytes = (total_bytes + 127u) & ~127ull;
+  }
+  P.conc_rounds = std::max(1u, std::min((uint32_t)P.rounds.size(), kMaxConcRounds));
+  P.blob_bytes = total_bytes;
+  return VB2_OK;
+}
+
 int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phred, PackedSample *out,
                 std::string *err) {
   auto fail = [&](const char *m) { if (err) *err = m; return (int)VB2_ERR_INVALID; };
@@ -83,19 +209,8 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
   };
   P.known_af = d.known_af != nullptr;
 
-  // Per-(class, q, g) single-read emission A_bc[g] = E[g]*e + N[g]*(1-e)
-  // (COND_LK, ContaminationEstimator.h:164-177; same expression as h:223-224 with g1 == g2).
   double a_ref[kNumQual][3], a_alt[kNumQual][3], log_other[kNumQual];
-  for (int q = 0; q < kNumQual; ++q) {
-    const double e = phred[q], ne = 1.0 - e;
-    a_ref[q][0] = 0.0 * e + 1.0 * ne;
-    a_ref[q][1] = (1.0 / 6.0) * e + 0.5 * ne;
-    a_ref[q][2] = (1.0 / 3.0) * e + 0.0 * ne;
-    a_alt[q][0] = (1.0 / 3.0) * e + 0.0 * ne;
-    a_alt[q][1] = (1.0 / 6.0) * e + 0.5 * ne;
-    a_alt[q][2] = 0.0 * e + 1.0 * ne;
-    log_other[q] = std::log((2.0 / 3.0) * e + 0.0 * ne);
-  }
+  emission_tables(phred, a_ref, a_alt, log_other);
 
   // ---- 1. skip rules (h:238-249) and per-marker class counts ---------------------------------
   unsigned n_threads = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
@@ -152,12 +267,8 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
   std::iota(order.begin(), order.end(), 0u);
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
   lap("2 sort markers");
-  // ---- 3. cut into 32-marker slices, costliest first; slice s belongs to shard s % shard_count ----
-  // Cost of a slice in quarter rows, as the kernel spends its time: a row of four real reads in every lane = 4,
-  // a uniform ragged tail = 2, a row that needs per-byte filler checks = 7, and 15 for the per-slice work
-  // (allele frequencies, priors, marginal, pipeline bookkeeping).
+  // ---- 3. cut into 32-marker slices ---------------------------------------------------------------
   const size_t total_slices = (order.size() + kSliceMarkers - 1) / kSliceMarkers;
-  struct SliceGeom { uint32_t wr, wa, cost; size_t first; };
   std::vector<SliceGeom> all_geom(total_slices);
   for (size_t s = 0; s < total_slices; ++s) {
     uint32_t wr = 0, wa = 0, fr = 0xFFFFFFFFu, fa = 0xFFFFFFFFu, nr0 = 0, na0 = 0;
@@ -174,95 +285,23 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
       same_r = same_r && m.n_ref == nr0;
       same_a = same_a && m.n_alt == na0;
     }
-    const uint32_t rr = wr - fr, ra = wa - fa;
-    const bool tail_r = same_r && rr == 1, tail_a = same_a && ra == 1;
-    const uint32_t cost = 4u * (fr + fa) + (tail_r ? 2u : 7u * rr) + (tail_a ? 2u : 7u * ra) + 15u;
-    all_geom[s] = {wr, wa, cost, s * kSliceMarkers};
+    all_geom[s] = {wr, wa, slice_cost(wr, wa, fr, fa, same_r, same_a), (uint32_t)(s * kSliceMarkers)};
   }
-  std::stable_sort(all_geom.begin(), all_geom.end(), [](const SliceGeom &a, const SliceGeom &b) {
-    return a.cost != b.cost ? a.cost > b.cost : a.wr + a.wa > b.wr + b.wa;
-  });
-  std::vector<SliceGeom> geom;
-  for (size_t s = d.shard_rank; s < total_slices; s += shard_count) geom.push_back(all_geom[s]);
-  P.n_slices = (uint32_t)geom.size();
-  P.marker_index.assign((size_t)P.n_slices * kSliceMarkers, 0xFFFFFFFFu);
-
   lap("3 slices");
-  // ---- 4. blob layout ------------------------------------------------------------------------------
-  BlobLayout &L = P.layout;
-  L.panel_elem = cfg.panel_fp64 ? 8u : 4u;
-  uint32_t off = kBlobHeaderBytes;
-  if (P.known_af) {
-    L.off_kaf = off; off += kSliceMarkers * 8u;
-  } else {
-    L.off_ud = off;  off += P.n_pc * kSliceMarkers * L.panel_elem;
-    L.off_mu = off;  off += kSliceMarkers * L.panel_elem;
-    off = (off + 7u) & ~7u;
-  }
-  L.off_diag = off;  off += 3u * kSliceMarkers * 8u;
-  L.off_words = off;
-
-  // ---- 5. deal the slices to SM sub-partition bins in rounds ------------------------------------------
-  // Round r = the slices [r * n_bins, (r+1) * n_bins) of the cost order, one per bin.  Inside a round the
-  // costliest slice goes to the bin that has the least work so far (so the bins stay level whatever the cost
-  // profile is); a partial last round is dealt first, so the bins that own one blob more start with that handicap.  Bins are only labels, so they
-  // are renumbered at the end to put the bins that own a blob in the last round last: in every round the bins
-  // that own a blob are then a contiguous range and blob k of the round belongs to bin first_bin + k.
-  P.grid_x = std::max(1u, std::min(cfg.max_ctas ? cfg.max_ctas : 1u, (P.n_slices + kBinsPerCta - 1) / kBinsPerCta));
-  if (cfg.min_rounds > 1) P.grid_x = std::max(1u, std::min(P.grid_x, P.n_slices / (kBinsPerCta * cfg.min_rounds)));
-  P.n_bins = P.grid_x * kBinsPerCta;
-  std::vector<uint32_t> slice_bin(P.n_slices, 0);  // provisional bin label of slice j
+  std::vector<SliceGeom> geom;
+  std::vector<uint32_t> blob_slice;
   {
-    std::vector<uint64_t> load(P.n_bins, 0);
-    std::vector<uint32_t> by_load(P.n_bins);
-    std::iota(by_load.begin(), by_load.end(), 0u);
-    // the partial last round first: its slices are the handicap of the bins that will own six instead of five
-    const uint32_t n_full_rounds = P.n_slices / P.n_bins;
-    for (uint32_t j = n_full_rounds * P.n_bins, i = 0; j < P.n_slices; ++j, ++i) {
-      slice_bin[j] = i;
-      load[i] += geom[j].cost;
-    }
-    for (uint32_t r = 0; r < n_full_rounds; ++r) {
-      const uint32_t j0 = r * P.n_bins;
-      std::stable_sort(by_load.begin(), by_load.end(), [&](uint32_t a, uint32_t b) { return load[a] < load[b]; });
-      for (uint32_t i = 0; i < P.n_bins; ++i) {  // slice j0 + i is the (i+1)-th costliest of the round
-        slice_bin[j0 + i] = by_load[i];
-        load[by_load[i]] += geom[j0 + i].cost;
-      }
-    }
-    // renumber: bins without a blob in the (partial) last round first, in their old order
-    const uint32_t rem = P.n_slices % P.n_bins;
-    if (rem) {
-      std::vector<uint8_t> in_last(P.n_bins, 0);
-      for (uint32_t j = P.n_slices - rem; j < P.n_slices; ++j) in_last[slice_bin[j]] = 1;
-      std::vector<uint32_t> relabel(P.n_bins);
-      uint32_t next_short = 0, next_long = P.n_bins - rem;
-      for (uint32_t b = 0; b < P.n_bins; ++b) relabel[b] = in_last[b] ? next_long++ : next_short++;
-      for (uint32_t &b : slice_bin) b = relabel[b];
-    }
+    std::string lerr;
+    if (plan_layout(all_geom, P.n_pc, P.known_af, d.shard_rank, shard_count, cfg, &P, &geom, &blob_slice, &lerr) != VB2_OK)
+      return fail(lerr.c_str());
   }
-  // blob_of[r * n_bins + (bin - first_bin of round r)] = the slice stored there
-  std::vector<uint32_t> blob_slice(P.n_slices, 0);
-  uint64_t total_bytes = 0;
-  for (uint32_t j0 = 0, r = 0; j0 < P.n_slices; j0 += P.n_bins, ++r) {
-    const uint32_t cnt = std::min(P.n_bins, P.n_slices - j0);
-    uint32_t wmax = 0;
-    for (uint32_t j = j0; j < j0 + cnt; ++j) wmax = std::max(wmax, geom[j].wr + geom[j].wa);
-    const uint64_t stride64 = (uint64_t)L.off_words + (uint64_t)wmax * 128u;  // off_words % 16 == 0
-    if (stride64 > 0x7FFFFFF0ull) return fail("marker too deep: one blob would exceed 2 GiB");
-    Round R{total_bytes, (uint32_t)stride64, P.n_bins - cnt, cnt, wmax};
-    for (uint32_t j = j0; j < j0 + cnt; ++j) blob_slice[j0 + (slice_bin[j] - R.first_bin)] = j;
-    P.rounds.push_back(R);
-    P.max_stride = std::max(P.max_stride, R.stride);
-    total_bytes += (uint64_t)R.stride * cnt;
-    total_bytes = (total_bytes + 127u) & ~127ull;
-  }
-  P.conc_rounds = std::max(1u, std::min((uint32_t)P.rounds.size(), kMaxConcRounds));
-  P.blob.assign((size_t)total_bytes, 0xFF);  // 0xFF = pad byte everywhere a read is not written
+  P.marker_index.assign((size_t)P.n_slices * kSliceMarkers, 0xFFFFFFFFu);
+  P.blob.assign((size_t)P.blob_bytes, 0xFF);  // 0xFF = pad byte everywhere a read is not written
+  BlobLayout &L = P.layout;
 
   lap("4-5 layout, rounds, alloc");
   // ---- 6. fill ------------------------------------------------------------------------------------
-  struct SliceTotals { long double other = 0.0L; uint64_t used = 0, streamed = 0, folded = 0; uint32_t markers = 0; };
+  struct SliceTotals { uint32_t other_hist[kNumQual] = {}; uint64_t used = 0, streamed = 0, folded = 0; uint32_t markers = 0; };
   std::vector<SliceTotals> totals(P.n_slices);
   parallel_chunks(P.n_slices, n_threads, [&](size_t q0, size_t q1, unsigned) {
   for (uint32_t q = (uint32_t)q0; q < (uint32_t)q1; ++q) {  // q = blob position: round q / n_bins, k-th blob of it
@@ -325,7 +364,7 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
         const int bc = classify_base(d.bases[jj], alt);
         const int q = clamp_qual(d.quals[jj]);
         if (bc == 2) {
-          T.other += (long double)log_other[q];
+          ++T.other_hist[q];
           ++T.folded;
         } else {
           ++hist[bc][q];
@@ -353,12 +392,12 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
     std::memcpy(blob, hdr, sizeof(hdr));
   }
   }, 64);
-  long double other_sum = 0.0L;
-  for (const SliceTotals &T : totals) {  // slice order: the same sum whatever the thread count
-    other_sum += T.other;
+  uint64_t other_hist[kNumQual] = {};
+  for (const SliceTotals &T : totals) {
+    for (int q = 0; q < kNumQual; ++q) other_hist[q] += T.other_hist[q];
     P.reads_used += T.used; P.reads_streamed += T.streamed; P.reads_folded += T.folded; P.n_used += T.markers;
   }
-  P.log_other_const = (double)other_sum;
+  P.log_other_const = other_const(other_hist, log_other);
   lap("6 fill blobs");
   return VB2_OK;
 }

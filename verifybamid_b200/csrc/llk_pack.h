@@ -74,6 +74,7 @@ struct PackedSample {
   uint32_t max_stride = 0;      // largest blob stride (bytes)
   bool known_af = false;
   uint64_t reads_used = 0, reads_streamed = 0, reads_folded = 0;
+  uint64_t blob_bytes = 0;      // size of the image
   double log_other_const = 0.0;
   BlobLayout layout;
   std::vector<Round> rounds;
@@ -86,6 +87,19 @@ struct PackedSample {
   std::vector<uint32_t> marker_index; // [n_slices*32] panel row per (blob, lane) in image order: blob q is the
                                       // (q % n_bins)-th blob of round q / n_bins, i.e. of bin first_bin + q % n_bins
 };
+
+// Geometry of one 32-marker slice: ref / alt word rows, its cost, and where its markers start in the sorted marker order.
+struct SliceGeom {
+  uint32_t wr, wa, cost, first;
+};
+uint32_t slice_cost(uint32_t wr, uint32_t wa, uint32_t full_ref, uint32_t full_alt, bool same_ref, bool same_alt);
+// Cost order, sharding, the deal to bins, the round table (everything of the layout that is not per-read work); shared
+// by the host flatten and the device flatten.  all_geom[s] = slice s of the sorted marker order.
+int plan_layout(std::vector<SliceGeom> all_geom, uint32_t n_pc, bool known_af, uint32_t shard_rank, uint32_t shard_count,
+                const PackConfig &cfg, PackedSample *out, std::vector<SliceGeom> *geom, std::vector<uint32_t> *blob_slice,
+                std::string *err);
+void emission_tables(const double *phred, double (*a_ref)[3], double (*a_alt)[3], double *log_other);
+double other_const(const uint64_t *hist, const double *log_other);
 
 // Returns VB2_OK or VB2_ERR_INVALID (message in *err).  phred[q] = 10^(-q/10), q = 0..93.
 int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phred, PackedSample *out,

@@ -30,7 +30,9 @@ VB2_MAX_PC = 16
 VB2_MAX_BATCH = 4096
 VB2_MIN_MAX_DIM = 9
 
-_STATUS = {1: "VB2_ERR_INVALID", 2: "VB2_ERR_NO_DEVICE", 3: "VB2_ERR_CUDA", 4: "VB2_ERR_NOMEM", 5: "VB2_ERR_TIMEOUT"}
+VB2_ERR_UNSUPPORTED = 6
+_STATUS = {1: "VB2_ERR_INVALID", 2: "VB2_ERR_NO_DEVICE", 3: "VB2_ERR_CUDA", 4: "VB2_ERR_NOMEM", 5: "VB2_ERR_TIMEOUT",
+           6: "VB2_ERR_UNSUPPORTED"}
 
 # every symbol include/vb2_llk.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_warmup", "vb2_llk_create", "vb2_llk_destroy", "vb2_llk_get_info",
@@ -38,7 +40,9 @@ ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_warmup", "vb2_llk
                "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free",
                "vb2_llk_time_device", "vb2_llk_time_device_many", "vb2_llk_time_host", "vb2_llk_trace",
                "vb2_llk_session_begin", "vb2_llk_session_end", "vb2_llk_minimize",
-               "vb2_peer_create", "vb2_peer_connect", "vb2_peer_destroy", "vb2_llk_eval_many_device_peer")
+               "vb2_peer_create", "vb2_peer_connect", "vb2_peer_destroy", "vb2_llk_eval_many_device_peer",
+               "vb2_panel_create", "vb2_panel_destroy", "vb2_ingest_parse", "vb2_ingest_flatten", "vb2_ingest_destroy",
+               "vb2_llk_debug_image")
 
 
 class VB2Error(RuntimeError):
@@ -99,6 +103,26 @@ class _MinResult(ctypes.Structure):
                 ("best_alpha", ctypes.c_double)]
 
 
+class _PanelDesc(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("n_marker", ctypes.c_uint32), ("n_pc", ctypes.c_uint32),
+                ("ud_stride", ctypes.c_uint32), ("ud", ctypes.c_void_p), ("means", ctypes.c_void_p),
+                ("chrom_id", ctypes.c_void_p), ("pos", ctypes.c_void_p), ("alt_base", ctypes.c_void_p),
+                ("chrom_names", ctypes.c_char_p), ("n_chrom", ctypes.c_uint32), ("device", ctypes.c_int32)]
+
+
+class _IngestInfo(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("n_lines", ctypes.c_uint32), ("n_matched", ctypes.c_uint32),
+                ("pad_", ctypes.c_uint32), ("num_bases", ctypes.c_uint64), ("row_depth", ctypes.POINTER(ctypes.c_int32))]
+
+
+class _FlattenDesc(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("device", ctypes.c_int32), ("stream", ctypes.c_void_p),
+                ("flags", ctypes.c_uint32), ("panel_dtype", ctypes.c_int32), ("min_af", ctypes.c_double),
+                ("max_af", ctypes.c_double), ("sanity_disabled", ctypes.c_int32), ("shard_rank", ctypes.c_uint32),
+                ("shard_count", ctypes.c_uint32), ("pad_", ctypes.c_uint32), ("avg_depth", ctypes.c_double),
+                ("sd_depth", ctypes.c_double)]
+
+
 _lib = None
 
 
@@ -151,6 +175,19 @@ def load_library() -> ctypes.CDLL:
         if hasattr(lib, name):
             getattr(lib, name).restype = ctypes.c_int
             getattr(lib, name).argtypes = [ctypes.c_void_p]
+    lib.vb2_panel_create.restype = ctypes.c_int
+    lib.vb2_panel_create.argtypes = [ctypes.POINTER(_PanelDesc), ctypes.POINTER(ctypes.c_void_p)]
+    lib.vb2_panel_destroy.restype = None
+    lib.vb2_panel_destroy.argtypes = [ctypes.c_void_p]
+    lib.vb2_ingest_parse.restype = ctypes.c_int
+    lib.vb2_ingest_parse.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p),
+                                     ctypes.POINTER(_IngestInfo)]
+    lib.vb2_ingest_flatten.restype = ctypes.c_int
+    lib.vb2_ingest_flatten.argtypes = [ctypes.c_void_p, ctypes.POINTER(_FlattenDesc), ctypes.POINTER(ctypes.c_void_p)]
+    lib.vb2_ingest_destroy.restype = None
+    lib.vb2_ingest_destroy.argtypes = [ctypes.c_void_p]
+    lib.vb2_llk_debug_image.restype = ctypes.c_int
+    lib.vb2_llk_debug_image.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
     lib.vb2_peer_create.restype = ctypes.c_int
     lib.vb2_peer_create.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]
     lib.vb2_peer_connect.restype = ctypes.c_int
@@ -251,6 +288,81 @@ def pack_host(problem: PileupProblem, shard_rank: int = 0, shard_count: int = 1,
         return out
     finally:
         lib.vb2_llk_pack_free(ctypes.byref(v))
+
+
+class DevicePanel:
+    """A reference panel resident on the device for the device-side pileup ingest (vb2_panel_create)."""
+
+    def __init__(self, ud, means, chrom: Sequence[str], pos, alt_base, device: int = 0):
+        self._lib = load_library()
+        self.ud = np.ascontiguousarray(ud, dtype=np.float64)
+        self.means = np.ascontiguousarray(means, dtype=np.float64)
+        names = sorted(set(chrom))
+        index = {c: i for i, c in enumerate(names)}
+        self.chrom_id = np.array([index[c] for c in chrom], dtype=np.uint16)
+        self.pos = np.ascontiguousarray(pos, dtype=np.int32)
+        self.alt = np.ascontiguousarray(alt_base, dtype=np.uint8)
+        self.n_marker, self.n_pc = self.ud.shape
+        self.device = int(device)
+        d = _PanelDesc()
+        d.struct_size = ctypes.sizeof(_PanelDesc)
+        d.n_marker, d.n_pc, d.ud_stride = self.n_marker, self.n_pc, self.n_pc
+        d.ud, d.means = self.ud.ctypes.data, self.means.ctypes.data
+        d.chrom_id, d.pos, d.alt_base = self.chrom_id.ctypes.data, self.pos.ctypes.data, self.alt.ctypes.data
+        self._names = b"".join(c.encode() + b"\0" for c in names)
+        d.chrom_names = self._names
+        d.n_chrom = len(names)
+        d.device = self.device
+        self._panel = ctypes.c_void_p()
+        rc = self._lib.vb2_panel_create(ctypes.byref(d), ctypes.byref(self._panel))
+        if rc != VB2_OK:
+            raise VB2Error(rc, self._lib.vb2_last_error(None).decode())
+
+    def ingest(self, text: bytes, sanity_disabled: bool = False, panel_dtype: int = VB2_PANEL_FP32, batched: bool = False,
+               stats=None) -> "LLKEngine":
+        """Pileup text -> a resident engine, parsed and flattened on the device.  `stats(info) -> (avg_depth, sd_depth)`
+        is the caller's marker sanity check (default: the reference's IsSanityCheckOK arithmetic); raises VB2Error with
+        code VB2_ERR_UNSUPPORTED for text that needs the host reader."""
+        ing = ctypes.c_void_p()
+        info = _IngestInfo()
+        info.struct_size = ctypes.sizeof(_IngestInfo)
+        rc = self._lib.vb2_ingest_parse(self._panel, text, len(text), ctypes.byref(ing), ctypes.byref(info))
+        if rc != VB2_OK:
+            raise VB2Error(rc, self._lib.vb2_last_error(None).decode())
+        try:
+            depth = np.ctypeslib.as_array(info.row_depth, shape=(self.n_marker,)).copy() if self.n_marker else np.zeros(0, np.int32)
+            summary = {"n_lines": info.n_lines, "n_matched": info.n_matched, "num_bases": info.num_bases, "row_depth": depth}
+            if stats is not None:
+                avg, sd = stats(summary)
+            else:   # ContaminationEstimator.cpp:543-565 (int multiply, effectiveNumSite = matched lines)
+                avg = info.num_bases / info.n_matched if info.n_matched else float("nan")
+                have = depth[depth >= 0].astype(np.int64)
+                sq = float(np.sum((have.astype(np.int32) * have.astype(np.int32)).astype(np.int64)))
+                sd = float(np.sqrt(sq / info.n_matched - avg * avg)) if info.n_matched else float("nan")
+            f = _FlattenDesc()
+            f.struct_size = ctypes.sizeof(_FlattenDesc)
+            f.device = self.device
+            f.stream = None
+            f.flags = VB2_FLAG_BATCHED if batched else 0
+            f.panel_dtype = int(panel_dtype)
+            f.sanity_disabled = int(sanity_disabled)
+            f.shard_rank, f.shard_count = 0, 1
+            f.avg_depth, f.sd_depth = float(avg), float(sd)
+            ctx = ctypes.c_void_p()
+            rc = self._lib.vb2_ingest_flatten(ing, ctypes.byref(f), ctypes.byref(ctx))
+            if rc != VB2_OK:
+                raise VB2Error(rc, self._lib.vb2_last_error(None).decode())
+        finally:
+            self._lib.vb2_ingest_destroy(ing)
+        eng = LLKEngine.__new__(LLKEngine)
+        eng._lib, eng._ctx, eng.problem, eng.n_pc = self._lib, ctx, None, self.n_pc
+        eng.ingest_summary = dict(summary, avg_depth=float(avg), sd_depth=float(sd))
+        return eng
+
+    def close(self) -> None:
+        if self._panel:
+            self._lib.vb2_panel_destroy(self._panel)
+            self._panel = ctypes.c_void_p()
 
 
 class LLKEngine:
@@ -374,6 +486,12 @@ class LLKEngine:
         self._check(self._lib.vb2_llk_trace(self._ctx, a.ctypes.data, b.ctypes.data, float(alpha), stamps.ctypes.data,
                                             1024, ctypes.byref(n), ctypes.byref(llk)))
         return llk.value, stamps[:n.value]
+
+    def debug_image(self, n_bytes: int) -> np.ndarray:
+        """The first n_bytes of the image as it sits in device memory (tests)."""
+        out = np.empty(int(n_bytes), dtype=np.uint8)
+        self._check(self._lib.vb2_llk_debug_image(self._ctx, out.ctypes.data, int(n_bytes)))
+        return out
 
     def info(self) -> dict:
         i = _Info()
