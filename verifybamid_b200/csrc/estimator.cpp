@@ -234,9 +234,89 @@ ContaminationEstimator::ContaminationEstimator(int nPC, const ContaminationEstim
   means = panel.means;
   ChooseBed = panel.ChooseBed;
   PosVec = panel.PosVec;
+  panelOwner = &panel;
 }
 
-ContaminationEstimator::~ContaminationEstimator() { DestroyEngines(); }
+ContaminationEstimator::~ContaminationEstimator() {
+  DestroyEngines();
+  if (devIngest) vb2_ingest_destroy(devIngest);
+  if (devPanel && devPanelOwned) vb2_panel_destroy(devPanel);
+}
+
+vb2_panel *ContaminationEstimator::DevicePanel(int device) {
+  if (devPanel) return devPanel;
+  if (PosVec.size() < NumMarker || means.size() < NumMarker) return nullptr;
+  // chromosome names -> small integers; per row the position and the ALT base as ChooseBed resolves it (cpp:80)
+  std::vector<std::string> names;
+  std::unordered_map<std::string, uint16_t> id;
+  std::vector<uint16_t> chrom(NumMarker);
+  std::vector<int32_t> pos(NumMarker);
+  std::vector<char> alt(NumMarker);
+  std::vector<double> ud((size_t)NumMarker * numPC);
+  for (size_t i = 0; i < NumMarker; ++i) {
+    const std::string &chr = PosVec[i].first;
+    auto it = id.find(chr);
+    if (it == id.end()) {
+      if (names.size() >= 65535) return nullptr;
+      it = id.emplace(chr, (uint16_t)names.size()).first;
+      names.push_back(chr);
+    }
+    chrom[i] = it->second;
+    pos[i] = PosVec[i].second;
+    alt[i] = ChooseBed[chr][PosVec[i].second].second;
+    for (int k = 0; k < numPC; ++k) ud[i * numPC + k] = UD[i][k];
+  }
+  std::string blob;
+  for (const std::string &n : names) { blob += n; blob += '\0'; }
+  vb2_panel_desc d;
+  memset(&d, 0, sizeof(d));
+  d.struct_size = sizeof(d);
+  d.n_marker = NumMarker;
+  d.n_pc = (uint32_t)numPC;
+  d.ud_stride = (uint32_t)numPC;
+  d.ud = ud.data();
+  d.means = means.data();
+  d.chrom_id = chrom.data();
+  d.pos = pos.data();
+  d.alt_base = alt.data();
+  d.chrom_names = blob.data();
+  d.n_chrom = (uint32_t)names.size();
+  d.device = device;
+  if (vb2_panel_create(&d, &devPanel) != VB2_OK) {
+    devPanel = nullptr;
+    return nullptr;
+  }
+  devPanelOwned = true;
+  devPanelDevice = device;
+  return devPanel;
+}
+
+bool ContaminationEstimator::ReadPileupOnDevice(const std::string &pileupFile, int device) {
+  if (isAFknown || numGPU != 1 || getenv("VB2_HOST_INGEST")) return false;
+  // (a cohort shares the panel its panel estimator put on ONE device; samples on other devices use the host reader)
+  vb2_panel *panel = panelOwner ? (panelOwner->devPanelDevice == device ? panelOwner->devPanel : nullptr) : DevicePanel(device);
+  if (!panel) return false;
+  std::ifstream fin(pileupFile, std::ios::binary);
+  if (!fin.is_open()) error("open file %s failed!", pileupFile.c_str());
+  std::string text((std::istreambuf_iterator<char>(fin)), std::istreambuf_iterator<char>());
+  vb2_ingest_info info;
+  memset(&info, 0, sizeof(info));
+  info.struct_size = sizeof(info);
+  if (devIngest) { vb2_ingest_destroy(devIngest); devIngest = nullptr; }
+  const int rc = vb2_ingest_parse(panel, text.data(), text.size(), &devIngest, &info);
+  if (rc == VB2_ERR_UNSUPPORTED) {
+    notice("pileup text is read by the host (%s)", vb2_last_error(nullptr));
+    return false;
+  }
+  if (rc != VB2_OK) error("GPU pileup ingest: %s", vb2_last_error(nullptr));
+  viewer = SimplePileupViewer();
+  viewer.numBases = (long)info.num_bases;            // cpp:826
+  viewer.effectiveNumSite = (int)info.n_matched;     // cpp:829
+  viewer.avgDepth = (double)viewer.numBases / viewer.GetNumMarker();  // cpp:831
+  devRowDepth = info.row_depth;
+  isPileupInput = true;
+  return true;
+}
 
 void ContaminationEstimator::BuildResolvedMarkers() {
   resolvedMarkers.resize(NumMarker);
@@ -258,6 +338,32 @@ void ContaminationEstimator::BuildResolvedMarkers() {
 
 void ContaminationEstimator::CreateEngines() {
   DestroyEngines();
+  if (devIngest) {  // the pileup sits on the device already: flatten it there
+    vb2_flatten_desc f;
+    memset(&f, 0, sizeof(f));
+    f.struct_size = sizeof(f);
+    f.device = firstDevice;
+    f.panel_dtype = panelFp64 ? VB2_PANEL_FP64 : VB2_PANEL_FP32;
+    if (cohort) f.flags |= VB2_FLAG_BATCHED;
+    f.sanity_disabled = isSanityCheckDisabled ? 1 : 0;
+    f.avg_depth = viewer.avgDepth;
+    f.sd_depth = viewer.sdDepth;
+    vb2_llk_ctx *c = nullptr;
+    const int rc = vb2_ingest_flatten(devIngest, &f, &c);
+    vb2_ingest_destroy(devIngest);
+    devIngest = nullptr;
+    devRowDepth = nullptr;
+    if (rc != VB2_OK) error("cannot flatten the pileup on device %d: %s", firstDevice, vb2_last_error(nullptr));
+    engines.push_back(c);
+    vb2_llk_info info;
+    info.struct_size = sizeof(info);
+    if (vb2_llk_get_info(c, &info) == VB2_OK)
+      notice("GPU likelihood engine: 1 device(s), %llu markers / %llu reads resident in HBM (parsed and flattened on the device)",
+             (unsigned long long)info.markers_used, (unsigned long long)info.reads_used);
+    if (!cohort && !getenv("VB2_NO_SESSION") && vb2_llk_session_begin(c) == VB2_OK)
+      notice("evaluation session: resident kernel on 1 device(s)");
+    return;
+  }
   if (PosVec.size() < NumMarker || means.size() < NumMarker)
     error("SVD files disagree: %u rows in .UD, %d in .bed, %d in .mu", NumMarker, (int)PosVec.size(), (int)means.size());
   std::vector<double> ud((size_t)NumMarker * numPC);
@@ -327,7 +433,7 @@ void ContaminationEstimator::DestroyEngines() {
 
 int ContaminationEstimator::OptimizeLLK(const std::string &OutputPrefix) {
   AmoebaMinimizer myMinimizer;
-  BuildResolvedMarkers();
+  if (!devIngest) BuildResolvedMarkers();
   {
     PhaseTimer t("Flatten pileup into HBM");
     CreateEngines();
@@ -641,6 +747,11 @@ bool ContaminationEstimator::IsSanityCheckOK() {
   notice("Number of marker in Reference Matrix:%d", NumMarker);
   notice("Number of marker shared with input file:%d", viewer.GetNumMarker());
   auto depth_at = [&](size_t i, int &depth) -> bool {
+    if (devRowDepth) {  // the pileup was parsed on the device: the join is done, the depths are here
+      if (devRowDepth[i] < 0) return false;
+      depth = devRowDepth[i];
+      return true;
+    }
     auto chrIt = viewer.posIndex.find(PosVec[i].first);
     if (chrIt == viewer.posIndex.end()) return false;
     auto posIt = chrIt->second.find(PosVec[i].second);

@@ -86,6 +86,11 @@ class ContaminationEstimator {
   int ReadMean(const std::string &path);       // cpp:440-459
   int ReadAF(const std::string &path);         // cpp:461-487
   int ReadPileup(const std::string &pileupFile);  // cpp:495-499
+  // The same stage on the device (include/vb2_llk.h, vb2_ingest_*): the text is parsed, joined with the panel and --
+  // in CreateEngines -- flattened by the GPU; the host only sees the per-row depths its sanity check needs.  Returns
+  // false when the text needs the host reader (its parsing quirks, --KnownAF, marker shards): call ReadPileup then.
+  bool ReadPileupOnDevice(const std::string &pileupFile, int device);
+  vb2_panel *DevicePanel(int device);   // the panel on the device (created on first use, shared by a cohort)
   bool IsSanityCheckOK();                      // cpp:543-587
   void BuildResolvedMarkers();                 // cpp:67-86
   int OptimizeLLK(const std::string &OutputPrefix);  // cpp:88-190
@@ -101,6 +106,12 @@ class ContaminationEstimator {
   void CreateEngines();
   void DestroyEngines();
   std::vector<vb2_llk_ctx *> engines;
+  vb2_panel *devPanel = nullptr;        // owned unless borrowed from the cohort's panel estimator
+  bool devPanelOwned = false;
+  int devPanelDevice = -1;
+  const ContaminationEstimator *panelOwner = nullptr;  // cohort: the estimator whose panel this one shares
+  vb2_ingest *devIngest = nullptr;      // a pileup parsed on the device, waiting to be flattened
+  const int32_t *devRowDepth = nullptr; // per panel row: kept bases on its pileup line, -1 = no line
   double engineSeconds = 0;  // wall time spent inside ComputeMixLLKs
   long deviceSimplexEvals = 0;  // evaluations made by searches that ran on the device
 };

@@ -2185,6 +2185,7 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
     if (rc) return rc;
   }
   LaunchArgs A;
+  memset(&A, 0, sizeof(A));  // (every pointer a kernel tests for null starts out null)
   A.sample = ctx->S;
   A.samples = nullptr; A.slots = nullptr; A.jobs_dev = nullptr; A.recs = nullptr;
   A.d_out = d_out;

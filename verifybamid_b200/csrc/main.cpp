@@ -208,6 +208,7 @@ int run_cohort(const Options &o, const std::string &UDPath, const std::string &P
     PhaseTimer t("Load SVD reference data");
     panel.ReadSVDMatrix(UDPath, PCPath, MeanPath);
   }
+  if (o.knownAF == "Empty") panel.DevicePanel(o.device);  // the device-side pileup reader of the samples on that GPU
   std::vector<int> per_device(o.numGPU, 0);
   for (size_t i = 0; i < samples.size(); ++i) {
     samples[i].device = o.device + (int)(i % o.numGPU);
@@ -233,7 +234,7 @@ int run_cohort(const Options &o, const std::string &UDPath, const std::string &P
         E.firstDevice = smp.device;
         E.cohort = &C;
         E.cohortIndex = smp.local;
-        E.ReadPileup(smp.pileup);
+        if (!E.ReadPileupOnDevice(smp.pileup, smp.device)) E.ReadPileup(smp.pileup);
         if (!o.disableSanityCheck && !E.IsSanityCheckOK())
           throw std::runtime_error("Insufficient Available markers (sanity check)");
         E.OptimizeLLK(smp.prefix);
@@ -318,7 +319,13 @@ int execute(int argc, char **argv) {
   }
   {
     PhaseTimer t("Read pileup");
-    Estimator.ReadPileup(o.PileupFile);
+    // The device reader needs the CUDA context; --OutputPileup needs the reads on the host.
+    bool on_device = false;
+    if (!o.outputPileup && o.numGPU == 1) {
+      for (auto &x : warm) if (x.joinable()) x.join();
+      on_device = Estimator.ReadPileupOnDevice(o.PileupFile, o.device);
+    }
+    if (!on_device) Estimator.ReadPileup(o.PileupFile);
   }
 
   if (o.outputPileup) {  // main.cpp:336-369
@@ -353,7 +360,7 @@ int execute(int argc, char **argv) {
       exit(EXIT_FAILURE);
     }
   }
-  for (auto &x : warm) x.join();
+  for (auto &x : warm) if (x.joinable()) x.join();
   {
     PhaseTimer t("Optimize likelihood");
     Estimator.OptimizeLLK(o.outputPrefix);
