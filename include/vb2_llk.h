@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VB2_ABI_VERSION 1
+#define VB2_ABI_VERSION 2
 #define VB2_MAX_PC 16        /* largest n_pc a context accepts                               */
 #define VB2_MAX_BATCH 4096   /* largest n in one vb2_llk_eval_batch / vb2_llk_eval_many call */
 
@@ -112,6 +112,8 @@ typedef struct vb2_llk_desc {
   uint32_t shard_rank;
   uint32_t shard_count;
   void *stream; /* cudaStream_t to launch on; NULL = a stream owned by the context */
+  int64_t n_info; /* entries of info_offset minus one (viewer.baseInfo.size()); > 0: base_info_index is checked against
+                     it, 0: the caller vouches for the indices                                                   */
 } vb2_llk_desc;
 
 typedef struct vb2_llk_info {

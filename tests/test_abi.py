@@ -29,8 +29,10 @@ def test_header_symbols_are_exported():
 
 def test_abi_version_and_struct_sizes():
     lib = vb.load_library()
-    assert lib.vb2_abi_version() == 1
-    assert ctypes.sizeof(engine._Desc) == 144
+    assert lib.vb2_abi_version() == 2
+    assert ctypes.sizeof(engine._Desc) == 152          # (version 2: + n_info)
+    assert ctypes.sizeof(engine._Model) == 408 and ctypes.sizeof(engine._MinResult) == 192
+    assert ctypes.sizeof(engine._PanelDesc) == 72 and ctypes.sizeof(engine._FlattenDesc) == 72 and ctypes.sizeof(engine._IngestInfo) == 32
     # a descriptor with the wrong struct_size must be refused before anything is touched
     d = engine.make_desc(to_product(golden_problem(RESULT_PILEUP)))
     d.struct_size = 8

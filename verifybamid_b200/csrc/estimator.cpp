@@ -389,6 +389,7 @@ void ContaminationEstimator::CreateEngines() {
   d.alt_base = alt.data();
   d.known_af = isAFknown ? kaf.data() : nullptr;
   d.info_offset = viewer.infoOffset.data();
+  d.n_info = (int64_t)viewer.NumInfo();
   d.bases = viewer.bases.data();
   d.quals = viewer.quals.data();
   d.sanity_disabled = isSanityCheckDisabled ? 1 : 0;
@@ -438,6 +439,7 @@ int ContaminationEstimator::OptimizeLLK(const std::string &OutputPrefix) {
     PhaseTimer t("Flatten pileup into HBM");
     CreateEngines();
   }
+  if (onEnginesReady) onEnginesReady();
   {
     PhaseTimer t("Initialize likelihood");
     fn.Initialize();

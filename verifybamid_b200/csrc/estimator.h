@@ -6,6 +6,7 @@
 #define VB2_ESTIMATOR_H_
 
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -112,6 +113,7 @@ class ContaminationEstimator {
   const ContaminationEstimator *panelOwner = nullptr;  // cohort: the estimator whose panel this one shares
   vb2_ingest *devIngest = nullptr;      // a pileup parsed on the device, waiting to be flattened
   const int32_t *devRowDepth = nullptr; // per panel row: kept bases on its pileup line, -1 = no line
+  std::function<void()> onEnginesReady;  // called once the sample is resident (cohort: frees a flatten slot)
   double engineSeconds = 0;  // wall time spent inside ComputeMixLLKs
   long deviceSimplexEvals = 0;  // evaluations made by searches that ran on the device
 };

@@ -2136,9 +2136,13 @@ Geometry geometry(const vb2_llk_ctx *ctx, bool throughput) {
   const uint32_t want = throughput ? 1u : env_kc("VB2_LLK_LAT_KC", (uint32_t)kMaxConcRounds);
   g.kc = std::max(1u, std::min(want, S.n_rounds));
   if (S.n_rounds > kMaxMeetRounds) g.kc = 1;
-  g.n_buf = (g.kc < S.n_rounds || ctx->chunked) ? 2u : 1u;
-  g.threads = 128u * g.kc;
-  g.smem = 4u * g.kc * g.n_buf * S.buf_bytes + (g.kc > 1 ? S.n_rounds * 1024u : 0u);
+  for (;;) {  // (wide blobs -- sixteen fp64 PCs -- with many rounds: fewer rounds in flight rather than no launch at all)
+    g.n_buf = (g.kc < S.n_rounds || ctx->chunked) ? 2u : 1u;
+    g.threads = 128u * g.kc;
+    g.smem = 4u * g.kc * g.n_buf * S.buf_bytes + (g.kc > 1 ? S.n_rounds * 1024u : 0u);
+    if (g.smem <= 200u * 1024u || g.kc == 1) break;
+    --g.kc;
+  }
   return g;
 }
 

@@ -174,6 +174,11 @@ int plan_layout(std::vector<SliceGeom> all_geom, uint32_t n_pc, bool known_af, u
       if (err) *err = "marker too deep: one blob would exceed 2 GiB";
       return VB2_ERR_INVALID;
     }
+    for (uint32_t j = j0; j < j0 + cnt; ++j)
+      if (geom[j].wr > 0xFFFFu || geom[j].wa > 0xFFFFu) {  // (the blob header keeps the full-row counts in 16 bits each)
+        if (err) *err = "marker too deep: more than 262,140 reads of one allele on a site";
+        return VB2_ERR_INVALID;
+      }
     Round R{total_bytes, (uint32_t)stride64, P.n_bins - cnt, cnt, wmax};
     for (uint32_t j = j0; j < j0 + cnt; ++j) blob_slice[j0 + (slice_bin[j] - R.first_bin)] = j;
     P.rounds.push_back(R);
@@ -223,6 +228,7 @@ int pack_sample(const vb2_llk_desc &d, const PackConfig &cfg, const double *phre
     for (size_t i = i0; i < i1; ++i) {
       const int32_t idx = d.base_info_index[i];
       if (idx < 0) continue;
+      if (d.n_info > 0 && (int64_t)idx >= d.n_info) { part_err[t] = "base_info_index beyond n_info"; return; }
       const int64_t beg = d.info_offset[idx], end = d.info_offset[idx + 1];
       if (end < beg) { part_err[t] = "info_offset is not non-decreasing"; return; }
       const size_t size = (size_t)(end - beg);

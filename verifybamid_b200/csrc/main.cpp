@@ -6,6 +6,7 @@
 // Engine-only options: --NumGPU n (marker shards over devices 0..n-1), --Device d, --PanelFP64,
 // --PileupList file (cohort mode: many samples on one panel, evaluated in lock-step, see cohort.h).
 #include <chrono>
+#include <condition_variable>
 #include <unistd.h>
 #include <cmath>
 #include <cstdio>
@@ -218,6 +219,16 @@ int run_cohort(const Options &o, const std::string &UDPath, const std::string &P
   for (int d = 0; d < o.numGPU; ++d) coord.emplace_back(new CohortCoordinator(per_device[d], o.nPC));
 
   auto t0 = std::chrono::steady_clock::now();
+  // every sample gets its thread (the lock-step needs all of them alive), but only as many as there are cores read and
+  // flatten at the same time (the flatten itself runs up to eight threads)
+  struct Gate {
+    std::mutex mu;
+    std::condition_variable cv;
+    int free_slots;
+    void enter() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return free_slots > 0; }); --free_slots; }
+    void leave() { { std::lock_guard<std::mutex> l(mu); ++free_slots; } cv.notify_one(); }
+  } gate;
+  gate.free_slots = std::max(2, (int)std::thread::hardware_concurrency() / 2);
   std::vector<std::thread> workers, coordinators;
   for (int d = 0; d < o.numGPU; ++d)
     if (per_device[d]) coordinators.emplace_back([&, d]() { coord[d]->Run(); });
@@ -234,9 +245,12 @@ int run_cohort(const Options &o, const std::string &UDPath, const std::string &P
         E.firstDevice = smp.device;
         E.cohort = &C;
         E.cohortIndex = smp.local;
+        gate.enter();
+        struct Leave { Gate &g; bool done = false; void now() { if (!done) { done = true; g.leave(); } } ~Leave() { now(); } } leave{gate};
         if (!E.ReadPileupOnDevice(smp.pileup, smp.device)) E.ReadPileup(smp.pileup);
         if (!o.disableSanityCheck && !E.IsSanityCheckOK())
           throw std::runtime_error("Insufficient Available markers (sanity check)");
+        E.onEnginesReady = [&leave]() { leave.now(); };  // (the search itself waits on the GPU, not on a core)
         E.OptimizeLLK(smp.prefix);
         write_selfsm(E, smp.prefix);
         smp.ok = true;

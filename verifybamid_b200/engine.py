@@ -60,7 +60,8 @@ class _Desc(ctypes.Structure):
                 ("avg_depth", ctypes.c_double), ("sd_depth", ctypes.c_double),
                 ("min_af", ctypes.c_double), ("max_af", ctypes.c_double),
                 ("panel_dtype", ctypes.c_int32), ("flags", ctypes.c_uint32),
-                ("shard_rank", ctypes.c_uint32), ("shard_count", ctypes.c_uint32), ("stream", ctypes.c_void_p)]
+                ("shard_rank", ctypes.c_uint32), ("shard_count", ctypes.c_uint32), ("stream", ctypes.c_void_p),
+                ("n_info", ctypes.c_int64)]
 
 
 class _Info(ctypes.Structure):
@@ -216,7 +217,7 @@ def load_library() -> ctypes.CDLL:
     lib.vb2_llk_pack_host.argtypes = [ctypes.POINTER(_Desc), ctypes.c_uint32, ctypes.POINTER(_PackedView)]
     lib.vb2_llk_pack_free.restype = None
     lib.vb2_llk_pack_free.argtypes = [ctypes.POINTER(_PackedView)]
-    if lib.vb2_abi_version() != 1:
+    if lib.vb2_abi_version() != 2:
         raise RuntimeError("libvb2llk.so ABI version mismatch")
     _lib = lib
     return lib
@@ -259,6 +260,7 @@ def make_desc(problem: PileupProblem, device: int = 0, panel_dtype: int = VB2_PA
     d.flags = (0 if spin else VB2_FLAG_NO_SPIN) | (VB2_FLAG_BATCHED if batched else 0)
     d.shard_rank, d.shard_count = int(shard_rank), int(shard_count)
     d.stream = stream
+    d.n_info = max(0, int(problem.info_offset.size) - 1)
     return d
 
 
