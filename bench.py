@@ -463,12 +463,13 @@ def run_ours(args):
     if not cohort and world == 1:
         n1 = 500
         one_ms = vb.time_device(engines, 20, n1, start_pc, start_pc, 0.03) / n1
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of this kernel (profiles/): 7.266 MB per
-    # evaluation of the headline workload at N=1 = the stored image, no re-reads (algorithmic: 7.573 MB)
-    traffic = 7266305.0 * n_jobs if (args.config == "100k30x" and world == 1) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of this kernel (profiles/r02_llk_stream_
+    # kernel_digest.txt: 14,850,184,000 + 14,341,632 bytes for a launch of 2,048 evaluations): 7.258 MB per evaluation of the
+    # headline workload at N=1 = the stored image, no re-reads (algorithmic: 7.573 MB)
+    traffic = 7258069.0 * n_jobs if (args.config == "100k30x" and world == 1) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
-                "traffic_note": "bytes per launch of %d evaluations, from the committed ncu capture of this kernel (7.27 MB per "
+                "traffic_note": "bytes per launch of %d evaluations, from the committed ncu capture of this kernel (7.26 MB per "
                                 "evaluation = the stored image, no re-reads)" % n_jobs if traffic else None,
                 "peak_source": peak_src, "kernel": "llk_stream_kernel", "evaluations_per_launch": n_jobs,
                 "launch_us": launch_us, "us_per_evaluation": launch_us / n_jobs * (1 if not cohort else 1),

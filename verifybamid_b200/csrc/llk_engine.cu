@@ -45,6 +45,11 @@ namespace {
 constexpr int kMaxConcRounds = (int)vb2::kMaxConcRounds;  // rounds of a bin a one-evaluation CTA keeps in flight
 constexpr int kMaxWarps = 4 * kMaxConcRounds;  // 16 warps (4 per SM sub-partition): 128 registers per thread
 constexpr int kMaxThreads = kMaxWarps * 32;
+#ifndef VB2_SESSION_MAX_CONC
+#define VB2_SESSION_MAX_CONC 4   // rounds of a bin the resident kernel runs concurrently (4 warps each)
+#endif
+constexpr int kSessionMaxConc = VB2_SESSION_MAX_CONC;
+constexpr int kSessionMaxWarps = 4 * kSessionMaxConc;
 constexpr int kMaxArgJobs = 4;    // evaluations whose parameters travel in the kernel arguments
 constexpr int kMaxArgRounds = 16; // round-table entries that travel in the kernel arguments
 constexpr int kNumPairs = 6;      // off-diagonal genotype pairs
@@ -1483,14 +1488,14 @@ struct SessionArgs {
 // its own copy of the simplex, all-gathers the per-CTA partial sums of an evaluation through a two-bank mailbox in
 // L2, adds them in the one fixed order and steps its copy -- the same bits everywhere, and one L2 hop per evaluation.
 template <int NPC>
-__global__ void __launch_bounds__(kMaxThreads, 1)
+__global__ void __launch_bounds__(kSessionMaxWarps * 32, 1)
 llk_session_kernel(const __grid_constant__ SessionArgs A) {
   using Layout = typename std::conditional<NPC != 0, FixedLayout<NPC>, RuntimeLayout>::type;
   extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][n_items][buf_bytes], then the marginals
   __shared__ __align__(16) JobParams s_job;
   __shared__ double s_red[4];
-  __shared__ __align__(8) uint64_t s_bar[kMaxWarps];
-  __shared__ uint32_t s_item_r[kMaxWarps][kMaxSessionItems];
+  __shared__ __align__(8) uint64_t s_bar[kSessionMaxWarps];
+  __shared__ uint32_t s_item_r[kSessionMaxWarps][kMaxSessionItems];
   __shared__ uint32_t s_stop, s_mode;
   __shared__ __align__(16) NmState s_nm;
 
@@ -2040,7 +2045,9 @@ SessionGeometry session_geometry(const vb2_llk_ctx *ctx) {
   SessionGeometry g{1, 1, 0, false};
   const SampleDev &S = ctx->S;
   if (S.grid_x == 0 || ctx->chunked || ctx->rounds.size() > (size_t)kMaxArgRounds) return g;
-  g.kc = std::max(1u, std::min(env_kc("VB2_LLK_SESSION_KC", (uint32_t)kMaxConcRounds), S.n_rounds));
+  uint32_t want = (uint32_t)kSessionMaxConc;
+  if (const char *t = getenv("VB2_LLK_SESSION_KC")) want = (uint32_t)std::min<int>(std::max(1, atoi(t)), kSessionMaxConc);
+  g.kc = std::max(1u, std::min(want, S.n_rounds));
   g.n_items = (S.n_rounds + g.kc - 1) / g.kc;
   g.smem = 4u * g.kc * g.n_items * S.buf_bytes + S.n_rounds * 1024u;
   g.ok = g.n_items <= (uint32_t)kMaxSessionItems && g.smem <= 200u * 1024u;
