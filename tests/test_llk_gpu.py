@@ -97,6 +97,32 @@ def test_bit_reproducible_and_batch_equals_single(sample10k):
         assert big.tolist() == single * rep
 
 
+def test_both_many_evaluation_kernels_return_the_same_bits(sample10k, monkeypatch):
+    """The common shapes (fp32 panel, NumPC 2 or 4, blobs that fit a stage) run llk_flow_kernel (parameters in the
+    kernel arguments, eight warps per SM sub-partition); VB2_STREAM_KERNEL=queue sends them to llk_stream_kernel (task
+    queue) like every other shape.  Same device functions, same order: the same bits, also across the launches a
+    large batch is cut into and when jobs of several samples share a launch."""
+    panel = panels.load_bundled("1000g.phase3.10k.b37")
+    s4 = synth.make_sample(panel, n_pc=4, depth=25.0, alpha=0.04, seed=11, n_markers=6000)
+    rng = np.random.default_rng(17)
+    for prob, k in ((sample10k.problem, 2), (s4.problem, 4)):
+        n = 333                                                   # more jobs than one launch's argument table holds
+        pc1 = rng.normal(0, 0.02, (n, k)); pc2 = rng.normal(0, 0.02, (n, k)); al = rng.uniform(0.0, 1.0, n)
+        al[:3] = (0.0, 1.0, 0.5)
+        with vb.LLKEngine(prob) as eng, vb.LLKEngine(prob, shard_rank=1, shard_count=3, batched=True) as part:
+            monkeypatch.delenv("VB2_STREAM_KERNEL", raising=False)
+            flow = eng.eval_batch(pc1, pc2, al)
+            flow_mixed = vb.eval_many([eng if j % 3 else part for j in range(n)], pc1, pc2, al)
+            monkeypatch.setenv("VB2_STREAM_KERNEL", "queue")
+            queue = eng.eval_batch(pc1, pc2, al)
+            queue_mixed = vb.eval_many([eng if j % 3 else part for j in range(n)], pc1, pc2, al)
+            monkeypatch.delenv("VB2_STREAM_KERNEL", raising=False)
+            assert flow.tolist() == queue.tolist()
+            assert flow_mixed.tolist() == queue_mixed.tolist()
+            for j in (0, 1, 2, 150, 332):
+                assert flow[j] == eng.compute_mix_llks(pc1[j], pc2[j], al[j])
+
+
 def test_launch_geometry_does_not_change_the_bits(sample10k, monkeypatch):
     """One evaluation per launch runs 4*kc warps per CTA (kc rounds of a bin in flight at once); whatever kc, the
     marginals of a bin are multiplied up in the same order, so the result is the same to the bit."""

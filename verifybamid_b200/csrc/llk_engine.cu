@@ -55,6 +55,7 @@ constexpr int kMaxArgRounds = 16; // round-table entries that travel in the kern
 constexpr int kNumPairs = 6;      // off-diagonal genotype pairs
 constexpr uint32_t kChunkTargetBytes = 4096;  // shared-memory stage per warp
 constexpr int kTraceSlots = 16;
+constexpr uint32_t kQueueWords = 64;  // task counters of a many-evaluations batch (one per launch it is cut into)
 constexpr int kPhredArgs = 96;  // Phred errors 0..93 (+2 pad) that travel in the kernel arguments
 constexpr double kLn2 = 0.693147180559945309417232121458;
 
@@ -186,6 +187,20 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
       "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// Wait with a warp-uniform exit: every lane polls (try_wait suspends the thread for a hardware time slice) and the
+// warp leaves together on a vote -- so the compiler knows the warp is converged behind the wait.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (__all_sync(0xFFFFFFFFu, ok != 0)) break;
+  }
+}
 // expect-tx + bulk copy as ONE predicated pair (no branch: the caller's basic block stays whole)
 __device__ __forceinline__ void bulk_g2s_if(bool pred, void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile(
@@ -221,8 +236,8 @@ struct Quad {
 
 // Four reads of one lane.  ALT = alt-allele reads: acc[5-p] takes what a ref read gives acc[p].
 // Written breadth-first (all pairs advance together) so that dependent instructions sit >= 6 apart.
-template <bool ALT>
-__device__ __forceinline__ void eat4(double e0, double e1, double e2, double e3, const Quad &Q,
+template <bool ALT, typename QT>
+__device__ __forceinline__ void eat4(double e0, double e1, double e2, double e3, const QT &Q,
                                      double (&acc)[kNumPairs]) {
   const double s01 = e0 + e1, t01 = e0 * e1, s23 = e2 + e3, t23 = e2 * e3;
   double g[kNumPairs], h[kNumPairs];
@@ -253,8 +268,8 @@ __device__ __forceinline__ double phred_of(uint32_t w) {
   return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_e) + q * 8u);
 }
 
-template <bool ALT>
-__device__ __forceinline__ void eat_full_rows(const uint32_t *col, uint32_t n, const Quad &Q,
+template <bool ALT, typename QT>
+__device__ __forceinline__ void eat_full_rows(const uint32_t *col, uint32_t n, const QT &Q,
                                               double (&acc)[kNumPairs]) {
   if (n == 0) return;
   uint32_t w = col[0];
@@ -270,8 +285,8 @@ __device__ __forceinline__ void eat_full_rows(const uint32_t *col, uint32_t n, c
 
 // The ragged last word of a run when every lane holds the same number n (1..3) of reads in it: the
 // first n bytes are reads in all lanes, so no byte has to be inspected.  lin = {c0[6], c1[6]} (shared memory).
-template <bool ALT>
-__device__ __forceinline__ void eat_word_tail(uint32_t w, uint32_t n, const double *lin, const Quad &Q,
+template <bool ALT, typename QT>
+__device__ __forceinline__ void eat_word_tail(uint32_t w, uint32_t n, const double *lin, const QT &Q,
                                               double (&acc)[kNumPairs]) {
   const double e0 = s_e[w & 0xFFu];
   if (n == 1) {
@@ -318,9 +333,9 @@ __device__ __forceinline__ void eat_checked(const uint32_t *col, uint32_t n_rows
 // One run (the ref-allele or the alt-allele reads of the slice): n_full rows in which every lane holds four real
 // reads, then n_ragged rows that may hold fillers; when `tail` is 1..3 the (single) ragged row holds exactly
 // that many reads in every lane.
-template <bool ALT>
+template <bool ALT, typename QT>
 __device__ __forceinline__ void eat_rows(const uint32_t *col, uint32_t n_full, uint32_t n_ragged, uint32_t tail,
-                                         const double *lin, const Quad &Q, double (&acc)[kNumPairs]) {
+                                         const double *lin, const QT &Q, double (&acc)[kNumPairs]) {
   eat_full_rows<ALT>(col, n_full, Q, acc);
   if (n_ragged == 0) return;
   col += (size_t)n_full * 32;
@@ -332,9 +347,9 @@ __device__ __forceinline__ void eat_rows(const uint32_t *col, uint32_t n_full, u
 // compile time.  MERGED = true: ONE copy run twice with the accumulators reversed in between (acc[p] <-> acc[5-p]
 // is exactly what turns a ref read into an alt read) -- half the instructions to fetch, which is what bounds a
 // launch that evaluates once: its code arrives cold from L2 at about five cycles per instruction.
-template <bool MERGED>
+template <bool MERGED, typename QT>
 __device__ __forceinline__ void eat_runs(const uint32_t *col, uint32_t fr, uint32_t rr, uint32_t tr, uint32_t fa,
-                                         uint32_t ra, uint32_t ta, const double *lin, const Quad &Q,
+                                         uint32_t ra, uint32_t ta, const double *lin, const QT &Q,
                                          double (&acc)[kNumPairs]) {
   if constexpr (!MERGED) {
     eat_rows<false>(col, fr, rr, tr, lin, Q, acc);
@@ -432,8 +447,8 @@ __device__ __forceinline__ void marker_af(const uint8_t *blob, const Layout &Y, 
 struct SliceHeader {
   uint32_t wr, wa, n_valid, fr, fa, tails;
 };
-template <typename Layout>
-__device__ __forceinline__ void slice_begin(const uint8_t *buf, const Layout &Y, const JobParams &J, int lane,
+template <typename Layout, typename JobT>
+__device__ __forceinline__ void slice_begin(const uint8_t *buf, const Layout &Y, const JobT &J, int lane,
                                             SliceHeader &H, double (&acc)[kNumPairs], double &ldiag) {
   const uint4 hdr = *reinterpret_cast<const uint4 *>(buf);
   H.wr = hdr.x; H.wa = hdr.y; H.n_valid = hdr.z & 0xFFu; H.tails = hdr.z >> 8; H.fr = hdr.w & 0xFFFFu; H.fa = hdr.w >> 16;
@@ -456,9 +471,9 @@ __device__ __forceinline__ void slice_begin(const uint8_t *buf, const Layout &Y,
 
 // the word rows [t_lo, t_hi) of the slice, stored from `col` on (this lane's column): ref rows first,
 // then alt rows; rows [0,fr) and [wr, wr+fa) are filler-free in every lane.
-template <bool MERGED>
+template <bool MERGED, typename QT>
 __device__ __forceinline__ void slice_rows(const uint32_t *col, uint32_t t_lo, uint32_t t_hi, const SliceHeader &H,
-                                           const double *lin, const Quad &Q, double (&acc)[kNumPairs]) {
+                                           const double *lin, const QT &Q, double (&acc)[kNumPairs]) {
   if (t_hi > H.wr + H.wa) t_hi = H.wr + H.wa;
   if (t_hi < t_lo) t_hi = t_lo;
   auto clampu = [&](uint32_t x) { return x < t_lo ? t_lo : (x > t_hi ? t_hi : x); };
@@ -1129,6 +1144,191 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// the many-evaluations kernel, high-occupancy form (the common shapes: FixedLayout<2|4>, no chunking)
+// ---------------------------------------------------------------------------------------------
+// llk_stream_kernel keeps the read loop's 18 pair coefficients in per-thread registers (36 of its 128), and at 128
+// registers only four warps fit per SM sub-partition: the FP64 pipe idles 40 % of the time because a warp spends
+// half of a slice in the latency-bound phases around the read loops.  This kernel computes the same bits with
+// 62 registers, so eight warps fit per sub-partition:
+//   * everything an evaluation's arithmetic needs that is the same for all lanes -- the coefficients C0, C1, C2
+//     and c0, c1, the PCs -- travels in the KERNEL ARGUMENTS (constant bank; CUDA 12.1+ allows 32,764 bytes) and is
+//     read with a provably warp-uniform index, so the compiler fetches it into UNIFORM registers
+//     (LDCU c[0][UR + off]) and feeds it to the DFMAs as uniform operands;
+//   * for that the control flow around the read loops has to be provably uniform too: every value that steers it
+//     and is the same in all lanes only by construction (the task number lane 0 drew from the queue, the job of
+//     the stage being consumed, the slice's row counts read from the blob header) passes through a warp reduction
+//     or a vote (REDUX / VOTEU write uniform registers), and the mbarrier wait leaves on a vote;
+//   * no task records in shared memory: the few per-task facts (where the bin's blobs are, where its partial sum
+//     goes) are read from the job's record in L2 when the task is taken.
+// Tasks (job, bin) come from the same kind of queue as in llk_stream_kernel; every warp walks its task's blobs
+// behind a two-stage TMA pipeline that runs across tasks, multiplies the marginals up per lane in round order and
+// leaves the bin's sum in partials[job][bin]; llk_reduce_kernel adds them in the fixed order.  Same device
+// functions, same order of operations: the same bits as llk_stream_kernel, llk_kernel and llk_session_kernel
+// (tested).
+struct FlowJob {  // one job's share of the kernel arguments
+  double C1[kNumPairs], C2[kNumPairs];  // c0 c1 and c1^2: multiplicands of the read loop (one uniform operand per DFMA)
+  double c0[kNumPairs], c1[kNumPairs];  // (contiguous: the ragged-row code indexes them as one array)
+  double pc1[4], pc2[4];                // contaminant / intended PCs (NumPC <= 4)
+};
+// The read loop's view of a job: C0 = c0^2 is the ADDEND of the first DFMA of every pair, and a DFMA takes only one
+// uniform operand, so C0 lives in (per-thread) registers -- formed by the same product as everywhere else -- while
+// C1 and C2 stay in the constant bank / uniform registers.
+struct FlowQuad {
+  double C0[kNumPairs];
+  const double (&C1)[kNumPairs];
+  const double (&C2)[kNumPairs];
+};
+#ifndef VB2_FLOW_JOBS
+#define VB2_FLOW_JOBS 120
+#endif
+constexpr int kFlowJobs = VB2_FLOW_JOBS;
+struct FlowArgs {
+  const TaskRec *recs;     // job j of this launch = recs[j] (its sample, partial-sum slot, round table)
+  uint32_t n_jobs;         // <= kFlowJobs
+  uint32_t n_quads;        // bin quads (CTAs of a one-evaluation launch) per job in this launch
+  uint32_t stage_bytes;    // bytes per shared-memory stage
+  uint32_t pad_;
+  unsigned int *queue;     // next task to hand out; zero between launches (llk_reduce_kernel rewinds it)
+  double phred[kPhredArgs];
+  FlowJob jobs[kFlowJobs];
+};
+static_assert(sizeof(FlowArgs) <= 32764, "kernel arguments must stay below 32,764 bytes");
+
+#ifndef VB2_FLOW_CTAS_PER_SM
+#define VB2_FLOW_CTAS_PER_SM 8   // 64 registers: ptxas keeps C1/C2 in uniform registers up to here (at 72 it hoists them into vector registers and spills)
+#endif
+constexpr uint32_t kFlowLast = 0x80000000u;  // stage tag: the last blob of its (job, bin)
+template <int NPC>
+__global__ void __launch_bounds__(128, VB2_FLOW_CTAS_PER_SM)
+llk_flow_kernel(const __grid_constant__ FlowArgs F) {
+  using Layout = FixedLayout<NPC>;
+  extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][2][stage_bytes]
+  __shared__ __align__(8) uint64_t s_bar[4][2];
+  __shared__ double *s_dst[4][2];  // where the partial sum of the task whose last blob sits in a stage goes
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_jobs = F.n_jobs, n_quads = F.n_quads;
+  if (lane == 0) {
+    mbar_init(&s_bar[warp][0], 1);
+    mbar_init(&s_bar[warp][1], 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 256; i += 128) s_e[i] = i < kPhredArgs ? F.phred[i] : 1.0;
+  __syncthreads();  // the only CTA-wide barrier
+
+  const uint32_t stage_bytes = F.stage_bytes;
+  uint8_t *mybuf = s_buf + (size_t)warp * 2u * stage_bytes;
+  const Layout Y(F.recs[0].S);
+
+  // ---- issue side: tasks (job, bin) from a counter in HBM; the blobs of a task in round order -------------------
+  // A warp's first task is its own index, the following ones come from an atomic counter whose next value is
+  // fetched one task ahead (the warps of a persistent grid do not progress evenly -- the schedulers favour some
+  // -- so a static split leaves the pipe a third empty towards the end of a launch).  The task number reaches the
+  // lanes through a warp reduction: a broadcast the compiler knows to be uniform.
+  const uint32_t n_bins = n_quads * vb2::kBinsPerCta, n_tasks = n_jobs * n_bins;
+  uint32_t fetched = blockIdx.x * 4u + (uint32_t)warp;  // (lane 0) the next task of this warp
+  uint32_t i_job = 0;                // the job the cursor is in (uniform)
+  uint32_t i_mask = 0;               // rounds of the cursor's task still to issue (bit r = round r; lane r holds it)
+  const uint8_t *it_addr = nullptr;  // (lane r) where the bin's blob of round r is
+  uint32_t it_rows = 0;              // (lane r) its word rows
+  double *i_dst = nullptr;           // where the task's sum goes
+  bool i_done = false;               // the counter ran past the last task
+  // Lane r looks at round r of job `job` for bin `bin`; the ballot is the task's item mask.
+  auto load_table = [&](uint32_t job, uint32_t bin) {
+    const TaskRec &R = F.recs[job];
+    const uint32_t grid_x = R.S.grid_x;
+    const bool active = bin < vb2::kBinsPerCta * grid_x;  // eval_many: a sample may have fewer bins than the launch
+    bool mine = false;
+    if (active && (uint32_t)lane < R.S.n_rounds) {
+      const vb2::Round Rd = lane < kRecRounds ? R.rounds[lane] : R.S.rounds[lane];
+      if (bin - Rd.first_bin < Rd.count) {  // unsigned: also false when bin < first_bin
+        mine = true;
+        it_addr = R.S.blob + (Rd.base + (uint64_t)(bin - Rd.first_bin) * Rd.stride);
+        it_rows = Rd.rows;
+      }
+    }
+    i_dst = active ? R.S.partials + ((size_t)R.pslot * (vb2::kBinsPerCta * grid_x) + bin) : nullptr;
+    i_mask = __ballot_sync(0xFFFFFFFFu, mine);
+    if (i_mask == 0 && lane == 0 && i_dst) *i_dst = 0.0;  // (no blob at all: an empty bin still reports in)
+  };
+  // the next blob of this warp's sequence into stage b (every lane is done reading it); false: nothing left
+  uint32_t tag0 = 0, tag1 = 0;  // what sits (or is landing) in the two stages: the job, kFlowLast
+  auto produce = [&](uint32_t b) -> bool {
+    while (i_mask == 0) {
+      if (i_done) return false;
+      const uint32_t t = __reduce_or_sync(0xFFFFFFFFu, lane == 0 ? fetched : 0u);
+      if (t >= n_tasks) {
+        i_done = true;
+        return false;
+      }
+      if (lane == 0) fetched = atomicAdd(F.queue, 1u) + gridDim.x * 4u;  // (in flight while this task runs)
+      i_job = t / n_bins;
+      load_table(i_job, t - i_job * n_bins);
+    }
+    const int r = __ffs((int)i_mask) - 1;
+    i_mask &= i_mask - 1u;
+    const uint64_t addr = __shfl_sync(0xFFFFFFFFu, (unsigned long long)it_addr, r);
+    const uint32_t rows = __shfl_sync(0xFFFFFFFFu, it_rows, r);
+    const uint32_t tag = i_job | (i_mask == 0 ? kFlowLast : 0u);
+    if (lane == 0 && i_mask == 0) s_dst[warp][b] = i_dst;
+    bulk_g2s_if(lane == 0, mybuf + (size_t)b * stage_bytes, reinterpret_cast<const void *>(addr),
+                Layout::off_words + rows * 128u, &s_bar[warp][b]);
+    if (b) tag1 = tag;
+    else tag0 = tag;
+    return true;
+  };
+
+  // ---- consume ---------------------------------------------------------------------------------------------------
+  uint32_t in_flight = 0, cb = 0, parity = 0;
+  if (produce(0)) {
+    in_flight = 1;
+    if (produce(1)) in_flight = 2;
+  }
+  double vsum = 0.0, prod = 1.0;  // the running task: sum of log(marginal) = log(prod * 2^esum) + vsum
+  int esum = 0;
+  while (__any_sync(0xFFFFFFFFu, in_flight != 0)) {
+    // (the tag and the slice's row counts are the same in every lane; the reductions tell the compiler so)
+    mbar_wait_warp(&s_bar[warp][cb], (parity >> cb) & 1u);
+    parity ^= 1u << cb;
+    const uint32_t tag = __reduce_or_sync(0xFFFFFFFFu, cb ? tag1 : tag0);
+    const FlowJob &J = F.jobs[tag & 0xFFFFu];
+    const uint8_t *buf = mybuf + (size_t)cb * stage_bytes;
+    double acc[kNumPairs], ldiag;
+    SliceHeader H;
+    slice_begin(buf, Y, J, lane, H, acc, ldiag);
+    const uint32_t u_rows = __reduce_or_sync(0xFFFFFFFFu, H.wr | (H.wa << 16));
+    const uint32_t u_full = __reduce_or_sync(0xFFFFFFFFu, H.fr | (H.fa << 16));
+    const uint32_t u_tails = __reduce_or_sync(0xFFFFFFFFu, H.tails);
+    const uint32_t u_wr = u_rows & 0xFFFFu, u_wa = u_rows >> 16, u_fr = u_full & 0xFFFFu, u_fa = u_full >> 16;
+    FlowQuad Q{{0., 0., 0., 0., 0., 0.}, J.C1, J.C2};
+#pragma unroll
+    for (int p = 0; p < kNumPairs; ++p) Q.C0[p] = J.c0[p] * J.c0[p];
+    eat_runs<false>(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, u_fr, u_wr - u_fr, u_tails & 0xFu,
+                    u_fa, u_wa - u_fa, (u_tails >> 4) & 0xFu, J.c0, Q, acc);
+    // h:307-311, as in llk_kernel
+    const double L = ldiag + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + (acc[4] + acc[5]));
+    const double Lv = ((uint32_t)lane < H.n_valid && L > 0) ? L : 1.0;
+    if (Lv > 1e-280) prod *= Lv;
+    else vsum += cold_log(Lv);
+    {
+      const int hi = __double2hiint(prod);
+      esum += (hi >> 20) - 1023;
+      prod = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(prod));
+    }
+    if (tag & kFlowLast) {  // the task's last blob: its sum goes out
+      double v = vsum + fma((double)esum, kLn2, log(prod));
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      if (lane == 0) *s_dst[warp][cb] = v;
+      vsum = 0.0; prod = 1.0; esum = 0;
+    }
+    __syncwarp();  // every lane is done with stage cb
+    if (!produce(cb)) --in_flight;
+    cb ^= 1u;
+  }
+}
+
 // Behind llk_stream_kernel on the same stream: evaluation j's partials -> d_out[j] / mailbox slot j, in the fixed
 // order of llk_kernel (the four bins of a CTA, those lane-strided over the CTAs, then a tree); rewinds the queue.
 __global__ void __launch_bounds__(32, 1) llk_reduce_kernel(const __grid_constant__ LaunchArgs A) {
@@ -1149,7 +1349,8 @@ __global__ void __launch_bounds__(32, 1) llk_reduce_kernel(const __grid_constant
     if (A.d_out) A.d_out[job] = out;
     if (A.mbox)
       *reinterpret_cast<ulonglong2 *>(A.mbox + job) = make_ulonglong2((unsigned long long)__double_as_longlong(out), A.seq);
-    if (job == 0) A.queue[0] = 0u;
+    // the task counters of the launches this batch was cut into (llk_stream_kernel: one; llk_flow_kernel: one per kFlowJobs jobs)
+    if (job < (A.n_jobs + (uint32_t)kFlowJobs - 1u) / (uint32_t)kFlowJobs) A.queue[job] = 0u;
   }
   if (A.peer) {  // ---- fused with the collective: this shard's sum goes straight into every rank's buffer (NVLink stores)
     const PeerDev &P = *A.peer;
@@ -1822,8 +2023,63 @@ void launch_stream_as(uint32_t smem, cudaStream_t stream, const LaunchArgs &A, i
   const uint32_t grid = std::max(1u, std::min(cached_per_sm * (uint32_t)std::max(1, sm_count), (n_tasks + 3u) / 4u));
   llk_stream_kernel<NPC, CHUNKED><<<dim3(grid, 1, 1), dim3(128, 1, 1), smem, stream>>>(A);
 }
-void launch_stream(uint32_t smem, cudaStream_t stream, const LaunchArgs &A, int spec, bool chunked, int sm_count) {
-  if (chunked) launch_stream_as<0, true>(smem, stream, A, sm_count);
+// llk_flow_kernel over the jobs A.recs[0 .. A.n_jobs) (h_recs = the host copy of the same records): launches of at
+// most kFlowJobs jobs, each with its jobs' parameters in the kernel arguments.
+template <int NPC>
+void launch_flow_as(uint32_t smem, cudaStream_t stream, const LaunchArgs &A, const TaskRec *h_recs, int sm_count) {
+  static thread_local uint32_t cached_smem = ~0u, cached_per_sm = 0;  // (per instantiation and host thread)
+  if (cached_smem != smem) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, llk_flow_kernel<NPC>, 128, smem) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 1;
+    }
+    cached_per_sm = (uint32_t)per_sm;
+    cached_smem = smem;
+  }
+  static thread_local FlowArgs F;  // (31 KB: off the stack)
+  F.n_quads = std::max(1u, A.n_bins_max / vb2::kBinsPerCta);
+  F.stage_bytes = A.stage_bytes;
+  F.pad_ = 0;
+  memcpy(F.phred, A.phred, sizeof(F.phred));
+  uint32_t launch = 0;
+  for (uint32_t off = 0; off < A.n_jobs; off += (uint32_t)kFlowJobs, ++launch) {
+    F.recs = A.recs + off;
+    F.n_jobs = std::min<uint32_t>((uint32_t)kFlowJobs, A.n_jobs - off);
+    F.queue = A.queue + launch;  // (one task counter per launch of the batch)
+    for (uint32_t i = 0; i < F.n_jobs; ++i) {
+      const JobParams &J = h_recs[off + i].J;
+      FlowJob &D = F.jobs[i];
+      for (int p = 0; p < kNumPairs; ++p) {  // the products llk_stream_kernel forms on the device (load_quad)
+        D.C1[p] = J.c0[p] * J.c1[p];
+        D.C2[p] = J.c1[p] * J.c1[p];
+        D.c0[p] = J.c0[p];
+        D.c1[p] = J.c1[p];
+      }
+      for (int k = 0; k < 4; ++k) {
+        D.pc1[k] = J.pc1[k];
+        D.pc2[k] = J.pc2[k];
+      }
+    }
+    const uint32_t n_tasks = F.n_jobs * A.n_bins_max;
+    const uint32_t grid = std::max(1u, std::min(cached_per_sm * (uint32_t)std::max(1, sm_count), (n_tasks + 3u) / 4u));
+    llk_flow_kernel<NPC><<<dim3(grid, 1, 1), dim3(128, 1, 1), smem, stream>>>(F);
+  }
+}
+static_assert((VB2_MAX_BATCH + kFlowJobs - 1) / kFlowJobs <= (int)kQueueWords, "one task counter per launch of a batch");
+// 0: let the shape decide; 1: always llk_stream_kernel (task queue); set by VB2_STREAM_KERNEL=queue (A/B runs, tests)
+int stream_kernel_choice() {  // (read at every launch: the tests switch it inside one process)
+  const char *e = getenv("VB2_STREAM_KERNEL");
+  return (e && !strcmp(e, "queue")) ? 1 : 0;
+}
+void launch_stream(uint32_t smem, cudaStream_t stream, const LaunchArgs &A, const TaskRec *h_recs, int spec, bool chunked,
+                   int sm_count) {
+  bool flow = !chunked && (spec == 2 || spec == 4) && stream_kernel_choice() == 0;
+  for (uint32_t j = 0; flow && j < A.n_jobs; ++j) flow = h_recs[j].S.n_rounds <= 32u;  // (one item table per task)
+  if (flow) {
+    if (spec == 2) launch_flow_as<2>(smem, stream, A, h_recs, sm_count);
+    else launch_flow_as<4>(smem, stream, A, h_recs, sm_count);
+  } else if (chunked) launch_stream_as<0, true>(smem, stream, A, sm_count);
   else if (spec == 2) launch_stream_as<2, false>(smem, stream, A, sm_count);
   else if (spec == 4) launch_stream_as<4, false>(smem, stream, A, sm_count);
   else launch_stream_as<0, false>(smem, stream, A, sm_count);
@@ -2236,7 +2492,7 @@ int launch_batch(vb2_llk_ctx *ctx, int n, const double *pc1, const double *pc2, 
     if (seq_out) *seq_out = A.seq;
   }
   if (n > 1) {  // several evaluations: the persistent task-queue kernel
-    launch_stream(8u * A.stage_bytes, ctx->stream, A, ctx->spec, ctx->chunked, ctx->sm_count);
+    launch_stream(8u * A.stage_bytes, ctx->stream, A, ctx->h_recs, ctx->spec, ctx->chunked, ctx->sm_count);
     release_staging(ctx);
     VB2_CUDA(ctx, cudaGetLastError());
     return VB2_OK;
@@ -2262,6 +2518,10 @@ cudaError_t raise_smem_limits(int bytes) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_stream_kernel<NPC, CHUNKED>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if constexpr (!CHUNKED)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_session_kernel<NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if constexpr (!CHUNKED && NPC != 0) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_flow_kernel<NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(llk_flow_kernel<NPC>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  }
   return e;
 }
 int init_device_tables(vb2_llk_ctx *ctx, int device, int spec, bool chunked) {
@@ -2445,8 +2705,8 @@ int ctx_adopt_image(vb2_llk_ctx *ctx, const CreateParams &cp, const PackedSample
   memset(ctx->h_mbox, 0, sizeof(Slot) * ctx->mbox_slots);
   VB2_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->d_mbox, ctx->h_mbox, 0));
   VB2_CUDA(ctx, cudaMalloc(&ctx->d_out, sizeof(double) * VB2_MAX_BATCH));
-  VB2_CUDA(ctx, cudaMalloc(&ctx->d_queue, 2 * sizeof(unsigned int)));
-  VB2_CUDA(ctx, cudaMemsetAsync(ctx->d_queue, 0, 2 * sizeof(unsigned int), ctx->stream));
+  VB2_CUDA(ctx, cudaMalloc(&ctx->d_queue, kQueueWords * sizeof(unsigned int)));
+  VB2_CUDA(ctx, cudaMemsetAsync(ctx->d_queue, 0, kQueueWords * sizeof(unsigned int), ctx->stream));
   VB2_CUDA(ctx, cudaMalloc(&ctx->d_sample, sizeof(SampleDev)));
   if ((rc = ensure_slots(ctx, 8))) return rc;
   VB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2734,7 +2994,7 @@ static int fire_many(vb2_llk_ctx *lead, bool to_mailbox, unsigned long long *seq
     int rca = init_device_tables(lead, lead->device, lead->many_spec, lead->many_chunked);
     if (rca) return rca;
   }
-  launch_stream(8u * A.stage_bytes, lead->stream, A, lead->many_spec, lead->many_chunked, lead->sm_count);
+  launch_stream(8u * A.stage_bytes, lead->stream, A, lead->h_recs, lead->many_spec, lead->many_chunked, lead->sm_count);
   if (peer) {
     const unsigned long long patience = (unsigned long long)(20000.0 * peer->clock_khz);  // 20 s
     llk_gather_kernel<<<dim3((lead->many_n + 255u) / 256u, 1, 1), dim3(256, 1, 1), 0, lead->stream>>>(
