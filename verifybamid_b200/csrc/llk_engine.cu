@@ -189,7 +189,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
 }
 // Wait with a warp-uniform exit: every lane polls (try_wait suspends the thread for a hardware time slice) and the
 // warp leaves together on a vote -- so the compiler knows the warp is converged behind the wait.
-__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {  // bar = shared-window address
   for (;;) {
     uint32_t ok;
     asm volatile(
@@ -197,7 +197,7 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
         ".reg .pred P1;\n"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
         "selp.u32 %0, 1, 0, P1;\n"
-        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (__all_sync(0xFFFFFFFFu, ok != 0)) break;
   }
 }
@@ -231,6 +231,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __noinline__ double cold_log(double x) { return log(x); }
 
 struct Quad {
+  static constexpr bool kPrefetchRows = true;  // the read loop fetches row t+1 before the arithmetic of row t
   double C0[kNumPairs], C1[kNumPairs], C2[kNumPairs];
 };
 
@@ -261,16 +262,25 @@ __device__ __forceinline__ void eat4(double e0, double e1, double e2, double e3,
 // word and the four table look-ups of row t+1 are issued before the arithmetic of row t -- also after the last
 // row: the loop reads one row past the run (the next run, or the 128-byte pad every stage buffer ends with) and
 // drops what it read, which keeps the loop free of a peeled copy.
-// Phred error of byte b (0..3) of word w: one byte-extract and one multiply-add form the shared-memory address.
+// Phred error of byte b (0..3) of word w.
 template <int B>
 __device__ __forceinline__ double phred_of(uint32_t w) {
-  const uint32_t q = __byte_perm(w, 0u, 0x4440u + B);  // (0, 0, 0, byte B)
-  return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_e) + q * 8u);
+  // 8 * byte B of w in ONE instruction: a four-way byte dot product with (8 in position B, 0 elsewhere) -- IDP.4A
+  const uint32_t off = (uint32_t)__dp4a(w, 0x8u << (8 * B), 0u);
+  return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_e) + off);
 }
 
 template <bool ALT, typename QT>
 __device__ __forceinline__ void eat_full_rows(const uint32_t *col, uint32_t n, const QT &Q,
                                               double (&acc)[kNumPairs]) {
+  if constexpr (!QT::kPrefetchRows) {  // (enough warps per scheduler to cover the look-ups: no row in flight, fewer registers)
+#pragma unroll 1
+    for (uint32_t t = 0; t < n; ++t) {
+      const uint32_t w = col[t * 32];
+      eat4<ALT>(phred_of<0>(w), phred_of<1>(w), phred_of<2>(w), phred_of<3>(w), Q, acc);
+    }
+    return;
+  }
   if (n == 0) return;
   uint32_t w = col[0];
   double e0 = phred_of<0>(w), e1 = phred_of<1>(w), e2 = phred_of<2>(w), e3 = phred_of<3>(w);
@@ -1174,7 +1184,11 @@ struct FlowJob {  // one job's share of the kernel arguments
 // The read loop's view of a job: C0 = c0^2 is the ADDEND of the first DFMA of every pair, and a DFMA takes only one
 // uniform operand, so C0 lives in (per-thread) registers -- formed by the same product as everywhere else -- while
 // C1 and C2 stay in the constant bank / uniform registers.
+#ifndef VB2_FLOW_PREFETCH_ROWS
+#define VB2_FLOW_PREFETCH_ROWS 0   // 1: the read loop fetches row t+1 before the arithmetic of row t (A/B builds)
+#endif
 struct FlowQuad {
+  static constexpr bool kPrefetchRows = VB2_FLOW_PREFETCH_ROWS != 0;
   double C0[kNumPairs];
   const double (&C1)[kNumPairs];
   const double (&C2)[kNumPairs];
@@ -1195,12 +1209,15 @@ struct FlowArgs {
 };
 static_assert(sizeof(FlowArgs) <= 32764, "kernel arguments must stay below 32,764 bytes");
 
-#ifndef VB2_FLOW_CTAS_PER_SM
-#define VB2_FLOW_CTAS_PER_SM 8   // 64 registers: ptxas keeps C1/C2 in uniform registers up to here (at 72 it hoists them into vector registers and spills)
+// The register cap is what steers ptxas here: with 56 registers (min-blocks 9) it keeps C1/C2 in uniform registers
+// and nothing spills; given 64 it hoists them into vector registers for the short read loop and then spills the
+// accumulators.  Shared memory admits eight CTAs per SM for a 30x sample either way.
+#ifndef VB2_FLOW_MIN_BLOCKS
+#define VB2_FLOW_MIN_BLOCKS 9
 #endif
 constexpr uint32_t kFlowLast = 0x80000000u;  // stage tag: the last blob of its (job, bin)
 template <int NPC>
-__global__ void __launch_bounds__(128, VB2_FLOW_CTAS_PER_SM)
+__global__ void __launch_bounds__(128, VB2_FLOW_MIN_BLOCKS)
 llk_flow_kernel(const __grid_constant__ FlowArgs F) {
   using Layout = FixedLayout<NPC>;
   extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][2][stage_bytes]
@@ -1219,6 +1236,7 @@ llk_flow_kernel(const __grid_constant__ FlowArgs F) {
 
   const uint32_t stage_bytes = F.stage_bytes;
   uint8_t *mybuf = s_buf + (size_t)warp * 2u * stage_bytes;
+  const uint32_t buf0 = smem_u32(mybuf), bar0 = smem_u32(&s_bar[warp][0]);  // (shared-window addresses, formed once)
   const Layout Y(F.recs[0].S);
 
   // ---- issue side: tasks (job, bin) from a counter in HBM; the blobs of a task in round order -------------------
@@ -1266,14 +1284,17 @@ llk_flow_kernel(const __grid_constant__ FlowArgs F) {
       i_job = t / n_bins;
       load_table(i_job, t - i_job * n_bins);
     }
+    // the lane that holds the item fires its copy (no shuffles: every lane has its own blob's address and size)
     const int r = __ffs((int)i_mask) - 1;
     i_mask &= i_mask - 1u;
-    const uint64_t addr = __shfl_sync(0xFFFFFFFFu, (unsigned long long)it_addr, r);
-    const uint32_t rows = __shfl_sync(0xFFFFFFFFu, it_rows, r);
     const uint32_t tag = i_job | (i_mask == 0 ? kFlowLast : 0u);
-    if (lane == 0 && i_mask == 0) s_dst[warp][b] = i_dst;
-    bulk_g2s_if(lane == 0, mybuf + (size_t)b * stage_bytes, reinterpret_cast<const void *>(addr),
-                Layout::off_words + rows * 128u, &s_bar[warp][b]);
+    if (lane == r) {
+      if (i_mask == 0) s_dst[warp][b] = i_dst;
+      const uint32_t bytes = Layout::off_words + it_rows * 128u, bar = bar0 + 8u * b;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       buf0 + b * stage_bytes), "l"(it_addr), "r"(bytes), "r"(bar) : "memory");
+    }
     if (b) tag1 = tag;
     else tag0 = tag;
     return true;
@@ -1289,7 +1310,7 @@ llk_flow_kernel(const __grid_constant__ FlowArgs F) {
   int esum = 0;
   while (__any_sync(0xFFFFFFFFu, in_flight != 0)) {
     // (the tag and the slice's row counts are the same in every lane; the reductions tell the compiler so)
-    mbar_wait_warp(&s_bar[warp][cb], (parity >> cb) & 1u);
+    mbar_wait_warp(bar0 + 8u * cb, (parity >> cb) & 1u);
     parity ^= 1u << cb;
     const uint32_t tag = __reduce_or_sync(0xFFFFFFFFu, cb ? tag1 : tag0);
     const FlowJob &J = F.jobs[tag & 0xFFFFu];
@@ -1320,7 +1341,7 @@ llk_flow_kernel(const __grid_constant__ FlowArgs F) {
       double v = vsum + fma((double)esum, kLn2, log(prod));
 #pragma unroll
       for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-      if (lane == 0) *s_dst[warp][cb] = v;
+      if (lane == 0) *s_dst[warp][cb] = v;  // (written by the lane that issued the blob, before the votes of the wait)
       vsum = 0.0; prod = 1.0; esum = 0;
     }
     __syncwarp();  // every lane is done with stage cb
