@@ -406,7 +406,8 @@ def run_ours(args):
             ev1.record(stream)
             barrier()
             dev_ms = ev0.elapsed_time(ev1)
-        launches = 2 * args.steps           # llk_stream_kernel + llk_reduce_kernel per step
+        plan = engines[0].batch_plan(n_jobs)   # which many-evaluations kernel, how many launches of it per step
+        launches = (plan["kernel_launches"] + 1 + (1 if peer is not None else 0)) * args.steps   # ... + llk_reduce_kernel (+ llk_gather_kernel)
         keep_busy(0.5)                      # clocks under the same load, for the sampler
         barrier()
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -463,21 +464,26 @@ def run_ours(args):
     if not cohort and world == 1:
         n1 = 500
         one_ms = vb.time_device(engines, 20, n1, start_pc, start_pc, 0.03) / n1
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of this kernel (profiles/r02_llk_stream_
-    # kernel_digest.txt: 14,850,184,000 + 14,341,632 bytes for a launch of 2,048 evaluations): 7.258 MB per evaluation of the
-    # headline workload at N=1 = the stored image, no re-reads (algorithmic: 7.573 MB)
-    traffic = 7258069.0 * n_jobs if (args.config == "100k30x" and world == 1) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of the kernel, per evaluation of the headline
+    # workload at N=1 (profiles/r02_llk_flow_kernel_digest.txt: 847,955,712 + 5,540,608 bytes for a launch of 120 evaluations;
+    # profiles/r02_llk_stream_kernel_digest.txt: 14,850,184,000 + 14,341,632 bytes for 2,048): the stored image, no re-reads
+    # (algorithmic: 7.573 MB per evaluation)
+    per_eval_traffic = {"llk_flow_kernel": 7112469.0, "llk_stream_kernel": 7258069.0}[plan["kernel"]]
+    traffic = per_eval_traffic * n_jobs if (args.config == "100k30x" and world == 1) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
-                "traffic_note": "bytes per launch of %d evaluations, from the committed ncu capture of this kernel (7.26 MB per "
-                                "evaluation = the stored image, no re-reads)" % n_jobs if traffic else None,
-                "peak_source": peak_src, "kernel": "llk_stream_kernel", "evaluations_per_launch": n_jobs,
+                "traffic_note": "bytes per step of %d evaluations, from the committed ncu capture of this kernel (%.2f MB per "
+                                "evaluation = the stored image, no re-reads)" % (n_jobs, per_eval_traffic / 1e6) if traffic else None,
+                "peak_source": peak_src, "kernel": plan["kernel"], "evaluations_per_launch": n_jobs,
+                "kernel_launches_per_step": plan["kernel_launches"], "evaluations_per_kernel_launch": plan["jobs_per_launch"],
                 "launch_us": launch_us, "us_per_evaluation": launch_us / n_jobs * (1 if not cohort else 1),
                 "us_per_evaluation_one_launch_each": one_ms * 1e3 if one_ms else None,
                 "algorithmic_bytes_per_launch": alg_launch, "device_bytes_per_launch": dev_launch,
                 "includes_allreduce": collective,
-                "note": "co-bound by the FP64 pipe: 10 fp64 instructions per streamed read + ~40 per marker -> >= 1.9 us per "
-                        "evaluation of the headline workload at 64 fp64 lanes/clk/SM (DESIGN.md section 4)"}
+                "note": "bound by instruction issue, not by HBM: an FP64 warp-instruction holds a B200 sub-partition's issue slot for "
+                        "two cycles (tools/microbench_mix.cu), so an evaluation costs >= 2*F + G cycles per sub-partition with "
+                        "F = 1,939 fp64 and G ~ 2,540 other warp-instructions (10 fp64 per streamed read + ~90 per 32-marker slice): "
+                        "3.2 us for this instruction mix, 1.97 us for the fp64 instructions alone (DESIGN.md section 4)"}
 
     # ---- e2e: the public C-ABI call with HOST buffers, host<->device traffic inside the timed region ----------------
     e2e_extra, r_last = {}, None

@@ -305,6 +305,13 @@ typedef struct vb2_llk_min_result {
 int vb2_llk_minimize(vb2_llk_ctx *ctx, const vb2_llk_model *model, const double *start, double scale, double ftol,
                      int64_t cycle_max, double llk1_in, vb2_llk_min_result *result);
 
+/* How a batched call (vb2_llk_eval_batch / _many) over n evaluations of samples shaped like ctx's is launched:
+ * *flow = 1 when it runs llk_flow_kernel (fp32 panel, NumPC 2 or 4, default AF clamps, no --KnownAF, every blob fits a
+ * shared-memory stage; parameters in the kernel arguments), 0 for llk_stream_kernel (any shape); *kernel_launches = launches
+ * of that kernel the batch is cut into (the one llk_reduce_kernel launch behind them not counted); *jobs_per_launch = the
+ * most evaluations one of them carries.  Measurement aid (bench.py reports it); nothing is launched. */
+int vb2_llk_batch_plan(const vb2_llk_ctx *ctx, int n, int *flow, int *kernel_launches, int *jobs_per_launch);
+
 /* Block until everything queued on the context's stream has finished. */
 int vb2_llk_sync(vb2_llk_ctx *ctx);
 

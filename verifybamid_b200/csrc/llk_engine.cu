@@ -2093,10 +2093,13 @@ int stream_kernel_choice() {  // (read at every launch: the tests switch it insi
   const char *e = getenv("VB2_STREAM_KERNEL");
   return (e && !strcmp(e, "queue")) ? 1 : 0;
 }
+// llk_flow_kernel serves the fixed layouts whose blobs fit a stage and whose bins have at most 32 rounds (one item table
+// per task); everything else goes to llk_stream_kernel
+bool flow_shape(int spec, bool chunked) { return !chunked && (spec == 2 || spec == 4) && stream_kernel_choice() == 0; }
 void launch_stream(uint32_t smem, cudaStream_t stream, const LaunchArgs &A, const TaskRec *h_recs, int spec, bool chunked,
                    int sm_count) {
-  bool flow = !chunked && (spec == 2 || spec == 4) && stream_kernel_choice() == 0;
-  for (uint32_t j = 0; flow && j < A.n_jobs; ++j) flow = h_recs[j].S.n_rounds <= 32u;  // (one item table per task)
+  bool flow = flow_shape(spec, chunked);
+  for (uint32_t j = 0; flow && j < A.n_jobs; ++j) flow = h_recs[j].S.n_rounds <= 32u;
   if (flow) {
     if (spec == 2) launch_flow_as<2>(smem, stream, A, h_recs, sm_count);
     else launch_flow_as<4>(smem, stream, A, h_recs, sm_count);
@@ -2568,6 +2571,16 @@ int init_device_tables(vb2_llk_ctx *ctx, int device, int spec, bool chunked) {
 extern "C" {
 
 int vb2_abi_version(void) { return VB2_ABI_VERSION; }
+
+int vb2_llk_batch_plan(const vb2_llk_ctx *ctx, int n, int *flow, int *kernel_launches, int *jobs_per_launch) {
+  if (!ctx || n <= 0 || n > VB2_MAX_BATCH || !flow || !kernel_launches || !jobs_per_launch)
+    return set_err(const_cast<vb2_llk_ctx *>(ctx), VB2_ERR_INVALID, "vb2_llk_batch_plan: bad argument");
+  const bool f = n > 1 && flow_shape(ctx->spec, ctx->chunked) && ctx->S.n_rounds <= 32u;
+  *flow = f ? 1 : 0;
+  *kernel_launches = f ? (n + kFlowJobs - 1) / kFlowJobs : 1;
+  *jobs_per_launch = f ? std::min(n, kFlowJobs) : n;
+  return VB2_OK;
+}
 
 int vb2_device_count(void) {
   int n = 0;

@@ -37,7 +37,7 @@ _STATUS = {1: "VB2_ERR_INVALID", 2: "VB2_ERR_NO_DEVICE", 3: "VB2_ERR_CUDA", 4: "
 # every symbol include/vb2_llk.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = ("vb2_abi_version", "vb2_device_count", "vb2_llk_warmup", "vb2_llk_create", "vb2_llk_destroy", "vb2_llk_get_info",
                "vb2_llk_eval", "vb2_llk_eval_begin", "vb2_llk_eval_end", "vb2_llk_eval_batch", "vb2_llk_eval_batch_device", "vb2_llk_eval_many", "vb2_llk_eval_many_device",
-               "vb2_llk_sync", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free",
+               "vb2_llk_sync", "vb2_llk_batch_plan", "vb2_last_error", "vb2_llk_pack_host", "vb2_llk_pack_free",
                "vb2_llk_time_device", "vb2_llk_time_device_many", "vb2_llk_time_host", "vb2_llk_trace",
                "vb2_llk_session_begin", "vb2_llk_session_end", "vb2_llk_minimize",
                "vb2_peer_create", "vb2_peer_connect", "vb2_peer_destroy", "vb2_llk_eval_many_device_peer",
@@ -203,6 +203,9 @@ def load_library() -> ctypes.CDLL:
                                      ctypes.c_int64, ctypes.c_double, ctypes.POINTER(_MinResult)]
     lib.vb2_llk_sync.restype = ctypes.c_int
     lib.vb2_llk_sync.argtypes = [ctypes.c_void_p]
+    lib.vb2_llk_batch_plan.restype = ctypes.c_int
+    lib.vb2_llk_batch_plan.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                       ctypes.POINTER(ctypes.c_int)]
     lib.vb2_llk_time_device.restype = ctypes.c_int
     lib.vb2_llk_time_device.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
@@ -445,6 +448,13 @@ class LLKEngine:
 
     def sync(self) -> None:
         self._check(self._lib.vb2_llk_sync(self._ctx))
+
+    def batch_plan(self, n: int) -> dict:
+        """How a batched call over n evaluations of samples shaped like this one is launched (nothing is launched)."""
+        flow, launches, jobs = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.vb2_llk_batch_plan(self._ctx, int(n), ctypes.byref(flow), ctypes.byref(launches), ctypes.byref(jobs)))
+        return {"kernel": "llk_flow_kernel" if flow.value else "llk_stream_kernel", "kernel_launches": launches.value,
+                "jobs_per_launch": jobs.value}
 
     def session_begin(self) -> None:
         """Resident kernel with the sample in shared memory: compute_mix_llks rings a doorbell until session_end()."""
