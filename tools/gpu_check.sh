@@ -18,13 +18,17 @@ done
 timeout 200 python tools/trace_latency.py > $out/trace.txt 2>&1
 timeout 200 python tools/ingest_time.py > $out/ingest_time.txt 2>/dev/null
 VB2_CLI_TIMING=1 bash tools/gpu_cli_time.sh $tag/cli > $out/cli_time.txt 2>&1
-bash tools/gpu_phase.sh $tag > $out/phase_tail.txt 2>&1
 # profiler passes: a number printed under ncu is never a bench value; --no-session because a resident kernel cannot be replayed
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-session > $out/bench_under_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:llk_stream_kernel -s 3 -c 1 -f -o $out/prof_stream \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:llk_flow_kernel -s 30 -c 1 -f -o $out/prof_flow \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-session > $out/ncu_flow.log 2>&1
+VB2_STREAM_KERNEL=queue timeout 600 ncu --set full --clock-control none --import-source on -k regex:llk_stream_kernel -s 3 -c 1 -f -o $out/prof_stream \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-session > $out/ncu_stream.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:llk_kernel -s 40 -c 1 -f -o $out/prof_latency \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-session > $out/ncu_latency.log 2>&1
+./tools/microbench_fp64 > $out/microbench_fp64.txt 2>&1
+./tools/microbench_mix > $out/microbench_mix.txt 2>&1
+VB2_STREAM_KERNEL=queue timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $out/bench_queue_kernel.json 2>> $out/bench.err
 tail -3 $out/pytest_gpu.log; tail -2 $out/smoke.log; tail -3 $out/bench.err
 cut -c1-400 $out/bench.json; echo; cut -c1-300 $out/bench_reference.json

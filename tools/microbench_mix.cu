@@ -13,11 +13,11 @@
 
 template <int NR, int G>
 __global__ void __launch_bounds__(128, 8) k_mix(double *out, const double *in, int iters, double ca, double cb, unsigned m) {
-  double x[12], y[12], z[12];
+  double x[12], y[6], z[4];
   unsigned u[12];
 #pragma unroll
   for (int j = 0; j < 12; ++j) {
-    x[j] = in[j] + threadIdx.x; y[j] = in[12 + j] * 1e-3; z[j] = in[24 + j];
+    x[j] = in[j] + threadIdx.x; y[j % 6] = in[12 + j] * 1e-3; z[j % 4] = in[24 + j];
     u[j] = threadIdx.x * 7u + j;
   }
 #pragma unroll 1
@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(128, 8) k_mix(double *out, const double *in, i
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
       if (NR == 1) x[j] = fma(x[j], cb, ca);
-      if (NR == 2) x[j] = fma(x[j], cb, y[j]);
-      if (NR == 3) x[j] = fma(x[j], z[j], y[j]);
+      if (NR == 2) x[j] = fma(x[j], cb, y[j % 6]);
+      if (NR == 3) x[j] = fma(x[j], z[j % 4], y[j % 6]);
 #pragma unroll
       for (int g = 0; g < G; ++g) u[j] = (u[j] ^ m) + u[(j + 1 + g) % 12];   // LOP3 + IADD (register operands)
     }
