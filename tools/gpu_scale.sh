@@ -24,6 +24,7 @@ for n in "$@"; do
   else
     run $n nccl
     run $n peer --collective peer
+    VB2_STREAM_KERNEL=queue run $n queue
   fi
   last=$n
 done

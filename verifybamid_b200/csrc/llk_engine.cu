@@ -1226,6 +1226,8 @@ llk_flow_kernel(const __grid_constant__ FlowArgs F) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_jobs = F.n_jobs, n_quads = F.n_quads;
+  // the next launch of the batch may move in as soon as this one leaves room (nothing here is an input of it)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (lane == 0) {
     mbar_init(&s_bar[warp][0], 1);
     mbar_init(&s_bar[warp][1], 1);
@@ -2044,6 +2046,10 @@ void launch_stream_as(uint32_t smem, cudaStream_t stream, const LaunchArgs &A, i
   const uint32_t grid = std::max(1u, std::min(cached_per_sm * (uint32_t)std::max(1, sm_count), (n_tasks + 3u) / 4u));
   llk_stream_kernel<NPC, CHUNKED><<<dim3(grid, 1, 1), dim3(128, 1, 1), smem, stream>>>(A);
 }
+bool flow_overlap() {  // VB2_FLOW_PDL=0: the launches of a batch strictly one after the other (A/B runs)
+  const char *e = getenv("VB2_FLOW_PDL");
+  return !(e && e[0] == '0');
+}
 // llk_flow_kernel over the jobs A.recs[0 .. A.n_jobs) (h_recs = the host copy of the same records): launches of at
 // most kFlowJobs jobs, each with its jobs' parameters in the kernel arguments.
 template <int NPC>
@@ -2084,7 +2090,20 @@ void launch_flow_as(uint32_t smem, cudaStream_t stream, const LaunchArgs &A, con
     }
     const uint32_t n_tasks = F.n_jobs * A.n_bins_max;
     const uint32_t grid = std::max(1u, std::min(cached_per_sm * (uint32_t)std::max(1, sm_count), (n_tasks + 3u) / 4u));
-    llk_flow_kernel<NPC><<<dim3(grid, 1, 1), dim3(128, 1, 1), smem, stream>>>(F);
+    // The launches of a batch do not depend on each other (own jobs, own task counter, own partial-sum slots): with
+    // programmatic stream serialization the CTAs of launch i+1 move in as those of launch i run out of tasks, so the
+    // cut into launches costs no drained-GPU gap (llk_reduce_kernel behind them is an ordinary launch: it waits for all).
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(128, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (launch > 0 && flow_overlap()) ? 1 : 0;  // (the first launch of a batch waits for whatever precedes the batch)
+    cudaLaunchKernelEx(&cfg, llk_flow_kernel<NPC>, F);
   }
 }
 static_assert((VB2_MAX_BATCH + kFlowJobs - 1) / kFlowJobs <= (int)kQueueWords, "one task counter per launch of a batch");
