@@ -119,6 +119,11 @@ def test_both_many_evaluation_kernels_return_the_same_bits(sample10k, monkeypatc
             monkeypatch.delenv("VB2_STREAM_KERNEL", raising=False)
             assert flow.tolist() == queue.tolist()
             assert flow_mixed.tolist() == queue_mixed.tolist()
+            # what bench.py reports about a batch comes from the library, not from a constant
+            assert eng.batch_plan(n) == {"kernel": "llk_flow_kernel", "kernel_launches": 3, "jobs_per_launch": 120}
+            monkeypatch.setenv("VB2_STREAM_KERNEL", "queue")
+            assert eng.batch_plan(n) == {"kernel": "llk_stream_kernel", "kernel_launches": 1, "jobs_per_launch": n}
+            monkeypatch.delenv("VB2_STREAM_KERNEL", raising=False)
             for j in (0, 1, 2, 150, 332):
                 assert flow[j] == eng.compute_mix_llks(pc1[j], pc2[j], al[j])
 
