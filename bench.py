@@ -465,10 +465,10 @@ def run_ours(args):
         n1 = 500
         one_ms = vb.time_device(engines, 20, n1, start_pc, start_pc, 0.03) / n1
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of the kernel, per evaluation of the headline
-    # workload at N=1 (profiles/r02_llk_flow_kernel_digest.txt: 847,955,712 + 5,540,608 bytes for a launch of 120 evaluations;
-    # profiles/r02_llk_stream_kernel_digest.txt: 14,850,184,000 + 14,341,632 bytes for 2,048): the stored image, no re-reads
+    # workload at N=1 (profiles/r02_llk_flow_kernel_digest.txt: 848,352,768 + 5,581,312 bytes for a launch of 120 evaluations;
+    # profiles/r02_llk_stream_kernel_digest.txt: 14,846,177,000 + 15,367,424 bytes for 2,048): the stored image, no re-reads
     # (algorithmic: 7.573 MB per evaluation)
-    per_eval_traffic = {"llk_flow_kernel": 7112469.0, "llk_stream_kernel": 7258069.0}[plan["kernel"]]
+    per_eval_traffic = {"llk_flow_kernel": 7116117.0, "llk_stream_kernel": 7256614.0}[plan["kernel"]]
     traffic = per_eval_traffic * n_jobs if (args.config == "100k30x" and world == 1) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
