@@ -6,6 +6,8 @@
 //        out: UD [M][K], PC [N][K], singular values [N or min(M,N)] fp32, row-major    SVDcalculator.cpp:258-361)
 //   vb2_svd_ref vcf <ref.vcf> <numSVDPCs> <gram 0|1> <skipMinSampleCountCheck 0|1> [includeChr,comma,separated]
 //        SVDcalculator::ProcessRefVCF (cpp:363-449): writes <ref.vcf>.UD/.mu/.bed/.V exactly as `--RefVCF` does
+//   vb2_svd_ref readvcf <ref.vcf> out.bin [includeChr]
+//        SVDcalculator::ReadVcf (cpp:22-224): int32 nMarkers, int32 nSamples, then the matrix [nMarkers][nSamples] int8
 #include "SVDcalculator.h"
 
 #include <cstdio>
@@ -62,5 +64,25 @@ int main(int argc, char **argv) {
     calc.ProcessRefVCF(argv[2], chr, atoi(argv[5]) != 0, atoi(argv[3]), atoi(argv[4]) != 0);
     return 0;
   }
-  return die("usage: gram|jacobi M N K in out  |  vcf path numSVDPCs gram skipCheck [includeChr]");
+  if (argc >= 4 && !strcmp(argv[1], "readvcf")) {  // SVDcalculator::ReadVcf alone: the genotype matrix it builds
+    std::unordered_set<std::string> chr;
+    if (argc >= 5) {
+      std::stringstream ss(argv[4]);
+      std::string tok;
+      while (std::getline(ss, tok, ','))
+        if (!tok.empty()) chr.insert(tok);
+    }
+    SVDcalculator calc;
+    std::vector<std::vector<char> > genotype;
+    int nS = 0, nM = 0;
+    calc.ReadVcf(argv[2], genotype, nS, nM, chr);
+    FILE *f = fopen(argv[3], "wb");
+    if (!f) return die("cannot write the output");
+    fwrite(&nM, 4, 1, f);
+    fwrite(&nS, 4, 1, f);
+    for (int i = 0; i < nM; ++i) fwrite(genotype[i].data(), 1, (size_t)nS, f);
+    fclose(f);
+    return 0;
+  }
+  return die("usage: gram|jacobi M N K in out  |  vcf path numSVDPCs gram skipCheck [includeChr]  |  readvcf path out [includeChr]");
 }

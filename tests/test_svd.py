@@ -7,12 +7,17 @@ reference test's (TestGramSVD.cpp:55-73): per column, sign-aligned, max deviatio
 the dominant column).  Tolerance: the reference allows 1e-2 between its two fp32 decompositions and observes ~1e-5;
 here GRAM_TOL = 1e-3 (measured 1e-6 .. 1e-5: fp32 accumulation order and a different eigensolver)."""
 import ctypes
+import os
+import subprocess
 
 import numpy as np
 import pytest
 
-from verifybamid_b200 import svd
+from verifybamid_b200 import host, svd
 from oracle import svd_oracle as so
+from helpers import ROOT
+
+AUTOSOMES = [str(i) for i in range(1, 23)]
 
 GRAM_TOL = 1e-3
 needs_ref = pytest.mark.skipif(not so.reference_available(), reason="oracle/_ref/vb2_svd_ref not built")
@@ -101,3 +106,73 @@ def test_device_gram_svd_small_shapes_and_reproducibility():
     g = structured_genotypes(4000, 100, seed=5)
     r1, r2 = svd.svd_gram(g, 8), svd.svd_gram(g, 8)                # no atomics: the same bits every time
     assert (r1["ud"] == r2["ud"]).all() and (r1["singular"] == r2["singular"]).all()
+
+
+@pytest.fixture(scope="module")
+def test_vcf(tmp_path_factory):
+    path = str(tmp_path_factory.mktemp("refvcf") / "panel.vcf")
+    so.write_test_vcf(path)
+    return path
+
+
+@needs_ref
+def test_host_vcf_reader_builds_the_reference_genotype_matrix(test_vcf):
+    """ReadVcf (cpp:22-224) of csrc/svd_panel.cpp against the reference's own: FILTER / multi-allelic / non-SNP /
+    chromosome / missing-rate rules, PL > GL > GT priority, unparsed samples kept as -1 -- the same matrix, bit for bit."""
+    for chrs in (AUTOSOMES, []):
+        want = so.reference_read_vcf(test_vcf, chrs)
+        got = host.read_vcf(test_vcf, chrs)
+        assert got["genotype"].shape == want.shape and (got["genotype"] == want).all()
+        assert want.shape[1] == 64 and 5000 < want.shape[0] < 5400 and (want == -1).any()
+    assert set(got["chrom"]) == {"1", "2", "X"} and len(got["pos"]) == want.shape[0]
+    assert set(host.read_vcf(test_vcf, AUTOSOMES)["chrom"]) == {"1", "2"}
+
+
+def test_host_vcf_reader_reports_malformed_input(tmp_path, capfd):
+    bad = tmp_path / "bad.vcf"
+    bad.write_text("##fileformat=VCFv4.1\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\tB\n"
+                   "1\t100\t.\tA\tC\t.\tPASS\t.\tGT:PL\t0/0\t0/1:3,0,9\n")
+    with pytest.raises(RuntimeError):                            # libVcfFile.cpp:931-934 (error() prints, then throws)
+        host.read_vcf(str(bad))
+    assert "do not match" in capfd.readouterr().err
+    dup = tmp_path / "dup.vcf"
+    dup.write_text("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\n"
+                   "1\t100\t.\tA\tC\t.\tPASS\t.\tGT\t0/0\n1\t100\t.\tA\tG\t.\tPASS\t.\tGT\t0/1\n")
+    with pytest.raises(RuntimeError):                            # cpp:60-63
+        host.read_vcf(str(dup))
+    assert "Duplicated Marker" in capfd.readouterr().err
+
+
+def _read_table(path, skip_first_column=False):
+    rows = [line.rstrip("\t\n").split("\t") for line in open(path)]
+    return np.array([[float(x) for x in (r[1:] if skip_first_column else r)] for r in rows])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_refvcf_writes_the_reference_panel_files(test_vcf, tmp_path):
+    """`--RefVCF` end to end (main.cpp:232-257, ProcessRefVCF cpp:363-449, WriteSVD cpp:471-513): .bed and .mu are the
+    reference's byte for byte (the means are exact); .UD and .V agree column by column up to the eigensolver's sign."""
+    import shutil
+    ours, ref = str(tmp_path / "ours.vcf"), str(tmp_path / "ref.vcf")
+    shutil.copy(test_vcf, ours); shutil.copy(test_vcf, ref)
+    so.reference_process_vcf(ref, 10, True, True, AUTOSOMES)
+    cli = os.path.join(ROOT, "verifybamid_b200", "VerifyBamID")
+    r = subprocess.run([cli, "--RefVCF", ours, "--SkipMinSampleCountCheck", "--NumSVDPCs", "10", "--GramSVD"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Success!" in r.stderr and "eigendecomposition" in r.stderr
+    assert open(ours + ".bed").read() == open(ref + ".bed").read()
+    assert open(ours + ".mu").read() == open(ref + ".mu").read()
+    ud, rud = _read_table(ours + ".UD"), _read_table(ref + ".UD")
+    v, rv = _read_table(ours + ".V", True), _read_table(ref + ".V", True)
+    assert ud.shape == rud.shape == (sum(1 for _ in open(ref + ".bed")), 10) and v.shape == rv.shape == (64, 10)
+    assert [l.split("\t")[0] for l in open(ours + ".V")] == [l.split("\t")[0] for l in open(ref + ".V")]
+    scale = float(np.linalg.norm(rud[:, 0]))
+    for c in range(10):        # (files carry 6 significant digits)
+        tol = GRAM_TOL if c < 3 else 1e-2
+        assert so.column_error(rud[:, c], ud[:, c], scale) <= tol, ("UD", c)
+        assert so.column_error(rv[:, c], v[:, c], 1.0) <= tol, ("V", c)
+    # without --SkipMinSampleCountCheck a 64-sample panel is refused, as in the reference (cpp:383-396)
+    r = subprocess.run([cli, "--RefVCF", ours], capture_output=True, text=True)
+    assert r.returncode != 0 and "Insufficient number of individuals" in r.stderr

@@ -12,6 +12,7 @@
 #include "amoeba.h"
 #include "cohort.h"
 #include "estimator.h"
+#include "svd_panel.h"
 
 using namespace vb2;
 
@@ -155,4 +156,45 @@ void vb2_host_free(void *h) {
   delete L;
 }
 
+
+// SVDcalculator::ReadVcf on the host (svd_panel.cpp): the genotype matrix [markers][samples] (-1..2) and the marker keys.
+// Returns a handle (nullptr on failure, message in err[0..err_len)); sizes through n_marker / n_sample.
+struct VcfLoaded {
+  SVDcalculator calc;
+  std::vector<int8_t> genotype;
+};
+void *vb2_host_read_vcf(const char *path, const char *include_chr_csv, int *n_marker, int *n_sample, char *err, int err_len) {
+  VcfLoaded *L = new VcfLoaded();
+  try {
+    std::unordered_set<std::string> chr;
+    std::string csv = include_chr_csv ? include_chr_csv : "", tok;
+    size_t b = 0;
+    while (b <= csv.size()) {
+      const size_t e = csv.find(',', b);
+      tok = csv.substr(b, e == std::string::npos ? std::string::npos : e - b);
+      if (!tok.empty()) chr.insert(tok);
+      if (e == std::string::npos) break;
+      b = e + 1;
+    }
+    L->calc.ReadVcf(path, L->genotype, *n_sample, *n_marker, chr);
+    L->calc.numMarker = *n_marker;
+    L->calc.numIndividual = *n_sample;
+    return L;
+  } catch (const std::exception &ex) {
+    if (err && err_len > 0) {
+      strncpy(err, ex.what(), (size_t)err_len - 1);
+      err[err_len - 1] = 0;
+    }
+    delete L;
+    return nullptr;
+  }
+}
+// genotype [n_marker * n_sample] int8, pos [n_marker] int32, ref / alt [n_marker] char
+void vb2_host_vcf_copy(void *h, int8_t *genotype, int32_t *pos, char *ref, char *alt) {
+  VcfLoaded *L = static_cast<VcfLoaded *>(h);
+  memcpy(genotype, L->genotype.data(), L->genotype.size());
+  for (size_t i = 0; i < L->calc.pos.size(); ++i) { pos[i] = L->calc.pos[i]; ref[i] = L->calc.refAllele[i]; alt[i] = L->calc.altAllele[i]; }
+}
+const char *vb2_host_vcf_chrom(void *h, int i) { return static_cast<VcfLoaded *>(h)->calc.chrom[(size_t)i].c_str(); }
+void vb2_host_vcf_free(void *h) { delete static_cast<VcfLoaded *>(h); }
 }  // extern "C"

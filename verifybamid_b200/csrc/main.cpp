@@ -2,7 +2,7 @@
 // reference for the likelihood path (main.cpp:56-414 of the reference): same option names, same
 // defaults, same <out>.selfSM / <out>.Ancestry / <out>.Pileup files, same stdout lines.
 //   --BamFile needs htslib (absent here): give --PileupFile instead.
-//   --RefVCF (SVD panel construction) is a separate offline workload and is not built.
+//   --RefVCF (SVD panel construction): svd_panel.cpp + libvb2svd.so (plain-text VCF; the decomposition runs on the device).
 // Engine-only options: --NumGPU n (marker shards over devices 0..n-1), --Device d, --PanelFP64,
 // --PileupList file (cohort mode: many samples on one panel, evaluated in lock-step, see cohort.h).
 #include <chrono>
@@ -25,6 +25,7 @@
 
 #include "cohort.h"
 #include "estimator.h"
+#include "svd_panel.h"
 
 using namespace vb2;
 
@@ -39,6 +40,13 @@ struct Options {
   int seed = 12345, nPC = 2, nthread = 4;  // main.cpp:79
   int numGPU = 1, device = 0;
   bool panelFp64 = false;
+  // --RefVCF (main.cpp:63-73)
+  int numSVDPCs = 10;
+  bool skipMinSampleCountCheck = false, gramSVD = false;
+  std::string includeChrStr = "1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,"
+                              "chr1,chr2,chr3,chr4,chr5,chr6,chr7,chr8,chr9,chr10,"
+                              "chr11,chr12,chr13,chr14,chr15,chr16,chr17,chr18,chr19,"
+                              "chr20,chr21,chr22";
 };
 
 bool ieq(const std::string &a, const char *b) {
@@ -98,6 +106,10 @@ bool parse(int argc, char **argv, Options &o) {
     else if (ieq(name, "OutputPileup")) o.outputPileup = true;
     else if (ieq(name, "Verbose")) o.verbose = true;
     else if (ieq(name, "RefVCF")) value(o.RefVCF);
+    else if (ieq(name, "NumSVDPCs")) ivalue(o.numSVDPCs);
+    else if (ieq(name, "SkipMinSampleCountCheck")) o.skipMinSampleCountCheck = true;
+    else if (ieq(name, "GramSVD")) o.gramSVD = true;
+    else if (ieq(name, "IncludeChr")) value(o.includeChrStr);
     else if (ieq(name, "UDPath")) value(o.UDPath);
     else if (ieq(name, "MeanPath")) value(o.MeanPath);
     else if (ieq(name, "BedPath")) value(o.BedPath);
@@ -286,8 +298,22 @@ int execute(int argc, char **argv) {
   Options o;
   parse(argc, argv, o);
 
-  if (o.RefVCF != "Empty") {
-    error("--RefVCF (SVD panel construction) is not part of this engine; build the panel with the reference tool");
+  if (o.RefVCF != "Empty") {  // main.cpp:232-257: SVD on the fly, then done
+    notice("Specified --RefVCF reference panel VCF file, doing SVD on the fly...");
+    notice("This procedure will generate SVD matrices as [RefVCF path].UD and [RefVCF path].mu");
+    notice("You may specify --SVDPrefix [RefVCF path](or --UDPath [RefVCF path].UD and --MeanPath [RefVCF path].mu) in future use");
+    std::unordered_set<std::string> includeChrSet;
+    {
+      std::stringstream ss(o.includeChrStr);
+      std::string token;
+      while (std::getline(ss, token, ','))
+        if (!token.empty()) includeChrSet.insert(token);
+    }
+    notice("--IncludeChr: filtering to %d chromosome name(s)", (int)includeChrSet.size());
+    SVDcalculator calculator;
+    calculator.ProcessRefVCF(o.RefVCF, includeChrSet, o.skipMinSampleCountCheck, o.numSVDPCs, o.gramSVD, o.device);
+    notice("Success!");
+    return 0;
   }
   if (o.SVDPrefix == "Empty") {  // main.cpp:214-231
     if (o.UDPath == "Empty") error("--UDPath is required when --RefVCF is absent");

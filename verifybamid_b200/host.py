@@ -45,6 +45,15 @@ def load_library() -> ctypes.CDLL:
                                                  ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         lib.vb2_host_free.restype = None
         lib.vb2_host_free.argtypes = [ctypes.c_void_p]
+        lib.vb2_host_read_vcf.restype = ctypes.c_void_p
+        lib.vb2_host_read_vcf.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                          ctypes.c_char_p, ctypes.c_int]
+        lib.vb2_host_vcf_copy.restype = None
+        lib.vb2_host_vcf_copy.argtypes = [ctypes.c_void_p] * 5
+        lib.vb2_host_vcf_chrom.restype = ctypes.c_char_p
+        lib.vb2_host_vcf_chrom.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.vb2_host_vcf_free.restype = None
+        lib.vb2_host_vcf_free.argtypes = [ctypes.c_void_p]
         _lib = lib
     return _lib
 
@@ -99,3 +108,23 @@ def load_problem(svd_prefix: str, pileup: str, n_pc: int = 2, disable_sanity: bo
                       "effective_num_site": eff.value, "num_marker": m, "sanity_ok": bool(ok.value)}
     finally:
         lib.vb2_host_free(h)
+
+
+def read_vcf(path: str, include_chr: Sequence[str] = ()):
+    """SVDcalculator::ReadVcf of the host side (csrc/svd_panel.cpp): dict(genotype int8 [markers][samples], chrom, pos, ref, alt)."""
+    lib = load_library()
+    nm, ns = ctypes.c_int(), ctypes.c_int()
+    err = ctypes.create_string_buffer(512)
+    h = lib.vb2_host_read_vcf(path.encode(), ",".join(include_chr).encode(), ctypes.byref(nm), ctypes.byref(ns), err, 512)
+    if not h:
+        raise RuntimeError(err.value.decode())
+    try:
+        g = np.zeros((nm.value, ns.value), np.int8)
+        pos = np.zeros(nm.value, np.int32)
+        ref = np.zeros(nm.value, np.uint8)
+        alt = np.zeros(nm.value, np.uint8)
+        lib.vb2_host_vcf_copy(h, g.ctypes.data, pos.ctypes.data, ref.ctypes.data, alt.ctypes.data)
+        chrom = [lib.vb2_host_vcf_chrom(h, i).decode() for i in range(nm.value)]
+    finally:
+        lib.vb2_host_vcf_free(h)
+    return {"genotype": g, "chrom": chrom, "pos": pos, "ref": ref.tobytes().decode(), "alt": alt.tobytes().decode()}
