@@ -126,6 +126,10 @@ def test_host_vcf_reader_builds_the_reference_genotype_matrix(test_vcf):
         assert want.shape[1] == 64 and 5000 < want.shape[0] < 5400 and (want == -1).any()
     assert set(got["chrom"]) == {"1", "2", "X"} and len(got["pos"]) == want.shape[0]
     assert set(host.read_vcf(test_vcf, AUTOSOMES)["chrom"]) == {"1", "2"}
+    import gzip, shutil                                           # a compressed panel reads the same (zlib)
+    with open(test_vcf, "rb") as fi, gzip.open(test_vcf + ".gz", "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    assert (host.read_vcf(test_vcf + ".gz", AUTOSOMES)["genotype"] == so.reference_read_vcf(test_vcf, AUTOSOMES)).all()
 
 
 def test_host_vcf_reader_reports_malformed_input(tmp_path, capfd):

@@ -2,7 +2,7 @@
 // reference for the likelihood path (main.cpp:56-414 of the reference): same option names, same
 // defaults, same <out>.selfSM / <out>.Ancestry / <out>.Pileup files, same stdout lines.
 //   --BamFile needs htslib (absent here): give --PileupFile instead.
-//   --RefVCF (SVD panel construction): svd_panel.cpp + libvb2svd.so (plain-text VCF; the decomposition runs on the device).
+//   --RefVCF (SVD panel construction): svd_panel.cpp + libvb2svd.so (plain or gzip VCF; the decomposition runs on the device).
 // Engine-only options: --NumGPU n (marker shards over devices 0..n-1), --Device d, --PanelFP64,
 // --PileupList file (cohort mode: many samples on one panel, evaluated in lock-step, see cohort.h).
 #include <chrono>
@@ -70,7 +70,10 @@ void usage() {
           "  --NumGPU [Int] (1)  --Device [Int] (0)  --PanelFP64     (engine options)\n"
           "  --PileupList [String]  cohort mode: one '<pileup> [<output prefix>]' per line, all samples on the same\n"
           "                         panel, evaluated in lock-step (one launch per simplex step for the whole cohort;\n"
-          "                         with --NumGPU n the samples are spread over n devices)\n");
+          "                         with --NumGPU n the samples are spread over n devices)\n"
+          "  --RefVCF [String]      build the panel instead: reference VCF (plain or .gz) -> [RefVCF].UD/.mu/.bed/.V,\n"
+          "                         SVD on the GPU;  --NumSVDPCs [Int] (10)  --SkipMinSampleCountCheck  --GramSVD\n"
+          "                         --IncludeChr a,b,... (default: autosomes 1..22 / chr1..chr22)\n");
 }
 
 // libStatGen-style long options: "--Name value", booleans are presence flags (params.cpp:114-185)

@@ -2,6 +2,7 @@
 #include "svd_panel.h"
 
 #include <dlfcn.h>
+#include <zlib.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -47,6 +48,35 @@ void upper(std::string &s) {
   for (char &c : s) c = (char)toupper((unsigned char)c);
 }
 
+// one line at a time from a plain or gzip-compressed file (a panel VCF line carries thousands of samples)
+class LineReader {
+ public:
+  explicit LineReader(const std::string &path) : f_(gzopen(path.c_str(), "rb")), buf_(1 << 20) {
+    if (f_) gzbuffer(f_, 1 << 20);
+  }
+  ~LineReader() {
+    if (f_) gzclose(f_);
+  }
+  bool ok() const { return f_ != nullptr; }
+  bool getline(std::string &line) {
+    line.clear();
+    for (;;) {
+      if (!gzgets(f_, buf_.data(), (int)buf_.size())) return !line.empty();
+      const size_t n = strlen(buf_.data());
+      line.append(buf_.data(), n);
+      if (n && line.back() == '\n') {
+        line.pop_back();
+        return true;
+      }
+      if (gzeof(f_)) return true;
+    }
+  }
+
+ private:
+  gzFile f_;
+  std::vector<char> buf_;
+};
+
 // libvb2svd.so sits next to the executable / libvb2llk.so; it is loaded only when --RefVCF asks for it, so the
 // likelihood path never maps cuSOLVER.
 typedef int (*svd_gram_fn)(const vb2_svd_desc *);
@@ -73,15 +103,13 @@ void load_svd_library(svd_gram_fn *gram, svd_err_fn *err) {
 int SVDcalculator::ReadVcf(const std::string &VcfPath, std::vector<int8_t> &genotype, int &nSamples, int &nMarkers,
                            const std::unordered_set<std::string> &includeChr) {
   const long maxPhred = 255;  // cpp:27
-  if (VcfPath.size() > 3 && VcfPath.compare(VcfPath.size() - 3, 3, ".gz") == 0)
-    error("--RefVCF: compressed VCF is not supported by this build (no zlib): decompress %s first", VcfPath.c_str());
-  std::ifstream in(VcfPath);
-  if (!in) error("Failed to open VCF file %s", VcfPath.c_str());
+  LineReader in(VcfPath);  // plain text or gzip / bgzip (zlib reads both)
+  if (!in.ok()) error("Failed to open VCF file %s", VcfPath.c_str());
   std::string line;
   std::vector<std::string> cols, alts, filters, fmt, vals, three, alleles;
   // header (libVcfFile.cpp:238-330): meta lines, then #CHROM ... FORMAT sample1 sample2 ...
   bool have_header = false;
-  while (std::getline(in, line)) {
+  while (in.getline(line)) {
     if (!line.empty() && line.back() == '\r') line.pop_back();
     if (line.compare(0, 2, "##") == 0) continue;
     if (line.compare(0, 6, "#CHROM") == 0) {
@@ -101,7 +129,7 @@ int SVDcalculator::ReadVcf(const std::string &VcfPath, std::vector<int8_t> &geno
   std::string markerName, prevMarkerName;
   std::vector<int8_t> perMarkerGeno((size_t)nSamples);
   long lineNo = 0;
-  while (std::getline(in, line)) {
+  while (in.getline(line)) {
     ++lineNo;
     if (!line.empty() && line.back() == '\r') line.pop_back();
     if (line.empty()) continue;

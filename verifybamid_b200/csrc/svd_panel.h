@@ -13,7 +13,7 @@ namespace vb2 {
 
 class SVDcalculator {
  public:
-  // ReadVcf (cpp:22-224): plain-text VCF; PASS, bi-allelic SNPs on the included chromosomes; per sample the most
+  // ReadVcf (cpp:22-224): plain-text or gzip-compressed VCF; PASS, bi-allelic SNPs on the included chromosomes; per sample the most
   // likely genotype from PL, else GL, else GT; markers with more than 20 % unparsed samples are dropped; a sample
   // that could not be parsed at a kept marker stays -1 in the matrix (as in the reference).
   int ReadVcf(const std::string &VcfPath, std::vector<int8_t> &genotype, int &nSamples, int &nMarkers,
