@@ -232,7 +232,11 @@ __device__ __noinline__ double cold_log(double x) { return log(x); }
 
 struct Quad {
   static constexpr bool kPrefetchRows = true;  // the read loop fetches row t+1 before the arithmetic of row t
+  static constexpr bool kDotAddress = true;    // Phred look-up address by IDP.4A (see phred_of)
   double C0[kNumPairs], C1[kNumPairs], C2[kNumPairs];
+};
+struct StreamQuad : Quad {                     // llk_stream_kernel's holder
+  static constexpr bool kDotAddress = false;
 };
 
 // Four reads of one lane.  ALT = alt-allele reads: acc[5-p] takes what a ref read gives acc[p].
@@ -263,10 +267,18 @@ __device__ __forceinline__ void eat4(double e0, double e1, double e2, double e3,
 // row: the loop reads one row past the run (the next run, or the 128-byte pad every stage buffer ends with) and
 // drops what it read, which keeps the loop free of a peeled copy.
 // Phred error of byte b (0..3) of word w.
-template <int B>
+// DOT: measured per kernel (tools/gpu_ab_prmt.sh) -- the byte dot product is faster in llk_flow_kernel and in the
+// resident kernel (7.60 vs 7.93 us per dependent evaluation), the extract + multiply-add pair in llk_stream_kernel
+// (3.19-3.24 vs 3.28 us), so the coefficient holder of a kernel says which one its read loop uses (kDotAddress).
+template <int B, bool DOT = true>
 __device__ __forceinline__ double phred_of(uint32_t w) {
-  // 8 * byte B of w in ONE instruction: a four-way byte dot product with (8 in position B, 0 elsewhere) -- IDP.4A
-  const uint32_t off = (uint32_t)__dp4a(w, 0x8u << (8 * B), 0u);
+  uint32_t off;
+  if (DOT) {
+    // 8 * byte B of w in ONE instruction: a four-way byte dot product with (8 in position B, 0 elsewhere) -- IDP.4A
+    off = (uint32_t)__dp4a(w, 0x8u << (8 * B), 0u);
+  } else {
+    off = __byte_perm(w, 0u, 0x4440u + B) * 8u;  // (0, 0, 0, byte B) * 8
+  }
   return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_e) + off);
 }
 
@@ -283,11 +295,12 @@ __device__ __forceinline__ void eat_full_rows(const uint32_t *col, uint32_t n, c
   }
   if (n == 0) return;
   uint32_t w = col[0];
-  double e0 = phred_of<0>(w), e1 = phred_of<1>(w), e2 = phred_of<2>(w), e3 = phred_of<3>(w);
+  double e0 = phred_of<0, QT::kDotAddress>(w), e1 = phred_of<1, QT::kDotAddress>(w), e2 = phred_of<2, QT::kDotAddress>(w), e3 = phred_of<3, QT::kDotAddress>(w);
 #pragma unroll 1
   for (uint32_t t = 1; t <= n; ++t) {
     w = col[t * 32];
-    const double n0 = phred_of<0>(w), n1 = phred_of<1>(w), n2 = phred_of<2>(w), n3 = phred_of<3>(w);
+    const double n0 = phred_of<0, QT::kDotAddress>(w), n1 = phred_of<1, QT::kDotAddress>(w), n2 = phred_of<2, QT::kDotAddress>(w),
+                 n3 = phred_of<3, QT::kDotAddress>(w);
     eat4<ALT>(e0, e1, e2, e3, Q, acc);
     e0 = n0; e1 = n1; e2 = n2; e3 = n3;
   }
@@ -1019,7 +1032,7 @@ llk_stream_kernel(const __grid_constant__ LaunchArgs A) {
   auto task_value = [&]() { return vsum + fma((double)esum, kLn2, log(prod)); };
   uint32_t c_bin = 0;
   const TaskRec *c_rec = &s_rec[warp][0];  // the record of the task being consumed
-  Quad Q;
+  StreamQuad Q;
   auto load_quad = [&]() {
 #pragma unroll
     for (int p = 0; p < kNumPairs; ++p) {
@@ -1189,6 +1202,7 @@ struct FlowJob {  // one job's share of the kernel arguments
 #endif
 struct FlowQuad {
   static constexpr bool kPrefetchRows = VB2_FLOW_PREFETCH_ROWS != 0;
+  static constexpr bool kDotAddress = true;
   double C0[kNumPairs];
   const double (&C1)[kNumPairs];
   const double (&C2)[kNumPairs];
