@@ -12,12 +12,18 @@
 //   (iii) the marginal per marker (h:307-311); the marginals of a bin are multiplied up and one log
 //         per lane is taken; fixed-order lane / bin / CTA reduction in fp64 (h:232-236 is an OpenMP
 //         reduction), on the device or by the host over a host-mapped mailbox.
-// Three launch shapes of the same arithmetic (identical bits):
+// Four launch shapes of the same arithmetic (identical bits):
 //   llk_kernel          one evaluation per launch, one CTA per SM;
-//   llk_stream_kernel   many evaluations per launch: persistent grid, warps pull (evaluation, bin) tasks
-//                       from a queue; llk_reduce_kernel adds the per-bin partial sums;
+//   llk_flow_kernel     many evaluations per launch, the common shapes (fp32 panel, NumPC 2 or 4, blobs that fit a
+//                       stage): per-job coefficients in the kernel arguments -> uniform registers, 56 registers,
+//                       eight warps per SM sub-partition, launches of a batch overlapped;
+//   llk_stream_kernel   many evaluations per launch, any shape: persistent grid, warps pull (evaluation, bin) tasks
+//                       from a queue, task records by TMA; llk_reduce_kernel adds the per-bin partial sums of both;
 //   llk_session_kernel  resident: the sample stays in shared memory, evaluations arrive through a
-//                       host-mapped doorbell (vb2_llk_session_begin / _end).
+//                       host-mapped doorbell (vb2_llk_session_begin / _end), or a whole Nelder-Mead search runs
+//                       next to it (vb2_llk_minimize).
+// What bounds them on a B200 is FP64 instruction issue (an FP64 warp-instruction holds the issue slot for two cycles,
+// three with three register operands: tools/microbench_fp64.cu, microbench_mix.cu).
 // Everything that is evaluation-invariant was folded at create time by llk_pack.cpp.
 //
 // There is NO CPU fallback in this file: without a CUDA device every entry point fails.
