@@ -239,6 +239,7 @@ __device__ __noinline__ double cold_log(double x) { return log(x); }
 struct Quad {
   static constexpr bool kPrefetchRows = true;  // the read loop fetches row t+1 before the arithmetic of row t
   static constexpr bool kDotAddress = true;    // Phred look-up address by IDP.4A (see phred_of)
+  static constexpr uint32_t sel[4] = {0x8u, 0x800u, 0x80000u, 0x8000000u};  // (only the plain loop reads them)
   double C0[kNumPairs], C1[kNumPairs], C2[kNumPairs];
 };
 struct StreamQuad : Quad {                     // llk_stream_kernel's holder
@@ -288,14 +289,24 @@ __device__ __forceinline__ double phred_of(uint32_t w) {
   return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_e) + off);
 }
 
+// the same look-up with the selector (8 << 8*B) in a register
+__device__ __forceinline__ double phred_at(uint32_t w, uint32_t sel) {
+  return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_e) + (uint32_t)__dp4a(w, sel, 0u));
+}
+#ifndef VB2_FLOW_LOOP_UNROLL
+#define VB2_FLOW_LOOP_UNROLL 1
+#endif
+constexpr int kFlowLoopUnroll = VB2_FLOW_LOOP_UNROLL;  // rows per iteration of the plain read loop (A/B builds)
 template <bool ALT, typename QT>
 __device__ __forceinline__ void eat_full_rows(const uint32_t *col, uint32_t n, const QT &Q,
                                               double (&acc)[kNumPairs]) {
   if constexpr (!QT::kPrefetchRows) {  // (enough warps per scheduler to cover the look-ups: no row in flight, fewer registers)
-#pragma unroll 1
+#pragma unroll kFlowLoopUnroll
     for (uint32_t t = 0; t < n; ++t) {
       const uint32_t w = col[t * 32];
-      eat4<ALT>(phred_of<0>(w), phred_of<1>(w), phred_of<2>(w), phred_of<3>(w), Q, acc);
+      // (the four dot-product selectors are loop-invariant REGISTERS of the holder: as immediates ptxas re-creates them in
+      //  uniform registers every iteration -- four extra instructions per row)
+      eat4<ALT>(phred_at(w, Q.sel[0]), phred_at(w, Q.sel[1]), phred_at(w, Q.sel[2]), phred_at(w, Q.sel[3]), Q, acc);
     }
     return;
   }
@@ -1212,6 +1223,7 @@ struct FlowQuad {
   double C0[kNumPairs];
   const double (&C1)[kNumPairs];
   const double (&C2)[kNumPairs];
+  uint32_t sel[4];  // 8 << (8 * B): the byte dot product's selector of read B of a word (plain read loop)
 };
 #ifndef VB2_FLOW_JOBS
 #define VB2_FLOW_JOBS 120
@@ -1243,6 +1255,7 @@ llk_flow_kernel(const __grid_constant__ FlowArgs F) {
   extern __shared__ __align__(128) uint8_t s_buf[];  // [warp][2][stage_bytes]
   __shared__ __align__(8) uint64_t s_bar[4][2];
   __shared__ double *s_dst[4][2];  // where the partial sum of the task whose last blob sits in a stage goes
+  __shared__ uint32_t s_sel[4];    // 8 << 8B: the byte dot product's selectors (see the plain read loop)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_jobs = F.n_jobs, n_quads = F.n_quads;
@@ -1254,6 +1267,7 @@ llk_flow_kernel(const __grid_constant__ FlowArgs F) {
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 256; i += 128) s_e[i] = i < kPhredArgs ? F.phred[i] : 1.0;
+  if (threadIdx.x < 4) s_sel[threadIdx.x] = 0x8u << (8u * threadIdx.x);
   __syncthreads();  // the only CTA-wide barrier
 
   const uint32_t stage_bytes = F.stage_bytes;
@@ -1330,6 +1344,8 @@ llk_flow_kernel(const __grid_constant__ FlowArgs F) {
   }
   double vsum = 0.0, prod = 1.0;  // the running task: sum of log(marginal) = log(prod * 2^esum) + vsum
   int esum = 0;
+  // (read back from shared memory so that ptxas cannot fold them: they stay in four vector registers)
+  const uint32_t sel0 = s_sel[0], sel1 = s_sel[1], sel2 = s_sel[2], sel3 = s_sel[3];
   while (__any_sync(0xFFFFFFFFu, in_flight != 0)) {
     // (the tag and the slice's row counts are the same in every lane; the reductions tell the compiler so)
     mbar_wait_warp(bar0 + 8u * cb, (parity >> cb) & 1u);
@@ -1344,7 +1360,7 @@ llk_flow_kernel(const __grid_constant__ FlowArgs F) {
     const uint32_t u_full = __reduce_or_sync(0xFFFFFFFFu, H.fr | (H.fa << 16));
     const uint32_t u_tails = __reduce_or_sync(0xFFFFFFFFu, H.tails);
     const uint32_t u_wr = u_rows & 0xFFFFu, u_wa = u_rows >> 16, u_fr = u_full & 0xFFFFu, u_fa = u_full >> 16;
-    FlowQuad Q{{0., 0., 0., 0., 0., 0.}, J.C1, J.C2};
+    FlowQuad Q{{0., 0., 0., 0., 0., 0.}, J.C1, J.C2, {sel0, sel1, sel2, sel3}};
 #pragma unroll
     for (int p = 0; p < kNumPairs; ++p) Q.C0[p] = J.c0[p] * J.c0[p];
     eat_runs<false>(reinterpret_cast<const uint32_t *>(buf + Y.off_words) + lane, u_fr, u_wr - u_fr, u_tails & 0xFu,
