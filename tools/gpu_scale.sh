@@ -23,12 +23,14 @@ for n in "$@"; do
     timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/scale/bench_nccl_1gpu.json 2> gpurun_out/scale/err_nccl_1.txt
   else
     run $n nccl
-    run $n peer --collective peer
-    VB2_STREAM_KERNEL=queue run $n queue
+    if [ -z "$SCALE_QUICK" ]; then   # SCALE_QUICK=1: only the headline line per N
+      run $n peer --collective peer
+      VB2_STREAM_KERNEL=queue run $n queue
+    fi
   fi
   last=$n
 done
-if [ $last -gt 1 ]; then
+if [ $last -gt 1 ] && [ -z "$SCALE_QUICK" ]; then
   run $last batch64 --config batch64
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $last --master-addr 127.0.0.1 --master-port 29512 \
       tools/collective_ab.py > gpurun_out/scale/collective_ab_$last.txt 2>&1
