@@ -180,3 +180,46 @@ def test_cli_refvcf_writes_the_reference_panel_files(test_vcf, tmp_path):
     # without --SkipMinSampleCountCheck a 64-sample panel is refused, as in the reference (cpp:383-396)
     r = subprocess.run([cli, "--RefVCF", ours], capture_output=True, text=True)
     assert r.returncode != 0 and "Insufficient number of individuals" in r.stderr
+
+
+# ---- committed golden vectors (tests/golden/svd/*.npz, made from the reference's own code by tools/make_svd_golden.py) ----
+GOLD = os.path.join(ROOT, "tests", "golden", "svd")
+
+
+def test_restatement_and_host_reader_match_the_committed_goldens(tmp_path):
+    z = np.load(os.path.join(GOLD, "gram_300x40.npz"))
+    g = z["genotype"]
+    assert (g == so.lcg_genotypes(300, 40, 2024)).all()
+    a, mu = so.center(g)
+    assert (mu == z["mu"]).all()
+    ud, pc, sv = so.compute_svd_gram(a, 6)
+    compare(ud, pc, sv, z["gram_ud"], z["gram_pc"], z["gram_sv"], 6, 1e-4)
+    compare(z["gram_ud"], z["gram_pc"], z["gram_sv"], z["jacobi_ud"], z["jacobi_pc"], z["jacobi_sv"], 6, 1e-2)   # TestGramSVD's own claim
+    v = np.load(os.path.join(GOLD, "vcf_panel.npz"))
+    vcf = str(tmp_path / "panel.vcf")
+    so.write_test_vcf(vcf)
+    got = host.read_vcf(vcf, AUTOSOMES)
+    assert got["genotype"].shape == v["genotype"].shape and (got["genotype"] == v["genotype"]).all()
+    bed = ["%s\t%d\t%d\t%s\t%s" % (c, p - 1, p, r, a_) for c, p, r, a_ in zip(got["chrom"], got["pos"], got["ref"], got["alt"])]
+    assert bed == list(v["bed_text"])
+
+
+@pytest.mark.gpu
+def test_device_gram_svd_and_cli_match_the_committed_goldens(tmp_path):
+    z = np.load(os.path.join(GOLD, "gram_300x40.npz"))
+    r = svd.svd_gram(z["genotype"], 6)
+    assert (r["mu"] == z["mu"]).all()
+    compare(r["ud"], r["pc"], r["singular"], z["gram_ud"], z["gram_pc"], z["gram_sv"], 6, GRAM_TOL)
+    v = np.load(os.path.join(GOLD, "vcf_panel.npz"))
+    vcf = str(tmp_path / "panel.vcf")
+    so.write_test_vcf(vcf)
+    cli = os.path.join(ROOT, "verifybamid_b200", "VerifyBamID")
+    p = subprocess.run([cli, "--RefVCF", vcf, "--SkipMinSampleCountCheck"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert open(vcf + ".mu").read().splitlines() == list(v["mu_text"])
+    assert open(vcf + ".bed").read().splitlines() == list(v["bed_text"])
+    ud, vv = _read_table(vcf + ".UD"), _read_table(vcf + ".V", True)
+    scale = float(np.linalg.norm(v["ud"][:, 0]))
+    for c in range(10):
+        tol = GRAM_TOL if c < 3 else 1e-2
+        assert so.column_error(v["ud"][:, c], ud[:, c], scale) <= tol and so.column_error(v["v"][:, c], vv[:, c], 1.0) <= tol
