@@ -27,6 +27,7 @@ VB2_STREAM_KERNEL=queue timeout 600 ncu --set full --clock-control none --import
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-session > $out/ncu_stream.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:llk_kernel -s 40 -c 1 -f -o $out/prof_latency \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-session > $out/ncu_latency.log 2>&1
+for mb in fp64 mix; do [ -x tools/microbench_$mb ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench_$mb tools/microbench_$mb.cu; done
 ./tools/microbench_fp64 > $out/microbench_fp64.txt 2>&1
 ./tools/microbench_mix > $out/microbench_mix.txt 2>&1
 VB2_STREAM_KERNEL=queue timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $out/bench_queue_kernel.json 2>> $out/bench.err
