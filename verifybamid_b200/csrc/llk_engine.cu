@@ -1241,11 +1241,12 @@ struct FlowArgs {
 };
 static_assert(sizeof(FlowArgs) <= 32764, "kernel arguments must stay below 32,764 bytes");
 
-// The register cap is what steers ptxas here: with 56 registers (min-blocks 9) it keeps C1/C2 in uniform registers
-// and nothing spills; given 64 it hoists them into vector registers for the short read loop and then spills the
-// accumulators.  Shared memory admits eight CTAs per SM for a 30x sample either way.
+// The register cap steers ptxas here: whether it keeps C1/C2 in uniform registers (wanted) or hoists them into vector
+// registers for the short read loop and then spills the accumulators depends on its estimate of the pressure, and that
+// changed with the code around the loop (an earlier version needed a 56-register cap; this one is in uniform mode at
+// 64 with no spills, and the extra registers save re-derived addresses: 2.84 vs 2.89 us).  tools/gpu_ab.sh decides.
 #ifndef VB2_FLOW_MIN_BLOCKS
-#define VB2_FLOW_MIN_BLOCKS 9
+#define VB2_FLOW_MIN_BLOCKS 8
 #endif
 constexpr uint32_t kFlowLast = 0x80000000u;  // stage tag: the last blob of its (job, bin)
 template <int NPC>
@@ -1272,7 +1273,22 @@ llk_flow_kernel(const __grid_constant__ FlowArgs F) {
 
   const uint32_t stage_bytes = F.stage_bytes;
   uint8_t *mybuf = s_buf + (size_t)warp * 2u * stage_bytes;
+#ifndef VB2_FLOW_OPAQUE_ADDR
+#define VB2_FLOW_OPAQUE_ADDR 1   // 0: plain expressions, which ptxas re-derives from the thread index in every slice (A/B builds)
+#endif
+#if VB2_FLOW_OPAQUE_ADDR
+  // shared-window addresses of this warp's stages and mbarriers, read back from shared memory so that ptxas keeps them
+  // in two registers instead of re-deriving them from the thread index in every slice
+  __shared__ uint32_t s_addr[4][2];
+  if (lane == 0) {
+    s_addr[warp][0] = smem_u32(mybuf);
+    s_addr[warp][1] = smem_u32(&s_bar[warp][0]);
+  }
+  __syncwarp();
+  const uint32_t buf0 = s_addr[warp][0], bar0 = s_addr[warp][1];
+#else
   const uint32_t buf0 = smem_u32(mybuf), bar0 = smem_u32(&s_bar[warp][0]);  // (shared-window addresses, formed once)
+#endif
   const Layout Y(F.recs[0].S);
 
   // ---- issue side: tasks (job, bin) from a counter in HBM; the blobs of a task in round order -------------------
@@ -1352,7 +1368,11 @@ llk_flow_kernel(const __grid_constant__ FlowArgs F) {
     parity ^= 1u << cb;
     const uint32_t tag = __reduce_or_sync(0xFFFFFFFFu, cb ? tag1 : tag0);
     const FlowJob &J = F.jobs[tag & 0xFFFFu];
+#if VB2_FLOW_OPAQUE_ADDR
+    const uint8_t *buf = static_cast<const uint8_t *>(__cvta_shared_to_generic(buf0 + cb * stage_bytes));
+#else
     const uint8_t *buf = mybuf + (size_t)cb * stage_bytes;
+#endif
     double acc[kNumPairs], ldiag;
     SliceHeader H;
     slice_begin(buf, Y, J, lane, H, acc, ldiag);
