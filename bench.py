@@ -465,10 +465,10 @@ def run_ours(args):
         n1 = 500
         one_ms = vb.time_device(engines, 20, n1, start_pc, start_pc, 0.03) / n1
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of the kernel, per evaluation of the headline
-    # workload at N=1 (profiles/r02_llk_flow_kernel_digest.txt: 854,247,936 + 4,747,264 bytes for a launch of 120 evaluations;
+    # workload at N=1 (profiles/r02_llk_flow_kernel_digest.txt: 849,343,744 + 4,357,632 bytes for a launch of 120 evaluations;
     # profiles/r02_llk_stream_kernel_digest.txt: 14,846,177,000 + 15,367,424 bytes for 2,048): the stored image, no re-reads
     # (algorithmic: 7.573 MB per evaluation)
-    per_eval_traffic = {"llk_flow_kernel": 7158293.0, "llk_stream_kernel": 7256614.0}[plan["kernel"]]
+    per_eval_traffic = {"llk_flow_kernel": 7114178.0, "llk_stream_kernel": 7256614.0}[plan["kernel"]]
     traffic = per_eval_traffic * n_jobs if (args.config == "100k30x" and world == 1) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
@@ -482,8 +482,8 @@ def run_ours(args):
                 "includes_allreduce": collective,
                 "note": "bound by instruction issue, not by HBM: an FP64 warp-instruction holds a B200 sub-partition's issue slot for "
                         "two cycles (tools/microbench_mix.cu), so an evaluation costs >= 2*F + G cycles per sub-partition with "
-                        "F = 1,939 fp64 and G ~ 2,410 other warp-instructions (10 fp64 per streamed read + ~90 per 32-marker slice): "
-                        "3.2 us for this instruction mix, 1.97 us for the fp64 instructions alone (DESIGN.md section 4)"}
+                        "F = 1,939 fp64 and G ~ 2,280 other warp-instructions (10 fp64 per streamed read + ~90 per 32-marker slice): "
+                        "3.1 us for this instruction mix, 1.97 us for the fp64 instructions alone (DESIGN.md section 4)"}
 
     # ---- e2e: the public C-ABI call with HOST buffers, host<->device traffic inside the timed region ----------------
     e2e_extra, r_last = {}, None
