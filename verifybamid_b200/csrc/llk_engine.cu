@@ -15,7 +15,7 @@
 // Four launch shapes of the same arithmetic (identical bits):
 //   llk_kernel          one evaluation per launch, one CTA per SM;
 //   llk_flow_kernel     many evaluations per launch, the common shapes (fp32 panel, NumPC 2 or 4, blobs that fit a
-//                       stage): per-job coefficients in the kernel arguments -> uniform registers, 56 registers,
+//                       stage): per-job coefficients in the kernel arguments -> uniform registers, 64 registers,
 //                       eight warps per SM sub-partition, launches of a batch overlapped;
 //   llk_stream_kernel   many evaluations per launch, any shape: persistent grid, warps pull (evaluation, bin) tasks
 //                       from a queue, task records by TMA; llk_reduce_kernel adds the per-bin partial sums of both;
